@@ -1,0 +1,504 @@
+// hive_core.cuh -- warp-per-game Hive position evaluator for sm_100a.
+//
+// One warp owns one game.  Lane p (0..21) owns piece p (white Q,B0,B1,S0,S1,G0,G1,G2,A0,A1,A2
+// then the same for black -- reference order, inventory_frame.py:47-99 / env_hive.py:71-87);
+// every lane keeps whole 144-cell boards in registers as a linear bit string (cell = q*12+r,
+// 5 x u32), so translating a board along one of the six torus directions (tile.py:111-123) is a
+// handful of funnel shifts and no shuffles.  Board-wide facts (occupancy, colour masks) are
+// OR-reduced across lanes with REDUX (__reduce_or_sync), stack heights come from
+// __match_any_sync, the per-piece searches (one-hive flood, Ant flood, 3-step Spider walk,
+// Grasshopper line flood) run concurrently in the lanes that own such a piece, and results are
+// combined into the dense 1584-bit legal mask and the 56 network planes in shared memory.
+//
+// What is computed is exactly what the reference computes in GamePlay.move()'s tail
+// (hive_engine/env_hive.py:170-171): pre_actions() (env_hive.py:196-304, move_checker.py:9-55,
+// pieces.py:35-158) and make_state_value() (env_hive.py:320-485), bug-for-bug (SURVEY.md
+// Appendix A/B).  No code is shared with oracle/hive_oracle.c.
+#pragma once
+#ifndef HIVE_EMU
+#include <cuda_runtime.h>
+#endif
+#include <stdint.h>
+
+namespace hive {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int HAND = 255;
+constexpr int N_PIECE = 22;
+constexpr int N_PLANE = 56;
+constexpr int LEGAL_WORDS = 50;      // 1584 bits -> 49.5 u32 (25 u64)
+constexpr int START_CELL = 6 * 12 + 6;   // tile.py:156,188 Start_Tile
+constexpr int TURN2_CELL = 5 * 12 + 6;   // core_index ('M','13'), env_hive.py:157-159
+
+enum PieceType { T_QUEEN = 0, T_BEETLE = 1, T_SPIDER = 2, T_HOPPER = 3, T_ANT = 4 };
+
+// ------------------------------------------------------------------------------------------
+// 384-byte game record in HBM (DESIGN.md "state record").
+struct __align__(16) GameRec {
+    uint8_t cell[N_PIECE];     // q*12+r, HAND = in inventory
+    uint8_t level[N_PIECE];    // index in its stack (env_hive.py:119,125)
+    uint8_t turn;              // 1-based (game_state.py:38)
+    uint8_t winner;            // 0 none, 1 white, 2 black
+    uint8_t done;              // game_is_over() (move_checker.py:140-165)
+    uint8_t flags;
+    uint32_t episode;          // bumped by every reset of this slot
+    uint32_t steps;            // env steps taken in this slot
+    uint32_t n_legal;
+    uint32_t pad;
+    uint32_t hist[2][4][2][5]; // [side][age][own-any, opp-any] boards (env_hive.py:431-445)
+};
+static_assert(sizeof(GameRec) == 384, "GameRec must stay 384 bytes");
+
+// per-warp shared-memory scratch
+struct WarpScratch {
+    uint32_t planes[N_PLANE][5];   // bit boards of the 56 planes (plane 31 unused: it is the turn)
+    uint32_t legal[LEGAL_WORDS];
+    uint32_t occ[5];
+    uint32_t moves[N_PIECE][5];    // action list per piece (own) / mobility set (opponent)
+    uint32_t hist[2][4][2][5];
+};
+
+// ------------------------------------------------------------------------------------------
+// 144-bit boards
+struct BB { uint32_t w[5]; };
+
+// column-0 / column-11 positions of each 12-cell row inside the linear bit string
+#define HIVE_COLFIRST(i) ((i) == 0 ? 0x01001001u : (i) == 1 ? 0x10010010u : (i) == 2 ? 0x00100100u : (i) == 3 ? 0x01001001u : 0x00000010u)
+#define HIVE_COLLAST(i)  ((i) == 0 ? 0x00800800u : (i) == 1 ? 0x08008008u : (i) == 2 ? 0x80080080u : (i) == 3 ? 0x00800800u : 0x00008008u)
+
+__device__ __forceinline__ BB bb_zero() { BB r; r.w[0] = r.w[1] = r.w[2] = r.w[3] = r.w[4] = 0; return r; }
+__device__ __forceinline__ BB bb_bit(int c) {
+    BB r; uint32_t b = 1u << (c & 31); int wi = c >> 5;
+#pragma unroll
+    for (int i = 0; i < 5; i++) r.w[i] = (wi == i) ? b : 0u;
+    return r;
+}
+__device__ __forceinline__ BB operator|(const BB& a, const BB& b) { BB r;
+#pragma unroll
+    for (int i = 0; i < 5; i++) r.w[i] = a.w[i] | b.w[i]; return r; }
+__device__ __forceinline__ BB operator&(const BB& a, const BB& b) { BB r;
+#pragma unroll
+    for (int i = 0; i < 5; i++) r.w[i] = a.w[i] & b.w[i]; return r; }
+__device__ __forceinline__ BB operator^(const BB& a, const BB& b) { BB r;
+#pragma unroll
+    for (int i = 0; i < 5; i++) r.w[i] = a.w[i] ^ b.w[i]; return r; }
+__device__ __forceinline__ BB bb_andn(const BB& a, const BB& b) { BB r;   // a & ~b
+#pragma unroll
+    for (int i = 0; i < 5; i++) r.w[i] = a.w[i] & ~b.w[i]; return r; }
+__device__ __forceinline__ bool bb_any(const BB& a) { return (a.w[0] | a.w[1] | a.w[2] | a.w[3] | a.w[4]) != 0; }
+__device__ __forceinline__ bool bb_eq(const BB& a, const BB& b) {
+    return ((a.w[0] ^ b.w[0]) | (a.w[1] ^ b.w[1]) | (a.w[2] ^ b.w[2]) | (a.w[3] ^ b.w[3]) | (a.w[4] ^ b.w[4])) == 0; }
+__device__ __forceinline__ int bb_popc(const BB& a) {
+    return __popc(a.w[0]) + __popc(a.w[1]) + __popc(a.w[2]) + __popc(a.w[3]) + __popc(a.w[4]); }
+__device__ __forceinline__ bool bb_test(const BB& a, int c) {
+    uint32_t w = c < 64 ? (c < 32 ? a.w[0] : a.w[1]) : (c < 96 ? a.w[2] : (c < 128 ? a.w[3] : a.w[4]));
+    return (w >> (c & 31)) & 1u;
+}
+__device__ __forceinline__ bool words_test(const uint32_t* w, int c) { return (w[c >> 5] >> (c & 31)) & 1u; }
+
+// (q, r) -> (q, r+1 mod 12)
+__device__ __forceinline__ BB bb_colL(const BB& x) {
+    BB r;
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        uint32_t shl = (i == 0) ? (x.w[0] << 1) : __funnelshift_l(x.w[i - 1], x.w[i], 1);
+        uint32_t shr = (i == 4) ? (x.w[4] >> 11) : __funnelshift_r(x.w[i], x.w[i + 1], 11);
+        uint32_t f = HIVE_COLFIRST(i);
+        r.w[i] = (shl & ~f) | (shr & f);
+    }
+    r.w[4] &= 0xFFFFu;
+    return r;
+}
+// (q, r) -> (q, r-1 mod 12)
+__device__ __forceinline__ BB bb_colR(const BB& x) {
+    BB r;
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        uint32_t shr = (i == 4) ? (x.w[4] >> 1) : __funnelshift_r(x.w[i], x.w[i + 1], 1);
+        uint32_t shl = (i == 0) ? (x.w[0] << 11) : __funnelshift_l(x.w[i - 1], x.w[i], 11);
+        uint32_t l = HIVE_COLLAST(i);
+        r.w[i] = (shr & ~l) | (shl & l);
+    }
+    r.w[4] &= 0xFFFFu;
+    return r;
+}
+// (q, r) -> (q+1 mod 12, r)
+__device__ __forceinline__ BB bb_up(const BB& x) {
+    BB r;
+    r.w[0] = (x.w[0] << 12) | (x.w[4] >> 4);
+    r.w[1] = __funnelshift_l(x.w[0], x.w[1], 12);
+    r.w[2] = __funnelshift_l(x.w[1], x.w[2], 12);
+    r.w[3] = __funnelshift_l(x.w[2], x.w[3], 12);
+    r.w[4] = __funnelshift_l(x.w[3], x.w[4], 12) & 0xFFFFu;
+    return r;
+}
+// (q, r) -> (q-1 mod 12, r)
+__device__ __forceinline__ BB bb_down(const BB& x) {
+    BB r;
+    r.w[0] = __funnelshift_r(x.w[0], x.w[1], 12);
+    r.w[1] = __funnelshift_r(x.w[1], x.w[2], 12);
+    r.w[2] = __funnelshift_r(x.w[2], x.w[3], 12);
+    r.w[3] = __funnelshift_r(x.w[3], x.w[4], 12);
+    r.w[4] = (x.w[4] >> 12) | ((x.w[0] & 0xFFFu) << 4);
+    return r;
+}
+// union of the six torus neighbours of every set cell (tile.py:114-121)
+__device__ __forceinline__ BB bb_nbrs(const BB& x) {
+    BB a = bb_colL(x), b = bb_colR(x);
+    BB u = bb_up(x | a), d = bb_down(x | b);
+    return a | b | u | d;
+}
+
+// direction ring d0=(+1,0) d1=(+1,+1) d2=(0,+1) d3=(-1,0) d4=(-1,-1) d5=(0,-1): consecutive
+// directions are adjacent, so the two common neighbours of c and c+d_i are c+d_{i-1}, c+d_{i+1}.
+__device__ __forceinline__ int cell_up(int c)   { c += 12; return c >= 144 ? c - 144 : c; }
+__device__ __forceinline__ int cell_down(int c) { c -= 12; return c < 0 ? c + 144 : c; }
+__device__ __forceinline__ int cell_colL(int c) { return (c % 12 == 11) ? c - 11 : c + 1; }
+__device__ __forceinline__ int cell_colR(int c) { return (c % 12 == 0) ? c + 11 : c - 1; }
+__device__ __forceinline__ int cell_nbr(int c, int i) {
+    switch (i) {
+        case 0: return cell_up(c);
+        case 1: return cell_up(cell_colL(c));
+        case 2: return cell_colL(c);
+        case 3: return cell_down(c);
+        case 4: return cell_down(cell_colR(c));
+        default: return cell_colR(c);
+    }
+}
+__device__ __forceinline__ uint32_t rot6l(uint32_t x) { return ((x << 1) | (x >> 5)) & 63u; }
+__device__ __forceinline__ uint32_t rot6r(uint32_t x) { return ((x >> 1) | (x << 5)) & 63u; }
+
+__device__ __forceinline__ BB warp_or(const BB& x) {
+    BB r;
+#pragma unroll
+    for (int i = 0; i < 5; i++) r.w[i] = __reduce_or_sync(FULL, x.w[i]);
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// Slide relation R of Ant / Spider (move_checker.py:189-214 inside path_exists :235-240), in
+// destination form: arriving at n along d_i is allowed iff n is empty and exactly one of
+// n+d_{i-2}, n+d_{i+2} (the two flanks of the step) is occupied.  `occp` has the mover lifted.
+struct Slide { BB g[6]; };
+
+__device__ __forceinline__ void slide_init(Slide& s, const BB& occp) {
+    BB cL = bb_colL(occp), cR = bb_colR(occp);
+    BB o0 = bb_down(occp), o3 = bb_up(occp), o1 = bb_down(cR), o4 = bb_up(cL);
+    const BB& o2 = cR; const BB& o5 = cL;
+    s.g[0] = bb_andn(o4 ^ o2, occp);
+    s.g[1] = bb_andn(o5 ^ o3, occp);
+    s.g[2] = bb_andn(o0 ^ o4, occp);
+    s.g[3] = bb_andn(o1 ^ o5, occp);
+    s.g[4] = bb_andn(o2 ^ o0, occp);
+    s.g[5] = bb_andn(o3 ^ o1, occp);
+}
+__device__ __forceinline__ BB slide_step(const Slide& s, const BB& x) {
+    BB a = bb_colL(x), b = bb_colR(x);
+    BB r = (bb_up(x) & s.g[0]) | (bb_up(a) & s.g[1]) | (a & s.g[2]);
+    r = r | (bb_down(x) & s.g[3]) | (bb_down(b) & s.g[4]) | (b & s.g[5]);
+    return r;
+}
+
+// move_checker.py:106-137; nq/first-queen colour derived from the two queen cells
+__device__ __forceinline__ bool obeys_queen_by_4(int turn, bool wq_on, bool bq_on, bool mover_queen, int mover_color) {
+    int nq = (int)wq_on + (int)bq_on;
+    if (nq == 2) return true;
+    if (nq == 0) return mover_queen && ((turn == 7 && mover_color == 0) || (turn == 8 && mover_color == 1));
+    bool c_white = wq_on;
+    if (c_white) return turn == 7 || mover_queen;      // (white,7) -> True ; (white,8) -> mover is a Queen
+    return turn == 8 || mover_queen;                   // (black,8) -> True ; (black,7) -> mover is a Queen
+}
+
+struct EvalResult { int n_legal; int done; int winner; };
+
+// ------------------------------------------------------------------------------------------
+// Evaluate the position held by the warp: legal mask + planes into `sm`, history push.
+// All 32 lanes must call this converged.  `hop_lines` = 144x5 u32 table of is_straight_line
+// masks (move_checker.py:249-265).
+__device__ __noinline__ EvalResult evaluate_position(WarpScratch& sm, int lane, int cell, int level, int turn,
+                                                     bool push_history, int prev_winner,
+                                                     const uint32_t* __restrict__ hop_lines) {
+    const int side = (turn & 1) ? 0 : 1;                 // game_state.py:58-62
+    const bool valid = lane < N_PIECE;
+    const int color = lane >= 11 ? 1 : 0;
+    const int k = lane - 11 * color;
+    const int type = (k == 0) ? T_QUEEN : (k <= 2) ? T_BEETLE : (k <= 4) ? T_SPIDER : (k <= 7) ? T_HOPPER : T_ANT;
+    const bool own = valid && (color == side);
+    const bool on_board = valid && cell != HAND;
+
+    // ---- zero the scratch outputs
+    {
+        uint32_t* pz = &sm.planes[0][0];
+        for (int i = lane; i < N_PLANE * 5; i += 32) pz[i] = 0;
+        for (int i = lane; i < LEGAL_WORDS; i += 32) sm.legal[i] = 0;
+    }
+
+    // ---- stacks: pieces sharing a cell (tile.pieces); top piece <=> level+1 == len (env_hive.py:213)
+    const unsigned peers = __match_any_sync(FULL, on_board ? cell : 256 + lane);
+    const int height = __popc(peers);
+    const bool top = on_board && (level == height - 1);
+
+    const BB src = on_board ? bb_bit(cell) : bb_zero();
+    const BB own_all = warp_or(own ? src : bb_zero());
+    const BB opp_all = warp_or((valid && !own) ? src : bb_zero());
+    const BB occ = own_all | opp_all;
+    const BB top_opp = warp_or((top && !own) ? src : bb_zero());
+    if (lane < 5) sm.occ[lane] = occ.w[lane];
+
+    const int cq_w = __shfl_sync(FULL, cell, 0), cq_b = __shfl_sync(FULL, cell, 11);
+    const bool wq_on = cq_w != HAND, bq_on = cq_b != HAND;
+    const int cq_own = side == 0 ? cq_w : cq_b, cq_opp = side == 0 ? cq_b : cq_w;
+    const bool ownq_on = cq_own != HAND;
+    __syncwarp();
+
+    // ---- ring occupancy around each on-board piece
+    uint32_t ring = 0;
+    if (on_board) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) ring |= (uint32_t)words_test(sm.occ, cell_nbr(cell, i)) << i;
+    }
+
+    // ---- one hive (move_checker.py:58-83 / env_hive.py:509-530): lift the top piece, flood
+    bool pinned = false;
+    if (top && height == 1) {
+        uint32_t arcs = __popc(ring & ~rot6l(ring));
+        if (ring == 0) pinned = true;              // nothing left on the board -> `return False`
+        else if (arcs > 1) {
+            const BB occp = occ ^ src;
+            const BB goal = bb_nbrs(src) & occp;
+            BB x = bb_bit(cell_nbr(cell, __ffs(ring) - 1));
+            for (;;) {
+                BB nx = x | (bb_nbrs(x) & occp);
+                if (bb_eq(nx & goal, goal)) break;
+                if (bb_eq(nx, x)) { pinned = true; break; }
+                x = nx;
+            }
+        }
+    }
+    const bool can_move = top && !pinned;
+    // opponent mobility is only consumed through the own queen's neighbourhood (env_hive.py:459-478)
+    const bool active = can_move && (own || ownq_on);
+
+    // ---- turn gates shared by every candidate of this piece (move_checker.py:38-55)
+    bool gate = true;
+    if (turn <= 2) gate = false;                                             // no on-board mover can exist / matter
+    else if (turn <= 6) gate = ownq_on;                                      // queen_is_on_board: colour by turn parity
+    else if (turn <= 8) gate = obeys_queen_by_4(turn, wq_on, bq_on, type == T_QUEEN, color);
+
+    BB mv = bb_zero();
+    if (active && gate) {
+        if (type == T_QUEEN) {                                               // pieces.py:35-44
+            uint32_t ok = ~ring & (rot6l(ring) ^ rot6r(ring)) & 63u;
+#pragma unroll
+            for (int i = 0; i < 6; i++) if ((ok >> i) & 1u) mv = mv | bb_bit(cell_nbr(cell, i));
+        } else if (type == T_BEETLE) {                                       // pieces.py:100-113
+            uint32_t fl = rot6l(ring), fr = rot6r(ring);                     // bit i: flank c+d_{i-1} / c+d_{i+1}
+            uint32_t k1 = fl ^ fr, k0 = ~(fl | fr) & 63u;
+            uint32_t ok = k1 | ring | (height > 1 ? 63u : 0u);
+            if (k0 & ~ok) {
+                // k==0: allowed iff the target has an occupied neighbour other than `old`
+                // (len(new_adjacents_with_pieces) - 1 != 0, move_checker.py:205-207)
+                const BB hns = bb_nbrs(occ ^ src);
+#pragma unroll
+                for (int i = 0; i < 6; i++)
+                    if (((k0 & ~ok) >> i) & 1u) { if (bb_test(hns, cell_nbr(cell, i))) ok |= 1u << i; }
+            }
+#pragma unroll
+            for (int i = 0; i < 6; i++) if ((ok >> i) & 1u) mv = mv | bb_bit(cell_nbr(cell, i));
+        } else if (type == T_HOPPER) {                                       // pieces.py:128-158
+            BB line;
+#pragma unroll
+            for (int i = 0; i < 5; i++) line.w[i] = __ldg(hop_lines + cell * 5 + i);
+            const BB walk = occ & line;
+            BB v = src;
+            for (;;) {
+                BB nv = v | (bb_nbrs(v) & walk);
+                if (bb_eq(nv, v)) break;
+                v = nv;
+            }
+            mv = bb_andn(bb_andn(bb_nbrs(v) & line, occ), bb_nbrs(src));
+        } else {                                                             // Ant / Spider
+            const BB occp = occ ^ src;
+            Slide sl;
+            slide_init(sl, occp);
+            if (type == T_ANT) {                                             // pieces.py:59-63
+                BB x = src;
+                for (;;) {
+                    BB nx = x | slide_step(sl, x);
+                    if (bb_eq(nx, x)) break;
+                    x = nx;
+                }
+                mv = bb_andn(x, src);
+            } else {                                                         // pieces.py:78-85
+#pragma unroll 1
+                for (int i = 0; i < 6; i++) {
+                    const BB ti = bb_bit(cell_nbr(cell, i));
+                    const BB a = ti & sl.g[i];
+                    if (!bb_any(a)) continue;
+                    const BB b = bb_andn(slide_step(sl, a), src);
+                    const BB c = bb_andn(slide_step(sl, b), src | a);
+                    mv = mv | c;
+                }
+                // end check with the spider back on `old`: adjacent target with both flanks occupied
+                uint32_t k2 = rot6l(ring) & rot6r(ring);
+#pragma unroll
+                for (int i = 0; i < 6; i++) if ((k2 >> i) & 1u) mv = bb_andn(mv, bb_bit(cell_nbr(cell, i)));
+            }
+        }
+    }
+
+    // ---- placements (env_hive.py:217-225; move_checker.py:168-179): first in-hand piece per type
+    const unsigned in_hand = __ballot_sync(FULL, own && !on_board);
+    if (own && !on_board) {
+        const unsigned same_type_before = in_hand & ((1u << lane) - 1u) &
+            (type == T_QUEEN ? 0x00000801u : type == T_BEETLE ? 0x00003006u : type == T_SPIDER ? 0x0000C018u
+             : type == T_HOPPER ? 0x000700E0u : 0x00380700u);
+        if (same_type_before == 0) {
+            if (turn == 1) mv = bb_bit(START_CELL);
+            else if (turn == 2) mv = bb_andn(bb_nbrs(occ), occ) & bb_bit(TURN2_CELL);
+            else {
+                bool ok = true;
+                if (turn == 7 || turn == 8) ok = obeys_queen_by_4(turn, wq_on, bq_on, type == T_QUEEN, color);
+                if (ok) mv = bb_andn(bb_andn(bb_nbrs(occ), occ), bb_nbrs(top_opp));
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---- publish move boards; dense legal mask a = cell*11 + k (env_hive.py:287-304)
+    if (valid) {
+#pragma unroll
+        for (int i = 0; i < 5; i++) sm.moves[lane][i] = mv.w[i];
+    }
+    int n_mine = 0;
+    if (own) {
+        n_mine = bb_popc(mv);
+#pragma unroll
+        for (int i = 0; i < 5; i++) {
+            uint32_t m = mv.w[i];
+            while (m) {
+                int b = __ffs(m) - 1; m &= m - 1;
+                int a = (i * 32 + b) * 11 + k;
+                atomicOr(&sm.legal[a >> 5], 1u << (a & 31));
+            }
+        }
+    }
+    int n_legal = n_mine;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n_legal += __shfl_xor_sync(FULL, n_legal, o);
+
+    // ---- terminal test (move_checker.py:140-165)
+    const unsigned surrounded = __ballot_sync(FULL, on_board && type == T_QUEEN && ring == 63u);
+    const bool ws = surrounded & 1u, bs = (surrounded >> 11) & 1u;
+    EvalResult res;
+    res.n_legal = n_legal;
+    res.done = ws || bs;
+    res.winner = (ws && bs) ? prev_winner : ws ? 2 : bs ? 1 : prev_winner;
+
+    // ---- planes (env_hive.py:320-447); "own" = side to move
+    if (on_board) {
+        const uint32_t bit = 1u << (cell & 31); const int wi = cell >> 5;
+        sm.planes[(own ? 0 : 12) + k][wi] = bit;                          // 0-10 / 12-22
+        if (type == T_BEETLE && level >= 2)                               // 24-26 / 27-29
+            atomicOr(&sm.planes[(own ? 24 : 27) + level - 2][wi], bit);
+        if (own ? (!top || !bb_any(mv)) : (!top || pinned))               // 34 / 35
+            atomicOr(&sm.planes[own ? 34 : 35][wi], bit);
+        if (type == T_QUEEN) {                                            // 32 / 33
+#pragma unroll
+            for (int i = 0; i < 6; i++)
+                if ((ring >> i) & 1u) { int c = cell_nbr(cell, i); atomicOr(&sm.planes[own ? 32 : 33][c >> 5], 1u << (c & 31)); }
+        }
+    }
+    if (lane < 5) {
+        sm.planes[11][lane] = own_all.w[lane];
+        sm.planes[23][lane] = opp_all.w[lane];
+        sm.planes[30][lane] = occ.w[lane];
+    }
+    {   // 36..43 history of the side to move
+        const uint32_t* h = &sm.hist[side][0][0][0];
+        for (int i = lane; i < 40; i += 32) (&sm.planes[36][0])[i] = h[i];
+    }
+    __syncwarp();
+    // 44+j: opponent pieces able to reach the j-th empty neighbour of the own queen;
+    // 50+j: own on-board pieces whose action list holds the j-th empty neighbour of the opponent queen.
+    // j follows tile.adjacent_tiles order = board_tiles order: q descending, then r ascending.
+    {
+        const int qc = own ? cq_opp : cq_own;      // own pieces look at the opponent queen and vice versa
+        if (on_board && qc != HAND && (own || active)) {
+            int nb[6], key[6];
+#pragma unroll
+            for (int i = 0; i < 6; i++) { nb[i] = cell_nbr(qc, i); key[i] = (11 - nb[i] / 12) * 12 + nb[i] % 12; }
+            const uint32_t bit = 1u << (cell & 31); const int wi = cell >> 5;
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                if (words_test(sm.occ, nb[i]) || !bb_test(mv, nb[i])) continue;
+                int j = 0;
+#pragma unroll
+                for (int t = 0; t < 6; t++) j += key[t] < key[i];
+                atomicOr(&sm.planes[(own ? 50 : 44) + j][wi], bit);
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---- history push (env_hive.py:436-445): only after a real move / at reset
+    if (push_history) {
+        uint32_t* h = &sm.hist[side][0][0][0];
+        uint32_t keep = (lane < 30) ? h[lane] : 0;         // ages 0..2 -> 1..3
+        __syncwarp();
+        if (lane < 30) h[10 + lane] = keep;
+        if (lane < 5) { h[lane] = own_all.w[lane]; h[5 + lane] = opp_all.w[lane]; }
+        __syncwarp();
+    }
+    return res;
+}
+
+// ------------------------------------------------------------------------------------------
+// Expand the 56 bit planes to bf16 CHW [56][144] (16,128 B) with coalesced 16-byte stores.
+__device__ __forceinline__ void store_planes_bf16(const WarpScratch& sm, int lane, int turn, uint16_t* __restrict__ out) {
+    const uint8_t* bytes = reinterpret_cast<const uint8_t*>(&sm.planes[0][0]);   // 20 B per plane, 18 used
+    // bf16(turn): turn <= 255 is exact in bf16 (8 significant bits)
+    const uint32_t tb = __float_as_uint((float)turn) >> 16;
+    const uint32_t tt = tb | (tb << 16);
+    uint4* o = reinterpret_cast<uint4*>(out);
+    for (int t = lane; t < N_PLANE * 18; t += 32) {
+        int p = t / 18, j = t - p * 18;
+        uint32_t x = bytes[p * 20 + j];
+        uint4 v;
+        v.x = (((x     ) & 1u) | (((x     ) & 2u) << 15)) * 0x3F80u;
+        v.y = (((x >> 2) & 1u) | (((x >> 2) & 2u) << 15)) * 0x3F80u;
+        v.z = (((x >> 4) & 1u) | (((x >> 4) & 2u) << 15)) * 0x3F80u;
+        v.w = (((x >> 6) & 1u) | (((x >> 6) & 2u) << 15)) * 0x3F80u;
+        if (p == 31) v = make_uint4(tt, tt, tt, tt);
+        o[t] = v;
+    }
+}
+
+// splitmix64 -- counter-based action choice of SURVEY 8d Config 2
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+
+// index of the kth (0-based) set bit of a 50-word mask held in memory readable by the warp
+__device__ __forceinline__ int select_kth_action(const uint32_t* words, int lane, int kth) {
+    uint32_t w0 = 0, w1 = 0;
+    if (lane < 25) { w0 = words[2 * lane]; w1 = words[2 * lane + 1]; }
+    int c = __popc(w0) + __popc(w1), incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+    const unsigned hit = __ballot_sync(FULL, incl > kth);
+    const int owner = __ffs(hit) - 1;
+    int ans = -1;
+    if (lane == owner) {
+        int r = kth - (incl - c);
+        uint64_t m = ((uint64_t)w1 << 32) | w0;
+        for (int i = 0; i < r; i++) m &= m - 1;
+        ans = lane * 64 + __ffsll((long long)m) - 1;
+    }
+    return __shfl_sync(FULL, ans, owner < 0 ? 0 : owner);
+}
+
+}  // namespace hive

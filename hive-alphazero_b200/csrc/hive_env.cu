@@ -1,0 +1,355 @@
+// hive_env.cu -- environment kernels + C ABI (include/hive_b200.h) for sm_100a.
+//
+// One kernel, `hive_env_kernel`, is the whole GamePlay.move() of the reference
+// (hive_engine/env_hive.py:99-171) for a batch of games: apply the action, regenerate the legal
+// set of the new side to move, encode its 56 planes, push history, test for the end of the game.
+// One warp per game (hive_core.cuh), 4 games per CTA.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/hive_b200.h"
+#include "hive_env_kernel.cuh"
+
+using namespace hive;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CUDA_TRY(x)                                                                           \
+    do {                                                                                      \
+        cudaError_t e_ = (x);                                                                 \
+        if (e_ != cudaSuccess) return fail(HIVE_E_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+// move_checker.py:249-265 on raw (non-modular) deltas, as 144 masks of 144 bits
+void build_hop_lines(std::vector<uint32_t>& t) {
+    t.assign(144 * 5, 0);
+    for (int o = 0; o < 144; o++)
+        for (int x = 0; x < 144; x++) {
+            int q1 = o / 12, r1 = o % 12, q2 = x / 12, r2 = x % 12;
+            int d1 = q1 - q2, d2 = 12 - d1, dx = d1 < d2 ? d1 : d2;
+            d1 = r1 - r2; d2 = 12 - d1;
+            int dy = d1 < d2 ? d1 : d2;
+            if (q1 == q2 || r1 == r2 || dy == dx) t[o * 5 + (x >> 5)] |= 1u << (x & 31);
+        }
+}
+
+}  // namespace
+
+struct hive_env {
+    int n = 0, device = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    bool own_stream = false;
+    GameRec* recs = nullptr;
+    uint32_t* legal = nullptr;
+    int32_t* count = nullptr;
+    uint16_t* planes = nullptr;
+    int32_t* d_actions[2] = {nullptr, nullptr};
+    int act_flip = 0;
+    uint8_t* d_mask = nullptr;
+    uint32_t* hop_lines = nullptr;
+    cudaEvent_t copy_done = nullptr, t0 = nullptr, t1 = nullptr;
+    bool timing = false;
+    long long launches = 0;
+};
+
+namespace {
+
+int launch_env(hive_env* h, int op, const int32_t* actions, const uint8_t* mask, uint64_t seed, int max_turn,
+               int auto_reset, int32_t* chosen) {
+    EnvArgs a;
+    a.recs = h->recs; a.legal = h->legal; a.count = h->count; a.planes = h->planes;
+    a.actions = actions; a.mask = mask; a.chosen = chosen; a.hop_lines = h->hop_lines;
+    a.seed = seed; a.n = h->n; a.op = op; a.max_turn = max_turn; a.auto_reset = auto_reset;
+    const int blocks = (h->n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    if (h->timing) CUDA_TRY(cudaEventRecord(h->t0, h->stream));
+    hive_env_kernel<<<blocks, WARPS_PER_CTA * 32, 0, h->stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    if (h->timing) CUDA_TRY(cudaEventRecord(h->t1, h->stream));
+    h->launches++;
+    return 0;
+}
+
+int check(const hive_env* h) { return h && h->n > 0 ? 0 : fail(HIVE_E_HANDLE, "bad handle"); }
+
+}  // namespace
+
+extern "C" {
+
+const char* hive_last_error(void) { return g_err.c_str(); }
+int hive_abi_version(void) { return 1; }
+
+int hive_create(int n_games, int device, void* stream, hive_env_t** out) {
+    if (!out || n_games <= 0) return fail(HIVE_E_ARG, "hive_create: bad arguments");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(HIVE_E_CUDA, std::string("hive_create: no CUDA device (") + cudaGetErrorString(e) +
+                                     "); this library has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(HIVE_E_ARG, "hive_create: bad device index");
+    CUDA_TRY(cudaSetDevice(device));
+    hive_env* h = new hive_env();
+    h->n = n_games; h->device = device;
+    if (stream) { h->stream = (cudaStream_t)stream; } else {
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->copy_done, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreate(&h->t0));
+    CUDA_TRY(cudaEventCreate(&h->t1));
+    const size_t n = (size_t)n_games;
+    CUDA_TRY(cudaMalloc(&h->recs, n * sizeof(GameRec)));
+    CUDA_TRY(cudaMalloc(&h->legal, n * LEGAL_WORDS * 4));
+    CUDA_TRY(cudaMalloc(&h->count, n * 4));
+    CUDA_TRY(cudaMalloc(&h->planes, n * HIVE_PLANES_ELEMS * 2));
+    CUDA_TRY(cudaMalloc(&h->d_actions[0], n * 4));
+    CUDA_TRY(cudaMalloc(&h->d_actions[1], n * 4));
+    CUDA_TRY(cudaMalloc(&h->d_mask, n));
+    CUDA_TRY(cudaMalloc(&h->hop_lines, 144 * 5 * 4));
+    std::vector<uint32_t> lines;
+    build_hop_lines(lines);
+    CUDA_TRY(cudaMemcpyAsync(h->hop_lines, lines.data(), lines.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->recs, 0, n * sizeof(GameRec), h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    int rc = launch_env(h, OP_RESET, nullptr, nullptr, 0, 0, 0, nullptr);
+    if (rc) { hive_destroy(h); return rc; }
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    *out = h;
+    return 0;
+}
+
+int hive_destroy(hive_env_t* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(h->recs); cudaFree(h->legal); cudaFree(h->count); cudaFree(h->planes);
+    cudaFree(h->d_actions[0]); cudaFree(h->d_actions[1]); cudaFree(h->d_mask); cudaFree(h->hop_lines);
+    if (h->copy_done) cudaEventDestroy(h->copy_done);
+    if (h->t0) cudaEventDestroy(h->t0);
+    if (h->t1) cudaEventDestroy(h->t1);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+int hive_num_games(const hive_env_t* h) { return h ? h->n : HIVE_E_HANDLE; }
+
+int hive_sync(hive_env_t* h) {
+    if (check(h)) return HIVE_E_HANDLE;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int hive_reset(hive_env_t* h, const uint8_t* game_mask) {
+    if (check(h)) return HIVE_E_HANDLE;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const uint8_t* dm = nullptr;
+    if (game_mask) {
+        CUDA_TRY(cudaMemcpyAsync(h->d_mask, game_mask, h->n, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        dm = h->d_mask;
+    }
+    return launch_env(h, OP_RESET, nullptr, dm, 0, 0, 0, nullptr);
+}
+
+int hive_step(hive_env_t* h, const int32_t* actions_dev) {
+    if (check(h)) return HIVE_E_HANDLE;
+    if (!actions_dev) return fail(HIVE_E_ARG, "hive_step: null actions");
+    CUDA_TRY(cudaSetDevice(h->device));
+    return launch_env(h, OP_STEP, actions_dev, nullptr, 0, 0, 0, nullptr);
+}
+
+int hive_step_host(hive_env_t* h, const int32_t* actions) {
+    if (check(h)) return HIVE_E_HANDLE;
+    if (!actions) return fail(HIVE_E_ARG, "hive_step_host: null actions");
+    CUDA_TRY(cudaSetDevice(h->device));
+    // double-buffered device copy of the actions on a side stream: the caller's buffer is free
+    // again when this returns, and the previous step may still be reading the other buffer.
+    int32_t* d = h->d_actions[h->act_flip];
+    h->act_flip ^= 1;
+    CUDA_TRY(cudaMemcpyAsync(d, actions, (size_t)h->n * 4, cudaMemcpyHostToDevice, h->copy_stream));
+    CUDA_TRY(cudaEventRecord(h->copy_done, h->copy_stream));
+    CUDA_TRY(cudaStreamWaitEvent(h->stream, h->copy_done, 0));
+    int rc = launch_env(h, OP_STEP, d, nullptr, 0, 0, 0, nullptr);
+    CUDA_TRY(cudaEventSynchronize(h->copy_done));
+    return rc;
+}
+
+int hive_step_random(hive_env_t* h, uint64_t seed, int max_turn, int auto_reset, int32_t* chosen_dev) {
+    if (check(h)) return HIVE_E_HANDLE;
+    if (max_turn < 1 || max_turn > 250) return fail(HIVE_E_ARG, "hive_step_random: max_turn out of range");
+    CUDA_TRY(cudaSetDevice(h->device));
+    return launch_env(h, OP_RANDOM, nullptr, nullptr, seed, max_turn, auto_reset, chosen_dev);
+}
+
+int hive_legal_host(hive_env_t* h, uint64_t* mask, int32_t* count) {
+    if (check(h)) return HIVE_E_HANDLE;
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (mask) CUDA_TRY(cudaMemcpyAsync(mask, h->legal, (size_t)h->n * LEGAL_WORDS * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (count) CUDA_TRY(cudaMemcpyAsync(count, h->count, (size_t)h->n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int hive_encode_host(hive_env_t* h, uint16_t* planes_bf16) {
+    if (check(h)) return HIVE_E_HANDLE;
+    if (!planes_bf16) return fail(HIVE_E_ARG, "hive_encode_host: null output");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemcpyAsync(planes_bf16, h->planes, (size_t)h->n * HIVE_PLANES_ELEMS * 2, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+static int fetch_recs(hive_env_t* h, std::vector<GameRec>& out, int first, int cnt) {
+    out.resize(cnt);
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemcpyAsync(out.data(), h->recs + first, (size_t)cnt * sizeof(GameRec), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int hive_status_host(hive_env_t* h, int32_t* turn, int8_t* winner, uint8_t* done) {
+    if (check(h)) return HIVE_E_HANDLE;
+    std::vector<GameRec> r;
+    int rc = fetch_recs(h, r, 0, h->n);
+    if (rc) return rc;
+    for (int i = 0; i < h->n; i++) {
+        if (turn) turn[i] = r[i].turn;
+        if (winner) winner[i] = (int8_t)r[i].winner;
+        if (done) done[i] = r[i].done;
+    }
+    return 0;
+}
+
+int hive_counters_host(hive_env_t* h, uint32_t* steps, uint32_t* episodes) {
+    if (check(h)) return HIVE_E_HANDLE;
+    std::vector<GameRec> r;
+    int rc = fetch_recs(h, r, 0, h->n);
+    if (rc) return rc;
+    for (int i = 0; i < h->n; i++) {
+        if (steps) steps[i] = r[i].steps;
+        if (episodes) episodes[i] = r[i].episode;
+    }
+    return 0;
+}
+
+int hive_dump_state(hive_env_t* h, int game, int32_t* turn, uint8_t* cells, uint8_t* levels) {
+    if (check(h)) return HIVE_E_HANDLE;
+    if (game < 0 || game >= h->n) return fail(HIVE_E_ARG, "hive_dump_state: bad game index");
+    std::vector<GameRec> r;
+    int rc = fetch_recs(h, r, game, 1);
+    if (rc) return rc;
+    if (turn) *turn = r[0].turn;
+    if (cells) memcpy(cells, r[0].cell, N_PIECE);
+    if (levels) memcpy(levels, r[0].level, N_PIECE);
+    return 0;
+}
+
+int hive_load_state(hive_env_t* h, int game, int turn, const uint8_t* cells, const uint8_t* levels) {
+    if (check(h)) return HIVE_E_HANDLE;
+    if (game < 0 || game >= h->n || !cells || !levels || turn < 1 || turn > 250)
+        return fail(HIVE_E_ARG, "hive_load_state: bad arguments");
+    // validate stacks: levels at each cell must be 0..height-1 without gaps
+    int height[144] = {0};
+    for (int lvl = 0; lvl < 5; lvl++)
+        for (int p = 0; p < N_PIECE; p++)
+            if (cells[p] != HAND && levels[p] == lvl) {
+                if (cells[p] >= 144 || height[cells[p]] != lvl) return fail(HIVE_E_ARG, "hive_load_state: inconsistent stacks");
+                height[cells[p]]++;
+            }
+    for (int p = 0; p < N_PIECE; p++)
+        if (cells[p] != HAND && levels[p] > 4) return fail(HIVE_E_ARG, "hive_load_state: level > 4");
+    GameRec rec;
+    memset(&rec, 0, sizeof rec);
+    memcpy(rec.cell, cells, N_PIECE);
+    memcpy(rec.level, levels, N_PIECE);
+    rec.turn = (uint8_t)turn;
+    CUDA_TRY(cudaSetDevice(h->device));
+    std::vector<GameRec> old;
+    int rc = fetch_recs(h, old, game, 1);
+    if (rc) return rc;
+    rec.episode = old[0].episode; rec.steps = old[0].steps;
+    std::vector<uint8_t> mask(h->n, 0);
+    mask[game] = 1;
+    CUDA_TRY(cudaMemcpyAsync(h->recs + game, &rec, sizeof rec, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_mask, mask.data(), h->n, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return launch_env(h, OP_EVAL, nullptr, h->d_mask, 0, 0, 0, nullptr);
+}
+
+int hive_copy_state(hive_env_t* dst, int dst_game, hive_env_t* src, int src_game) {
+    if (check(dst) || check(src)) return HIVE_E_HANDLE;
+    if (dst_game < 0 || dst_game >= dst->n || src_game < 0 || src_game >= src->n)
+        return fail(HIVE_E_ARG, "hive_copy_state: bad game index");
+    if (dst->device != src->device) return fail(HIVE_E_ARG, "hive_copy_state: handles on different devices");
+    CUDA_TRY(cudaSetDevice(dst->device));
+    CUDA_TRY(cudaStreamSynchronize(src->stream));
+    CUDA_TRY(cudaMemcpyAsync(dst->recs + dst_game, src->recs + src_game, sizeof(GameRec), cudaMemcpyDeviceToDevice, dst->stream));
+    CUDA_TRY(cudaMemcpyAsync(dst->legal + (size_t)dst_game * LEGAL_WORDS, src->legal + (size_t)src_game * LEGAL_WORDS,
+                             LEGAL_WORDS * 4, cudaMemcpyDeviceToDevice, dst->stream));
+    CUDA_TRY(cudaMemcpyAsync(dst->count + dst_game, src->count + src_game, 4, cudaMemcpyDeviceToDevice, dst->stream));
+    CUDA_TRY(cudaMemcpyAsync(dst->planes + (size_t)dst_game * HIVE_PLANES_ELEMS, src->planes + (size_t)src_game * HIVE_PLANES_ELEMS,
+                             HIVE_PLANES_ELEMS * 2, cudaMemcpyDeviceToDevice, dst->stream));
+    return 0;
+}
+
+// GamePlay.state_key (env_hive.py:150-168): board_tiles order (q descending, r ascending), '.' or
+// the 2-char ids of the stack bottom->top, then the player digit.
+int hive_state_key(hive_env_t* h, int game, char* buf, int buflen) {
+    if (check(h)) return HIVE_E_HANDLE;
+    if (game < 0 || game >= h->n || !buf || buflen < 200) return fail(HIVE_E_ARG, "hive_state_key: bad arguments (buflen >= 200)");
+    std::vector<GameRec> r;
+    int rc = fetch_recs(h, r, game, 1);
+    if (rc) return rc;
+    static const char tch[11] = {'Q', 'B', 'B', 'S', 'S', 'G', 'G', 'G', 'A', 'A', 'A'};
+    static const char num[11] = {'0', '0', '1', '0', '1', '0', '1', '2', '0', '1', '2'};
+    int n = 0;
+    for (int q = 11; q >= 0; q--)
+        for (int c12 = 0; c12 < 12; c12++) {
+            const int c = q * 12 + c12;
+            bool any = false;
+            for (int lvl = 0; lvl < 5; lvl++)
+                for (int p = 0; p < N_PIECE; p++)
+                    if (r[0].cell[p] == c && r[0].level[p] == lvl) {
+                        char ch = tch[p % 11];
+                        if (p >= 11) ch = (char)(ch - 'A' + 'a');
+                        buf[n++] = ch; buf[n++] = num[p % 11];
+                        any = true;
+                    }
+            if (!any) buf[n++] = '.';
+        }
+    buf[n++] = (char)('0' + ((r[0].turn & 1) ? 0 : 1));
+    buf[n] = 0;
+    return n;
+}
+
+void* hive_dev_state(hive_env_t* h) { return h ? h->recs : nullptr; }
+void* hive_dev_legal(hive_env_t* h) { return h ? h->legal : nullptr; }
+void* hive_dev_count(hive_env_t* h) { return h ? h->count : nullptr; }
+void* hive_dev_planes(hive_env_t* h) { return h ? h->planes : nullptr; }
+long long hive_launch_count(const hive_env_t* h) { return h ? h->launches : 0; }
+
+int hive_set_timing(hive_env_t* h, int on) {
+    if (check(h)) return HIVE_E_HANDLE;
+    h->timing = on != 0;
+    return 0;
+}
+
+float hive_last_kernel_ms(hive_env_t* h) {
+    if (!h || !h->timing) return 0.f;
+    float ms = 0.f;
+    if (cudaEventSynchronize(h->t1) != cudaSuccess) return 0.f;
+    if (cudaEventElapsedTime(&ms, h->t0, h->t1) != cudaSuccess) return 0.f;
+    return ms;
+}
+
+}  // extern "C"

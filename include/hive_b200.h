@@ -1,0 +1,108 @@
+/*
+ * hive_b200.h -- C ABI of the B200-native Hive environment / search hot path.
+ *
+ * The reference (HaiDangDang/hive-Alphazero) has no FFI layer: its hot path is the Python
+ * classes GamePlay (hive_engine/env_hive.py:24) and HivePlayer (woker/solo_play.py:69).  These
+ * entry points are what a binding for that path replaces; each cites the reference interface it
+ * stands in for.  Plain pointers and sizes only; no torch / CUDA types in any signature.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error (HIVE_E_*); hive_last_error() gives text.
+ *   - a handle owns `n_games` independent games on one GPU; all work is stream-ordered.
+ *   - `_host` entry points take HOST buffers and copy inside the call (the reference-facing
+ *     plugin path); the others take DEVICE pointers (or expose library-owned device arenas) so a
+ *     resident pipeline never leaves HBM.
+ *   - action ids are the reference's: a = q*132 + r*11 + piece_idx = cell*11 + piece_idx
+ *     (hive_engine/config.py:10, env_hive.py:107-114); -1 = pass (env_hive.py:100-103);
+ *     HIVE_NOOP leaves that game untouched.
+ *   - there is no CPU fallback: without a CUDA device hive_create fails with HIVE_E_CUDA.
+ */
+#ifndef HIVE_B200_H
+#define HIVE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HIVE_ACTION_SPACE 1584      /* hive_engine/config.py:10 */
+#define HIVE_STATE_FEATURES 56      /* hive_engine/config.py:21 */
+#define HIVE_CELLS 144
+#define HIVE_PIECES 22
+#define HIVE_LEGAL_U64 25           /* 1584-bit mask */
+#define HIVE_HAND 255
+#define HIVE_NOOP (-2)
+#define HIVE_PLANES_ELEMS (HIVE_STATE_FEATURES * HIVE_CELLS)   /* bf16 per game, CHW */
+#define HIVE_STATE_BYTES 384
+
+#define HIVE_E_ARG (-1)
+#define HIVE_E_CUDA (-2)
+#define HIVE_E_HANDLE (-3)
+
+typedef struct hive_env hive_env_t;
+
+const char* hive_last_error(void);
+int hive_abi_version(void);
+
+/* GamePlay(HEIGHT_MAP, WIDTH_MAP) x n_games  (env_hive.py:26-97).  `stream` is a cudaStream_t
+ * passed as void* (NULL = library-created non-blocking stream).  Games start reset. */
+int hive_create(int n_games, int device, void* stream, hive_env_t** out);
+int hive_destroy(hive_env_t* h);
+int hive_num_games(const hive_env_t* h);
+int hive_sync(hive_env_t* h);
+
+/* GamePlay.new_game (env_hive.py:61-97) for games with mask[g] != 0 (NULL = all). Host mask. */
+int hive_reset(hive_env_t* h, const uint8_t* game_mask);
+
+/* GamePlay.move(action) (env_hive.py:99-171) for every game: apply, regenerate the legal set of
+ * the new side to move and encode its 56 planes. */
+int hive_step_host(hive_env_t* h, const int32_t* actions);          /* host int32[n] */
+int hive_step(hive_env_t* h, const int32_t* actions_dev);           /* device int32[n] */
+
+/* On-device rollout policy of the benchmark (SURVEY 8d Config 2): a = A[x % len(A)],
+ * x = splitmix64(seed ^ game_id<<32 ^ turn), game_id = slot + n_games*episode; pass when A is
+ * empty.  With auto_reset, a finished game (game_is_over() or turn >= max_turn, the
+ * MAX_GAME_LENGTH cut of self_play.py:162) is reset instead of stepped.  `chosen_dev` (optional,
+ * device int32[n]) receives the action taken (HIVE_NOOP for a reset / idle slot). */
+int hive_step_random(hive_env_t* h, uint64_t seed, int max_turn, int auto_reset, int32_t* chosen_dev);
+
+/* GamePlay.actions() (env_hive.py:182): bit a of mask[g] set <=> action a legal; count = len. */
+int hive_legal_host(hive_env_t* h, uint64_t* mask /*[n][25]*/, int32_t* count /*[n]*/);
+/* GamePlay.encode_board() (env_hive.py:306-318), bf16, CHW [n][56][144] (the layout
+ * api_hive.py:61 feeds the net after transpose(2,0,1)). */
+int hive_encode_host(hive_env_t* h, uint16_t* planes_bf16);
+/* state.turn, winner (0 none / 1 white / 2 black, settings.py:3-4), game_is_over()
+ * (move_checker.py:140-165).  Any pointer may be NULL. */
+int hive_status_host(hive_env_t* h, int32_t* turn, int8_t* winner, uint8_t* done);
+/* counters: env steps and episodes per slot */
+int hive_counters_host(hive_env_t* h, uint32_t* steps, uint32_t* episodes);
+
+/* GamePlay.state_key (env_hive.py:150-168) of one game, NUL-terminated; returns length. */
+int hive_state_key(hive_env_t* h, int game, char* buf, int buflen);
+
+/* position injection / extraction: turn + per-piece cell (HIVE_HAND = inventory) and stack
+ * level, white pieces 0..10 then black, order Q,B0,B1,S0,S1,G0,G1,G2,A0,A1,A2
+ * (env_hive.py:71-87).  History is cleared by load. */
+int hive_load_state(hive_env_t* h, int game, int turn, const uint8_t* cells, const uint8_t* levels);
+int hive_dump_state(hive_env_t* h, int game, int32_t* turn, uint8_t* cells, uint8_t* levels);
+/* whole-record snapshot (HIVE_STATE_BYTES each) -- the deepcopy(env) of solo_play.py:158 */
+int hive_copy_state(hive_env_t* dst, int dst_game, hive_env_t* src, int src_game);
+
+/* library-owned device arenas (valid until hive_destroy): */
+void* hive_dev_state(hive_env_t* h);     /* [n] x 384-byte records                    */
+void* hive_dev_legal(hive_env_t* h);     /* [n][25] uint64                            */
+void* hive_dev_count(hive_env_t* h);     /* [n] int32                                 */
+void* hive_dev_planes(hive_env_t* h);    /* [n][56][144] bf16                         */
+
+/* launches issued by this handle since creation (bench.py's gpu_launches) */
+long long hive_launch_count(const hive_env_t* h);
+/* last kernel's device time in ms measured with events on the handle's stream (0 if timing is
+ * off); hive_set_timing(h,1) enables per-launch events. */
+int hive_set_timing(hive_env_t* h, int on);
+float hive_last_kernel_ms(hive_env_t* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIVE_B200_H */

@@ -1,0 +1,7 @@
+"""Inert stand-in for matplotlib.pyplot."""
+
+
+def __getattr__(name):
+    def _noop(*a, **k):
+        return None
+    return _noop

@@ -1,0 +1,45 @@
+// emu_env.cpp -- runs hive_env_kernel (verbatim device source) on the CPU warp emulator.
+// TEST INFRASTRUCTURE: lets `pytest -m "not gpu"` differential-test the kernel logic against the
+// oracle.  Never loaded by the product package.
+#include "cuda_emu.h"
+#include <vector>
+#include "../../hive-alphazero_b200/csrc/hive_env_kernel.cuh"
+
+using namespace hive;
+
+static std::vector<uint32_t> g_lines;
+static void build_lines() {
+    if (!g_lines.empty()) return;
+    g_lines.assign(144 * 5, 0);
+    for (int o = 0; o < 144; o++)
+        for (int x = 0; x < 144; x++) {
+            int q1 = o / 12, r1 = o % 12, q2 = x / 12, r2 = x % 12;
+            int d1 = q1 - q2, d2 = 12 - d1, dx = d1 < d2 ? d1 : d2;
+            d1 = r1 - r2; d2 = 12 - d1;
+            int dy = d1 < d2 ? d1 : d2;
+            if (q1 == q2 || r1 == r2 || dy == dx) g_lines[o * 5 + (x >> 5)] |= 1u << (x & 31);
+        }
+}
+
+static void lane_main(void* p) { hive_env_kernel(*(EnvArgs*)p); }
+
+extern "C" {
+
+// state: n x 384 B records; legal: n x 50 u32; count: n; planes: n x 8064 u16
+int emu_env_run(void* recs, uint32_t* legal, int32_t* count, uint16_t* planes, int n, int op,
+                const int32_t* actions, const uint8_t* mask, uint64_t seed, int max_turn, int auto_reset,
+                int32_t* chosen, uint64_t sched_seed) {
+    build_lines();
+    EnvArgs a;
+    a.recs = (GameRec*)recs; a.legal = legal; a.count = count; a.planes = planes;
+    a.actions = actions; a.mask = mask; a.chosen = chosen; a.hop_lines = g_lines.data();
+    a.seed = seed; a.n = n; a.op = op; a.max_turn = max_turn; a.auto_reset = auto_reset;
+    for (int g = 0; g < n; g++) {
+        int rc = emu::run_warp(lane_main, &a, g / WARPS_PER_CTA, g % WARPS_PER_CTA, sched_seed + (uint64_t)g);
+        if (rc) return rc;
+    }
+    return 0;
+}
+const char* emu_last_error() { return emu::last_error(); }
+int emu_rec_bytes() { return (int)sizeof(GameRec); }
+}
