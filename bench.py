@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json metric on its quoted configuration.
+
+Workload (config.workload): BASELINE configs[1] -- batched legal-move generation + step +
+56-plane encode for 16,384 concurrent random games per GPU (on-device counter-based policy,
+auto-reset at game end / turn 55).  One "step" = one launch of the env kernel over the whole
+batch = one GamePlay.move() per live game.
+
+  value     env-steps/s, whole job, state resident in HBM (device-timed, CUDA events on the
+            stream the kernel runs on, max over ranks)
+  e2e       same metric through the reference-facing C-ABI path with HOST buffers: every step
+            copies the actions H2D from pinned memory, runs the kernel, reads legal masks /
+            counts / status back D2H and picks the next actions on the host
+  roofline  HBM: 17,094 algorithmic bytes per env-step (SURVEY 8d / DESIGN.md) over the measured
+            copy bandwidth of MEASURED_PEAKS.json
+  cpu_baseline  the oracle port (oracle/hive_oracle.c) on the host cores, bounded sample
+
+`--impl reference` times the CPU arm alone (the reference is pure Python and cannot travel to the
+GPU box; the C restatement pinned to it by tests/golden stands in, kind="port").
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_ENV_STEP = 16128 + 198 + 768          # bf16 planes + legal mask + state record r/w
+METRIC = "env_steps_per_s"
+UNIT = "env-steps/s"
+WORKLOAD = ("configs[1]: batched legal-move gen + step + plane encode, 16,384 concurrent random games "
+            "per B200 (bit-exact vs ref)")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--games", type=int, default=16384, help="concurrent games per GPU")
+    ap.add_argument("--seed", type=int, default=20261018)
+    ap.add_argument("--max-turn", type=int, default=55)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("hive_env_kernel_dram_bytes_per_launch")
+        except Exception:
+            pass
+    return None
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.01):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:      # noqa
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def cpu_port_rate(seed, budget_s, threads, max_turn):
+    """Bounded CPU sample: full counter-seeded games on `threads` host threads for ~budget_s."""
+    from oracle import hive_oracle as ho
+    t0 = time.perf_counter()
+    pilot_games = 2 * threads
+    pilot_steps = ho.play_many(seed, 0, pilot_games, max_turn, threads)
+    pilot_dt = max(time.perf_counter() - t0, 1e-6)
+    games = max(pilot_games, int(pilot_games * budget_s / pilot_dt))
+    t0 = time.perf_counter()
+    steps = ho.play_many(seed, pilot_games, games, max_turn, threads)
+    dt = time.perf_counter() - t0
+    return steps / dt, games, steps, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import hive_oracle as ho
+    threads = os.cpu_count() or 1
+    # size one "step" (a bounded sample of full games) so the whole run ends within ~2 minutes
+    t0 = time.perf_counter()
+    pilot = ho.play_many(args.seed, 0, 2 * threads, args.max_turn, threads)
+    rate = pilot / max(time.perf_counter() - t0, 1e-6)
+    per_step_s = 100.0 / max(args.steps + args.warmup, 1)
+    games_per_step = max(threads, int(rate * per_step_s / 54.0))
+    first = 2 * threads
+    for _ in range(args.warmup):
+        ho.play_many(args.seed, first, games_per_step, args.max_turn, threads)
+        first += games_per_step
+    total = 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        total += ho.play_many(args.seed, first, games_per_step, args.max_turn, threads)
+        first += games_per_step
+    dt = time.perf_counter() - t0
+    value = total / dt
+    sample = "%d steps x %d full random games (counter-seeded, to terminal/turn %d) = %d env steps in %.1f s" % (
+        args.steps, games_per_step, args.max_turn, total, dt)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic (counter-seeded random-legal-move games from reset)",
+        "config": {"workload": WORKLOAD, "reference_arm": "oracle/hive_oracle.c port of the Python reference "
+                   "(the reference itself is pure Python at ~38 env-steps/s/core and is absent on the GPU box)",
+                   "games_per_step": games_per_step, "max_turn": args.max_turn},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import numpy as np
+    import torch
+    import hive_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def allmax(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    hive_b200.build()
+    n = args.games
+    stream = torch.cuda.Stream()
+    batch = hive_b200.HiveBatch(n, device=local_rank, stream=stream.cuda_stream)
+    seed = args.seed + 1000003 * rank            # independent games per rank (sharded, no data-path collective)
+
+    # ------------------------------------------------------------------ resident (device-timed)
+    for _ in range(max(args.warmup, 3)):
+        batch.step_random(seed, args.max_turn, True)
+    batch.sync()
+    steps0 = int(batch.counters()[0].astype(np.int64).sum())
+    launches0 = batch.launches
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        batch.step_random(seed, args.max_turn, True)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    launches = batch.launches - launches0
+    env_steps = int(batch.counters()[0].astype(np.int64).sum()) - steps0
+    ms_max = allmax(ms)
+    env_steps_all = allsum(float(env_steps))
+    value = env_steps_all / (ms_max * 1e-3)
+
+    # roofline of the dominant (only) kernel, this rank
+    peak, peak_src = measured_peak()
+    per_launch_bytes = BYTES_PER_ENV_STEP * env_steps / max(launches, 1)
+    launch_s = ms * 1e-3 / max(launches, 1)
+    achieved = per_launch_bytes / launch_s / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(), "kernel": "hive_env_kernel", "peak_source": peak_src,
+                "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP,
+                "env_steps_per_launch": env_steps / max(launches, 1), "launch_us": launch_s * 1e6}
+
+    # ------------------------------------------------------------------ e2e (host buffers)
+    k_e2e = min(args.steps, 1500)
+    mask_h = torch.empty((n, 25), dtype=torch.int64).pin_memory()
+    count_h = torch.empty(n, dtype=torch.int32).pin_memory()
+    status_h = torch.empty(n, dtype=torch.int32).pin_memory()
+    actions_h = torch.empty(n, dtype=torch.int32).pin_memory()
+    mask_np, count_np = mask_h.numpy().view(np.uint64), count_h.numpy()
+    status_np, actions_np = status_h.numpy().view(np.uint32), actions_h.numpy()
+    _, episodes = batch.counters()
+    episodes = episodes.copy()
+
+    def e2e_step():
+        batch.legal_into(mask_h.data_ptr(), count_h.data_ptr())        # D2H 200 B + 4 B per game
+        batch.status_packed_into(status_h.data_ptr())                  # D2H 4 B per game
+        hive_b200.host_pick_actions(mask_np, count_np, status_np, episodes, seed, args.max_turn, actions_np)
+        batch.step_ptr(actions_h.data_ptr())                           # H2D 4 B per game + kernel
+
+    for _ in range(3):
+        e2e_step()
+    batch.sync()
+    s0 = int(batch.counters()[0].astype(np.int64).sum())
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(k_e2e):
+        e2e_step()
+    batch.legal_into(mask_h.data_ptr(), count_h.data_ptr())            # the last step's result
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    barrier()
+    e2e_steps = int(batch.counters()[0].astype(np.int64).sum()) - s0
+    e2e_value = allsum(float(e2e_steps)) / allmax(dt)
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": (200 + 4 + 4) * n,
+           "steps": k_e2e, "note": "per-GPU bytes per kernel launch; host picks actions with the C-ABI twin "
+           "of the device policy; planes stay in HBM for the net"}
+
+    # ------------------------------------------------------------------ CPU baseline (rank 0, N=1)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        rate, games, steps_cpu, dt_cpu = cpu_port_rate(args.seed, 12.0, threads, args.max_turn)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "%d full random games (same counter-based policy, from reset to terminal/turn %d) = "
+                         "%d env steps in %.1f s on %d threads" % (games, args.max_turn, steps_cpu, dt_cpu, threads)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_max / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic (random-legal-move games from reset, "
+            "counter-based splitmix64 policy; planes emitted as bf16)",
+            "config": {"workload": WORKLOAD, "games_per_gpu": n, "max_turn": args.max_turn, "auto_reset": True,
+                       "parallelism": "games sharded %d-way, no data-path collective" % world,
+                       "cache": "per-GPU working set %.0f MB (state+legal+planes) > 126 MB L2: inputs larger than L2"
+                                % (n * (384 + 200 + 8 + 16128) / 1e6)},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

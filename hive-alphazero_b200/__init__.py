@@ -1,0 +1,13 @@
+"""hive-alphazero_b200 -- B200-native Hive self-play hot path (env step, move generation, plane
+encoder, PUCT search) behind the reference's GamePlay / HivePlayer interface.
+
+The package name carries a hyphen; import it as ``import hive_b200`` (root-level alias) or with
+``importlib.import_module("hive-alphazero_b200")``.
+"""
+from . import config
+from ._build import LIB_PATH, build
+from ._capi import ENV_SYMBOLS, HiveError, lib
+from .env import GamePlay, HiveBatch, host_pick_actions
+
+__all__ = ["config", "build", "lib", "LIB_PATH", "ENV_SYMBOLS", "HiveError", "GamePlay", "HiveBatch",
+           "host_pick_actions"]

@@ -1,0 +1,67 @@
+"""ctypes binding of include/hive_b200.h.  There is deliberately no fallback: if the CUDA
+library is missing or no GPU is present, calls fail loudly."""
+import ctypes
+import os
+
+from ._build import LIB_PATH
+
+_lib = None
+
+ENV_SYMBOLS = [
+    "hive_last_error", "hive_abi_version", "hive_create", "hive_destroy", "hive_num_games", "hive_sync",
+    "hive_reset", "hive_step_host", "hive_step", "hive_step_random", "hive_legal_host", "hive_encode_host",
+    "hive_status_host", "hive_status_packed_host", "hive_host_pick_actions", "hive_counters_host", "hive_state_key", "hive_load_state", "hive_dump_state",
+    "hive_copy_state", "hive_dev_state", "hive_dev_legal", "hive_dev_count", "hive_dev_status", "hive_dev_planes",
+    "hive_launch_count", "hive_set_timing", "hive_last_kernel_ms",
+]
+
+
+class HiveError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise HiveError("CUDA extension %s is missing -- run __graft_entry__.build() "
+                        "(there is no CPU fallback)" % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64
+    L.hive_last_error.restype = ctypes.c_char_p
+    L.hive_abi_version.restype = i32
+    L.hive_create.argtypes = [i32, i32, vp, ctypes.POINTER(vp)]
+    L.hive_destroy.argtypes = [vp]
+    L.hive_num_games.argtypes = [vp]
+    L.hive_sync.argtypes = [vp]
+    L.hive_reset.argtypes = [vp, vp]
+    L.hive_step_host.argtypes = [vp, vp]
+    L.hive_step.argtypes = [vp, vp]
+    L.hive_step_random.argtypes = [vp, u64, i32, i32, vp]
+    L.hive_legal_host.argtypes = [vp, vp, vp]
+    L.hive_encode_host.argtypes = [vp, vp]
+    L.hive_status_host.argtypes = [vp, vp, vp, vp]
+    L.hive_counters_host.argtypes = [vp, vp, vp]
+    L.hive_status_packed_host.argtypes = [vp, vp]
+    L.hive_host_pick_actions.argtypes = [i32, vp, vp, vp, vp, u64, i32, vp]
+    L.hive_state_key.argtypes = [vp, i32, ctypes.c_char_p, i32]
+    L.hive_load_state.argtypes = [vp, i32, i32, vp, vp]
+    L.hive_dump_state.argtypes = [vp, i32, vp, vp, vp]
+    L.hive_copy_state.argtypes = [vp, i32, vp, i32]
+    for name in ("hive_dev_state", "hive_dev_legal", "hive_dev_count", "hive_dev_status", "hive_dev_planes"):
+        getattr(L, name).argtypes = [vp]
+        getattr(L, name).restype = vp
+    L.hive_launch_count.argtypes = [vp]
+    L.hive_launch_count.restype = ctypes.c_longlong
+    L.hive_set_timing.argtypes = [vp, i32]
+    L.hive_last_kernel_ms.argtypes = [vp]
+    L.hive_last_kernel_ms.restype = ctypes.c_float
+    _lib = L
+    return L
+
+
+def check(rc, what=""):
+    if rc < 0:
+        raise HiveError("%s failed (%d): %s" % (what, rc, lib().hive_last_error().decode()))
+    return rc

@@ -51,6 +51,7 @@ struct hive_env {
     GameRec* recs = nullptr;
     uint32_t* legal = nullptr;
     int32_t* count = nullptr;
+    uint32_t* status = nullptr;
     uint16_t* planes = nullptr;
     int32_t* d_actions[2] = {nullptr, nullptr};
     int act_flip = 0;
@@ -66,7 +67,7 @@ namespace {
 int launch_env(hive_env* h, int op, const int32_t* actions, const uint8_t* mask, uint64_t seed, int max_turn,
                int auto_reset, int32_t* chosen) {
     EnvArgs a;
-    a.recs = h->recs; a.legal = h->legal; a.count = h->count; a.planes = h->planes;
+    a.recs = h->recs; a.legal = h->legal; a.count = h->count; a.status = h->status; a.planes = h->planes;
     a.actions = actions; a.mask = mask; a.chosen = chosen; a.hop_lines = h->hop_lines;
     a.seed = seed; a.n = h->n; a.op = op; a.max_turn = max_turn; a.auto_reset = auto_reset;
     const int blocks = (h->n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
@@ -109,6 +110,7 @@ int hive_create(int n_games, int device, void* stream, hive_env_t** out) {
     CUDA_TRY(cudaMalloc(&h->recs, n * sizeof(GameRec)));
     CUDA_TRY(cudaMalloc(&h->legal, n * LEGAL_WORDS * 4));
     CUDA_TRY(cudaMalloc(&h->count, n * 4));
+    CUDA_TRY(cudaMalloc(&h->status, n * 4));
     CUDA_TRY(cudaMalloc(&h->planes, n * HIVE_PLANES_ELEMS * 2));
     CUDA_TRY(cudaMalloc(&h->d_actions[0], n * 4));
     CUDA_TRY(cudaMalloc(&h->d_actions[1], n * 4));
@@ -119,7 +121,7 @@ int hive_create(int n_games, int device, void* stream, hive_env_t** out) {
     CUDA_TRY(cudaMemcpyAsync(h->hop_lines, lines.data(), lines.size() * 4, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemsetAsync(h->recs, 0, n * sizeof(GameRec), h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    int rc = launch_env(h, OP_RESET, nullptr, nullptr, 0, 0, 0, nullptr);
+    int rc = launch_env(h, OP_INIT, nullptr, nullptr, 0, 0, 0, nullptr);
     if (rc) { hive_destroy(h); return rc; }
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     *out = h;
@@ -130,7 +132,7 @@ int hive_destroy(hive_env_t* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    cudaFree(h->recs); cudaFree(h->legal); cudaFree(h->count); cudaFree(h->planes);
+    cudaFree(h->recs); cudaFree(h->legal); cudaFree(h->count); cudaFree(h->status); cudaFree(h->planes);
     cudaFree(h->d_actions[0]); cudaFree(h->d_actions[1]); cudaFree(h->d_mask); cudaFree(h->hop_lines);
     if (h->copy_done) cudaEventDestroy(h->copy_done);
     if (h->t0) cudaEventDestroy(h->t0);
@@ -217,15 +219,59 @@ static int fetch_recs(hive_env_t* h, std::vector<GameRec>& out, int first, int c
     return 0;
 }
 
+int hive_status_packed_host(hive_env_t* h, uint32_t* packed) {
+    if (check(h)) return HIVE_E_HANDLE;
+    if (!packed) return fail(HIVE_E_ARG, "hive_status_packed_host: null output");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemcpyAsync(packed, h->status, (size_t)h->n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 int hive_status_host(hive_env_t* h, int32_t* turn, int8_t* winner, uint8_t* done) {
     if (check(h)) return HIVE_E_HANDLE;
-    std::vector<GameRec> r;
-    int rc = fetch_recs(h, r, 0, h->n);
+    std::vector<uint32_t> st(h->n);
+    int rc = hive_status_packed_host(h, st.data());
     if (rc) return rc;
     for (int i = 0; i < h->n; i++) {
-        if (turn) turn[i] = r[i].turn;
-        if (winner) winner[i] = (int8_t)r[i].winner;
-        if (done) done[i] = r[i].done;
+        if (turn) turn[i] = st[i] & 0xFF;
+        if (winner) winner[i] = (int8_t)((st[i] >> 8) & 0xFF);
+        if (done) done[i] = (uint8_t)((st[i] >> 16) & 0xFF);
+    }
+    return 0;
+}
+
+static inline uint64_t host_splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+
+int hive_host_pick_actions(int n, const uint64_t* mask, const int32_t* count, const uint32_t* packed_status,
+                           uint32_t* episodes, uint64_t seed, int max_turn, int32_t* actions) {
+    if (n <= 0 || !mask || !count || !packed_status || !episodes || !actions)
+        return fail(HIVE_E_ARG, "hive_host_pick_actions: bad arguments");
+    for (int g = 0; g < n; g++) {
+        const uint32_t st = packed_status[g];
+        const int turn = st & 0xFF, done = (st >> 16) & 0xFF;
+        if (done || turn >= max_turn) { actions[g] = HIVE_RESET; episodes[g]++; continue; }
+        if (count[g] <= 0) { actions[g] = -1; continue; }
+        const uint64_t gid = (uint64_t)g + (uint64_t)n * episodes[g];
+        int k = (int)(host_splitmix64(seed ^ (gid << 32) ^ (uint64_t)turn) % (uint64_t)count[g]);
+        const uint64_t* m = mask + (size_t)g * HIVE_LEGAL_U64;
+        int a = -1;
+        for (int w = 0; w < HIVE_LEGAL_U64; w++) {
+            const int c = __builtin_popcountll(m[w]);
+            if (k < c) {
+                uint64_t x = m[w];
+                for (int i = 0; i < k; i++) x &= x - 1;
+                a = w * 64 + __builtin_ctzll(x);
+                break;
+            }
+            k -= c;
+        }
+        actions[g] = a;
     }
     return 0;
 }
@@ -297,6 +343,7 @@ int hive_copy_state(hive_env_t* dst, int dst_game, hive_env_t* src, int src_game
     CUDA_TRY(cudaMemcpyAsync(dst->legal + (size_t)dst_game * LEGAL_WORDS, src->legal + (size_t)src_game * LEGAL_WORDS,
                              LEGAL_WORDS * 4, cudaMemcpyDeviceToDevice, dst->stream));
     CUDA_TRY(cudaMemcpyAsync(dst->count + dst_game, src->count + src_game, 4, cudaMemcpyDeviceToDevice, dst->stream));
+    CUDA_TRY(cudaMemcpyAsync(dst->status + dst_game, src->status + src_game, 4, cudaMemcpyDeviceToDevice, dst->stream));
     CUDA_TRY(cudaMemcpyAsync(dst->planes + (size_t)dst_game * HIVE_PLANES_ELEMS, src->planes + (size_t)src_game * HIVE_PLANES_ELEMS,
                              HIVE_PLANES_ELEMS * 2, cudaMemcpyDeviceToDevice, dst->stream));
     return 0;
@@ -335,6 +382,7 @@ int hive_state_key(hive_env_t* h, int game, char* buf, int buflen) {
 void* hive_dev_state(hive_env_t* h) { return h ? h->recs : nullptr; }
 void* hive_dev_legal(hive_env_t* h) { return h ? h->legal : nullptr; }
 void* hive_dev_count(hive_env_t* h) { return h ? h->count : nullptr; }
+void* hive_dev_status(hive_env_t* h) { return h ? h->status : nullptr; }
 void* hive_dev_planes(hive_env_t* h) { return h ? h->planes : nullptr; }
 long long hive_launch_count(const hive_env_t* h) { return h ? h->launches : 0; }
 

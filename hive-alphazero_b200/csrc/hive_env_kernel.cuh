@@ -6,6 +6,9 @@
 #ifndef HIVE_NOOP
 #define HIVE_NOOP (-2)
 #endif
+#ifndef HIVE_RESET
+#define HIVE_RESET (-3)
+#endif
 #ifndef HIVE_PLANES_ELEMS
 #define HIVE_PLANES_ELEMS (56 * 144)
 #endif
@@ -13,12 +16,13 @@
 namespace hive {
 
 constexpr int WARPS_PER_CTA = 4;
-enum Op { OP_RESET = 0, OP_STEP = 1, OP_EVAL = 2, OP_RANDOM = 3 };
+enum Op { OP_RESET = 0, OP_STEP = 1, OP_EVAL = 2, OP_RANDOM = 3, OP_INIT = 4 };   // INIT = first reset, zeroes the counters
 
 struct EnvArgs {
     GameRec* recs;
     uint32_t* legal;       // [n][50]
     int32_t* count;        // [n]
+    uint32_t* status;      // [n] turn | winner<<8 | done<<16
     uint16_t* planes;      // [n][56*144] bf16
     const int32_t* actions;
     const uint8_t* mask;
@@ -50,9 +54,12 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) hive_env_kernel(EnvArgs a)
     if (a.op == OP_RESET) {
         if (a.mask && !a.mask[g]) return;
         do_reset = true;
+    } else if (a.op == OP_INIT) {
+        do_reset = true; episode = 0xFFFFFFFFu; steps = 0;      // first episode of the slot is number 0
     } else if (a.op == OP_STEP) {
         action = a.actions[g];
         if (action == HIVE_NOOP) return;
+        if (action == HIVE_RESET) do_reset = true;
     } else if (a.op == OP_EVAL) {
         if (a.mask && !a.mask[g]) return;
     } else {   // OP_RANDOM
@@ -95,6 +102,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) hive_env_kernel(EnvArgs a)
         w[11] = (uint32_t)turn | ((uint32_t)r.winner << 8) | ((uint32_t)r.done << 16);
         w[12] = episode; w[13] = steps; w[14] = (uint32_t)r.n_legal;
         a.count[g] = r.n_legal;
+        a.status[g] = w[11];
     }
     if (lane < 20) reinterpret_cast<uint4*>(rec->hist)[lane] = reinterpret_cast<const uint4*>(&sm.hist[0][0][0][0])[lane];
     if (lane < 25) reinterpret_cast<uint2*>(a.legal + (size_t)g * LEGAL_WORDS)[lane] = reinterpret_cast<const uint2*>(sm.legal)[lane];

@@ -1,0 +1,283 @@
+"""Host-side mirror of the reference's environment interface on top of the C ABI.
+
+* ``HiveBatch``  -- n independent games on one GPU (the batched API the hot path is built for).
+* ``GamePlay``   -- the reference's single-game class (hive_engine/env_hive.py:24), same method
+                    names, argument meaning and return types, backed by a 1-game ``HiveBatch``.
+
+Everything that computes (move generation, step, plane encoding, terminal test) runs in the
+sm_100a kernels of csrc/; this file only moves bytes and reshapes them.
+"""
+import copy
+import ctypes
+
+import numpy as np
+
+from . import config as C
+from ._capi import HiveError, check, lib
+
+
+def _bf16_to_f32(u16):
+    return (u16.astype(np.uint32) << 16).view(np.float32)
+
+
+class HiveBatch:
+    """n_games concurrent games resident in HBM (include/hive_b200.h)."""
+
+    def __init__(self, n_games, device=0, stream=None):
+        self.n = int(n_games)
+        self.device = int(device)
+        h = ctypes.c_void_p()
+        check(lib().hive_create(self.n, self.device, stream, ctypes.byref(h)), "hive_create")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().hive_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- stepping
+    def reset(self, mask=None):
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        if m is not None and m.shape != (self.n,):
+            raise ValueError("mask must have shape (n_games,)")
+        check(lib().hive_reset(self._h, None if m is None else m.ctypes.data), "hive_reset")
+
+    def step(self, actions):
+        """GamePlay.move for every game; actions int32[n] in host memory (-1 pass, NOOP skip)."""
+        a = np.ascontiguousarray(actions, dtype=np.int32)
+        if a.shape != (self.n,):
+            raise ValueError("actions must have shape (n_games,)")
+        check(lib().hive_step_host(self._h, a.ctypes.data), "hive_step_host")
+
+    def step_ptr(self, host_ptr):
+        """Same, from a raw host pointer (e.g. pinned memory)."""
+        check(lib().hive_step_host(self._h, host_ptr), "hive_step_host")
+
+    def step_device(self, actions_dev_ptr):
+        check(lib().hive_step(self._h, actions_dev_ptr), "hive_step")
+
+    def step_random(self, seed, max_turn=C.MAX_GAME_LENGTH, auto_reset=True, chosen_dev_ptr=None):
+        check(lib().hive_step_random(self._h, seed, max_turn, 1 if auto_reset else 0, chosen_dev_ptr),
+              "hive_step_random")
+
+    def sync(self):
+        check(lib().hive_sync(self._h), "hive_sync")
+
+    # ---- results (host copies)
+    def legal_mask(self):
+        """(mask uint64[n,25], count int32[n])."""
+        mask = np.empty((self.n, 25), dtype=np.uint64)
+        count = np.empty(self.n, dtype=np.int32)
+        check(lib().hive_legal_host(self._h, mask.ctypes.data, count.ctypes.data), "hive_legal_host")
+        return mask, count
+
+    def legal_into(self, mask_ptr, count_ptr):
+        check(lib().hive_legal_host(self._h, mask_ptr, count_ptr), "hive_legal_host")
+
+    def actions(self, g=None):
+        """Sorted legal action ids (GamePlay.actions) of game g, or a list for all games."""
+        mask, _ = self.legal_mask()
+        bits = np.unpackbits(mask.view(np.uint8), axis=1, bitorder="little")[:, :C.ACTION_SPACE]
+        if g is not None:
+            return np.nonzero(bits[g])[0].astype(np.int32)
+        return [np.nonzero(b)[0].astype(np.int32) for b in bits]
+
+    def planes_bf16(self):
+        out = np.empty((self.n, C.STATE_FEATURES, 144), dtype=np.uint16)
+        check(lib().hive_encode_host(self._h, out.ctypes.data), "hive_encode_host")
+        return out
+
+    def planes(self):
+        """float32 [n,56,12,12] (CHW, what the net consumes)."""
+        return _bf16_to_f32(self.planes_bf16()).reshape(self.n, C.STATE_FEATURES, 12, 12)
+
+    def status(self):
+        turn = np.empty(self.n, dtype=np.int32)
+        winner = np.empty(self.n, dtype=np.int8)
+        done = np.empty(self.n, dtype=np.uint8)
+        check(lib().hive_status_host(self._h, turn.ctypes.data, winner.ctypes.data, done.ctypes.data),
+              "hive_status_host")
+        return turn, winner, done
+
+    def status_packed_into(self, host_ptr):
+        check(lib().hive_status_packed_host(self._h, host_ptr), "hive_status_packed_host")
+
+    def counters(self):
+        steps = np.empty(self.n, dtype=np.uint32)
+        episodes = np.empty(self.n, dtype=np.uint32)
+        check(lib().hive_counters_host(self._h, steps.ctypes.data, episodes.ctypes.data), "hive_counters_host")
+        return steps, episodes
+
+    def state_key(self, g):
+        buf = ctypes.create_string_buffer(256)
+        n = check(lib().hive_state_key(self._h, int(g), buf, 256), "hive_state_key")
+        return buf.raw[:n].decode()
+
+    def load_state(self, g, turn, cells, levels):
+        c = np.ascontiguousarray(cells, dtype=np.uint8)
+        l = np.ascontiguousarray(levels, dtype=np.uint8)
+        if c.shape != (22,) or l.shape != (22,):
+            raise ValueError("cells/levels must have 22 entries")
+        check(lib().hive_load_state(self._h, int(g), int(turn), c.ctypes.data, l.ctypes.data), "hive_load_state")
+
+    def dump_state(self, g):
+        turn = ctypes.c_int32()
+        c = np.empty(22, dtype=np.uint8)
+        l = np.empty(22, dtype=np.uint8)
+        check(lib().hive_dump_state(self._h, int(g), ctypes.byref(turn), c.ctypes.data, l.ctypes.data),
+              "hive_dump_state")
+        return turn.value, c, l
+
+    def copy_state_from(self, g, other, og):
+        check(lib().hive_copy_state(self._h, int(g), other._h, int(og)), "hive_copy_state")
+
+    # ---- device arenas
+    @property
+    def dev_planes(self): return lib().hive_dev_planes(self._h)
+    @property
+    def dev_legal(self): return lib().hive_dev_legal(self._h)
+    @property
+    def dev_count(self): return lib().hive_dev_count(self._h)
+    @property
+    def dev_state(self): return lib().hive_dev_state(self._h)
+    @property
+    def dev_status(self): return lib().hive_dev_status(self._h)
+    @property
+    def launches(self): return lib().hive_launch_count(self._h)
+
+    def set_timing(self, on): check(lib().hive_set_timing(self._h, 1 if on else 0), "hive_set_timing")
+    def last_kernel_ms(self): return float(lib().hive_last_kernel_ms(self._h))
+
+
+def host_pick_actions(mask, count, packed_status, episodes, seed, max_turn, actions_out):
+    """hive_host_pick_actions on numpy arrays (all preallocated, C-contiguous)."""
+    n = len(count)
+    check(lib().hive_host_pick_actions(n, mask.ctypes.data, count.ctypes.data, packed_status.ctypes.data,
+                                       episodes.ctypes.data, seed, max_turn, actions_out.ctypes.data),
+          "hive_host_pick_actions")
+
+
+class _State:
+    """The slice of Game_State (game_state.py:10-119) the hot-path callers read."""
+
+    def __init__(self, env):
+        self._env = env
+        self.winner = None
+
+    @property
+    def turn(self):
+        return int(self._env._batch.status()[0][0])
+
+    def player(self):          # game_state.py:58-62
+        return 0 if self.turn % 2 == 1 else 1
+
+
+class GamePlay:
+    """Drop-in for hive_engine/env_hive.py::GamePlay on the hot path.
+
+    ``debug=True`` makes ``move`` raise ValueError on an action outside ``actions()``; the default
+    mirrors the reference, which does not validate (assert commented out, env_hive.py:129-144).
+    """
+
+    def __init__(self, HEIGHT_MAP=C.HEIGHT - 100, WIDTH_MAP=C.WIDTH - 500, second_force=False, device=0, debug=False):
+        self.HEIGHT_MAP, self.WIDTH_MAP = HEIGHT_MAP, WIDTH_MAP
+        self.second_force = True
+        self.debug = debug
+        self._device = device
+        self._batch = HiveBatch(1, device=device)
+        self.state = _State(self)
+        self._stale_key_player = None
+        self._refresh()
+
+    # -- internal
+    def _refresh(self):
+        self.encoded_action = self._batch.actions(0).tolist()
+
+    def new_game(self):                                   # env_hive.py:61-97
+        self._batch.reset()
+        self.state.winner = None
+        self._stale_key_player = None
+        self._refresh()
+
+    def move(self, move, with_skip=False):                # env_hive.py:99-171
+        move = int(move)
+        if self.debug and move != -1 and move not in self.encoded_action:
+            raise ValueError("illegal action %d at turn %d" % (move, self.state.turn))
+        if move < -1 or move >= C.ACTION_SPACE:
+            raise IndexError("action %d out of range" % move)
+        self._batch.step(np.array([move], dtype=np.int32))
+        self._stale_key_player = None
+        self._refresh()
+
+    def actions(self):                                    # env_hive.py:182
+        return self.encoded_action
+
+    def encode_board(self, player="N"):                   # env_hive.py:306-318
+        side = "W" if self.state.player() == 0 else "B"
+        if player == "N":
+            player = side
+        if player != side:
+            raise KeyError(player)                        # state_final only holds the side to move
+        p = self._batch.planes()[0]                       # (56,12,12) float32
+        return np.ascontiguousarray(p.transpose(1, 2, 0)).astype(np.float64)
+
+    def game_is_over(self):                               # move_checker.py:140-165
+        _, winner, done = self._batch.status()
+        if winner[0] == 1:
+            self.state.winner = C.PIECE_WHITE
+        elif winner[0] == 2:
+            self.state.winner = C.PIECE_BLACK
+        return bool(done[0])
+
+    def turn(self):
+        return self.state.turn
+
+    def player(self):
+        return self.state.player()
+
+    @property
+    def state_key(self):                                  # env_hive.py:150-168
+        key = self._batch.state_key(0)
+        if self._stale_key_player is not None:            # skip_turn leaves the key untouched (:493-496)
+            key = key[:-1] + self._stale_key_player
+        return key
+
+    def skip_turn(self):                                  # env_hive.py:493-496
+        stale = self.state_key[-1]
+        self._batch.step(np.array([-1], dtype=np.int32))
+        self._stale_key_player = stale
+        self._refresh()
+
+    def decode_action(self, action):                      # env_hive.py:498-507
+        action = int(action)
+        cell, k = divmod(action, 11)
+        q, r = divmod(cell, 12)
+        return "<class 'pieces.%s'>%d" % (C.PIECE_CLASS[k], C.PIECE_NUM[k]), (C.index_char[q], C.index_number[r])
+
+    def position(self):
+        """(turn, cells[22], levels[22]) -- see hive_dump_state."""
+        return self._batch.dump_state(0)
+
+    def load_position(self, turn, cells, levels):
+        self._batch.load_state(0, turn, cells, levels)
+        self._stale_key_player = None
+        self._refresh()
+
+    def __deepcopy__(self, memo):                         # solo_play.py:158 deep-copies the env
+        other = GamePlay.__new__(GamePlay)
+        other.HEIGHT_MAP, other.WIDTH_MAP = self.HEIGHT_MAP, self.WIDTH_MAP
+        other.second_force, other.debug, other._device = self.second_force, self.debug, self._device
+        other._batch = HiveBatch(1, device=self._device)
+        other._batch.copy_state_from(0, self._batch, 0)
+        other._batch.sync()
+        other.state = _State(other)
+        other.state.winner = self.state.winner
+        other._stale_key_player = self._stale_key_player
+        other.encoded_action = list(self.encoded_action)
+        return other

@@ -14,7 +14,7 @@
  *     resident pipeline never leaves HBM.
  *   - action ids are the reference's: a = q*132 + r*11 + piece_idx = cell*11 + piece_idx
  *     (hive_engine/config.py:10, env_hive.py:107-114); -1 = pass (env_hive.py:100-103);
- *     HIVE_NOOP leaves that game untouched.
+ *     HIVE_NOOP leaves that game untouched, HIVE_RESET starts a new game in that slot.
  *   - there is no CPU fallback: without a CUDA device hive_create fails with HIVE_E_CUDA.
  */
 #ifndef HIVE_B200_H
@@ -33,6 +33,7 @@ extern "C" {
 #define HIVE_LEGAL_U64 25           /* 1584-bit mask */
 #define HIVE_HAND 255
 #define HIVE_NOOP (-2)
+#define HIVE_RESET (-3)                /* as an action: new_game() for that game inside the step */
 #define HIVE_PLANES_ELEMS (HIVE_STATE_FEATURES * HIVE_CELLS)   /* bf16 per game, CHW */
 #define HIVE_STATE_BYTES 384
 
@@ -75,6 +76,14 @@ int hive_encode_host(hive_env_t* h, uint16_t* planes_bf16);
 /* state.turn, winner (0 none / 1 white / 2 black, settings.py:3-4), game_is_over()
  * (move_checker.py:140-165).  Any pointer may be NULL. */
 int hive_status_host(hive_env_t* h, int32_t* turn, int8_t* winner, uint8_t* done);
+/* the same three fields packed per game: turn | winner<<8 | done<<16 (one 4-byte D2H per game) */
+int hive_status_packed_host(hive_env_t* h, uint32_t* packed);
+/* Host-side twin of hive_step_random's action rule for callers that drive hive_step_host from
+ * host buffers: actions[g] = HIVE_RESET if the game is over or turn >= max_turn (episodes[g] is
+ * then incremented), -1 if count[g]==0, else the (x % count[g])-th set bit of mask[g] with
+ * x = splitmix64(seed ^ (g + n*episodes[g])<<32 ^ turn).  Pure host code, no GPU work. */
+int hive_host_pick_actions(int n, const uint64_t* mask, const int32_t* count, const uint32_t* packed_status,
+                           uint32_t* episodes, uint64_t seed, int max_turn, int32_t* actions);
 /* counters: env steps and episodes per slot */
 int hive_counters_host(hive_env_t* h, uint32_t* steps, uint32_t* episodes);
 
@@ -93,6 +102,7 @@ int hive_copy_state(hive_env_t* dst, int dst_game, hive_env_t* src, int src_game
 void* hive_dev_state(hive_env_t* h);     /* [n] x 384-byte records                    */
 void* hive_dev_legal(hive_env_t* h);     /* [n][25] uint64                            */
 void* hive_dev_count(hive_env_t* h);     /* [n] int32                                 */
+void* hive_dev_status(hive_env_t* h);    /* [n] uint32 turn | winner<<8 | done<<16    */
 void* hive_dev_planes(hive_env_t* h);    /* [n][56][144] bf16                         */
 
 /* launches issued by this handle since creation (bench.py's gpu_launches) */

@@ -11,7 +11,7 @@ _CSRC = os.path.join(os.path.dirname(os.path.dirname(_HERE)), "hive-alphazero_b2
 _LIB = os.path.join(_HERE, "libhive_emu.so")
 _lib = None
 
-OP_RESET, OP_STEP, OP_EVAL, OP_RANDOM = 0, 1, 2, 3
+OP_RESET, OP_STEP, OP_EVAL, OP_RANDOM, OP_INIT = 0, 1, 2, 3, 4
 NOOP = -2
 
 
@@ -31,7 +31,7 @@ def lib():
         build()
         L = ctypes.CDLL(_LIB)
         vp = ctypes.c_void_p
-        L.emu_env_run.argtypes = [vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_uint64,
+        L.emu_env_run.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_uint64,
                                   ctypes.c_int, ctypes.c_int, vp, ctypes.c_uint64]
         L.emu_env_run.restype = ctypes.c_int
         L.emu_last_error.restype = ctypes.c_char_p
@@ -47,17 +47,18 @@ class EmuBatch:
         self.recs = np.zeros((n, 384), dtype=np.uint8)
         self.legal = np.zeros((n, 50), dtype=np.uint32)
         self.count = np.zeros(n, dtype=np.int32)
+        self.status = np.zeros(n, dtype=np.uint32)
         self.planes = np.zeros((n, 56 * 144), dtype=np.uint16)
         self.chosen = np.zeros(n, dtype=np.int32)
         self.sched_seed = sched_seed
-        self._run(OP_RESET)
+        self._run(OP_INIT)
 
     def _run(self, op, actions=None, mask=None, seed=0, max_turn=55, auto_reset=0):
         self.sched_seed += 7919
         a = None if actions is None else np.ascontiguousarray(actions, dtype=np.int32)
         m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
         rc = lib().emu_env_run(self.recs.ctypes.data, self.legal.ctypes.data, self.count.ctypes.data,
-                               self.planes.ctypes.data, self.n, op,
+                               self.status.ctypes.data, self.planes.ctypes.data, self.n, op,
                                None if a is None else a.ctypes.data, None if m is None else m.ctypes.data,
                                seed, max_turn, auto_reset, self.chosen.ctypes.data, self.sched_seed)
         if rc:

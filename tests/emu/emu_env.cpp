@@ -26,12 +26,12 @@ static void lane_main(void* p) { hive_env_kernel(*(EnvArgs*)p); }
 extern "C" {
 
 // state: n x 384 B records; legal: n x 50 u32; count: n; planes: n x 8064 u16
-int emu_env_run(void* recs, uint32_t* legal, int32_t* count, uint16_t* planes, int n, int op,
+int emu_env_run(void* recs, uint32_t* legal, int32_t* count, uint32_t* status, uint16_t* planes, int n, int op,
                 const int32_t* actions, const uint8_t* mask, uint64_t seed, int max_turn, int auto_reset,
                 int32_t* chosen, uint64_t sched_seed) {
     build_lines();
     EnvArgs a;
-    a.recs = (GameRec*)recs; a.legal = legal; a.count = count; a.planes = planes;
+    a.recs = (GameRec*)recs; a.legal = legal; a.count = count; a.status = status; a.planes = planes;
     a.actions = actions; a.mask = mask; a.chosen = chosen; a.hop_lines = g_lines.data();
     a.seed = seed; a.n = n; a.op = op; a.max_turn = max_turn; a.auto_reset = auto_reset;
     for (int g = 0; g < n; g++) {

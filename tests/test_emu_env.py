@@ -1,0 +1,88 @@
+"""The product's CUDA device source, run on the CPU lock-step warp emulator (tests/emu), against
+the oracle and the reference's golden vectors.  This is the no-GPU safety net for kernel logic;
+the `-m gpu` tests repeat the comparison on the real device through the C ABI."""
+import numpy as np
+import pytest
+
+from oracle.hive_oracle import OracleEnv
+from tests.emu.emu import EmuBatch
+
+
+def _compare(e, g, o):
+    ot, oc, ol = o.position()
+    assert e.turn(g) == ot
+    assert (e.cells(g) == oc).all() and (e.levels(g) == ol).all()
+    assert e.actions(g).tolist() == o.actions().tolist()
+    assert e.count[g] == len(o.actions())
+    assert (e.planes_u8(g) == o.planes()).all()
+    assert e.done(g) == o.game_is_over() and e.winner(g) == o.winner
+
+
+@pytest.mark.parametrize("seed", range(0, 40))
+def test_uniform_games(seed):
+    rng = np.random.RandomState(9000 + seed)
+    e, o = EmuBatch(1, sched_seed=seed), OracleEnv()
+    while True:
+        _compare(e, 0, o)
+        if o.game_is_over() or o.turn >= 55:
+            break
+        acts = o.actions()
+        a = int(acts[rng.randint(len(acts))]) if len(acts) else -1
+        o.move(a)
+        e.step(np.array([a], dtype=np.int32))
+
+
+def test_golden_replay_including_tall_stacks(golden):
+    G = golden
+    starts = G["game_start"]
+    for g in range(len(starts) - 1):
+        e = EmuBatch(1, sched_seed=100 + g)
+        for i in range(starts[g], starts[g + 1]):
+            n = G["n_legal"][i]
+            assert e.turn(0) == G["turn"][i]
+            assert e.actions(0).tolist() == G["legal"][i][:n].tolist()
+            pl = e.planes_u8(0)
+            assert (pl[31] == G["plane31"][i]).all()
+            pl[31] = 0
+            assert (np.packbits(pl, axis=1, bitorder="little") == G["planes"][i]).all()
+            assert e.done(0) == bool(G["done"][i]) and e.winner(0) == G["winner"][i]
+            if G["action"][i] != -2:
+                e.step(np.array([G["action"][i]], dtype=np.int32))
+
+
+def test_random_policy_matches_oracle_rule():
+    n, seed = 3, 0xC0FFEE
+    e = EmuBatch(n, sched_seed=5)
+    oracles = [OracleEnv() for _ in range(n)]
+    episodes = [0] * n
+    for _ in range(70):
+        expect = []
+        for g in range(n):
+            o = oracles[g]
+            if o.game_is_over() or o.turn >= 55:
+                o.reset(); episodes[g] += 1
+                expect.append(-2)
+            else:
+                a = o.pick_action(seed, g + n * episodes[g])
+                o.move(a)
+                expect.append(a)
+        e.step_random(seed, max_turn=55, auto_reset=1)
+        assert e.chosen.tolist() == expect
+        for g in range(n):
+            _compare(e, g, oracles[g])
+
+
+def test_noop_and_masked_reset():
+    e = EmuBatch(2, sched_seed=3)
+    o = OracleEnv()
+    e.step(np.array([858, -2], dtype=np.int32))
+    o.move(858)
+    _compare(e, 0, o)
+    assert e.turn(1) == 1
+    e.reset(mask=np.array([1, 0], dtype=np.uint8))
+    o.reset()
+    _compare(e, 0, o)
+    e.step(np.array([-1, -1], dtype=np.int32))      # pass: turn advances, no history push
+    o.move(-1)
+    _compare(e, 0, o)
+    _compare(e, 1, o)

@@ -1,0 +1,193 @@
+"""Parity tests proper: the sm_100a kernels, called through the C ABI (HiveBatch / GamePlay),
+against the CPU oracle on identical seeded inputs and against the reference's golden vectors.
+Bit-exact bar: legal sets, planes, turn/winner/done, state_key, transcripts."""
+import copy
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def hb():
+    import hive_b200
+    return hive_b200
+
+
+def _u8_planes(bf16):
+    return (bf16.astype(np.uint32) << 16).view(np.float32).astype(np.uint8)
+
+
+def test_lockstep_256_games_vs_oracle(hb):
+    from oracle.hive_oracle import OracleEnv
+    n = 256
+    b = hb.HiveBatch(n)
+    oracles = [OracleEnv() for _ in range(n)]
+    rngs = [np.random.RandomState(40000 + g) for g in range(n)]
+    live = np.ones(n, dtype=bool)
+    plies = 0
+    while live.any():
+        mask, count = b.legal_mask()
+        bits = np.unpackbits(mask.view(np.uint8), axis=1, bitorder="little")[:, :1584]
+        planes = _u8_planes(b.planes_bf16())
+        turn, winner, done = b.status()
+        actions = np.full(n, -2, dtype=np.int32)
+        for g in range(n):
+            if not live[g]:
+                continue
+            o = oracles[g]
+            la = o.actions()
+            assert np.nonzero(bits[g])[0].tolist() == la.tolist(), (g, o.turn)
+            assert count[g] == len(la)
+            assert (planes[g] == o.planes()).all(), (g, o.turn)
+            od = o.game_is_over()
+            assert turn[g] == o.turn and bool(done[g]) == od and winner[g] == o.winner
+            if od or o.turn >= 55:
+                live[g] = False
+                assert b.state_key(g) == o.state_key
+                continue
+            a = int(la[rngs[g].randint(len(la))]) if len(la) else -1
+            o.move(a)
+            actions[g] = a
+            plies += 1
+        b.step(actions)
+    assert plies > n * 40
+
+
+def test_golden_replay_through_gameplay_facade(hb, golden):
+    G = golden
+    starts = G["game_start"]
+    env = hb.GamePlay()
+    for g in range(len(starts) - 1):
+        env.new_game()
+        for i in range(starts[g], starts[g + 1]):
+            n = G["n_legal"][i]
+            assert env.state.turn == G["turn"][i]
+            assert env.actions() == G["legal"][i][:n].tolist()
+            p = env.encode_board()
+            assert p.shape == (12, 12, 56) and p.dtype == np.float64
+            chw = p.transpose(2, 0, 1).reshape(56, 144)
+            assert (chw[31] == G["plane31"][i]).all()
+            chw = chw.astype(np.uint8)
+            chw[31] = 0
+            assert (np.packbits(chw, axis=1, bitorder="little") == G["planes"][i]).all()
+            assert env.state_key == str(G["key"][i])
+            assert env.game_is_over() == bool(G["done"][i])
+            w = env.state.winner
+            assert (0 if w is None else 1 if w == hb.config.PIECE_WHITE else 2) == G["winner"][i]
+            if G["action"][i] != -2:
+                env.move(int(G["action"][i]))
+
+
+def test_known_answers_and_facade_contract(hb):
+    env = hb.GamePlay(debug=True)
+    assert env.state.turn == 1 and env.state.player() == 0
+    assert env.actions() == [858, 859, 861, 863, 866]
+    assert env.state_key == "." * 144 + "0"
+    assert env.decode_action(858) == ("<class 'pieces.Queen'>0", ("N", "13"))
+    with pytest.raises(ValueError):
+        env.move(0)
+    env.move(858)
+    assert env.turn() == 2 and env.player() == 1
+    assert env.actions() == [726, 727, 729, 731, 734]
+    with pytest.raises(KeyError):
+        env.encode_board("W")               # only the side to move is encoded (env_hive.py:313-318)
+    twin = copy.deepcopy(env)
+    env.move(726)
+    assert twin.state.turn == 2 and twin.actions() == [726, 727, 729, 731, 734]
+    assert env.state.turn == 3 and len(env.actions()) == 14
+    assert env.state_key.replace(".", "") == "Q0q00"
+    key_before = env.state_key
+    env.skip_turn()                          # env_hive.py:493-496 leaves state_key untouched
+    assert env.state.turn == 4 and env.state_key == key_before
+    assert not env.game_is_over() and env.state.winner is None
+
+
+def test_load_state_positions_from_golden(hb, golden):
+    from oracle.hive_oracle import OracleEnv
+    G = golden
+    idx = np.argsort(-G["levels"].max(axis=1))[:64]            # the tallest stacks first
+    b = hb.HiveBatch(len(idx))
+    o = OracleEnv()
+    for g, i in enumerate(idx):
+        b.load_state(g, int(G["turn"][i]), G["cells"][i], G["levels"][i])
+    acts = b.actions()
+    planes = _u8_planes(b.planes_bf16())
+    for g, i in enumerate(idx):
+        n = G["n_legal"][i]
+        assert acts[g].tolist() == G["legal"][i][:n].tolist()
+        o.load(int(G["turn"][i]), G["cells"][i], G["levels"][i])     # history cleared in both
+        assert (planes[g] == o.planes()).all()
+        t, c, l = b.dump_state(g)
+        assert t == G["turn"][i] and (c == G["cells"][i]).all() and (l == G["levels"][i]).all()
+    with pytest.raises(hb.HiveError):
+        bad = G["levels"][idx[0]].copy()
+        bad[:] = 3
+        b.load_state(0, 9, G["cells"][idx[0]], bad)
+
+
+def test_step_random_full_size_16384(hb):
+    """BASELINE config 2 size: on-device policy, auto-reset; a 512-game subsample is replayed by
+    the oracle move for move, the whole batch is checked through size-independent properties."""
+    import torch
+    from oracle.hive_oracle import OracleEnv
+    n, seed, steps, sub = 16384, 20261018, 130, 512
+    b = hb.HiveBatch(n)
+    chosen = torch.empty(n, dtype=torch.int32, device="cuda")
+    oracles = [OracleEnv() for _ in range(sub)]
+    episodes = [0] * sub
+    total_steps = 0
+    for it in range(steps):
+        b.step_random(seed, max_turn=55, auto_reset=True, chosen_dev_ptr=chosen.data_ptr())
+        b.sync()
+        ch = chosen.cpu().numpy()
+        total_steps += int((ch != -2).sum())
+        for g in range(sub):
+            o = oracles[g]
+            if o.game_is_over() or o.turn >= 55:
+                o.reset(); episodes[g] += 1
+                assert ch[g] == -2
+            else:
+                a = o.pick_action(seed, g + n * episodes[g])
+                assert ch[g] == a, (it, g)
+                o.move(a)
+    mask, count = b.legal_mask()
+    planes = _u8_planes(b.planes_bf16())
+    turn, winner, done = b.status()
+    for g in range(sub):
+        o = oracles[g]
+        bits = np.unpackbits(mask[g].view(np.uint8), bitorder="little")[:1584]
+        assert np.nonzero(bits)[0].tolist() == o.actions().tolist()
+        assert (planes[g] == o.planes()).all()
+        assert turn[g] == o.turn and bool(done[g]) == o.game_is_over()
+    # properties over all 16,384 games
+    pop = np.unpackbits(mask.view(np.uint8), axis=1, bitorder="little").sum(axis=1)
+    assert (pop == count).all()
+    assert (turn >= 1).all() and (turn <= 55).all()
+    assert (planes[:, 30] == (planes[:, 11] | planes[:, 23])).all()
+    assert (planes[:, 31] == turn[:, None]).all()
+    assert (planes[:, 11] & planes[:, 23]).sum(axis=1).max() <= 4         # only stacks overlap
+    steps_ctr, episodes_ctr = b.counters()
+    assert int(steps_ctr.sum()) == total_steps
+    assert (episodes_ctr[:sub] == np.array(episodes)).all()
+
+
+def test_host_policy_twin_matches_device_policy(hb):
+    """hive_host_pick_actions (e2e path with host buffers) == hive_step_random (resident path)."""
+    n, seed = 1024, 77
+    dev, host = hb.HiveBatch(n), hb.HiveBatch(n)
+    episodes = np.zeros(n, dtype=np.uint32)
+    actions = np.empty(n, dtype=np.int32)
+    packed = np.empty(n, dtype=np.uint32)
+    for _ in range(120):
+        mask, count = host.legal_mask()
+        host.status_packed_into(packed.ctypes.data)
+        hb.host_pick_actions(mask, count, packed, episodes, seed, 55, actions)
+        host.step(actions)
+        dev.step_random(seed, max_turn=55, auto_reset=True)
+    m1, c1 = dev.legal_mask()
+    m2, c2 = host.legal_mask()
+    assert (m1 == m2).all() and (c1 == c2).all()
+    assert (dev.planes_bf16() == host.planes_bf16()).all()
+    assert [a.tolist() for a in dev.status()] == [a.tolist() for a in host.status()]
