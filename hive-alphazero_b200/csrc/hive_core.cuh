@@ -18,6 +18,7 @@
 #ifndef HIVE_EMU
 #include <cuda_runtime.h>
 #endif
+#include <stddef.h>
 #include <stdint.h>
 
 namespace hive {
@@ -49,14 +50,16 @@ struct __align__(16) GameRec {
 };
 static_assert(sizeof(GameRec) == 384, "GameRec must stay 384 bytes");
 
-// per-warp shared-memory scratch
-struct WarpScratch {
+// per-warp shared-memory scratch (hist / legal are moved with 16- and 8-byte vector accesses)
+struct __align__(16) WarpScratch {
+    uint32_t hist[2][4][2][5];     // 320 B, 16-byte aligned
     uint32_t planes[N_PLANE][5];   // bit boards of the 56 planes (plane 31 unused: it is the turn)
-    uint32_t legal[LEGAL_WORDS];
-    uint32_t occ[5];
+    uint32_t legal[LEGAL_WORDS + 2];
+    uint32_t occ[8];
     uint32_t moves[N_PIECE][5];    // action list per piece (own) / mobility set (opponent)
-    uint32_t hist[2][4][2][5];
 };
+static_assert(sizeof(WarpScratch) % 16 == 0, "WarpScratch must keep 16-byte alignment in arrays");
+static_assert(offsetof(WarpScratch, hist) % 16 == 0 && offsetof(WarpScratch, legal) % 8 == 0, "vector access alignment");
 
 // ------------------------------------------------------------------------------------------
 // 144-bit boards
