@@ -107,9 +107,10 @@ def test_known_answers_and_facade_contract(hb):
 def test_load_state_positions_from_golden(hb, golden):
     from oracle.hive_oracle import OracleEnv
     G = golden
-    idx = np.argsort(-G["levels"].max(axis=1))[:64]            # the tallest stacks first
+    idx = np.argsort(-G["levels"].max(axis=1).astype(np.int32), kind="stable")[:64]            # the tallest stacks first
     b = hb.HiveBatch(len(idx))
     o = OracleEnv()
+    assert G["levels"][idx[0]].max() >= 3
     for g, i in enumerate(idx):
         b.load_state(g, int(G["turn"][i]), G["cells"][i], G["levels"][i])
     acts = b.actions()
