@@ -7,7 +7,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libhive_b200.so")
+LIB_PATH = os.environ.get("HIVE_B200_LIB") or os.path.join(LIB_DIR, "libhive_b200.so")   # override: A/B builds
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -26,6 +26,8 @@ def _newest_source_mtime():
 def build(force=False, verbose=False):
     """nvcc -gencode arch=compute_100a,code=sm_100a ... -> lib/libhive_b200.so. Idempotent."""
     os.makedirs(LIB_DIR, exist_ok=True)
+    if os.environ.get("HIVE_B200_LIB"):
+        return LIB_PATH                      # externally built variant: use as is
     if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= _newest_source_mtime():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"

@@ -57,6 +57,9 @@ struct __align__(16) WarpScratch {
     uint32_t legal[LEGAL_WORDS + 2];
     uint32_t occ[8];
     uint32_t moves[N_PIECE][5];    // action list per piece (own) / mobility set (opponent)
+    uint32_t info[24];             // per piece: cell | height<<8 | top<<12 | ring<<16
+    uint32_t head[4];              // turn|cq_w<<8|cq_b<<16 ; pinned mask ; evaluated-this-launch flag
+    uint32_t pad[2];
 };
 static_assert(sizeof(WarpScratch) % 16 == 0, "WarpScratch must keep 16-byte alignment in arrays");
 static_assert(offsetof(WarpScratch, hist) % 16 == 0 && offsetof(WarpScratch, legal) % 8 == 0, "vector access alignment");
@@ -215,28 +218,36 @@ __device__ __forceinline__ bool obeys_queen_by_4(int turn, bool wq_on, bool bq_o
 struct EvalResult { int n_legal; int done; int winner; };
 
 // ------------------------------------------------------------------------------------------
-// Evaluate the position held by the warp: legal mask + planes into `sm`, history push.
-// All 32 lanes must call this converged.  `hop_lines` = 144x5 u32 table of is_straight_line
-// masks (move_checker.py:249-265).
-__device__ __noinline__ EvalResult evaluate_position(WarpScratch& sm, int lane, int cell, int level, int turn,
-                                                     bool push_history, int prev_winner,
-                                                     const uint32_t* __restrict__ hop_lines) {
+// The evaluation of a position runs in three phases inside one CTA that holds G games:
+//   phase A  (warp g <-> game g, lane p <-> piece p): stacks, occupancy, ring occupancy, placements,
+//            the planes that do not depend on mobility, terminal test; publishes one info word
+//            per piece in shared memory;
+//   phase B  (thread <-> one on-board piece of one of the G games, threads grouped BY PIECE TYPE so
+//            that a warp runs 32 Ant floods, or 32 Spider walks ... of several games at once):
+//            one-hive flood + the piece's move set -> shared memory;
+//   phase C  (warp g <-> game g again): dense legal mask, mobility planes 34/35/44-55, history push.
+// info word: cell | height<<8 | top<<12 | ring<<16.   head[0] = turn | cq_w<<8 | cq_b<<16,
+// head[1] = pinned-piece mask, head[2] = game is being evaluated in this launch.
+
+__device__ __forceinline__ int piece_type_of(int k) {
+    return (k == 0) ? T_QUEEN : (k <= 2) ? T_BEETLE : (k <= 4) ? T_SPIDER : (k <= 7) ? T_HOPPER : T_ANT;
+}
+
+__device__ __forceinline__ EvalResult eval_phase_a(WarpScratch& sm, int lane, int cell, int level, int turn, int prev_winner) {
     const int side = (turn & 1) ? 0 : 1;                 // game_state.py:58-62
     const bool valid = lane < N_PIECE;
     const int color = lane >= 11 ? 1 : 0;
     const int k = lane - 11 * color;
-    const int type = (k == 0) ? T_QUEEN : (k <= 2) ? T_BEETLE : (k <= 4) ? T_SPIDER : (k <= 7) ? T_HOPPER : T_ANT;
+    const int type = piece_type_of(k);
     const bool own = valid && (color == side);
     const bool on_board = valid && cell != HAND;
 
-    // ---- zero the scratch outputs
-    {
+    {   // zero the scratch outputs
         uint32_t* pz = &sm.planes[0][0];
         for (int i = lane; i < N_PLANE * 5; i += 32) pz[i] = 0;
         for (int i = lane; i < LEGAL_WORDS; i += 32) sm.legal[i] = 0;
     }
-
-    // ---- stacks: pieces sharing a cell (tile.pieces); top piece <=> level+1 == len (env_hive.py:213)
+    // stacks: pieces sharing a cell (tile.pieces); top piece <=> level+1 == len (env_hive.py:213)
     const unsigned peers = __match_any_sync(FULL, on_board ? cell : 256 + lane);
     const int height = __popc(peers);
     const bool top = on_board && (level == height - 1);
@@ -250,18 +261,94 @@ __device__ __noinline__ EvalResult evaluate_position(WarpScratch& sm, int lane, 
 
     const int cq_w = __shfl_sync(FULL, cell, 0), cq_b = __shfl_sync(FULL, cell, 11);
     const bool wq_on = cq_w != HAND, bq_on = cq_b != HAND;
-    const int cq_own = side == 0 ? cq_w : cq_b, cq_opp = side == 0 ? cq_b : cq_w;
-    const bool ownq_on = cq_own != HAND;
+    const unsigned in_hand = __ballot_sync(FULL, own && !on_board);
     __syncwarp();
 
-    // ---- ring occupancy around each on-board piece
-    uint32_t ring = 0;
+    uint32_t ring = 0;                                   // occupancy of the six neighbours
     if (on_board) {
 #pragma unroll
         for (int i = 0; i < 6; i++) ring |= (uint32_t)words_test(sm.occ, cell_nbr(cell, i)) << i;
     }
+    if (valid) sm.info[lane] = (uint32_t)cell | ((uint32_t)height << 8) | ((uint32_t)top << 12) | (ring << 16);
+    if (lane == 0) { sm.head[0] = (uint32_t)turn | ((uint32_t)cq_w << 8) | ((uint32_t)cq_b << 16); sm.head[1] = 0; }
 
-    // ---- one hive (move_checker.py:58-83 / env_hive.py:509-530): lift the top piece, flood
+    // placements (env_hive.py:217-225; move_checker.py:168-179): first in-hand piece per type
+    if (valid && !on_board) {
+        BB mv = bb_zero();
+        const unsigned same_type_before = in_hand & ((1u << lane) - 1u) &
+            (type == T_QUEEN ? 0x00000801u : type == T_BEETLE ? 0x00003006u : type == T_SPIDER ? 0x0000C018u
+             : type == T_HOPPER ? 0x000700E0u : 0x00380700u);
+        if (own && same_type_before == 0) {
+            if (turn == 1) mv = bb_bit(START_CELL);
+            else if (turn == 2) mv = bb_andn(bb_nbrs(occ), occ) & bb_bit(TURN2_CELL);
+            else {
+                bool ok = true;
+                if (turn == 7 || turn == 8) ok = obeys_queen_by_4(turn, wq_on, bq_on, type == T_QUEEN, color);
+                if (ok) mv = bb_andn(bb_andn(bb_nbrs(occ), occ), bb_nbrs(top_opp));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 5; i++) sm.moves[lane][i] = mv.w[i];
+    }
+
+    // terminal test (move_checker.py:140-165)
+    const unsigned surrounded = __ballot_sync(FULL, on_board && type == T_QUEEN && ring == 63u);
+    const bool ws = surrounded & 1u, bs = (surrounded >> 11) & 1u;
+    EvalResult res;
+    res.n_legal = 0;
+    res.done = ws || bs;
+    res.winner = (ws && bs) ? prev_winner : ws ? 2 : bs ? 1 : prev_winner;
+
+    // planes that do not depend on mobility (env_hive.py:320-447)
+    if (on_board) {
+        const uint32_t bit = 1u << (cell & 31); const int wi = cell >> 5;
+        sm.planes[(own ? 0 : 12) + k][wi] = bit;                          // 0-10 / 12-22
+        if (type == T_BEETLE && level >= 2)                               // 24-26 / 27-29
+            atomicOr(&sm.planes[(own ? 24 : 27) + level - 2][wi], bit);
+        if (!top) atomicOr(&sm.planes[own ? 34 : 35][wi], bit);           // covered pieces
+        if (type == T_QUEEN) {                                            // 32 / 33
+#pragma unroll
+            for (int i = 0; i < 6; i++)
+                if ((ring >> i) & 1u) { int c = cell_nbr(cell, i); atomicOr(&sm.planes[own ? 32 : 33][c >> 5], 1u << (c & 31)); }
+        }
+    }
+    if (lane < 5) {
+        sm.planes[11][lane] = own_all.w[lane];
+        sm.planes[23][lane] = opp_all.w[lane];
+        sm.planes[30][lane] = occ.w[lane];
+    }
+    {   // 36..43 history of the side to move
+        const uint32_t* h = &sm.hist[side][0][0][0];
+        for (int i = lane; i < 40; i += 32) (&sm.planes[36][0])[i] = h[i];
+    }
+    return res;
+}
+
+// phase B: one thread, one piece.  `hop_lines` = 144x5 u32 table of is_straight_line masks
+// (move_checker.py:249-265).
+__device__ __forceinline__ void eval_phase_b(WarpScratch& sm, int p, const uint32_t* __restrict__ hop_lines) {
+    const uint32_t info = sm.info[p];
+    const int cell = info & 0xFF;
+    if (cell == HAND) return;                            // placements were written in phase A
+    const int height = (info >> 8) & 0xF;
+    const bool top = (info >> 12) & 1u;
+    const uint32_t ring = (info >> 16) & 63u;
+    const uint32_t head = sm.head[0];
+    const int turn = head & 0xFF, cq_w = (head >> 8) & 0xFF, cq_b = (head >> 16) & 0xFF;
+    const int side = (turn & 1) ? 0 : 1;
+    const int color = p >= 11 ? 1 : 0;
+    const int k = p - 11 * color;
+    const int type = piece_type_of(k);
+    const bool own = color == side;
+    const bool wq_on = cq_w != HAND, bq_on = cq_b != HAND;
+    const bool ownq_on = (side == 0 ? cq_w : cq_b) != HAND;
+
+    BB occ;
+#pragma unroll
+    for (int i = 0; i < 5; i++) occ.w[i] = sm.occ[i];
+    const BB src = bb_bit(cell);
+
+    // one hive (move_checker.py:58-83 / env_hive.py:509-530): lift the top piece, flood
     bool pinned = false;
     if (top && height == 1) {
         uint32_t arcs = __popc(ring & ~rot6l(ring));
@@ -282,7 +369,7 @@ __device__ __noinline__ EvalResult evaluate_position(WarpScratch& sm, int lane, 
     // opponent mobility is only consumed through the own queen's neighbourhood (env_hive.py:459-478)
     const bool active = can_move && (own || ownq_on);
 
-    // ---- turn gates shared by every candidate of this piece (move_checker.py:38-55)
+    // turn gates shared by every candidate of this piece (move_checker.py:38-55)
     bool gate = true;
     if (turn <= 2) gate = false;                                             // no on-board mover can exist / matter
     else if (turn <= 6) gate = ownq_on;                                      // queen_is_on_board: colour by turn parity
@@ -333,7 +420,11 @@ __device__ __noinline__ EvalResult evaluate_position(WarpScratch& sm, int lane, 
                 }
                 mv = bb_andn(x, src);
             } else {                                                         // pieces.py:78-85
+#ifdef HIVE_SPIDER_ROLLED
 #pragma unroll 1
+#else
+#pragma unroll
+#endif
                 for (int i = 0; i < 6; i++) {
                     const BB ti = bb_bit(cell_nbr(cell, i));
                     const BB a = ti & sl.g[i];
@@ -349,30 +440,31 @@ __device__ __noinline__ EvalResult evaluate_position(WarpScratch& sm, int lane, 
             }
         }
     }
+#pragma unroll
+    for (int i = 0; i < 5; i++) sm.moves[p][i] = mv.w[i];
+    if (pinned) atomicOr(&sm.head[1], 1u << p);
+}
 
-    // ---- placements (env_hive.py:217-225; move_checker.py:168-179): first in-hand piece per type
-    const unsigned in_hand = __ballot_sync(FULL, own && !on_board);
-    if (own && !on_board) {
-        const unsigned same_type_before = in_hand & ((1u << lane) - 1u) &
-            (type == T_QUEEN ? 0x00000801u : type == T_BEETLE ? 0x00003006u : type == T_SPIDER ? 0x0000C018u
-             : type == T_HOPPER ? 0x000700E0u : 0x00380700u);
-        if (same_type_before == 0) {
-            if (turn == 1) mv = bb_bit(START_CELL);
-            else if (turn == 2) mv = bb_andn(bb_nbrs(occ), occ) & bb_bit(TURN2_CELL);
-            else {
-                bool ok = true;
-                if (turn == 7 || turn == 8) ok = obeys_queen_by_4(turn, wq_on, bq_on, type == T_QUEEN, color);
-                if (ok) mv = bb_andn(bb_andn(bb_nbrs(occ), occ), bb_nbrs(top_opp));
-            }
-        }
-    }
-    __syncwarp();
+__device__ __forceinline__ int eval_phase_c(WarpScratch& sm, int lane, int cell, int turn, bool push_history) {
+    const int side = (turn & 1) ? 0 : 1;
+    const bool valid = lane < N_PIECE;
+    const int color = lane >= 11 ? 1 : 0;
+    const int k = lane - 11 * color;
+    const bool own = valid && (color == side);
+    const bool on_board = valid && cell != HAND;
+    const uint32_t info = valid ? sm.info[lane] : 0u;
+    const bool top = (info >> 12) & 1u;
+    const bool pinned = (sm.head[1] >> lane) & 1u;
+    const uint32_t head = sm.head[0];
+    const int cq_w = (head >> 8) & 0xFF, cq_b = (head >> 16) & 0xFF;
+    const int cq_own = side == 0 ? cq_w : cq_b, cq_opp = side == 0 ? cq_b : cq_w;
 
-    // ---- publish move boards; dense legal mask a = cell*11 + k (env_hive.py:287-304)
+    BB mv = bb_zero();
     if (valid) {
 #pragma unroll
-        for (int i = 0; i < 5; i++) sm.moves[lane][i] = mv.w[i];
+        for (int i = 0; i < 5; i++) mv.w[i] = sm.moves[lane][i];
     }
+    // dense legal mask a = cell*11 + k (env_hive.py:287-304)
     int n_mine = 0;
     if (own) {
         n_mine = bb_popc(mv);
@@ -390,44 +482,16 @@ __device__ __noinline__ EvalResult evaluate_position(WarpScratch& sm, int lane, 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) n_legal += __shfl_xor_sync(FULL, n_legal, o);
 
-    // ---- terminal test (move_checker.py:140-165)
-    const unsigned surrounded = __ballot_sync(FULL, on_board && type == T_QUEEN && ring == 63u);
-    const bool ws = surrounded & 1u, bs = (surrounded >> 11) & 1u;
-    EvalResult res;
-    res.n_legal = n_legal;
-    res.done = ws || bs;
-    res.winner = (ws && bs) ? prev_winner : ws ? 2 : bs ? 1 : prev_winner;
-
-    // ---- planes (env_hive.py:320-447); "own" = side to move
-    if (on_board) {
+    if (on_board && top) {
         const uint32_t bit = 1u << (cell & 31); const int wi = cell >> 5;
-        sm.planes[(own ? 0 : 12) + k][wi] = bit;                          // 0-10 / 12-22
-        if (type == T_BEETLE && level >= 2)                               // 24-26 / 27-29
-            atomicOr(&sm.planes[(own ? 24 : 27) + level - 2][wi], bit);
-        if (own ? (!top || !bb_any(mv)) : (!top || pinned))               // 34 / 35
-            atomicOr(&sm.planes[own ? 34 : 35][wi], bit);
-        if (type == T_QUEEN) {                                            // 32 / 33
-#pragma unroll
-            for (int i = 0; i < 6; i++)
-                if ((ring >> i) & 1u) { int c = cell_nbr(cell, i); atomicOr(&sm.planes[own ? 32 : 33][c >> 5], 1u << (c & 31)); }
-        }
+        if (own ? !bb_any(mv) : pinned) atomicOr(&sm.planes[own ? 34 : 35][wi], bit);     // 34 / 35
     }
-    if (lane < 5) {
-        sm.planes[11][lane] = own_all.w[lane];
-        sm.planes[23][lane] = opp_all.w[lane];
-        sm.planes[30][lane] = occ.w[lane];
-    }
-    {   // 36..43 history of the side to move
-        const uint32_t* h = &sm.hist[side][0][0][0];
-        for (int i = lane; i < 40; i += 32) (&sm.planes[36][0])[i] = h[i];
-    }
-    __syncwarp();
     // 44+j: opponent pieces able to reach the j-th empty neighbour of the own queen;
     // 50+j: own on-board pieces whose action list holds the j-th empty neighbour of the opponent queen.
     // j follows tile.adjacent_tiles order = board_tiles order: q descending, then r ascending.
     {
         const int qc = own ? cq_opp : cq_own;      // own pieces look at the opponent queen and vice versa
-        if (on_board && qc != HAND && (own || active)) {
+        if (on_board && qc != HAND && bb_any(mv)) {
             int nb[6], key[6];
 #pragma unroll
             for (int i = 0; i < 6; i++) { nb[i] = cell_nbr(qc, i); key[i] = (11 - nb[i] / 12) * 12 + nb[i] % 12; }
@@ -443,37 +507,76 @@ __device__ __noinline__ EvalResult evaluate_position(WarpScratch& sm, int lane, 
         }
     }
     __syncwarp();
-
-    // ---- history push (env_hive.py:436-445): only after a real move / at reset
+    // history push (env_hive.py:436-445): only after a real move / at reset
     if (push_history) {
         uint32_t* h = &sm.hist[side][0][0][0];
         uint32_t keep = (lane < 30) ? h[lane] : 0;         // ages 0..2 -> 1..3
         __syncwarp();
         if (lane < 30) h[10 + lane] = keep;
-        if (lane < 5) { h[lane] = own_all.w[lane]; h[5 + lane] = opp_all.w[lane]; }
+        if (lane < 5) { h[lane] = sm.planes[11][lane]; h[5 + lane] = sm.planes[23][lane]; }
         __syncwarp();
     }
-    return res;
+    return n_legal;
 }
+
+// phase-B task layout: threads grouped by piece type so that warps are (nearly) homogeneous.
+// G = 8 : A[0,48) Q[48,64) G[64,112) pad[112,128) S[128,160) B[160,192)      -> 6 warps
+// G = 16: A[0,96) G[96,192) S[192,256) B[256,320) Q[320,352)                 -> 11 warps
+template <int G>
+__device__ __forceinline__ bool task_of_thread(int t, int& game, int& piece) {
+    int base, ipg, first;
+    if (G == 8) {
+        if (t < 48) { base = 0; ipg = 6; first = 8; }
+        else if (t < 64) { base = 48; ipg = 2; first = 0; }
+        else if (t < 112) { base = 64; ipg = 6; first = 5; }
+        else if (t < 128) return false;
+        else if (t < 160) { base = 128; ipg = 4; first = 3; }
+        else if (t < 192) { base = 160; ipg = 4; first = 1; }
+        else return false;
+    } else {
+        if (t < 6 * G) { base = 0; ipg = 6; first = 8; }
+        else if (t < 12 * G) { base = 6 * G; ipg = 6; first = 5; }
+        else if (t < 16 * G) { base = 12 * G; ipg = 4; first = 3; }
+        else if (t < 20 * G) { base = 16 * G; ipg = 4; first = 1; }
+        else if (t < 22 * G) { base = 20 * G; ipg = 2; first = 0; }
+        else return false;
+    }
+    const int idx = t - base, half = ipg >> 1;
+    game = idx / ipg;
+    const int j = idx - game * ipg;
+    const int color = j >= half ? 1 : 0;
+    piece = color * 11 + first + (j - color * half);
+    return true;
+}
+template <int G> struct PhaseB { static constexpr int kThreads = (G == 8) ? 192 : 22 * G; };
 
 // ------------------------------------------------------------------------------------------
 // Expand the 56 bit planes to bf16 CHW [56][144] (16,128 B) with coalesced 16-byte stores.
-__device__ __forceinline__ void store_planes_bf16(const WarpScratch& sm, int lane, int turn, uint16_t* __restrict__ out) {
+// `lut` = 16 x uint2 in shared memory: nibble -> four bf16 {0,1} values.
+__device__ __forceinline__ void fill_bf16_lut(uint2* lut, int t) {
+    if (t < 16) {
+        uint2 v;
+        v.x = ((t & 1) ? 0x3F80u : 0u) | ((t & 2) ? 0x3F800000u : 0u);
+        v.y = ((t & 4) ? 0x3F80u : 0u) | ((t & 8) ? 0x3F800000u : 0u);
+        lut[t] = v;
+    }
+}
+__device__ __forceinline__ void store_planes_bf16(const WarpScratch& sm, const uint2* lut, int lane, int turn,
+                                                  uint16_t* __restrict__ out) {
     const uint8_t* bytes = reinterpret_cast<const uint8_t*>(&sm.planes[0][0]);   // 20 B per plane, 18 used
     // bf16(turn): turn <= 255 is exact in bf16 (8 significant bits)
     const uint32_t tb = __float_as_uint((float)turn) >> 16;
     const uint32_t tt = tb | (tb << 16);
     uint4* o = reinterpret_cast<uint4*>(out);
+    int p = lane / 18, j = lane - p * 18;           // chunk t = p*18 + j, advanced by 32 = 18 + 14
     for (int t = lane; t < N_PLANE * 18; t += 32) {
-        int p = t / 18, j = t - p * 18;
-        uint32_t x = bytes[p * 20 + j];
-        uint4 v;
-        v.x = (((x     ) & 1u) | (((x     ) & 2u) << 15)) * 0x3F80u;
-        v.y = (((x >> 2) & 1u) | (((x >> 2) & 2u) << 15)) * 0x3F80u;
-        v.z = (((x >> 4) & 1u) | (((x >> 4) & 2u) << 15)) * 0x3F80u;
-        v.w = (((x >> 6) & 1u) | (((x >> 6) & 2u) << 15)) * 0x3F80u;
+        const uint32_t x = bytes[p * 20 + j];
+        const uint2 lo = lut[x & 15u], hi = lut[x >> 4];
+        uint4 v = make_uint4(lo.x, lo.y, hi.x, hi.y);
         if (p == 31) v = make_uint4(tt, tt, tt, tt);
         o[t] = v;
+        j += 14; p += 1;
+        if (j >= 18) { j -= 18; p += 1; }
     }
 }
 

@@ -3,7 +3,8 @@
 // One kernel, `hive_env_kernel`, is the whole GamePlay.move() of the reference
 // (hive_engine/env_hive.py:99-171) for a batch of games: apply the action, regenerate the legal
 // set of the new side to move, encode its 56 planes, push history, test for the end of the game.
-// One warp per game (hive_core.cuh), 4 games per CTA.
+// One warp per game, 8 games per CTA; the per-piece searches of the 8 games are regrouped by piece
+// type across the CTA's warps (hive_core.cuh, phases A/B/C).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -70,9 +71,9 @@ int launch_env(hive_env* h, int op, const int32_t* actions, const uint8_t* mask,
     a.recs = h->recs; a.legal = h->legal; a.count = h->count; a.status = h->status; a.planes = h->planes;
     a.actions = actions; a.mask = mask; a.chosen = chosen; a.hop_lines = h->hop_lines;
     a.seed = seed; a.n = h->n; a.op = op; a.max_turn = max_turn; a.auto_reset = auto_reset;
-    const int blocks = (h->n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    const int blocks = (h->n + GAMES_PER_CTA - 1) / GAMES_PER_CTA;
     if (h->timing) CUDA_TRY(cudaEventRecord(h->t0, h->stream));
-    hive_env_kernel<<<blocks, WARPS_PER_CTA * 32, 0, h->stream>>>(a);
+    hive_env_kernel<GAMES_PER_CTA><<<blocks, GAMES_PER_CTA * 32, 0, h->stream>>>(a);
     CUDA_TRY(cudaGetLastError());
     if (h->timing) CUDA_TRY(cudaEventRecord(h->t1, h->stream));
     h->launches++;

@@ -15,7 +15,10 @@
 
 namespace hive {
 
-constexpr int WARPS_PER_CTA = 4;
+constexpr int GAMES_PER_CTA = 8;                  // one warp per game, 8 games share a CTA
+#ifndef HIVE_MIN_CTAS
+#define HIVE_MIN_CTAS 3                           // resident CTAs per SM the register budget is set for
+#endif
 enum Op { OP_RESET = 0, OP_STEP = 1, OP_EVAL = 2, OP_RANDOM = 3, OP_INIT = 4 };   // INIT = first reset, zeroes the counters
 
 struct EnvArgs {
@@ -32,70 +35,94 @@ struct EnvArgs {
     int n, op, max_turn, auto_reset;
 };
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) hive_env_kernel(EnvArgs a) {
-    __shared__ WarpScratch scratch[WARPS_PER_CTA];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = blockIdx.x * WARPS_PER_CTA + warp;
-    if (g >= a.n) return;
+template <int G>
+__global__ void __launch_bounds__(G * 32, HIVE_MIN_CTAS) hive_env_kernel(EnvArgs a) {
+    __shared__ WarpScratch scratch[G];
+    __shared__ uint2 bf16_lut[16];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = blockIdx.x * G + warp;
     WarpScratch& sm = scratch[warp];
-    GameRec* rec = a.recs + g;
+    fill_bf16_lut(bf16_lut, tid);
 
-    int cell = HAND, level = 0;
-    if (lane < N_PIECE) { cell = rec->cell[lane]; level = rec->level[lane]; }
-    // header words: [11] = turn|winner|done|flags, [12] episode, [13] steps, [14] n_legal
-    const uint32_t* hw = reinterpret_cast<const uint32_t*>(rec);
-    const uint32_t h11 = hw[11];
-    int turn = h11 & 0xFF, winner = (h11 >> 8) & 0xFF, done = (h11 >> 16) & 0xFF;
-    uint32_t episode = hw[12], steps = hw[13], n_legal_prev = hw[14];
-    if (lane < 20) reinterpret_cast<uint4*>(&sm.hist[0][0][0][0])[lane] = reinterpret_cast<const uint4*>(rec->hist)[lane];
+    // ---------------- per-game prologue: decode the operation, apply the action (warp <-> game)
+    bool live = g < a.n;
+    int cell = HAND, level = 0, turn = 1, winner = 0;
+    uint32_t episode = 0, steps = 0;
+    bool push = false;
+    GameRec* rec = a.recs + (live ? g : 0);
+    if (live) {
+        if (lane < N_PIECE) { cell = rec->cell[lane]; level = rec->level[lane]; }
+        // header words: [11] = turn|winner|done|flags, [12] episode, [13] steps, [14] n_legal
+        const uint32_t* hw = reinterpret_cast<const uint32_t*>(rec);
+        const uint32_t h11 = hw[11];
+        turn = h11 & 0xFF; winner = (h11 >> 8) & 0xFF;
+        const int done = (h11 >> 16) & 0xFF;
+        episode = hw[12]; steps = hw[13];
+        const uint32_t n_legal_prev = hw[14];
+        if (lane < 20) reinterpret_cast<uint4*>(&sm.hist[0][0][0][0])[lane] = reinterpret_cast<const uint4*>(rec->hist)[lane];
 
-    bool do_reset = false, push = false;
-    int action = HIVE_NOOP;
-    if (a.op == OP_RESET) {
-        if (a.mask && !a.mask[g]) return;
-        do_reset = true;
-    } else if (a.op == OP_INIT) {
-        do_reset = true; episode = 0xFFFFFFFFu; steps = 0;      // first episode of the slot is number 0
-    } else if (a.op == OP_STEP) {
-        action = a.actions[g];
-        if (action == HIVE_NOOP) return;
-        if (action == HIVE_RESET) do_reset = true;
-    } else if (a.op == OP_EVAL) {
-        if (a.mask && !a.mask[g]) return;
-    } else {   // OP_RANDOM
-        if (done || turn >= a.max_turn) {
-            if (!a.auto_reset) { if (a.chosen && lane == 0) a.chosen[g] = HIVE_NOOP; return; }
-            do_reset = true;
-        } else if (n_legal_prev == 0) {
-            action = -1;
-        } else {
-            const uint64_t gid = (uint64_t)g + (uint64_t)a.n * episode;
-            const uint64_t x = splitmix64(a.seed ^ (gid << 32) ^ (uint64_t)turn);
-            action = select_kth_action(a.legal + (size_t)g * LEGAL_WORDS, lane, (int)(x % n_legal_prev));
+        bool do_reset = false;
+        int action = HIVE_NOOP;
+        if (a.op == OP_RESET) {
+            if (a.mask && !a.mask[g]) live = false; else do_reset = true;
+        } else if (a.op == OP_INIT) {
+            do_reset = true; episode = 0xFFFFFFFFu; steps = 0;      // first episode of the slot is number 0
+        } else if (a.op == OP_STEP) {
+            action = a.actions[g];
+            if (action == HIVE_NOOP) live = false;
+            if (action == HIVE_RESET) do_reset = true;
+        } else if (a.op == OP_EVAL) {
+            if (a.mask && !a.mask[g]) live = false;
+        } else {   // OP_RANDOM
+            if (done || turn >= a.max_turn) {
+                if (!a.auto_reset) live = false; else do_reset = true;
+            } else if (n_legal_prev == 0) {
+                action = -1;
+            } else {
+                const uint64_t gid = (uint64_t)g + (uint64_t)a.n * episode;
+                const uint64_t x = splitmix64(a.seed ^ (gid << 32) ^ (uint64_t)turn);
+                action = select_kth_action(a.legal + (size_t)g * LEGAL_WORDS, lane, (int)(x % n_legal_prev));
+            }
+            if (a.chosen && lane == 0) a.chosen[g] = (do_reset || !live) ? HIVE_NOOP : action;
         }
-        if (a.chosen && lane == 0) a.chosen[g] = do_reset ? HIVE_NOOP : action;
+        __syncwarp();
+        if (live) {
+            if (do_reset) {                                     // GamePlay.new_game, env_hive.py:61-97
+                cell = HAND; level = 0; turn = 1; winner = 0; episode++;
+                uint32_t* hz = &sm.hist[0][0][0][0];
+                for (int i = lane; i < 80; i += 32) hz[i] = 0;
+                push = true;                                    // add_history starts True (env_hive.py:51)
+            } else if (action >= 0) {                           // env_hive.py:105-148
+                const int side = (turn & 1) ? 0 : 1;
+                const int k = action % 11, end = action / 11, p = side * 11 + k;
+                const int h_end = __popc(__ballot_sync(FULL, cell == end));
+                if (lane == p) { cell = end; level = h_end; }   // level = len(end_tile.pieces) before the move
+                turn++; steps++; push = true;
+            } else if (action == -1) {                          // pass, env_hive.py:100-103
+                turn++; steps++;
+            }
+            __syncwarp();
+        }
     }
-    __syncwarp();
+    if (lane == 0) sm.head[2] = live ? 1u : 0u;
 
-    if (do_reset) {                                     // GamePlay.new_game, env_hive.py:61-97
-        cell = HAND; level = 0; turn = 1; winner = 0; episode++;
-        uint32_t* hz = &sm.hist[0][0][0][0];
-        for (int i = lane; i < 80; i += 32) hz[i] = 0;
-        push = true;                                    // add_history starts True (env_hive.py:51)
-    } else if (action >= 0) {                           // env_hive.py:105-148
-        const int side = (turn & 1) ? 0 : 1;
-        const int k = action % 11, end = action / 11, p = side * 11 + k;
-        const int h_end = __popc(__ballot_sync(FULL, cell == end));
-        if (lane == p) { cell = end; level = h_end; }   // level = len(end_tile.pieces) before the move
-        turn++; steps++; push = true;
-    } else if (action == -1) {                          // pass, env_hive.py:100-103
-        turn++; steps++;
+    // ---------------- phase A (warp <-> game)
+    EvalResult r;
+    r.n_legal = 0; r.done = 0; r.winner = 0;
+    if (live) r = eval_phase_a(sm, lane, cell, level, turn, winner);
+    __syncthreads();
+
+    // ---------------- phase B (thread <-> piece, warps grouped by piece type across the G games)
+    {
+        int tg, tp;
+        if (tid < PhaseB<G>::kThreads && task_of_thread<G>(tid, tg, tp) && scratch[tg].head[2])
+            eval_phase_b(scratch[tg], tp, a.hop_lines);
     }
-    __syncwarp();
+    __syncthreads();
 
-    const EvalResult r = evaluate_position(sm, lane, cell, level, turn, push, winner, a.hop_lines);
-
-    // ---- write back: state record, legal mask, count, planes
+    // ---------------- phase C (warp <-> game) + write back
+    if (!live) return;
+    r.n_legal = eval_phase_c(sm, lane, cell, turn, push);
     if (lane < N_PIECE) { rec->cell[lane] = (uint8_t)cell; rec->level[lane] = (uint8_t)level; }
     if (lane == 0) {
         uint32_t* w = reinterpret_cast<uint32_t*>(rec);
@@ -106,8 +133,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) hive_env_kernel(EnvArgs a)
     }
     if (lane < 20) reinterpret_cast<uint4*>(rec->hist)[lane] = reinterpret_cast<const uint4*>(&sm.hist[0][0][0][0])[lane];
     if (lane < 25) reinterpret_cast<uint2*>(a.legal + (size_t)g * LEGAL_WORDS)[lane] = reinterpret_cast<const uint2*>(sm.legal)[lane];
-    store_planes_bf16(sm, lane, turn, a.planes + (size_t)g * HIVE_PLANES_ELEMS);
+    store_planes_bf16(sm, bf16_lut, lane, turn, a.planes + (size_t)g * HIVE_PLANES_ELEMS);
 }
-
 
 }  // namespace hive

@@ -34,26 +34,26 @@ struct dim3emu { unsigned x, y, z; };
 
 namespace emu {
 
-enum Kind { K_NONE = 0, K_SHFL, K_SHFL_XOR, K_SHFL_UP, K_BALLOT, K_MATCH, K_REDOR, K_SYNC, K_DONE };
+enum Kind { K_NONE = 0, K_SHFL, K_SHFL_XOR, K_SHFL_UP, K_BALLOT, K_MATCH, K_REDOR, K_SYNC, K_BAR, K_DONE };
 
-struct Warp {
+constexpr int MAX_LANES = 1024;
+struct Block {
     ucontext_t sched;
-    ucontext_t ctx[32];
-    char* stack[32];
+    ucontext_t ctx[MAX_LANES];
+    char* stack[MAX_LANES];
+    int nlanes;
     int cur;
-    int kind[32];
-    int site[32];
-    uint32_t in[32], arg[32], out[32];
-    bool done[32];
+    int kind[MAX_LANES];          // collective the lane is parked at (K_NONE = runnable)
+    uint32_t in[MAX_LANES], arg[MAX_LANES], out[MAX_LANES];
+    bool done[MAX_LANES];
     uint64_t rng;
-    const char* error;
     long collectives;
 };
-extern Warp* W;
-extern thread_local dim3emu g_threadIdx, g_blockIdx;
+extern Block* W;
+extern thread_local dim3emu g_threadIdx, g_blockIdx, g_blockDim;
 
 inline void park(int kind, uint32_t in, uint32_t arg) {
-    Warp* w = W;
+    Block* w = W;
     int l = w->cur;
     w->kind[l] = kind; w->in[l] = in; w->arg[l] = arg;
     swapcontext(&w->ctx[l], &w->sched);
@@ -64,6 +64,7 @@ inline uint32_t result() { return W->out[W->cur]; }
 
 #define threadIdx (emu::g_threadIdx)
 #define blockIdx (emu::g_blockIdx)
+#define blockDim (emu::g_blockDim)
 
 static inline void emu_check_mask(unsigned m) { if (m != 0xffffffffu) { fprintf(stderr, "emu: only full-mask collectives supported\n"); abort(); } }
 static inline int __shfl_sync(unsigned m, int v, int src) { emu_check_mask(m); emu::park(emu::K_SHFL, (uint32_t)v, (uint32_t)src & 31); return (int)emu::result(); }
@@ -74,6 +75,7 @@ static inline unsigned __ballot_sync(unsigned m, bool p) { emu_check_mask(m); em
 static inline unsigned __match_any_sync(unsigned m, int v) { emu_check_mask(m); emu::park(emu::K_MATCH, (uint32_t)v, 0); return emu::result(); }
 static inline unsigned __reduce_or_sync(unsigned m, unsigned v) { emu_check_mask(m); emu::park(emu::K_REDOR, v, 0); return emu::result(); }
 static inline void __syncwarp(unsigned m = 0xffffffffu) { emu_check_mask(m); emu::park(emu::K_SYNC, 0, 0); }
+static inline void __syncthreads() { emu::park(emu::K_BAR, 0, 0); }
 
 static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
 static inline int __ffs(uint32_t x) { return __builtin_ffs((int)x); }
@@ -89,8 +91,8 @@ static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { uint32_t o = *p; *p 
 static inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; return o; }
 
 namespace emu {
-// Run `fn(arg)` as one warp (32 lanes) of block `block`, warp index `warp` in the block.
+// Run `fn(arg)` as one thread block of `nthreads` threads (multiple of 32), block index `block`.
 typedef void (*LaneFn)(void*);
-int run_warp(LaneFn fn, void* arg, int block, int warp, uint64_t seed);
+int run_block(LaneFn fn, void* arg, int block, int nthreads, uint64_t seed);
 const char* last_error();
 }  // namespace emu

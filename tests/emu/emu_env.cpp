@@ -21,7 +21,7 @@ static void build_lines() {
         }
 }
 
-static void lane_main(void* p) { hive_env_kernel(*(EnvArgs*)p); }
+static void lane_main(void* p) { hive_env_kernel<GAMES_PER_CTA>(*(EnvArgs*)p); }
 
 extern "C" {
 
@@ -34,8 +34,9 @@ int emu_env_run(void* recs, uint32_t* legal, int32_t* count, uint32_t* status, u
     a.recs = (GameRec*)recs; a.legal = legal; a.count = count; a.status = status; a.planes = planes;
     a.actions = actions; a.mask = mask; a.chosen = chosen; a.hop_lines = g_lines.data();
     a.seed = seed; a.n = n; a.op = op; a.max_turn = max_turn; a.auto_reset = auto_reset;
-    for (int g = 0; g < n; g++) {
-        int rc = emu::run_warp(lane_main, &a, g / WARPS_PER_CTA, g % WARPS_PER_CTA, sched_seed + (uint64_t)g);
+    const int blocks = (n + GAMES_PER_CTA - 1) / GAMES_PER_CTA;
+    for (int b = 0; b < blocks; b++) {
+        int rc = emu::run_block(lane_main, &a, b, GAMES_PER_CTA * 32, sched_seed + (uint64_t)b);
         if (rc) return rc;
     }
     return 0;
