@@ -63,6 +63,7 @@ struct __align__(16) WarpScratch {
 };
 static_assert(sizeof(WarpScratch) % 16 == 0, "WarpScratch must keep 16-byte alignment in arrays");
 static_assert(offsetof(WarpScratch, hist) % 16 == 0 && offsetof(WarpScratch, legal) % 8 == 0, "vector access alignment");
+static_assert(offsetof(WarpScratch, planes) % 16 == 0 && offsetof(WarpScratch, legal) == offsetof(WarpScratch, planes) + N_PLANE * 20, "planes+legal are zeroed as one 16-byte aligned run");
 
 // ------------------------------------------------------------------------------------------
 // 144-bit boards
@@ -229,11 +230,25 @@ struct EvalResult { int n_legal; int done; int winner; };
 // info word: cell | height<<8 | top<<12 | ring<<16.   head[0] = turn | cq_w<<8 | cq_b<<16,
 // head[1] = pinned-piece mask, head[2] = game is being evaluated in this launch.
 
+// CTA-wide compacted work queues (item = game_slot | piece<<4 | wants_moves<<9)
+constexpr int MAX_GAMES_PER_CTA = 16;
+struct CtaQueues {
+    uint32_t n_flood;
+    uint32_t n_mv[4];                                   // move classes: 0 Ant, 1 Grasshopper, 2 Spider, 3 Queen/Beetle
+    uint32_t pad[3];
+    uint16_t flood[MAX_GAMES_PER_CTA * N_PIECE];
+    uint16_t mv[4][MAX_GAMES_PER_CTA * 6];
+};
+__device__ __forceinline__ int move_class(int type) {
+    return type == T_ANT ? 0 : type == T_HOPPER ? 1 : type == T_SPIDER ? 2 : 3;
+}
+
 __device__ __forceinline__ int piece_type_of(int k) {
     return (k == 0) ? T_QUEEN : (k <= 2) ? T_BEETLE : (k <= 4) ? T_SPIDER : (k <= 7) ? T_HOPPER : T_ANT;
 }
 
-__device__ __forceinline__ EvalResult eval_phase_a(WarpScratch& sm, int lane, int cell, int level, int turn, int prev_winner) {
+__device__ __forceinline__ EvalResult eval_phase_a(WarpScratch& sm, CtaQueues& q, int game_slot, int lane, int cell, int level, int turn,
+                                                   int prev_winner) {
     const int side = (turn & 1) ? 0 : 1;                 // game_state.py:58-62
     const bool valid = lane < N_PIECE;
     const int color = lane >= 11 ? 1 : 0;
@@ -242,10 +257,11 @@ __device__ __forceinline__ EvalResult eval_phase_a(WarpScratch& sm, int lane, in
     const bool own = valid && (color == side);
     const bool on_board = valid && cell != HAND;
 
-    {   // zero the scratch outputs
-        uint32_t* pz = &sm.planes[0][0];
-        for (int i = lane; i < N_PLANE * 5; i += 32) pz[i] = 0;
-        for (int i = lane; i < LEGAL_WORDS; i += 32) sm.legal[i] = 0;
+    {   // zero the scratch outputs: planes (1120 B) and legal (208 B) are contiguous and 16-byte aligned
+        uint4* pz = reinterpret_cast<uint4*>(&sm.planes[0][0]);
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int i = 0; i < 3; i++) { const int t = lane + 32 * i; if (t < (N_PLANE * 20 + (LEGAL_WORDS + 2) * 4) / 16) pz[t] = z; }
     }
     // stacks: pieces sharing a cell (tile.pieces); top piece <=> level+1 == len (env_hive.py:213)
     const unsigned peers = __match_any_sync(FULL, on_board ? cell : 256 + lane);
@@ -270,7 +286,36 @@ __device__ __forceinline__ EvalResult eval_phase_a(WarpScratch& sm, int lane, in
         for (int i = 0; i < 6; i++) ring |= (uint32_t)words_test(sm.occ, cell_nbr(cell, i)) << i;
     }
     if (valid) sm.info[lane] = (uint32_t)cell | ((uint32_t)height << 8) | ((uint32_t)top << 12) | (ring << 16);
-    if (lane == 0) { sm.head[0] = (uint32_t)turn | ((uint32_t)cq_w << 8) | ((uint32_t)cq_b << 16); sm.head[1] = 0; }
+    if (lane == 0) { sm.head[0] = (uint32_t)turn | ((uint32_t)cq_w << 8) | ((uint32_t)cq_b << 16); }
+
+    // ---- which pieces need a one-hive flood / a move search: compacted CTA-wide work queues
+    {
+        const bool ownq_on = (side == 0 ? cq_w : cq_b) != HAND;
+        // turn gates shared by every candidate of a piece (move_checker.py:38-55)
+        bool gate = true;
+        if (turn <= 2) gate = false;                                         // no on-board mover can exist / matter
+        else if (turn <= 6) gate = ownq_on;                                  // queen_is_on_board: colour by turn parity
+        else if (turn <= 8) gate = obeys_queen_by_4(turn, wq_on, bq_on, type == T_QUEEN, color);
+        // opponent mobility is only consumed through the own queen's neighbourhood (env_hive.py:459-478)
+        const bool wants_moves = top && gate && (own || ownq_on);
+        bool pinned_now = false, need_flood = false;
+        if (top && height == 1) {
+            if (ring == 0) pinned_now = true;                                // nothing left on the board -> `return False`
+            else need_flood = __popc(ring & ~rot6l(ring)) > 1;               // >1 arc of neighbours: may be an articulation point
+        }
+        const unsigned pin_mask = __ballot_sync(FULL, pinned_now);
+        if (lane == 0) sm.head[1] = pin_mask;
+        if (on_board) {
+#pragma unroll
+            for (int i = 0; i < 5; i++) sm.moves[lane][i] = 0;
+            const uint32_t item = (uint32_t)game_slot | ((uint32_t)lane << 4) | ((uint32_t)wants_moves << 9);
+            if (need_flood) q.flood[atomicAdd(&q.n_flood, 1u)] = (uint16_t)item;
+            else if (wants_moves && !pinned_now) {
+                const int cls = move_class(type);
+                q.mv[cls][atomicAdd(&q.n_mv[cls], 1u)] = (uint16_t)item;
+            }
+        }
+    }
 
     // placements (env_hive.py:217-225; move_checker.py:168-179): first in-hand piece per type
     if (valid && !on_board) {
@@ -324,125 +369,151 @@ __device__ __forceinline__ EvalResult eval_phase_a(WarpScratch& sm, int lane, in
     return res;
 }
 
-// phase B: one thread, one piece.  `hop_lines` = 144x5 u32 table of is_straight_line masks
-// (move_checker.py:249-265).
-__device__ __forceinline__ void eval_phase_b(WarpScratch& sm, int p, const uint32_t* __restrict__ hop_lines) {
+// phase B1: one thread, one one-hive flood (move_checker.py:58-83 / env_hive.py:509-530): lift the
+// top piece and test that the rest of the hive stays connected.
+__device__ __forceinline__ void eval_flood(WarpScratch& sm, CtaQueues& q, uint32_t item) {
+    const int p = (item >> 4) & 31;
     const uint32_t info = sm.info[p];
     const int cell = info & 0xFF;
-    if (cell == HAND) return;                            // placements were written in phase A
-    const int height = (info >> 8) & 0xF;
-    const bool top = (info >> 12) & 1u;
     const uint32_t ring = (info >> 16) & 63u;
-    const uint32_t head = sm.head[0];
-    const int turn = head & 0xFF, cq_w = (head >> 8) & 0xFF, cq_b = (head >> 16) & 0xFF;
-    const int side = (turn & 1) ? 0 : 1;
-    const int color = p >= 11 ? 1 : 0;
-    const int k = p - 11 * color;
-    const int type = piece_type_of(k);
-    const bool own = color == side;
-    const bool wq_on = cq_w != HAND, bq_on = cq_b != HAND;
-    const bool ownq_on = (side == 0 ? cq_w : cq_b) != HAND;
+    BB occp;
+#pragma unroll
+    for (int i = 0; i < 5; i++) occp.w[i] = sm.occ[i];
+    const BB src = bb_bit(cell);
+    occp = occp ^ src;
+    const BB goal = bb_nbrs(src) & occp;
+    BB x = bb_bit(cell_nbr(cell, __ffs(ring) - 1));
+    bool pinned = false;
+    for (;;) {
+        BB nx = x | (bb_nbrs(x) & occp);
+        if (bb_eq(nx & goal, goal)) break;
+        if (bb_eq(nx, x)) { pinned = true; break; }
+        x = nx;
+    }
+    if (pinned) atomicOr(&sm.head[1], 1u << p);
+    else if ((item >> 9) & 1u) {
+        const int cls = move_class(piece_type_of(p >= 11 ? p - 11 : p));
+        q.mv[cls][atomicAdd(&q.n_mv[cls], 1u)] = (uint16_t)item;
+    }
+}
+
+// phase B2: one thread, the move set of one unpinned top piece whose turn gates are open.
+// `hop_lines` = 144x5 u32 table of is_straight_line masks (move_checker.py:249-265).
+__device__ __forceinline__ void eval_moves(WarpScratch& sm, int p, const uint32_t* __restrict__ hop_lines) {
+    const uint32_t info = sm.info[p];
+    const int cell = info & 0xFF;
+    const int height = (info >> 8) & 0xF;
+    const uint32_t ring = (info >> 16) & 63u;
+    const int type = piece_type_of(p >= 11 ? p - 11 : p);
+    uint32_t* row = sm.moves[p];
+
+    if (type == T_QUEEN || type == T_BEETLE) {
+        uint32_t ok;
+        if (type == T_QUEEN) {                                           // pieces.py:35-44
+            ok = ~ring & (rot6l(ring) ^ rot6r(ring)) & 63u;
+        } else {                                                         // pieces.py:100-113
+            uint32_t fl = rot6l(ring), fr = rot6r(ring);                 // bit i: flank c+d_{i-1} / c+d_{i+1}
+            uint32_t k1 = fl ^ fr, k0 = ~(fl | fr) & 63u;
+            ok = k1 | ring | (height > 1 ? 63u : 0u);
+            if (k0 & ~ok) {
+                // k==0: allowed iff the target has an occupied neighbour other than `old`
+                // (len(new_adjacents_with_pieces) - 1 != 0, move_checker.py:205-207)
+                BB o;
+#pragma unroll
+                for (int i = 0; i < 5; i++) o.w[i] = sm.occ[i];
+                const BB hns = bb_nbrs(o ^ bb_bit(cell));
+#pragma unroll
+                for (int i = 0; i < 6; i++)
+                    if (((k0 & ~ok) >> i) & 1u) { if (bb_test(hns, cell_nbr(cell, i))) ok |= 1u << i; }
+            }
+        }
+        // ring targets go straight into this piece's shared-memory row (zeroed in phase A)
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+            if ((ok >> i) & 1u) { const int c = cell_nbr(cell, i); row[c >> 5] |= 1u << (c & 31); }
+        return;
+    }
 
     BB occ;
 #pragma unroll
     for (int i = 0; i < 5; i++) occ.w[i] = sm.occ[i];
     const BB src = bb_bit(cell);
-
-    // one hive (move_checker.py:58-83 / env_hive.py:509-530): lift the top piece, flood
-    bool pinned = false;
-    if (top && height == 1) {
-        uint32_t arcs = __popc(ring & ~rot6l(ring));
-        if (ring == 0) pinned = true;              // nothing left on the board -> `return False`
-        else if (arcs > 1) {
-            const BB occp = occ ^ src;
-            const BB goal = bb_nbrs(src) & occp;
-            BB x = bb_bit(cell_nbr(cell, __ffs(ring) - 1));
+    BB mv;
+    if (type == T_HOPPER) {                                              // pieces.py:128-158
+        BB line;
+#pragma unroll
+        for (int i = 0; i < 5; i++) line.w[i] = __ldg(hop_lines + cell * 5 + i);
+        const BB walk = occ & line;
+        BB v = src;
+        for (;;) {
+            BB nv = v | (bb_nbrs(v) & walk);
+            if (bb_eq(nv, v)) break;
+            v = nv;
+        }
+        mv = bb_andn(bb_andn(bb_nbrs(v) & line, occ), bb_nbrs(src));
+    } else {                                                             // Ant / Spider
+        const BB occp = occ ^ src;
+        Slide sl;
+        slide_init(sl, occp);
+        if (type == T_ANT) {                                             // pieces.py:59-63
+            BB x = src;
             for (;;) {
-                BB nx = x | (bb_nbrs(x) & occp);
-                if (bb_eq(nx & goal, goal)) break;
-                if (bb_eq(nx, x)) { pinned = true; break; }
+                BB nx = x | slide_step(sl, x);
+                if (bb_eq(nx, x)) break;
                 x = nx;
             }
-        }
-    }
-    const bool can_move = top && !pinned;
-    // opponent mobility is only consumed through the own queen's neighbourhood (env_hive.py:459-478)
-    const bool active = can_move && (own || ownq_on);
-
-    // turn gates shared by every candidate of this piece (move_checker.py:38-55)
-    bool gate = true;
-    if (turn <= 2) gate = false;                                             // no on-board mover can exist / matter
-    else if (turn <= 6) gate = ownq_on;                                      // queen_is_on_board: colour by turn parity
-    else if (turn <= 8) gate = obeys_queen_by_4(turn, wq_on, bq_on, type == T_QUEEN, color);
-
-    BB mv = bb_zero();
-    if (active && gate) {
-        if (type == T_QUEEN) {                                               // pieces.py:35-44
-            uint32_t ok = ~ring & (rot6l(ring) ^ rot6r(ring)) & 63u;
-#pragma unroll
-            for (int i = 0; i < 6; i++) if ((ok >> i) & 1u) mv = mv | bb_bit(cell_nbr(cell, i));
-        } else if (type == T_BEETLE) {                                       // pieces.py:100-113
-            uint32_t fl = rot6l(ring), fr = rot6r(ring);                     // bit i: flank c+d_{i-1} / c+d_{i+1}
-            uint32_t k1 = fl ^ fr, k0 = ~(fl | fr) & 63u;
-            uint32_t ok = k1 | ring | (height > 1 ? 63u : 0u);
-            if (k0 & ~ok) {
-                // k==0: allowed iff the target has an occupied neighbour other than `old`
-                // (len(new_adjacents_with_pieces) - 1 != 0, move_checker.py:205-207)
-                const BB hns = bb_nbrs(occ ^ src);
-#pragma unroll
-                for (int i = 0; i < 6; i++)
-                    if (((k0 & ~ok) >> i) & 1u) { if (bb_test(hns, cell_nbr(cell, i))) ok |= 1u << i; }
-            }
-#pragma unroll
-            for (int i = 0; i < 6; i++) if ((ok >> i) & 1u) mv = mv | bb_bit(cell_nbr(cell, i));
-        } else if (type == T_HOPPER) {                                       // pieces.py:128-158
-            BB line;
-#pragma unroll
-            for (int i = 0; i < 5; i++) line.w[i] = __ldg(hop_lines + cell * 5 + i);
-            const BB walk = occ & line;
-            BB v = src;
-            for (;;) {
-                BB nv = v | (bb_nbrs(v) & walk);
-                if (bb_eq(nv, v)) break;
-                v = nv;
-            }
-            mv = bb_andn(bb_andn(bb_nbrs(v) & line, occ), bb_nbrs(src));
-        } else {                                                             // Ant / Spider
-            const BB occp = occ ^ src;
-            Slide sl;
-            slide_init(sl, occp);
-            if (type == T_ANT) {                                             // pieces.py:59-63
-                BB x = src;
-                for (;;) {
-                    BB nx = x | slide_step(sl, x);
-                    if (bb_eq(nx, x)) break;
-                    x = nx;
-                }
-                mv = bb_andn(x, src);
-            } else {                                                         // pieces.py:78-85
+            mv = bb_andn(x, src);
+        } else {                                                         // pieces.py:78-85
+            mv = bb_zero();
 #ifdef HIVE_SPIDER_ROLLED
 #pragma unroll 1
 #else
 #pragma unroll
 #endif
-                for (int i = 0; i < 6; i++) {
-                    const BB ti = bb_bit(cell_nbr(cell, i));
-                    const BB a = ti & sl.g[i];
-                    if (!bb_any(a)) continue;
-                    const BB b = bb_andn(slide_step(sl, a), src);
-                    const BB c = bb_andn(slide_step(sl, b), src | a);
-                    mv = mv | c;
-                }
-                // end check with the spider back on `old`: adjacent target with both flanks occupied
-                uint32_t k2 = rot6l(ring) & rot6r(ring);
-#pragma unroll
-                for (int i = 0; i < 6; i++) if ((k2 >> i) & 1u) mv = bb_andn(mv, bb_bit(cell_nbr(cell, i)));
+            for (int i = 0; i < 6; i++) {
+                const int c1 = cell_nbr(cell, i);
+                if (!bb_test(sl.g[i], c1)) continue;
+                const BB a = bb_bit(c1);
+                const BB b = bb_andn(slide_step(sl, a), src);
+                const BB c = bb_andn(slide_step(sl, b), src | a);
+                mv = mv | c;
             }
         }
     }
 #pragma unroll
-    for (int i = 0; i < 5; i++) sm.moves[p][i] = mv.w[i];
-    if (pinned) atomicOr(&sm.head[1], 1u << p);
+    for (int i = 0; i < 5; i++) row[i] = mv.w[i];
+    if (type == T_SPIDER) {
+        // end check with the spider back on `old`: adjacent target with both flanks occupied
+        const uint32_t k2 = rot6l(ring) & rot6r(ring);
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+            if ((k2 >> i) & 1u) { const int c = cell_nbr(cell, i); row[c >> 5] &= ~(1u << (c & 31)); }
+    }
+}
+
+// Run the two compacted phases for the whole CTA (all threads call this; contains barriers).
+__device__ __forceinline__ void eval_phase_b(WarpScratch* scratch, CtaQueues& q, int tid, int nthreads,
+                                             const uint32_t* __restrict__ hop_lines) {
+    const int nf = (int)q.n_flood;
+    for (int t = tid; t < nf; t += nthreads) {
+        const uint32_t item = q.flood[t];
+        eval_flood(scratch[item & 15u], q, item);
+    }
+    __syncthreads();
+    // move classes start at warp boundaries so that warps stay homogeneous
+    const int n0 = (int)q.n_mv[0], n1 = (int)q.n_mv[1], n2 = (int)q.n_mv[2], n3 = (int)q.n_mv[3];
+    const int s1 = (n0 + 31) & ~31, s2 = s1 + ((n1 + 31) & ~31), s3 = s2 + ((n2 + 31) & ~31), total = s3 + n3;
+    for (int t = tid; t < total; t += nthreads) {
+        int cls, idx, cnt;
+        if (t < s1) { cls = 0; idx = t; cnt = n0; }
+        else if (t < s2) { cls = 1; idx = t - s1; cnt = n1; }
+        else if (t < s3) { cls = 2; idx = t - s2; cnt = n2; }
+        else { cls = 3; idx = t - s3; cnt = n3; }
+        if (idx < cnt) {
+            const uint32_t item = q.mv[cls][idx];
+            eval_moves(scratch[item & 15u], (item >> 4) & 31, hop_lines);
+        }
+    }
 }
 
 __device__ __forceinline__ int eval_phase_c(WarpScratch& sm, int lane, int cell, int turn, bool push_history) {
@@ -464,16 +535,19 @@ __device__ __forceinline__ int eval_phase_c(WarpScratch& sm, int lane, int cell,
 #pragma unroll
         for (int i = 0; i < 5; i++) mv.w[i] = sm.moves[lane][i];
     }
-    // dense legal mask a = cell*11 + k (env_hive.py:287-304)
+    // dense legal mask a = cell*11 + k (env_hive.py:287-304): the 11 own pieces x 5 board words are
+    // 55 work items spread over the 32 lanes, so no lane walks more than two words
     int n_mine = 0;
-    if (own) {
-        n_mine = bb_popc(mv);
 #pragma unroll
-        for (int i = 0; i < 5; i++) {
-            uint32_t m = mv.w[i];
+    for (int r = 0; r < 2; r++) {
+        const int item = lane + 32 * r;
+        if (item < 55) {
+            const int kk = item / 5, w = item - kk * 5;
+            uint32_t m = sm.moves[side * 11 + kk][w];
+            n_mine += __popc(m);
             while (m) {
-                int b = __ffs(m) - 1; m &= m - 1;
-                int a = (i * 32 + b) * 11 + k;
+                const int b = __ffs(m) - 1; m &= m - 1;
+                const int a = (w * 32 + b) * 11 + kk;
                 atomicOr(&sm.legal[a >> 5], 1u << (a & 31));
             }
         }
@@ -519,37 +593,6 @@ __device__ __forceinline__ int eval_phase_c(WarpScratch& sm, int lane, int cell,
     return n_legal;
 }
 
-// phase-B task layout: threads grouped by piece type so that warps are (nearly) homogeneous.
-// G = 8 : A[0,48) Q[48,64) G[64,112) pad[112,128) S[128,160) B[160,192)      -> 6 warps
-// G = 16: A[0,96) G[96,192) S[192,256) B[256,320) Q[320,352)                 -> 11 warps
-template <int G>
-__device__ __forceinline__ bool task_of_thread(int t, int& game, int& piece) {
-    int base, ipg, first;
-    if (G == 8) {
-        if (t < 48) { base = 0; ipg = 6; first = 8; }
-        else if (t < 64) { base = 48; ipg = 2; first = 0; }
-        else if (t < 112) { base = 64; ipg = 6; first = 5; }
-        else if (t < 128) return false;
-        else if (t < 160) { base = 128; ipg = 4; first = 3; }
-        else if (t < 192) { base = 160; ipg = 4; first = 1; }
-        else return false;
-    } else {
-        if (t < 6 * G) { base = 0; ipg = 6; first = 8; }
-        else if (t < 12 * G) { base = 6 * G; ipg = 6; first = 5; }
-        else if (t < 16 * G) { base = 12 * G; ipg = 4; first = 3; }
-        else if (t < 20 * G) { base = 16 * G; ipg = 4; first = 1; }
-        else if (t < 22 * G) { base = 20 * G; ipg = 2; first = 0; }
-        else return false;
-    }
-    const int idx = t - base, half = ipg >> 1;
-    game = idx / ipg;
-    const int j = idx - game * ipg;
-    const int color = j >= half ? 1 : 0;
-    piece = color * 11 + first + (j - color * half);
-    return true;
-}
-template <int G> struct PhaseB { static constexpr int kThreads = (G == 8) ? 192 : 22 * G; };
-
 // ------------------------------------------------------------------------------------------
 // Expand the 56 bit planes to bf16 CHW [56][144] (16,128 B) with coalesced 16-byte stores.
 // `lut` = 16 x uint2 in shared memory: nibble -> four bf16 {0,1} values.
@@ -567,16 +610,32 @@ __device__ __forceinline__ void store_planes_bf16(const WarpScratch& sm, const u
     // bf16(turn): turn <= 255 is exact in bf16 (8 significant bits)
     const uint32_t tb = __float_as_uint((float)turn) >> 16;
     const uint32_t tt = tb | (tb << 16);
-    uint4* o = reinterpret_cast<uint4*>(out);
-    int p = lane / 18, j = lane - p * 18;           // chunk t = p*18 + j, advanced by 32 = 18 + 14
-    for (int t = lane; t < N_PLANE * 18; t += 32) {
-        const uint32_t x = bytes[p * 20 + j];
+    const uint4 turn4 = make_uint4(tt, tt, tt, tt);
+    // main part: half-warp h writes bytes 0..15 of plane 2i+h (16 chunks = 256 contiguous bytes);
+    // every address is base + compile-time offset.
+    const int half = lane >> 4, j = lane & 15;
+    const uint8_t* b = bytes + half * 20 + j;
+    uint4* o = reinterpret_cast<uint4*>(out) + half * 18 + j;
+#pragma unroll
+    for (int i = 0; i < N_PLANE / 2; i++) {
+        const uint32_t x = b[i * 40];
         const uint2 lo = lut[x & 15u], hi = lut[x >> 4];
         uint4 v = make_uint4(lo.x, lo.y, hi.x, hi.y);
-        if (p == 31) v = make_uint4(tt, tt, tt, tt);
-        o[t] = v;
-        j += 14; p += 1;
-        if (j >= 18) { j -= 18; p += 1; }
+        if (i == 15 && half) v = turn4;                         // plane 31 = the turn number
+        o[i * 36] = v;
+    }
+    // tail: bytes 16,17 of every plane (112 chunks)
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int u = lane + 32 * i;
+        if (u < 2 * N_PLANE) {
+            const int p = u >> 1, jj = 16 + (u & 1);
+            const uint32_t x = bytes[p * 20 + jj];
+            const uint2 lo = lut[x & 15u], hi = lut[x >> 4];
+            uint4 v = make_uint4(lo.x, lo.y, hi.x, hi.y);
+            if (p == 31) v = turn4;
+            reinterpret_cast<uint4*>(out)[p * 18 + jj] = v;
+        }
     }
 }
 

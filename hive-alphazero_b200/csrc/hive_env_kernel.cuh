@@ -37,12 +37,16 @@ struct EnvArgs {
 
 template <int G>
 __global__ void __launch_bounds__(G * 32, HIVE_MIN_CTAS) hive_env_kernel(EnvArgs a) {
+    static_assert(G <= MAX_GAMES_PER_CTA, "queue item encoding holds 4 bits of game slot");
     __shared__ WarpScratch scratch[G];
+    __shared__ CtaQueues queues;
     __shared__ uint2 bf16_lut[16];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.x * G + warp;
     WarpScratch& sm = scratch[warp];
     fill_bf16_lut(bf16_lut, tid);
+    if (tid < 5) (&queues.n_flood)[tid] = 0;
+    __syncthreads();
 
     // ---------------- per-game prologue: decode the operation, apply the action (warp <-> game)
     bool live = g < a.n;
@@ -104,20 +108,15 @@ __global__ void __launch_bounds__(G * 32, HIVE_MIN_CTAS) hive_env_kernel(EnvArgs
             __syncwarp();
         }
     }
-    if (lane == 0) sm.head[2] = live ? 1u : 0u;
 
     // ---------------- phase A (warp <-> game)
     EvalResult r;
     r.n_legal = 0; r.done = 0; r.winner = 0;
-    if (live) r = eval_phase_a(sm, lane, cell, level, turn, winner);
+    if (live) r = eval_phase_a(sm, queues, warp, lane, cell, level, turn, winner);
     __syncthreads();
 
-    // ---------------- phase B (thread <-> piece, warps grouped by piece type across the G games)
-    {
-        int tg, tp;
-        if (tid < PhaseB<G>::kThreads && task_of_thread<G>(tid, tg, tp) && scratch[tg].head[2])
-            eval_phase_b(scratch[tg], tp, a.hop_lines);
-    }
+    // ---------------- phase B (thread <-> queued piece task; floods, then moves grouped by piece type)
+    eval_phase_b(scratch, queues, tid, G * 32, a.hop_lines);
     __syncthreads();
 
     // ---------------- phase C (warp <-> game) + write back

@@ -86,3 +86,22 @@ def test_noop_and_masked_reset():
     o.move(-1)
     _compare(e, 0, o)
     _compare(e, 1, o)
+
+
+def test_batch_of_nine_games_two_ctas():
+    """9 games = one full 8-game CTA + a partial one: exercises the CTA-wide work queues."""
+    n = 9
+    e = EmuBatch(n, sched_seed=11)
+    oracles = [OracleEnv() for _ in range(n)]
+    rngs = [np.random.RandomState(500 + g) for g in range(n)]
+    for _ in range(56):
+        actions = np.full(n, -2, dtype=np.int32)
+        for g, o in enumerate(oracles):
+            _compare(e, g, o)
+            if o.game_is_over() or o.turn >= 55:
+                continue
+            acts = o.actions()
+            a = int(acts[rngs[g].randint(len(acts))]) if len(acts) else -1
+            o.move(a)
+            actions[g] = a
+        e.step(actions)
