@@ -50,20 +50,42 @@ struct __align__(16) GameRec {
 };
 static_assert(sizeof(GameRec) == 384, "GameRec must stay 384 bytes");
 
-// per-warp shared-memory scratch (hist / legal are moved with 16- and 8-byte vector accesses)
+// per-warp shared-memory scratch of the encode kernel (hist / legal move with vector accesses)
 struct __align__(16) WarpScratch {
     uint32_t hist[2][4][2][5];     // 320 B, 16-byte aligned
     uint32_t planes[N_PLANE][5];   // bit boards of the 56 planes (plane 31 unused: it is the turn)
     uint32_t legal[LEGAL_WORDS + 2];
-    uint32_t occ[8];
-    uint32_t moves[N_PIECE][5];    // action list per piece (own) / mobility set (opponent)
-    uint32_t info[24];             // per piece: cell | height<<8 | top<<12 | ring<<16
-    uint32_t head[4];              // turn|cq_w<<8|cq_b<<16 ; pinned mask ; evaluated-this-launch flag
-    uint32_t pad[2];
 };
 static_assert(sizeof(WarpScratch) % 16 == 0, "WarpScratch must keep 16-byte alignment in arrays");
 static_assert(offsetof(WarpScratch, hist) % 16 == 0 && offsetof(WarpScratch, legal) % 8 == 0, "vector access alignment");
 static_assert(offsetof(WarpScratch, planes) % 16 == 0 && offsetof(WarpScratch, legal) == offsetof(WarpScratch, planes) + N_PLANE * 20, "planes+legal are zeroed as one 16-byte aligned run");
+
+// Per-game intermediate record handed from kernel to kernel through L2 (656 B, never leaves the
+// 126 MB L2 at 16,384 games):
+//   info[p] = cell | height<<8 | top<<12 | level<<13 | ring<<16 (ring = occupancy of the six neighbours)
+//   head[0] = turn | cq_w<<8 | cq_b<<16, head[1] = pinned-piece mask,
+//   head[2] = live | push_history<<1 | prev_winner<<8
+struct __align__(16) GameScratch {
+    uint32_t info[24];
+    uint32_t head[4];
+    uint32_t occ[8];
+    uint32_t own_all[8];
+    uint32_t opp_all[8];
+    uint32_t moves[N_PIECE][5];    // action list per piece (own) / mobility set (opponent)
+    uint32_t pad[2];
+};
+static_assert(sizeof(GameScratch) == 656, "GameScratch layout");
+
+// Work queues of one group of G games (item = game_slot | piece<<4 | wants_moves<<9)
+constexpr int GROUP = 16;          // games per CTA / per work-queue group
+struct __align__(16) GroupQueues {
+    uint32_t n_flood;
+    uint32_t n_mv[4];              // move classes: 0 Ant, 1 Grasshopper, 2 Spider, 3 Queen/Beetle
+    uint32_t pad[3];
+    uint16_t flood[GROUP * N_PIECE];
+    uint16_t mv[4][GROUP * 6];
+};
+static_assert(sizeof(GroupQueues) % 16 == 0, "GroupQueues is copied with 16-byte accesses");
 
 // ------------------------------------------------------------------------------------------
 // 144-bit boards
@@ -219,36 +241,22 @@ __device__ __forceinline__ bool obeys_queen_by_4(int turn, bool wq_on, bool bq_o
 struct EvalResult { int n_legal; int done; int winner; };
 
 // ------------------------------------------------------------------------------------------
-// The evaluation of a position runs in three phases inside one CTA that holds G games:
-//   phase A  (warp g <-> game g, lane p <-> piece p): stacks, occupancy, ring occupancy, placements,
-//            the planes that do not depend on mobility, terminal test; publishes one info word
-//            per piece in shared memory;
-//   phase B  (thread <-> one on-board piece of one of the G games, threads grouped BY PIECE TYPE so
-//            that a warp runs 32 Ant floods, or 32 Spider walks ... of several games at once):
-//            one-hive flood + the piece's move set -> shared memory;
-//   phase C  (warp g <-> game g again): dense legal mask, mobility planes 34/35/44-55, history push.
-// info word: cell | height<<8 | top<<12 | ring<<16.   head[0] = turn | cq_w<<8 | cq_b<<16,
-// head[1] = pinned-piece mask, head[2] = game is being evaluated in this launch.
-
-// CTA-wide compacted work queues (item = game_slot | piece<<4 | wants_moves<<9)
-constexpr int MAX_GAMES_PER_CTA = 16;
-struct CtaQueues {
-    uint32_t n_flood;
-    uint32_t n_mv[4];                                   // move classes: 0 Ant, 1 Grasshopper, 2 Spider, 3 Queen/Beetle
-    uint32_t pad[3];
-    uint16_t flood[MAX_GAMES_PER_CTA * N_PIECE];
-    uint16_t mv[4][MAX_GAMES_PER_CTA * 6];
-};
+// A position is evaluated by three kernels (hive_env_kernel.cuh):
+//   analyse (warp <-> game, lane p <-> piece p): stacks, occupancy, ring occupancy, placements,
+//            turn gates; publishes one info word per piece and queues the pieces that need a
+//            one-hive flood and/or a move search;
+//   search  (thread <-> queued piece of a 16-game group, move searches grouped BY PIECE TYPE so a
+//            warp runs Ant floods, or Spider walks ... of several games at once);
+//   encode  (warp <-> game again): dense legal mask, the 56 planes, history push, terminal test.
 __device__ __forceinline__ int move_class(int type) {
     return type == T_ANT ? 0 : type == T_HOPPER ? 1 : type == T_SPIDER ? 2 : 3;
 }
-
 __device__ __forceinline__ int piece_type_of(int k) {
     return (k == 0) ? T_QUEEN : (k <= 2) ? T_BEETLE : (k <= 4) ? T_SPIDER : (k <= 7) ? T_HOPPER : T_ANT;
 }
 
-__device__ __forceinline__ EvalResult eval_phase_a(WarpScratch& sm, CtaQueues& q, int game_slot, int lane, int cell, int level, int turn,
-                                                   int prev_winner) {
+__device__ __forceinline__ void eval_analyse(GameScratch& gs, GroupQueues& q, int game_slot, int lane, int cell, int level,
+                                             int turn, bool push_history, int prev_winner) {
     const int side = (turn & 1) ? 0 : 1;                 // game_state.py:58-62
     const bool valid = lane < N_PIECE;
     const int color = lane >= 11 ? 1 : 0;
@@ -257,12 +265,6 @@ __device__ __forceinline__ EvalResult eval_phase_a(WarpScratch& sm, CtaQueues& q
     const bool own = valid && (color == side);
     const bool on_board = valid && cell != HAND;
 
-    {   // zero the scratch outputs: planes (1120 B) and legal (208 B) are contiguous and 16-byte aligned
-        uint4* pz = reinterpret_cast<uint4*>(&sm.planes[0][0]);
-        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-        for (int i = 0; i < 3; i++) { const int t = lane + 32 * i; if (t < (N_PLANE * 20 + (LEGAL_WORDS + 2) * 4) / 16) pz[t] = z; }
-    }
     // stacks: pieces sharing a cell (tile.pieces); top piece <=> level+1 == len (env_hive.py:213)
     const unsigned peers = __match_any_sync(FULL, on_board ? cell : 256 + lane);
     const int height = __popc(peers);
@@ -273,53 +275,36 @@ __device__ __forceinline__ EvalResult eval_phase_a(WarpScratch& sm, CtaQueues& q
     const BB opp_all = warp_or((valid && !own) ? src : bb_zero());
     const BB occ = own_all | opp_all;
     const BB top_opp = warp_or((top && !own) ? src : bb_zero());
-    if (lane < 5) sm.occ[lane] = occ.w[lane];
 
     const int cq_w = __shfl_sync(FULL, cell, 0), cq_b = __shfl_sync(FULL, cell, 11);
     const bool wq_on = cq_w != HAND, bq_on = cq_b != HAND;
+    const bool ownq_on = (side == 0 ? cq_w : cq_b) != HAND;
     const unsigned in_hand = __ballot_sync(FULL, own && !on_board);
-    __syncwarp();
 
     uint32_t ring = 0;                                   // occupancy of the six neighbours
     if (on_board) {
 #pragma unroll
-        for (int i = 0; i < 6; i++) ring |= (uint32_t)words_test(sm.occ, cell_nbr(cell, i)) << i;
-    }
-    if (valid) sm.info[lane] = (uint32_t)cell | ((uint32_t)height << 8) | ((uint32_t)top << 12) | (ring << 16);
-    if (lane == 0) { sm.head[0] = (uint32_t)turn | ((uint32_t)cq_w << 8) | ((uint32_t)cq_b << 16); }
-
-    // ---- which pieces need a one-hive flood / a move search: compacted CTA-wide work queues
-    {
-        const bool ownq_on = (side == 0 ? cq_w : cq_b) != HAND;
-        // turn gates shared by every candidate of a piece (move_checker.py:38-55)
-        bool gate = true;
-        if (turn <= 2) gate = false;                                         // no on-board mover can exist / matter
-        else if (turn <= 6) gate = ownq_on;                                  // queen_is_on_board: colour by turn parity
-        else if (turn <= 8) gate = obeys_queen_by_4(turn, wq_on, bq_on, type == T_QUEEN, color);
-        // opponent mobility is only consumed through the own queen's neighbourhood (env_hive.py:459-478)
-        const bool wants_moves = top && gate && (own || ownq_on);
-        bool pinned_now = false, need_flood = false;
-        if (top && height == 1) {
-            if (ring == 0) pinned_now = true;                                // nothing left on the board -> `return False`
-            else need_flood = __popc(ring & ~rot6l(ring)) > 1;               // >1 arc of neighbours: may be an articulation point
-        }
-        const unsigned pin_mask = __ballot_sync(FULL, pinned_now);
-        if (lane == 0) sm.head[1] = pin_mask;
-        if (on_board) {
-#pragma unroll
-            for (int i = 0; i < 5; i++) sm.moves[lane][i] = 0;
-            const uint32_t item = (uint32_t)game_slot | ((uint32_t)lane << 4) | ((uint32_t)wants_moves << 9);
-            if (need_flood) q.flood[atomicAdd(&q.n_flood, 1u)] = (uint16_t)item;
-            else if (wants_moves && !pinned_now) {
-                const int cls = move_class(type);
-                q.mv[cls][atomicAdd(&q.n_mv[cls], 1u)] = (uint16_t)item;
-            }
-        }
+        for (int i = 0; i < 6; i++) ring |= (uint32_t)bb_test(occ, cell_nbr(cell, i)) << i;
     }
 
-    // placements (env_hive.py:217-225; move_checker.py:168-179): first in-hand piece per type
+    // turn gates shared by every candidate of a piece (move_checker.py:38-55)
+    bool gate = true;
+    if (turn <= 2) gate = false;                                             // no on-board mover can exist / matter
+    else if (turn <= 6) gate = ownq_on;                                      // queen_is_on_board: colour by turn parity
+    else if (turn <= 8) gate = obeys_queen_by_4(turn, wq_on, bq_on, type == T_QUEEN, color);
+    // opponent mobility is only consumed through the own queen's neighbourhood (env_hive.py:459-478)
+    const bool wants_moves = top && gate && (own || ownq_on);
+    bool pinned_now = false, need_flood = false;
+    if (top && height == 1) {
+        if (ring == 0) pinned_now = true;                                    // nothing left on the board -> `return False`
+        else need_flood = __popc(ring & ~rot6l(ring)) > 1;                   // >1 arc of neighbours: may be an articulation point
+    }
+    const unsigned pin_mask = __ballot_sync(FULL, pinned_now);
+
+    // moves row: zero for on-board pieces (the search kernel fills movers), placements for the hand
+    BB mv = bb_zero();
     if (valid && !on_board) {
-        BB mv = bb_zero();
+        // placements (env_hive.py:217-225; move_checker.py:168-179): first in-hand piece per type
         const unsigned same_type_before = in_hand & ((1u << lane) - 1u) &
             (type == T_QUEEN ? 0x00000801u : type == T_BEETLE ? 0x00003006u : type == T_SPIDER ? 0x0000C018u
              : type == T_HOPPER ? 0x000700E0u : 0x00380700u);
@@ -332,53 +317,38 @@ __device__ __forceinline__ EvalResult eval_phase_a(WarpScratch& sm, CtaQueues& q
                 if (ok) mv = bb_andn(bb_andn(bb_nbrs(occ), occ), bb_nbrs(top_opp));
             }
         }
-#pragma unroll
-        for (int i = 0; i < 5; i++) sm.moves[lane][i] = mv.w[i];
     }
-
-    // terminal test (move_checker.py:140-165)
-    const unsigned surrounded = __ballot_sync(FULL, on_board && type == T_QUEEN && ring == 63u);
-    const bool ws = surrounded & 1u, bs = (surrounded >> 11) & 1u;
-    EvalResult res;
-    res.n_legal = 0;
-    res.done = ws || bs;
-    res.winner = (ws && bs) ? prev_winner : ws ? 2 : bs ? 1 : prev_winner;
-
-    // planes that do not depend on mobility (env_hive.py:320-447)
-    if (on_board) {
-        const uint32_t bit = 1u << (cell & 31); const int wi = cell >> 5;
-        sm.planes[(own ? 0 : 12) + k][wi] = bit;                          // 0-10 / 12-22
-        if (type == T_BEETLE && level >= 2)                               // 24-26 / 27-29
-            atomicOr(&sm.planes[(own ? 24 : 27) + level - 2][wi], bit);
-        if (!top) atomicOr(&sm.planes[own ? 34 : 35][wi], bit);           // covered pieces
-        if (type == T_QUEEN) {                                            // 32 / 33
+    if (valid) {
 #pragma unroll
-            for (int i = 0; i < 6; i++)
-                if ((ring >> i) & 1u) { int c = cell_nbr(cell, i); atomicOr(&sm.planes[own ? 32 : 33][c >> 5], 1u << (c & 31)); }
+        for (int i = 0; i < 5; i++) gs.moves[lane][i] = mv.w[i];
+        gs.info[lane] = (uint32_t)cell | ((uint32_t)height << 8) | ((uint32_t)top << 12) | ((uint32_t)level << 13) | (ring << 16);
+    }
+    if (lane < 5) { gs.occ[lane] = occ.w[lane]; gs.own_all[lane] = own_all.w[lane]; gs.opp_all[lane] = opp_all.w[lane]; }
+    if (lane == 0) {
+        gs.head[0] = (uint32_t)turn | ((uint32_t)cq_w << 8) | ((uint32_t)cq_b << 16);
+        gs.head[1] = pin_mask;
+        gs.head[2] = 1u | ((uint32_t)push_history << 1) | ((uint32_t)prev_winner << 8);
+    }
+    if (on_board) {
+        const uint32_t item = (uint32_t)game_slot | ((uint32_t)lane << 4) | ((uint32_t)wants_moves << 9);
+        if (need_flood) q.flood[atomicAdd(&q.n_flood, 1u)] = (uint16_t)item;
+        else if (wants_moves && !pinned_now) {
+            const int cls = move_class(type);
+            q.mv[cls][atomicAdd(&q.n_mv[cls], 1u)] = (uint16_t)item;
         }
     }
-    if (lane < 5) {
-        sm.planes[11][lane] = own_all.w[lane];
-        sm.planes[23][lane] = opp_all.w[lane];
-        sm.planes[30][lane] = occ.w[lane];
-    }
-    {   // 36..43 history of the side to move
-        const uint32_t* h = &sm.hist[side][0][0][0];
-        for (int i = lane; i < 40; i += 32) (&sm.planes[36][0])[i] = h[i];
-    }
-    return res;
 }
 
-// phase B1: one thread, one one-hive flood (move_checker.py:58-83 / env_hive.py:509-530): lift the
-// top piece and test that the rest of the hive stays connected.
-__device__ __forceinline__ void eval_flood(WarpScratch& sm, CtaQueues& q, uint32_t item) {
+// search, part 1: one thread, one one-hive flood (move_checker.py:58-83 / env_hive.py:509-530):
+// lift the top piece and test that the rest of the hive stays connected.
+__device__ __forceinline__ void eval_flood(GameScratch& gs, GroupQueues& q, uint32_t item) {
     const int p = (item >> 4) & 31;
-    const uint32_t info = sm.info[p];
+    const uint32_t info = gs.info[p];
     const int cell = info & 0xFF;
     const uint32_t ring = (info >> 16) & 63u;
     BB occp;
 #pragma unroll
-    for (int i = 0; i < 5; i++) occp.w[i] = sm.occ[i];
+    for (int i = 0; i < 5; i++) occp.w[i] = gs.occ[i];
     const BB src = bb_bit(cell);
     occp = occp ^ src;
     const BB goal = bb_nbrs(src) & occp;
@@ -390,22 +360,25 @@ __device__ __forceinline__ void eval_flood(WarpScratch& sm, CtaQueues& q, uint32
         if (bb_eq(nx, x)) { pinned = true; break; }
         x = nx;
     }
-    if (pinned) atomicOr(&sm.head[1], 1u << p);
+    if (pinned) atomicOr(&gs.head[1], 1u << p);
     else if ((item >> 9) & 1u) {
         const int cls = move_class(piece_type_of(p >= 11 ? p - 11 : p));
         q.mv[cls][atomicAdd(&q.n_mv[cls], 1u)] = (uint16_t)item;
     }
 }
 
-// phase B2: one thread, the move set of one unpinned top piece whose turn gates are open.
+// search, part 2: one thread, the move set of one unpinned top piece whose turn gates are open.
 // `hop_lines` = 144x5 u32 table of is_straight_line masks (move_checker.py:249-265).
-__device__ __forceinline__ void eval_moves(WarpScratch& sm, int p, const uint32_t* __restrict__ hop_lines) {
-    const uint32_t info = sm.info[p];
+__device__ __forceinline__ void eval_moves(GameScratch& gs, int p, const uint32_t* __restrict__ hop_lines) {
+    const uint32_t info = gs.info[p];
     const int cell = info & 0xFF;
     const int height = (info >> 8) & 0xF;
     const uint32_t ring = (info >> 16) & 63u;
     const int type = piece_type_of(p >= 11 ? p - 11 : p);
-    uint32_t* row = sm.moves[p];
+    uint32_t* row = gs.moves[p];
+    BB occ;
+#pragma unroll
+    for (int i = 0; i < 5; i++) occ.w[i] = gs.occ[i];
 
     if (type == T_QUEEN || type == T_BEETLE) {
         uint32_t ok;
@@ -418,25 +391,25 @@ __device__ __forceinline__ void eval_moves(WarpScratch& sm, int p, const uint32_
             if (k0 & ~ok) {
                 // k==0: allowed iff the target has an occupied neighbour other than `old`
                 // (len(new_adjacents_with_pieces) - 1 != 0, move_checker.py:205-207)
-                BB o;
-#pragma unroll
-                for (int i = 0; i < 5; i++) o.w[i] = sm.occ[i];
-                const BB hns = bb_nbrs(o ^ bb_bit(cell));
+                const BB hns = bb_nbrs(occ ^ bb_bit(cell));
 #pragma unroll
                 for (int i = 0; i < 6; i++)
                     if (((k0 & ~ok) >> i) & 1u) { if (bb_test(hns, cell_nbr(cell, i))) ok |= 1u << i; }
             }
         }
-        // ring targets go straight into this piece's shared-memory row (zeroed in phase A)
+        uint32_t w[5] = {0u, 0u, 0u, 0u, 0u};
 #pragma unroll
         for (int i = 0; i < 6; i++)
-            if ((ok >> i) & 1u) { const int c = cell_nbr(cell, i); row[c >> 5] |= 1u << (c & 31); }
+            if ((ok >> i) & 1u) {
+                const int c = cell_nbr(cell, i); const uint32_t bit = 1u << (c & 31); const int wi = c >> 5;
+#pragma unroll
+                for (int j = 0; j < 5; j++) w[j] |= (wi == j) ? bit : 0u;
+            }
+#pragma unroll
+        for (int i = 0; i < 5; i++) row[i] = w[i];
         return;
     }
 
-    BB occ;
-#pragma unroll
-    for (int i = 0; i < 5; i++) occ.w[i] = sm.occ[i];
     const BB src = bb_bit(cell);
     BB mv;
     if (type == T_HOPPER) {                                              // pieces.py:128-158
@@ -478,72 +451,62 @@ __device__ __forceinline__ void eval_moves(WarpScratch& sm, int p, const uint32_
                 const BB c = bb_andn(slide_step(sl, b), src | a);
                 mv = mv | c;
             }
+            // end check with the spider back on `old`: adjacent target with both flanks occupied
+            const uint32_t k2 = rot6l(ring) & rot6r(ring);
+#pragma unroll
+            for (int i = 0; i < 6; i++)
+                if ((k2 >> i) & 1u) mv = bb_andn(mv, bb_bit(cell_nbr(cell, i)));
         }
     }
 #pragma unroll
     for (int i = 0; i < 5; i++) row[i] = mv.w[i];
-    if (type == T_SPIDER) {
-        // end check with the spider back on `old`: adjacent target with both flanks occupied
-        const uint32_t k2 = rot6l(ring) & rot6r(ring);
-#pragma unroll
-        for (int i = 0; i < 6; i++)
-            if ((k2 >> i) & 1u) { const int c = cell_nbr(cell, i); row[c >> 5] &= ~(1u << (c & 31)); }
-    }
 }
 
-// Run the two compacted phases for the whole CTA (all threads call this; contains barriers).
-__device__ __forceinline__ void eval_phase_b(WarpScratch* scratch, CtaQueues& q, int tid, int nthreads,
-                                             const uint32_t* __restrict__ hop_lines) {
-    const int nf = (int)q.n_flood;
-    for (int t = tid; t < nf; t += nthreads) {
-        const uint32_t item = q.flood[t];
-        eval_flood(scratch[item & 15u], q, item);
-    }
-    __syncthreads();
-    // move classes start at warp boundaries so that warps stay homogeneous
-    const int n0 = (int)q.n_mv[0], n1 = (int)q.n_mv[1], n2 = (int)q.n_mv[2], n3 = (int)q.n_mv[3];
-    const int s1 = (n0 + 31) & ~31, s2 = s1 + ((n1 + 31) & ~31), s3 = s2 + ((n2 + 31) & ~31), total = s3 + n3;
-    for (int t = tid; t < total; t += nthreads) {
-        int cls, idx, cnt;
-        if (t < s1) { cls = 0; idx = t; cnt = n0; }
-        else if (t < s2) { cls = 1; idx = t - s1; cnt = n1; }
-        else if (t < s3) { cls = 2; idx = t - s2; cnt = n2; }
-        else { cls = 3; idx = t - s3; cnt = n3; }
-        if (idx < cnt) {
-            const uint32_t item = q.mv[cls][idx];
-            eval_moves(scratch[item & 15u], (item >> 4) & 31, hop_lines);
-        }
-    }
-}
-
-__device__ __forceinline__ int eval_phase_c(WarpScratch& sm, int lane, int cell, int turn, bool push_history) {
+// encode: legal mask + all 56 planes (env_hive.py:287-304, 320-447) into shared
+// memory, history push, terminal test.  "own" = side to move.
+__device__ __forceinline__ EvalResult eval_encode(WarpScratch& sm, const GameScratch& gs, int lane) {
+    const uint32_t head = gs.head[0], flags = gs.head[2];
+    const int turn = head & 0xFF, cq_w = (head >> 8) & 0xFF, cq_b = (head >> 16) & 0xFF;
+    const bool push_history = (flags >> 1) & 1u;
+    const int prev_winner = (flags >> 8) & 0xFF;
     const int side = (turn & 1) ? 0 : 1;
     const bool valid = lane < N_PIECE;
     const int color = lane >= 11 ? 1 : 0;
     const int k = lane - 11 * color;
+    const int type = piece_type_of(k);
     const bool own = valid && (color == side);
+    const uint32_t info = valid ? gs.info[lane] : (uint32_t)HAND;
+    const int cell = info & 0xFF, level = (info >> 13) & 7;
     const bool on_board = valid && cell != HAND;
-    const uint32_t info = valid ? sm.info[lane] : 0u;
     const bool top = (info >> 12) & 1u;
-    const bool pinned = (sm.head[1] >> lane) & 1u;
-    const uint32_t head = sm.head[0];
-    const int cq_w = (head >> 8) & 0xFF, cq_b = (head >> 16) & 0xFF;
+    const uint32_t ring = (info >> 16) & 63u;
+    const bool pinned = (gs.head[1] >> lane) & 1u;
     const int cq_own = side == 0 ? cq_w : cq_b, cq_opp = side == 0 ? cq_b : cq_w;
 
+    {   // zero the scratch outputs: planes (1120 B) and legal (208 B) are contiguous and 16-byte aligned
+        uint4* pz = reinterpret_cast<uint4*>(&sm.planes[0][0]);
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int i = 0; i < 3; i++) { const int t = lane + 32 * i; if (t < (N_PLANE * 20 + (LEGAL_WORDS + 2) * 4) / 16) pz[t] = z; }
+    }
     BB mv = bb_zero();
     if (valid) {
 #pragma unroll
-        for (int i = 0; i < 5; i++) mv.w[i] = sm.moves[lane][i];
+        for (int i = 0; i < 5; i++) mv.w[i] = gs.moves[lane][i];
     }
-    // dense legal mask a = cell*11 + k (env_hive.py:287-304): the 11 own pieces x 5 board words are
-    // 55 work items spread over the 32 lanes, so no lane walks more than two words
+    uint32_t occ_w = 0, own_w = 0, opp_w = 0;
+    if (lane < 5) { occ_w = gs.occ[lane]; own_w = gs.own_all[lane]; opp_w = gs.opp_all[lane]; }
+    __syncwarp();
+
+    // dense legal mask a = cell*11 + k: the 11 own pieces x 5 board words are 55 work items spread
+    // over the 32 lanes, so no lane walks more than two words
     int n_mine = 0;
 #pragma unroll
     for (int r = 0; r < 2; r++) {
         const int item = lane + 32 * r;
         if (item < 55) {
             const int kk = item / 5, w = item - kk * 5;
-            uint32_t m = sm.moves[side * 11 + kk][w];
+            uint32_t m = gs.moves[side * 11 + kk][w];
             n_mine += __popc(m);
             while (m) {
                 const int b = __ffs(m) - 1; m &= m - 1;
@@ -556,29 +519,52 @@ __device__ __forceinline__ int eval_phase_c(WarpScratch& sm, int lane, int cell,
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) n_legal += __shfl_xor_sync(FULL, n_legal, o);
 
-    if (on_board && top) {
+    // terminal test (move_checker.py:140-165)
+    const unsigned surrounded = __ballot_sync(FULL, on_board && type == T_QUEEN && ring == 63u);
+    const bool ws = surrounded & 1u, bs = (surrounded >> 11) & 1u;
+    EvalResult res;
+    res.n_legal = n_legal;
+    res.done = ws || bs;
+    res.winner = (ws && bs) ? prev_winner : ws ? 2 : bs ? 1 : prev_winner;
+
+    if (on_board) {
         const uint32_t bit = 1u << (cell & 31); const int wi = cell >> 5;
-        if (own ? !bb_any(mv) : pinned) atomicOr(&sm.planes[own ? 34 : 35][wi], bit);     // 34 / 35
-    }
-    // 44+j: opponent pieces able to reach the j-th empty neighbour of the own queen;
-    // 50+j: own on-board pieces whose action list holds the j-th empty neighbour of the opponent queen.
-    // j follows tile.adjacent_tiles order = board_tiles order: q descending, then r ascending.
-    {
+        sm.planes[(own ? 0 : 12) + k][wi] = bit;                          // 0-10 / 12-22
+        if (type == T_BEETLE && level >= 2)                               // 24-26 / 27-29
+            atomicOr(&sm.planes[(own ? 24 : 27) + level - 2][wi], bit);
+        // 34: own pieces without a legal action; 35: opponent pieces covered or pinned
+        if (!top || (own ? !bb_any(mv) : pinned)) atomicOr(&sm.planes[own ? 34 : 35][wi], bit);
+        if (type == T_QUEEN) {                                            // 32 / 33
+#pragma unroll
+            for (int i = 0; i < 6; i++)
+                if ((ring >> i) & 1u) { int c = cell_nbr(cell, i); atomicOr(&sm.planes[own ? 32 : 33][c >> 5], 1u << (c & 31)); }
+        }
+        // 44+j: opponent pieces able to reach the j-th empty neighbour of the own queen;
+        // 50+j: own on-board pieces whose action list holds the j-th empty neighbour of the opponent queen.
+        // j follows tile.adjacent_tiles order = board_tiles order: q descending, then r ascending.
         const int qc = own ? cq_opp : cq_own;      // own pieces look at the opponent queen and vice versa
-        if (on_board && qc != HAND && bb_any(mv)) {
+        if (qc != HAND && bb_any(mv)) {
             int nb[6], key[6];
 #pragma unroll
             for (int i = 0; i < 6; i++) { nb[i] = cell_nbr(qc, i); key[i] = (11 - nb[i] / 12) * 12 + nb[i] % 12; }
-            const uint32_t bit = 1u << (cell & 31); const int wi = cell >> 5;
 #pragma unroll
             for (int i = 0; i < 6; i++) {
-                if (words_test(sm.occ, nb[i]) || !bb_test(mv, nb[i])) continue;
+                if (words_test(gs.occ, nb[i]) || !bb_test(mv, nb[i])) continue;
                 int j = 0;
 #pragma unroll
                 for (int t = 0; t < 6; t++) j += key[t] < key[i];
                 atomicOr(&sm.planes[(own ? 50 : 44) + j][wi], bit);
             }
         }
+    }
+    if (lane < 5) {
+        sm.planes[11][lane] = own_w;
+        sm.planes[23][lane] = opp_w;
+        sm.planes[30][lane] = occ_w;
+    }
+    {   // 36..43 history of the side to move
+        const uint32_t* h = &sm.hist[side][0][0][0];
+        for (int i = lane; i < 40; i += 32) (&sm.planes[36][0])[i] = h[i];
     }
     __syncwarp();
     // history push (env_hive.py:436-445): only after a real move / at reset
@@ -587,10 +573,10 @@ __device__ __forceinline__ int eval_phase_c(WarpScratch& sm, int lane, int cell,
         uint32_t keep = (lane < 30) ? h[lane] : 0;         // ages 0..2 -> 1..3
         __syncwarp();
         if (lane < 30) h[10 + lane] = keep;
-        if (lane < 5) { h[lane] = sm.planes[11][lane]; h[5 + lane] = sm.planes[23][lane]; }
+        if (lane < 5) { h[lane] = own_w; h[5 + lane] = opp_w; }
         __syncwarp();
     }
-    return n_legal;
+    return res;
 }
 
 // ------------------------------------------------------------------------------------------

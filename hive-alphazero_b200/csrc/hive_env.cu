@@ -3,8 +3,8 @@
 // One kernel, `hive_env_kernel`, is the whole GamePlay.move() of the reference
 // (hive_engine/env_hive.py:99-171) for a batch of games: apply the action, regenerate the legal
 // set of the new side to move, encode its 56 planes, push history, test for the end of the game.
-// One warp per game, 8 games per CTA; the per-piece searches of the 8 games are regrouped by piece
-// type across the CTA's warps (hive_core.cuh, phases A/B/C).
+// Three kernels per step (hive_env_kernel.cuh): analyse (warp per game) -> search (thread per queued
+// piece, grouped by piece type over 16-game groups) -> encode (warp per game).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -54,6 +54,8 @@ struct hive_env {
     int32_t* count = nullptr;
     uint32_t* status = nullptr;
     uint16_t* planes = nullptr;
+    GameScratch* scratch = nullptr;
+    GroupQueues* queues = nullptr;
     int32_t* d_actions[2] = {nullptr, nullptr};
     int act_flip = 0;
     uint8_t* d_mask = nullptr;
@@ -71,11 +73,16 @@ int launch_env(hive_env* h, int op, const int32_t* actions, const uint8_t* mask,
     a.recs = h->recs; a.legal = h->legal; a.count = h->count; a.status = h->status; a.planes = h->planes;
     a.actions = actions; a.mask = mask; a.chosen = chosen; a.hop_lines = h->hop_lines;
     a.seed = seed; a.n = h->n; a.op = op; a.max_turn = max_turn; a.auto_reset = auto_reset;
-    const int blocks = (h->n + GAMES_PER_CTA - 1) / GAMES_PER_CTA;
+    a.scratch = h->scratch; a.queues = h->queues;
+    const int groups = (h->n + GROUP - 1) / GROUP;
+    const int enc_blocks = (h->n + HIVE_ENCODE_WARPS - 1) / HIVE_ENCODE_WARPS;
     if (h->timing) CUDA_TRY(cudaEventRecord(h->t0, h->stream));
-    hive_env_kernel<GAMES_PER_CTA><<<blocks, GAMES_PER_CTA * 32, 0, h->stream>>>(a);
+    hive_analyse_kernel<<<groups, GROUP * 32, 0, h->stream>>>(a);
+    hive_search_kernel<<<groups, SEARCH_THREADS, 0, h->stream>>>(a);
+    hive_encode_kernel<<<enc_blocks, HIVE_ENCODE_WARPS * 32, 0, h->stream>>>(a);
     CUDA_TRY(cudaGetLastError());
     if (h->timing) CUDA_TRY(cudaEventRecord(h->t1, h->stream));
+    h->launches += 2;
     h->launches++;
     return 0;
 }
@@ -113,6 +120,8 @@ int hive_create(int n_games, int device, void* stream, hive_env_t** out) {
     CUDA_TRY(cudaMalloc(&h->count, n * 4));
     CUDA_TRY(cudaMalloc(&h->status, n * 4));
     CUDA_TRY(cudaMalloc(&h->planes, n * HIVE_PLANES_ELEMS * 2));
+    CUDA_TRY(cudaMalloc(&h->scratch, n * sizeof(GameScratch)));
+    CUDA_TRY(cudaMalloc(&h->queues, ((n + GROUP - 1) / GROUP) * sizeof(GroupQueues)));
     CUDA_TRY(cudaMalloc(&h->d_actions[0], n * 4));
     CUDA_TRY(cudaMalloc(&h->d_actions[1], n * 4));
     CUDA_TRY(cudaMalloc(&h->d_mask, n));
@@ -133,7 +142,7 @@ int hive_destroy(hive_env_t* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    cudaFree(h->recs); cudaFree(h->legal); cudaFree(h->count); cudaFree(h->status); cudaFree(h->planes);
+    cudaFree(h->recs); cudaFree(h->legal); cudaFree(h->count); cudaFree(h->status); cudaFree(h->planes); cudaFree(h->scratch); cudaFree(h->queues);
     cudaFree(h->d_actions[0]); cudaFree(h->d_actions[1]); cudaFree(h->d_mask); cudaFree(h->hop_lines);
     if (h->copy_done) cudaEventDestroy(h->copy_done);
     if (h->t0) cudaEventDestroy(h->t0);

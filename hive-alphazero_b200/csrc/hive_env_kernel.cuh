@@ -15,9 +15,8 @@
 
 namespace hive {
 
-constexpr int GAMES_PER_CTA = 8;                  // one warp per game, 8 games share a CTA
-#ifndef HIVE_MIN_CTAS
-#define HIVE_MIN_CTAS 3                           // resident CTAs per SM the register budget is set for
+#ifndef HIVE_ENCODE_WARPS
+#define HIVE_ENCODE_WARPS 8                        // games per CTA of the encode kernel
 #endif
 enum Op { OP_RESET = 0, OP_STEP = 1, OP_EVAL = 2, OP_RANDOM = 3, OP_INIT = 4 };   // INIT = first reset, zeroes the counters
 
@@ -27,6 +26,8 @@ struct EnvArgs {
     int32_t* count;        // [n]
     uint32_t* status;      // [n] turn | winner<<8 | done<<16
     uint16_t* planes;      // [n][56*144] bf16
+    GameScratch* scratch;  // [n] kernel-to-kernel intermediates (L2 resident)
+    GroupQueues* queues;   // [ceil(n/GROUP)]
     const int32_t* actions;
     const uint8_t* mask;
     int32_t* chosen;
@@ -35,37 +36,28 @@ struct EnvArgs {
     int n, op, max_turn, auto_reset;
 };
 
-template <int G>
-__global__ void __launch_bounds__(G * 32, HIVE_MIN_CTAS) hive_env_kernel(EnvArgs a) {
-    static_assert(G <= MAX_GAMES_PER_CTA, "queue item encoding holds 4 bits of game slot");
-    __shared__ WarpScratch scratch[G];
-    __shared__ CtaQueues queues;
-    __shared__ uint2 bf16_lut[16];
+// ---- kernel 1: decode the operation, apply the action, analyse the new position (warp <-> game)
+__global__ void __launch_bounds__(GROUP * 32) hive_analyse_kernel(EnvArgs a) {
+    __shared__ GroupQueues q;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = blockIdx.x * G + warp;
-    WarpScratch& sm = scratch[warp];
-    fill_bf16_lut(bf16_lut, tid);
-    if (tid < 5) (&queues.n_flood)[tid] = 0;
+    const int g = blockIdx.x * GROUP + warp;
+    if (tid < 5) (&q.n_flood)[tid] = 0;
     __syncthreads();
 
-    // ---------------- per-game prologue: decode the operation, apply the action (warp <-> game)
     bool live = g < a.n;
-    int cell = HAND, level = 0, turn = 1, winner = 0;
-    uint32_t episode = 0, steps = 0;
-    bool push = false;
-    GameRec* rec = a.recs + (live ? g : 0);
     if (live) {
+        GameRec* rec = a.recs + g;
+        int cell = HAND, level = 0;
         if (lane < N_PIECE) { cell = rec->cell[lane]; level = rec->level[lane]; }
         // header words: [11] = turn|winner|done|flags, [12] episode, [13] steps, [14] n_legal
-        const uint32_t* hw = reinterpret_cast<const uint32_t*>(rec);
+        uint32_t* hw = reinterpret_cast<uint32_t*>(rec);
         const uint32_t h11 = hw[11];
-        turn = h11 & 0xFF; winner = (h11 >> 8) & 0xFF;
+        int turn = h11 & 0xFF, winner = (h11 >> 8) & 0xFF;
         const int done = (h11 >> 16) & 0xFF;
-        episode = hw[12]; steps = hw[13];
+        uint32_t episode = hw[12], steps = hw[13];
         const uint32_t n_legal_prev = hw[14];
-        if (lane < 20) reinterpret_cast<uint4*>(&sm.hist[0][0][0][0])[lane] = reinterpret_cast<const uint4*>(rec->hist)[lane];
 
-        bool do_reset = false;
+        bool do_reset = false, push = false;
         int action = HIVE_NOOP;
         if (a.op == OP_RESET) {
             if (a.mask && !a.mask[g]) live = false; else do_reset = true;
@@ -93,8 +85,7 @@ __global__ void __launch_bounds__(G * 32, HIVE_MIN_CTAS) hive_env_kernel(EnvArgs
         if (live) {
             if (do_reset) {                                     // GamePlay.new_game, env_hive.py:61-97
                 cell = HAND; level = 0; turn = 1; winner = 0; episode++;
-                uint32_t* hz = &sm.hist[0][0][0][0];
-                for (int i = lane; i < 80; i += 32) hz[i] = 0;
+                if (lane < 20) reinterpret_cast<uint4*>(rec->hist)[lane] = make_uint4(0u, 0u, 0u, 0u);
                 push = true;                                    // add_history starts True (env_hive.py:51)
             } else if (action >= 0) {                           // env_hive.py:105-148
                 const int side = (turn & 1) ? 0 : 1;
@@ -106,29 +97,79 @@ __global__ void __launch_bounds__(G * 32, HIVE_MIN_CTAS) hive_env_kernel(EnvArgs
                 turn++; steps++;
             }
             __syncwarp();
+            if (lane < N_PIECE) { rec->cell[lane] = (uint8_t)cell; rec->level[lane] = (uint8_t)level; }
+            if (lane == 0) { hw[12] = episode; hw[13] = steps; }
+            eval_analyse(a.scratch[g], q, warp, lane, cell, level, turn, push, winner);
+        } else if (lane == 0) {
+            a.scratch[g].head[2] = 0;                           // not evaluated in this launch
         }
     }
-
-    // ---------------- phase A (warp <-> game)
-    EvalResult r;
-    r.n_legal = 0; r.done = 0; r.winner = 0;
-    if (live) r = eval_phase_a(sm, queues, warp, lane, cell, level, turn, winner);
     __syncthreads();
+    {   // publish this group's work queues
+        const uint4* src = reinterpret_cast<const uint4*>(&q);
+        uint4* dst = reinterpret_cast<uint4*>(a.queues + blockIdx.x);
+        for (int i = tid; i < (int)(sizeof(GroupQueues) / 16); i += GROUP * 32) dst[i] = src[i];
+    }
+}
 
-    // ---------------- phase B (thread <-> queued piece task; floods, then moves grouped by piece type)
-    eval_phase_b(scratch, queues, tid, G * 32, a.hop_lines);
+// ---- kernel 2: one-hive floods, then move searches grouped by piece type (thread <-> queued piece)
+constexpr int SEARCH_THREADS = 128;
+__global__ void __launch_bounds__(SEARCH_THREADS) hive_search_kernel(EnvArgs a) {
+    __shared__ GroupQueues q;
+    const int tid = threadIdx.x;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(a.queues + blockIdx.x);
+        uint4* dst = reinterpret_cast<uint4*>(&q);
+        for (int i = tid; i < (int)(sizeof(GroupQueues) / 16); i += SEARCH_THREADS) dst[i] = src[i];
+    }
     __syncthreads();
+    GameScratch* base = a.scratch + (size_t)blockIdx.x * GROUP;
+    const int nf = (int)q.n_flood;
+    __syncthreads();                                   // everyone has read n_flood / the pre-flood counts are final
+    for (int t = tid; t < nf; t += SEARCH_THREADS) {
+        const uint32_t item = q.flood[t];
+        eval_flood(base[item & 15u], q, item);
+    }
+    __syncthreads();
+    // move classes start at warp boundaries so that warps stay homogeneous
+    const int n0 = (int)q.n_mv[0], n1 = (int)q.n_mv[1], n2 = (int)q.n_mv[2], n3 = (int)q.n_mv[3];
+    const int s1 = (n0 + 31) & ~31, s2 = s1 + ((n1 + 31) & ~31), s3 = s2 + ((n2 + 31) & ~31), total = s3 + n3;
+    for (int t = tid; t < total; t += SEARCH_THREADS) {
+        int cls, idx, cnt;
+        if (t < s1) { cls = 0; idx = t; cnt = n0; }
+        else if (t < s2) { cls = 1; idx = t - s1; cnt = n1; }
+        else if (t < s3) { cls = 2; idx = t - s2; cnt = n2; }
+        else { cls = 3; idx = t - s3; cnt = n3; }
+        if (idx < cnt) {
+            const uint32_t item = q.mv[cls][idx];
+            eval_moves(base[item & 15u], (item >> 4) & 31, a.hop_lines);
+        }
+    }
+}
 
-    // ---------------- phase C (warp <-> game) + write back
-    if (!live) return;
-    r.n_legal = eval_phase_c(sm, lane, cell, turn, push);
-    if (lane < N_PIECE) { rec->cell[lane] = (uint8_t)cell; rec->level[lane] = (uint8_t)level; }
+// ---- kernel 3: legal mask, planes, history, terminal test, outputs (warp <-> game)
+__global__ void __launch_bounds__(HIVE_ENCODE_WARPS * 32) hive_encode_kernel(EnvArgs a) {
+    __shared__ WarpScratch scratch[HIVE_ENCODE_WARPS];
+    __shared__ uint2 bf16_lut[16];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = blockIdx.x * HIVE_ENCODE_WARPS + warp;
+    fill_bf16_lut(bf16_lut, tid);
+    __syncthreads();
+    if (g >= a.n) return;
+    const GameScratch& gs = a.scratch[g];
+    if (!(gs.head[2] & 1u)) return;
+    WarpScratch& sm = scratch[warp];
+    GameRec* rec = a.recs + g;
+    if (lane < 20) reinterpret_cast<uint4*>(&sm.hist[0][0][0][0])[lane] = reinterpret_cast<const uint4*>(rec->hist)[lane];
+    __syncwarp();
+    const EvalResult r = eval_encode(sm, gs, lane);
+    const int turn = gs.head[0] & 0xFF;
     if (lane == 0) {
         uint32_t* w = reinterpret_cast<uint32_t*>(rec);
-        w[11] = (uint32_t)turn | ((uint32_t)r.winner << 8) | ((uint32_t)r.done << 16);
-        w[12] = episode; w[13] = steps; w[14] = (uint32_t)r.n_legal;
+        const uint32_t st = (uint32_t)turn | ((uint32_t)r.winner << 8) | ((uint32_t)r.done << 16);
+        w[11] = st; w[14] = (uint32_t)r.n_legal;
         a.count[g] = r.n_legal;
-        a.status[g] = w[11];
+        a.status[g] = st;
     }
     if (lane < 20) reinterpret_cast<uint4*>(rec->hist)[lane] = reinterpret_cast<const uint4*>(&sm.hist[0][0][0][0])[lane];
     if (lane < 25) reinterpret_cast<uint2*>(a.legal + (size_t)g * LEGAL_WORDS)[lane] = reinterpret_cast<const uint2*>(sm.legal)[lane];

@@ -21,7 +21,9 @@ static void build_lines() {
         }
 }
 
-static void lane_main(void* p) { hive_env_kernel<GAMES_PER_CTA>(*(EnvArgs*)p); }
+static void k_analyse(void* p) { hive_analyse_kernel(*(EnvArgs*)p); }
+static void k_search(void* p) { hive_search_kernel(*(EnvArgs*)p); }
+static void k_encode(void* p) { hive_encode_kernel(*(EnvArgs*)p); }
 
 extern "C" {
 
@@ -34,9 +36,23 @@ int emu_env_run(void* recs, uint32_t* legal, int32_t* count, uint32_t* status, u
     a.recs = (GameRec*)recs; a.legal = legal; a.count = count; a.status = status; a.planes = planes;
     a.actions = actions; a.mask = mask; a.chosen = chosen; a.hop_lines = g_lines.data();
     a.seed = seed; a.n = n; a.op = op; a.max_turn = max_turn; a.auto_reset = auto_reset;
-    const int blocks = (n + GAMES_PER_CTA - 1) / GAMES_PER_CTA;
-    for (int b = 0; b < blocks; b++) {
-        int rc = emu::run_block(lane_main, &a, b, GAMES_PER_CTA * 32, sched_seed + (uint64_t)b);
+    static std::vector<GameScratch> scratch;
+    static std::vector<GroupQueues> queues;
+    const int groups = (n + GROUP - 1) / GROUP;
+    if ((int)scratch.size() < n) scratch.resize(n);
+    if ((int)queues.size() < groups) queues.resize(groups);
+    a.scratch = scratch.data(); a.queues = queues.data();
+    for (int b = 0; b < groups; b++) {
+        int rc = emu::run_block(k_analyse, &a, b, GROUP * 32, sched_seed + (uint64_t)b);
+        if (rc) return rc;
+    }
+    for (int b = 0; b < groups; b++) {
+        int rc = emu::run_block(k_search, &a, b, SEARCH_THREADS, sched_seed + 1000 + (uint64_t)b);
+        if (rc) return rc;
+    }
+    const int enc_blocks = (n + HIVE_ENCODE_WARPS - 1) / HIVE_ENCODE_WARPS;
+    for (int b = 0; b < enc_blocks; b++) {
+        int rc = emu::run_block(k_encode, &a, b, HIVE_ENCODE_WARPS * 32, sched_seed + 2000 + (uint64_t)b);
         if (rc) return rc;
     }
     return 0;
