@@ -76,16 +76,23 @@ struct __align__(16) GameScratch {
 };
 static_assert(sizeof(GameScratch) == 656, "GameScratch layout");
 
-// Work queues of one group of G games (item = game_slot | piece<<4 | wants_moves<<9)
-constexpr int GROUP = 16;          // games per CTA / per work-queue group
+// Work queues.  The analyse kernel first collects the items of its 16 games in shared memory
+// (GroupQueues), then reserves a slice of the batch-wide queues with one atomic per class and CTA.
+// item = game<<6 | piece<<1 | wants_moves
+constexpr int GROUP = 16;          // games per CTA of the analyse kernel
 struct __align__(16) GroupQueues {
     uint32_t n_flood;
     uint32_t n_mv[4];              // move classes: 0 Ant, 1 Grasshopper, 2 Spider, 3 Queen/Beetle
-    uint32_t pad[3];
+    uint32_t base[5];              // reserved offsets in the batch-wide queues
+    uint32_t pad[2];
     uint16_t flood[GROUP * N_PIECE];
     uint16_t mv[4][GROUP * 6];
 };
-static_assert(sizeof(GroupQueues) % 16 == 0, "GroupQueues is copied with 16-byte accesses");
+struct BatchQueues {
+    uint32_t* counters;            // [8]: n_flood, n_mv[4]
+    uint32_t* flood;               // capacity n*22
+    uint32_t* mv[4];               // capacity n*6 each
+};
 
 // ------------------------------------------------------------------------------------------
 // 144-bit boards
@@ -340,9 +347,8 @@ __device__ __forceinline__ void eval_analyse(GameScratch& gs, GroupQueues& q, in
 }
 
 // search, part 1: one thread, one one-hive flood (move_checker.py:58-83 / env_hive.py:509-530):
-// lift the top piece and test that the rest of the hive stays connected.
-__device__ __forceinline__ void eval_flood(GameScratch& gs, GroupQueues& q, uint32_t item) {
-    const int p = (item >> 4) & 31;
+// lift the top piece and test that the rest of the hive stays connected.  Returns true if pinned.
+__device__ __forceinline__ bool eval_flood(GameScratch& gs, int p) {
     const uint32_t info = gs.info[p];
     const int cell = info & 0xFF;
     const uint32_t ring = (info >> 16) & 63u;
@@ -353,17 +359,11 @@ __device__ __forceinline__ void eval_flood(GameScratch& gs, GroupQueues& q, uint
     occp = occp ^ src;
     const BB goal = bb_nbrs(src) & occp;
     BB x = bb_bit(cell_nbr(cell, __ffs(ring) - 1));
-    bool pinned = false;
     for (;;) {
         BB nx = x | (bb_nbrs(x) & occp);
-        if (bb_eq(nx & goal, goal)) break;
-        if (bb_eq(nx, x)) { pinned = true; break; }
+        if (bb_eq(nx & goal, goal)) return false;
+        if (bb_eq(nx, x)) return true;
         x = nx;
-    }
-    if (pinned) atomicOr(&gs.head[1], 1u << p);
-    else if ((item >> 9) & 1u) {
-        const int cls = move_class(piece_type_of(p >= 11 ? p - 11 : p));
-        q.mv[cls][atomicAdd(&q.n_mv[cls], 1u)] = (uint16_t)item;
     }
 }
 

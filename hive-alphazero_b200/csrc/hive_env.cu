@@ -3,8 +3,8 @@
 // One kernel, `hive_env_kernel`, is the whole GamePlay.move() of the reference
 // (hive_engine/env_hive.py:99-171) for a batch of games: apply the action, regenerate the legal
 // set of the new side to move, encode its 56 planes, push history, test for the end of the game.
-// Three kernels per step (hive_env_kernel.cuh): analyse (warp per game) -> search (thread per queued
-// piece, grouped by piece type over 16-game groups) -> encode (warp per game).
+// Four kernels per step (hive_env_kernel.cuh): analyse (warp per game) -> flood -> moves (thread per
+// queued piece from batch-wide queues, move searches grouped by piece type) -> encode (warp per game).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -55,7 +55,8 @@ struct hive_env {
     uint32_t* status = nullptr;
     uint16_t* planes = nullptr;
     GameScratch* scratch = nullptr;
-    GroupQueues* queues = nullptr;
+    BatchQueues bq = {};
+    int search_blocks = 0;
     int32_t* d_actions[2] = {nullptr, nullptr};
     int act_flip = 0;
     uint8_t* d_mask = nullptr;
@@ -73,16 +74,17 @@ int launch_env(hive_env* h, int op, const int32_t* actions, const uint8_t* mask,
     a.recs = h->recs; a.legal = h->legal; a.count = h->count; a.status = h->status; a.planes = h->planes;
     a.actions = actions; a.mask = mask; a.chosen = chosen; a.hop_lines = h->hop_lines;
     a.seed = seed; a.n = h->n; a.op = op; a.max_turn = max_turn; a.auto_reset = auto_reset;
-    a.scratch = h->scratch; a.queues = h->queues;
+    a.scratch = h->scratch; a.bq = h->bq;
     const int groups = (h->n + GROUP - 1) / GROUP;
     const int enc_blocks = (h->n + HIVE_ENCODE_WARPS - 1) / HIVE_ENCODE_WARPS;
     if (h->timing) CUDA_TRY(cudaEventRecord(h->t0, h->stream));
     hive_analyse_kernel<<<groups, GROUP * 32, 0, h->stream>>>(a);
-    hive_search_kernel<<<groups, SEARCH_THREADS, 0, h->stream>>>(a);
+    hive_flood_kernel<<<h->search_blocks, SEARCH_THREADS, 0, h->stream>>>(a);
+    hive_moves_kernel<<<h->search_blocks, SEARCH_THREADS, 0, h->stream>>>(a);
     hive_encode_kernel<<<enc_blocks, HIVE_ENCODE_WARPS * 32, 0, h->stream>>>(a);
     CUDA_TRY(cudaGetLastError());
     if (h->timing) CUDA_TRY(cudaEventRecord(h->t1, h->stream));
-    h->launches += 2;
+    h->launches += 3;
     h->launches++;
     return 0;
 }
@@ -121,7 +123,17 @@ int hive_create(int n_games, int device, void* stream, hive_env_t** out) {
     CUDA_TRY(cudaMalloc(&h->status, n * 4));
     CUDA_TRY(cudaMalloc(&h->planes, n * HIVE_PLANES_ELEMS * 2));
     CUDA_TRY(cudaMalloc(&h->scratch, n * sizeof(GameScratch)));
-    CUDA_TRY(cudaMalloc(&h->queues, ((n + GROUP - 1) / GROUP) * sizeof(GroupQueues)));
+    CUDA_TRY(cudaMalloc(&h->bq.counters, 8 * 4));
+    CUDA_TRY(cudaMemsetAsync(h->bq.counters, 0, 8 * 4, h->stream));
+    CUDA_TRY(cudaMalloc(&h->bq.flood, n * N_PIECE * 4));
+    for (int c = 0; c < 4; c++) CUDA_TRY(cudaMalloc(&h->bq.mv[c], n * 6 * 4));
+    {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        const long long want = ((long long)n * N_PIECE + SEARCH_THREADS - 1) / SEARCH_THREADS;
+        const long long cap = (long long)sms * 16;                 // 16 x 128-thread CTAs fill an SM
+        h->search_blocks = (int)(want < cap ? want : cap);
+    }
     CUDA_TRY(cudaMalloc(&h->d_actions[0], n * 4));
     CUDA_TRY(cudaMalloc(&h->d_actions[1], n * 4));
     CUDA_TRY(cudaMalloc(&h->d_mask, n));
@@ -142,7 +154,8 @@ int hive_destroy(hive_env_t* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    cudaFree(h->recs); cudaFree(h->legal); cudaFree(h->count); cudaFree(h->status); cudaFree(h->planes); cudaFree(h->scratch); cudaFree(h->queues);
+    cudaFree(h->recs); cudaFree(h->legal); cudaFree(h->count); cudaFree(h->status); cudaFree(h->planes); cudaFree(h->scratch); cudaFree(h->bq.counters); cudaFree(h->bq.flood);
+    for (int c = 0; c < 4; c++) cudaFree(h->bq.mv[c]);
     cudaFree(h->d_actions[0]); cudaFree(h->d_actions[1]); cudaFree(h->d_mask); cudaFree(h->hop_lines);
     if (h->copy_done) cudaEventDestroy(h->copy_done);
     if (h->t0) cudaEventDestroy(h->t0);

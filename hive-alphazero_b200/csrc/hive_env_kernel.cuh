@@ -27,7 +27,7 @@ struct EnvArgs {
     uint32_t* status;      // [n] turn | winner<<8 | done<<16
     uint16_t* planes;      // [n][56*144] bf16
     GameScratch* scratch;  // [n] kernel-to-kernel intermediates (L2 resident)
-    GroupQueues* queues;   // [ceil(n/GROUP)]
+    BatchQueues bq;        // batch-wide work queues
     const int32_t* actions;
     const uint8_t* mask;
     int32_t* chosen;
@@ -105,55 +105,88 @@ __global__ void __launch_bounds__(GROUP * 32) hive_analyse_kernel(EnvArgs a) {
         }
     }
     __syncthreads();
-    {   // publish this group's work queues
-        const uint4* src = reinterpret_cast<const uint4*>(&q);
-        uint4* dst = reinterpret_cast<uint4*>(a.queues + blockIdx.x);
-        for (int i = tid; i < (int)(sizeof(GroupQueues) / 16); i += GROUP * 32) dst[i] = src[i];
+    // publish this group's work: reserve a slice of every batch-wide queue (one atomic per class and CTA)
+    if (tid < 5) { const uint32_t c = (&q.n_flood)[tid]; q.base[tid] = c ? atomicAdd(a.bq.counters + tid, c) : 0u; }
+    __syncthreads();
+    {
+        const uint32_t g0 = (uint32_t)blockIdx.x * GROUP;
+        const int nf = (int)q.n_flood;
+        for (int i = tid; i < nf; i += GROUP * 32) {
+            const uint32_t it = q.flood[i];
+            a.bq.flood[q.base[0] + i] = ((g0 + (it & 15u)) << 6) | (((it >> 4) & 31u) << 1) | ((it >> 9) & 1u);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int nm = (int)q.n_mv[c];
+            for (int i = tid; i < nm; i += GROUP * 32) {
+                const uint32_t it = q.mv[c][i];
+                a.bq.mv[c][q.base[1 + c] + i] = ((g0 + (it & 15u)) << 6) | (((it >> 4) & 31u) << 1) | 1u;
+            }
+        }
     }
 }
 
-// ---- kernel 2: one-hive floods, then move searches grouped by piece type (thread <-> queued piece)
+// ---- kernel 2: one-hive floods over the batch-wide flood queue (thread <-> queued piece)
 constexpr int SEARCH_THREADS = 128;
-__global__ void __launch_bounds__(SEARCH_THREADS) hive_search_kernel(EnvArgs a) {
-    __shared__ GroupQueues q;
-    const int tid = threadIdx.x;
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(a.queues + blockIdx.x);
-        uint4* dst = reinterpret_cast<uint4*>(&q);
-        for (int i = tid; i < (int)(sizeof(GroupQueues) / 16); i += SEARCH_THREADS) dst[i] = src[i];
+__global__ void __launch_bounds__(SEARCH_THREADS) hive_flood_kernel(EnvArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int nf = (int)a.bq.counters[0];
+    const int stride = gridDim.x * SEARCH_THREADS;
+    for (int t0 = (blockIdx.x * SEARCH_THREADS + threadIdx.x) - lane; t0 < nf; t0 += stride) {   // warp-uniform loop
+        const int t = t0 + lane;
+        bool push = false;
+        uint32_t item = 0;
+        int cls = 0;
+        if (t < nf) {
+            item = a.bq.flood[t];
+            const int p = (item >> 1) & 31;
+            GameScratch& gs = a.scratch[item >> 6];
+            const bool pinned = eval_flood(gs, p);
+            if (pinned) atomicOr(&gs.head[1], 1u << p);
+            else if (item & 1u) { push = true; cls = move_class(piece_type_of(p >= 11 ? p - 11 : p)); }
+        }
+        // survivors that want a move search join the move queues (one atomic per class and warp)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const unsigned m = __ballot_sync(FULL, push && cls == c);
+            if (m) {
+                uint32_t base = 0;
+                const int leader = __ffs(m) - 1;
+                if (lane == leader) base = atomicAdd(a.bq.counters + 1 + c, (uint32_t)__popc(m));
+                base = __shfl_sync(FULL, base, leader);
+                if (push && cls == c) a.bq.mv[c][base + __popc(m & ((1u << lane) - 1u))] = item;
+            }
+        }
     }
-    __syncthreads();
-    GameScratch* base = a.scratch + (size_t)blockIdx.x * GROUP;
-    const int nf = (int)q.n_flood;
-    __syncthreads();                                   // everyone has read n_flood / the pre-flood counts are final
-    for (int t = tid; t < nf; t += SEARCH_THREADS) {
-        const uint32_t item = q.flood[t];
-        eval_flood(base[item & 15u], q, item);
-    }
-    __syncthreads();
+}
+
+// ---- kernel 3: move searches, warps homogeneous in piece type (thread <-> queued piece)
+__global__ void __launch_bounds__(SEARCH_THREADS) hive_moves_kernel(EnvArgs a) {
     // move classes start at warp boundaries so that warps stay homogeneous
-    const int n0 = (int)q.n_mv[0], n1 = (int)q.n_mv[1], n2 = (int)q.n_mv[2], n3 = (int)q.n_mv[3];
+    const int n0 = (int)a.bq.counters[1], n1 = (int)a.bq.counters[2], n2 = (int)a.bq.counters[3], n3 = (int)a.bq.counters[4];
     const int s1 = (n0 + 31) & ~31, s2 = s1 + ((n1 + 31) & ~31), s3 = s2 + ((n2 + 31) & ~31), total = s3 + n3;
-    for (int t = tid; t < total; t += SEARCH_THREADS) {
+    const int stride = gridDim.x * SEARCH_THREADS;
+    for (int t = blockIdx.x * SEARCH_THREADS + threadIdx.x; t < total; t += stride) {
         int cls, idx, cnt;
         if (t < s1) { cls = 0; idx = t; cnt = n0; }
         else if (t < s2) { cls = 1; idx = t - s1; cnt = n1; }
         else if (t < s3) { cls = 2; idx = t - s2; cnt = n2; }
         else { cls = 3; idx = t - s3; cnt = n3; }
         if (idx < cnt) {
-            const uint32_t item = q.mv[cls][idx];
-            eval_moves(base[item & 15u], (item >> 4) & 31, a.hop_lines);
+            const uint32_t item = a.bq.mv[cls][idx];
+            eval_moves(a.scratch[item >> 6], (item >> 1) & 31, a.hop_lines);
         }
     }
 }
 
-// ---- kernel 3: legal mask, planes, history, terminal test, outputs (warp <-> game)
+// ---- kernel 4: legal mask, planes, history, terminal test, outputs (warp <-> game)
 __global__ void __launch_bounds__(HIVE_ENCODE_WARPS * 32) hive_encode_kernel(EnvArgs a) {
     __shared__ WarpScratch scratch[HIVE_ENCODE_WARPS];
     __shared__ uint2 bf16_lut[16];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.x * HIVE_ENCODE_WARPS + warp;
     fill_bf16_lut(bf16_lut, tid);
+    if (blockIdx.x == 0 && tid < 8) a.bq.counters[tid] = 0;     // the queues are consumed: reset for the next step
     __syncthreads();
     if (g >= a.n) return;
     const GameScratch& gs = a.scratch[g];

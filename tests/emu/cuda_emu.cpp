@@ -4,7 +4,7 @@
 namespace emu {
 
 Block* W = nullptr;
-thread_local dim3emu g_threadIdx, g_blockIdx, g_blockDim;
+thread_local dim3emu g_threadIdx, g_blockIdx, g_blockDim, g_gridDim = {1, 1, 1};
 static char g_errbuf[256];
 const char* last_error() { return g_errbuf; }
 

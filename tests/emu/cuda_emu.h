@@ -50,7 +50,7 @@ struct Block {
     long collectives;
 };
 extern Block* W;
-extern thread_local dim3emu g_threadIdx, g_blockIdx, g_blockDim;
+extern thread_local dim3emu g_threadIdx, g_blockIdx, g_blockDim, g_gridDim;
 
 inline void park(int kind, uint32_t in, uint32_t arg) {
     Block* w = W;
@@ -65,6 +65,7 @@ inline uint32_t result() { return W->out[W->cur]; }
 #define threadIdx (emu::g_threadIdx)
 #define blockIdx (emu::g_blockIdx)
 #define blockDim (emu::g_blockDim)
+#define gridDim (emu::g_gridDim)
 
 static inline void emu_check_mask(unsigned m) { if (m != 0xffffffffu) { fprintf(stderr, "emu: only full-mask collectives supported\n"); abort(); } }
 static inline int __shfl_sync(unsigned m, int v, int src) { emu_check_mask(m); emu::park(emu::K_SHFL, (uint32_t)v, (uint32_t)src & 31); return (int)emu::result(); }

@@ -22,7 +22,8 @@ static void build_lines() {
 }
 
 static void k_analyse(void* p) { hive_analyse_kernel(*(EnvArgs*)p); }
-static void k_search(void* p) { hive_search_kernel(*(EnvArgs*)p); }
+static void k_flood(void* p) { hive_flood_kernel(*(EnvArgs*)p); }
+static void k_moves(void* p) { hive_moves_kernel(*(EnvArgs*)p); }
 static void k_encode(void* p) { hive_encode_kernel(*(EnvArgs*)p); }
 
 extern "C" {
@@ -37,17 +38,26 @@ int emu_env_run(void* recs, uint32_t* legal, int32_t* count, uint32_t* status, u
     a.actions = actions; a.mask = mask; a.chosen = chosen; a.hop_lines = g_lines.data();
     a.seed = seed; a.n = n; a.op = op; a.max_turn = max_turn; a.auto_reset = auto_reset;
     static std::vector<GameScratch> scratch;
-    static std::vector<GroupQueues> queues;
+    static std::vector<uint32_t> counters(8, 0), qflood, qmv[4];
     const int groups = (n + GROUP - 1) / GROUP;
     if ((int)scratch.size() < n) scratch.resize(n);
-    if ((int)queues.size() < groups) queues.resize(groups);
-    a.scratch = scratch.data(); a.queues = queues.data();
+    if ((int)qflood.size() < n * N_PIECE) qflood.resize(n * N_PIECE);
+    for (int c = 0; c < 4; c++) if ((int)qmv[c].size() < n * 6) qmv[c].resize(n * 6);
+    a.scratch = scratch.data();
+    a.bq.counters = counters.data(); a.bq.flood = qflood.data();
+    for (int c = 0; c < 4; c++) a.bq.mv[c] = qmv[c].data();
     for (int b = 0; b < groups; b++) {
         int rc = emu::run_block(k_analyse, &a, b, GROUP * 32, sched_seed + (uint64_t)b);
         if (rc) return rc;
     }
-    for (int b = 0; b < groups; b++) {
-        int rc = emu::run_block(k_search, &a, b, SEARCH_THREADS, sched_seed + 1000 + (uint64_t)b);
+    const int search_blocks = 3;        // fewer blocks than work: exercises the grid-stride loops
+    emu::g_gridDim.x = search_blocks;
+    for (int b = 0; b < search_blocks; b++) {
+        int rc = emu::run_block(k_flood, &a, b, SEARCH_THREADS, sched_seed + 1000 + (uint64_t)b);
+        if (rc) return rc;
+    }
+    for (int b = 0; b < search_blocks; b++) {
+        int rc = emu::run_block(k_moves, &a, b, SEARCH_THREADS, sched_seed + 1500 + (uint64_t)b);
         if (rc) return rc;
     }
     const int enc_blocks = (n + HIVE_ENCODE_WARPS - 1) / HIVE_ENCODE_WARPS;
