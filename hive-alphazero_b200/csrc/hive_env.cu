@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -16,6 +17,10 @@
 
 #include "../../include/hive_b200.h"
 #include "hive_env_kernel.cuh"
+
+#ifndef HIVE_DEFAULT_SLICES
+#define HIVE_DEFAULT_SLICES 4
+#endif
 
 using namespace hive;
 
@@ -55,7 +60,12 @@ struct hive_env {
     uint32_t* status = nullptr;
     uint16_t* planes = nullptr;
     GameScratch* scratch = nullptr;
-    BatchQueues bq = {};
+    static constexpr int MAX_SUB = 8;
+    BatchQueues bq[MAX_SUB] = {};
+    int n_sub = 1;                  // the batch is cut into n_sub slices whose kernel chains overlap on side streams
+    int stagger = 1;
+    cudaStream_t sub_stream[MAX_SUB] = {};
+    cudaEvent_t fork_ev = nullptr, join_ev[MAX_SUB] = {}, stage_ev[MAX_SUB] = {};
     int search_blocks = 0;
     int32_t* d_actions[2] = {nullptr, nullptr};
     int act_flip = 0;
@@ -70,22 +80,47 @@ namespace {
 
 int launch_env(hive_env* h, int op, const int32_t* actions, const uint8_t* mask, uint64_t seed, int max_turn,
                int auto_reset, int32_t* chosen) {
-    EnvArgs a;
-    a.recs = h->recs; a.legal = h->legal; a.count = h->count; a.status = h->status; a.planes = h->planes;
-    a.actions = actions; a.mask = mask; a.chosen = chosen; a.hop_lines = h->hop_lines;
-    a.seed = seed; a.n = h->n; a.op = op; a.max_turn = max_turn; a.auto_reset = auto_reset;
-    a.scratch = h->scratch; a.bq = h->bq;
-    const int groups = (h->n + GROUP - 1) / GROUP;
-    const int enc_blocks = (h->n + HIVE_ENCODE_WARPS - 1) / HIVE_ENCODE_WARPS;
     if (h->timing) CUDA_TRY(cudaEventRecord(h->t0, h->stream));
-    hive_analyse_kernel<<<groups, GROUP * 32, 0, h->stream>>>(a);
-    hive_flood_kernel<<<h->search_blocks, SEARCH_THREADS, 0, h->stream>>>(a);
-    hive_moves_kernel<<<h->search_blocks, SEARCH_THREADS, 0, h->stream>>>(a);
-    hive_encode_kernel<<<enc_blocks, HIVE_ENCODE_WARPS * 32, 0, h->stream>>>(a);
-    CUDA_TRY(cudaGetLastError());
+    const int S = h->n_sub;
+    // slices are multiples of GROUP games so that CTAs never straddle two slices
+    const int per = ((h->n + S - 1) / S + GROUP - 1) / GROUP * GROUP;
+    if (S > 1) CUDA_TRY(cudaEventRecord(h->fork_ev, h->stream));
+    for (int s = 0; s < S; s++) {
+        const int off = s * per;
+        const int cnt = (off + per <= h->n) ? per : h->n - off;
+        if (cnt <= 0) break;
+        cudaStream_t st = (S > 1) ? h->sub_stream[s] : h->stream;
+        EnvArgs a;
+        a.recs = h->recs + off; a.legal = h->legal + (size_t)off * LEGAL_WORDS; a.count = h->count + off;
+        a.status = h->status + off; a.planes = h->planes + (size_t)off * HIVE_PLANES_ELEMS;
+        a.actions = actions ? actions + off : nullptr; a.mask = mask ? mask + off : nullptr;
+        a.chosen = chosen ? chosen + off : nullptr; a.hop_lines = h->hop_lines;
+        a.seed = seed; a.n = cnt; a.op = op; a.max_turn = max_turn; a.auto_reset = auto_reset;
+        a.g_offset = off; a.n_total = h->n;
+        a.scratch = h->scratch + off; a.bq = h->bq[s];
+        const int groups = (cnt + GROUP - 1) / GROUP;
+        const int enc_blocks = (cnt + HIVE_ENCODE_WARPS - 1) / HIVE_ENCODE_WARPS;
+        int sblocks = (int)(((long long)cnt * N_PIECE + SEARCH_THREADS - 1) / SEARCH_THREADS);
+        if (sblocks > h->search_blocks) sblocks = h->search_blocks;
+        if (S > 1) {
+            CUDA_TRY(cudaStreamWaitEvent(st, h->fork_ev, 0));
+            // stagger: slice s starts analysing when slice s-1 has finished analysing, so that the
+            // compute-bound kernels of one slice run under the memory-bound encode of another
+            if (h->stagger && s > 0) CUDA_TRY(cudaStreamWaitEvent(st, h->stage_ev[s - 1], 0));
+        }
+        hive_analyse_kernel<<<groups, GROUP * 32, 0, st>>>(a);
+        if (S > 1 && h->stagger) CUDA_TRY(cudaEventRecord(h->stage_ev[s], st));
+        hive_flood_kernel<<<sblocks, SEARCH_THREADS, 0, st>>>(a);
+        hive_moves_kernel<<<sblocks, SEARCH_THREADS, 0, st>>>(a);
+        hive_encode_kernel<<<enc_blocks, HIVE_ENCODE_WARPS * 32, 0, st>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        if (S > 1) {
+            CUDA_TRY(cudaEventRecord(h->join_ev[s], st));
+            CUDA_TRY(cudaStreamWaitEvent(h->stream, h->join_ev[s], 0));
+        }
+        h->launches += 4;
+    }
     if (h->timing) CUDA_TRY(cudaEventRecord(h->t1, h->stream));
-    h->launches += 3;
-    h->launches++;
     return 0;
 }
 
@@ -123,10 +158,26 @@ int hive_create(int n_games, int device, void* stream, hive_env_t** out) {
     CUDA_TRY(cudaMalloc(&h->status, n * 4));
     CUDA_TRY(cudaMalloc(&h->planes, n * HIVE_PLANES_ELEMS * 2));
     CUDA_TRY(cudaMalloc(&h->scratch, n * sizeof(GameScratch)));
-    CUDA_TRY(cudaMalloc(&h->bq.counters, 8 * 4));
-    CUDA_TRY(cudaMemsetAsync(h->bq.counters, 0, 8 * 4, h->stream));
-    CUDA_TRY(cudaMalloc(&h->bq.flood, n * N_PIECE * 4));
-    for (int c = 0; c < 4; c++) CUDA_TRY(cudaMalloc(&h->bq.mv[c], n * 6 * 4));
+    {
+        const char* e = getenv("HIVE_B200_SLICES");
+        int S = e ? atoi(e) : HIVE_DEFAULT_SLICES;
+        if (S < 1) S = 1;
+        if (S > hive_env::MAX_SUB) S = hive_env::MAX_SUB;
+        while (S > 1 && n_games < S * GROUP * 8) S--;         // small batches are not worth slicing
+        h->n_sub = S;
+        const char* g = getenv("HIVE_B200_STAGGER");
+        h->stagger = g ? atoi(g) : 0;
+    }
+    CUDA_TRY(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
+    for (int s = 0; s < h->n_sub; s++) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->sub_stream[s], cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->join_ev[s], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->stage_ev[s], cudaEventDisableTiming));
+        CUDA_TRY(cudaMalloc(&h->bq[s].counters, 8 * 4));
+        CUDA_TRY(cudaMemsetAsync(h->bq[s].counters, 0, 8 * 4, h->stream));
+        CUDA_TRY(cudaMalloc(&h->bq[s].flood, n * N_PIECE * 4 / h->n_sub + GROUP * N_PIECE * 4));
+        for (int c = 0; c < 4; c++) CUDA_TRY(cudaMalloc(&h->bq[s].mv[c], n * 6 * 4 / h->n_sub + GROUP * 6 * 4));
+    }
     {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -154,8 +205,15 @@ int hive_destroy(hive_env_t* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    cudaFree(h->recs); cudaFree(h->legal); cudaFree(h->count); cudaFree(h->status); cudaFree(h->planes); cudaFree(h->scratch); cudaFree(h->bq.counters); cudaFree(h->bq.flood);
-    for (int c = 0; c < 4; c++) cudaFree(h->bq.mv[c]);
+    cudaFree(h->recs); cudaFree(h->legal); cudaFree(h->count); cudaFree(h->status); cudaFree(h->planes); cudaFree(h->scratch);
+    for (int s = 0; s < h->n_sub; s++) {
+        cudaFree(h->bq[s].counters); cudaFree(h->bq[s].flood);
+        for (int c = 0; c < 4; c++) cudaFree(h->bq[s].mv[c]);
+        if (h->sub_stream[s]) cudaStreamDestroy(h->sub_stream[s]);
+        if (h->join_ev[s]) cudaEventDestroy(h->join_ev[s]);
+        if (h->stage_ev[s]) cudaEventDestroy(h->stage_ev[s]);
+    }
+    if (h->fork_ev) cudaEventDestroy(h->fork_ev);
     cudaFree(h->d_actions[0]); cudaFree(h->d_actions[1]); cudaFree(h->d_mask); cudaFree(h->hop_lines);
     if (h->copy_done) cudaEventDestroy(h->copy_done);
     if (h->t0) cudaEventDestroy(h->t0);

@@ -34,6 +34,7 @@ struct EnvArgs {
     const uint32_t* hop_lines;
     uint64_t seed;
     int n, op, max_turn, auto_reset;
+    int g_offset, n_total;   // this launch covers games [g_offset, g_offset+n) of a batch of n_total (pointers are pre-offset)
 };
 
 // ---- kernel 1: decode the operation, apply the action, analyse the new position (warp <-> game)
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(GROUP * 32) hive_analyse_kernel(EnvArgs a) {
             } else if (n_legal_prev == 0) {
                 action = -1;
             } else {
-                const uint64_t gid = (uint64_t)g + (uint64_t)a.n * episode;
+                const uint64_t gid = (uint64_t)(g + a.g_offset) + (uint64_t)a.n_total * episode;
                 const uint64_t x = splitmix64(a.seed ^ (gid << 32) ^ (uint64_t)turn);
                 action = select_kth_action(a.legal + (size_t)g * LEGAL_WORDS, lane, (int)(x % n_legal_prev));
             }

@@ -37,6 +37,7 @@ int emu_env_run(void* recs, uint32_t* legal, int32_t* count, uint32_t* status, u
     a.recs = (GameRec*)recs; a.legal = legal; a.count = count; a.status = status; a.planes = planes;
     a.actions = actions; a.mask = mask; a.chosen = chosen; a.hop_lines = g_lines.data();
     a.seed = seed; a.n = n; a.op = op; a.max_turn = max_turn; a.auto_reset = auto_reset;
+    a.g_offset = 0; a.n_total = n;
     static std::vector<GameScratch> scratch;
     static std::vector<uint32_t> counters(8, 0), qflood, qmv[4];
     const int groups = (n + GROUP - 1) / GROUP;
