@@ -6,8 +6,9 @@ The package name carries a hyphen; import it as ``import hive_b200`` (root-level
 """
 from . import config
 from ._build import LIB_PATH, build
-from ._capi import ENV_SYMBOLS, HiveError, lib
+from ._capi import ENV_SYMBOLS, MCTS_SYMBOLS, HiveError, lib
 from .env import GamePlay, HiveBatch, host_pick_actions
+from .mcts import HivePlayer, MctsBatch
 
 __all__ = ["config", "build", "lib", "LIB_PATH", "ENV_SYMBOLS", "HiveError", "GamePlay", "HiveBatch",
-           "host_pick_actions"]
+           "host_pick_actions", "HivePlayer", "MctsBatch", "MCTS_SYMBOLS"]

@@ -14,6 +14,11 @@ ENV_SYMBOLS = [
     "hive_copy_state", "hive_dev_state", "hive_dev_legal", "hive_dev_count", "hive_dev_status", "hive_dev_planes",
     "hive_launch_count", "hive_set_timing", "hive_last_kernel_ms",
 ]
+MCTS_SYMBOLS = [
+    "mcts_create", "mcts_destroy", "mcts_set_params", "mcts_set_root_noise_host", "mcts_begin", "mcts_descend",
+    "mcts_expand", "mcts_dev_leaf_planes", "mcts_dev_leaf_policy", "mcts_dev_leaf_value", "mcts_dev_pending_mask",
+    "mcts_leaf_planes_host", "mcts_set_leaf_eval_host", "mcts_policy_host", "mcts_root_stats_host", "mcts_launch_count",
+]
 
 
 class HiveError(RuntimeError):
@@ -57,6 +62,23 @@ def lib():
     L.hive_set_timing.argtypes = [vp, i32]
     L.hive_last_kernel_ms.argtypes = [vp]
     L.hive_last_kernel_ms.restype = ctypes.c_float
+    f64p, dbl = vp, ctypes.c_double
+    L.mcts_create.argtypes = [vp, i32, i32, ctypes.POINTER(vp)]
+    L.mcts_destroy.argtypes = [vp]
+    L.mcts_set_params.argtypes = [vp, i32, i32, u64]
+    L.mcts_set_root_noise_host.argtypes = [vp, vp, i32, i32]
+    L.mcts_begin.argtypes = [vp, vp]
+    L.mcts_descend.argtypes = [vp, vp]
+    L.mcts_expand.argtypes = [vp]
+    for name in ("mcts_dev_leaf_planes", "mcts_dev_leaf_policy", "mcts_dev_leaf_value", "mcts_dev_pending_mask"):
+        getattr(L, name).argtypes = [vp]
+        getattr(L, name).restype = vp
+    L.mcts_leaf_planes_host.argtypes = [vp, vp, vp]
+    L.mcts_set_leaf_eval_host.argtypes = [vp, vp, vp]
+    L.mcts_policy_host.argtypes = [vp, vp, vp, vp]
+    L.mcts_root_stats_host.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp]
+    L.mcts_launch_count.argtypes = [vp]
+    L.mcts_launch_count.restype = ctypes.c_longlong
     _lib = L
     return L
 

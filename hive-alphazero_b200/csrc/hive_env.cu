@@ -17,6 +17,7 @@
 
 #include "../../include/hive_b200.h"
 #include "hive_env_kernel.cuh"
+#include "hive_internal.h"
 
 #ifndef HIVE_DEFAULT_SLICES
 #define HIVE_DEFAULT_SLICES 4
@@ -28,12 +29,6 @@ namespace {
 
 // ------------------------------------------------------------------------------------------
 thread_local std::string g_err;
-int fail(int code, const std::string& msg) { g_err = msg; return code; }
-#define CUDA_TRY(x)                                                                           \
-    do {                                                                                      \
-        cudaError_t e_ = (x);                                                                 \
-        if (e_ != cudaSuccess) return fail(HIVE_E_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); \
-    } while (0)
 
 // move_checker.py:249-265 on raw (non-modular) deltas, as 144 masks of 144 bits
 void build_hop_lines(std::vector<uint32_t>& t) {
@@ -50,33 +45,9 @@ void build_hop_lines(std::vector<uint32_t>& t) {
 
 }  // namespace
 
-struct hive_env {
-    int n = 0, device = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
-    bool own_stream = false;
-    GameRec* recs = nullptr;
-    uint32_t* legal = nullptr;
-    int32_t* count = nullptr;
-    uint32_t* status = nullptr;
-    uint16_t* planes = nullptr;
-    GameScratch* scratch = nullptr;
-    static constexpr int MAX_SUB = 8;
-    BatchQueues bq[MAX_SUB] = {};
-    int n_sub = 1;                  // the batch is cut into n_sub slices whose kernel chains overlap on side streams
-    int stagger = 1;
-    cudaStream_t sub_stream[MAX_SUB] = {};
-    cudaEvent_t fork_ev = nullptr, join_ev[MAX_SUB] = {}, stage_ev[MAX_SUB] = {};
-    int search_blocks = 0;
-    int32_t* d_actions[2] = {nullptr, nullptr};
-    int act_flip = 0;
-    uint8_t* d_mask = nullptr;
-    uint32_t* hop_lines = nullptr;
-    cudaEvent_t copy_done = nullptr, t0 = nullptr, t1 = nullptr;
-    bool timing = false;
-    long long launches = 0;
-};
+namespace hive {
 
-namespace {
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
 int launch_env(hive_env* h, int op, const int32_t* actions, const uint8_t* mask, uint64_t seed, int max_turn,
                int auto_reset, int32_t* chosen) {
@@ -124,8 +95,10 @@ int launch_env(hive_env* h, int op, const int32_t* actions, const uint8_t* mask,
     return 0;
 }
 
-int check(const hive_env* h) { return h && h->n > 0 ? 0 : fail(HIVE_E_HANDLE, "bad handle"); }
+}  // namespace hive
 
+namespace {
+int check(const hive_env* h) { return h && h->n > 0 ? 0 : fail(HIVE_E_HANDLE, "bad handle"); }
 }  // namespace
 
 extern "C" {

@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(GROUP * 32) hive_analyse_kernel(EnvArgs a) {
             if (action == HIVE_RESET) do_reset = true;
         } else if (a.op == OP_EVAL) {
             if (a.mask && !a.mask[g]) live = false;
+            push = (h11 >> 24) & 1u;          // "push history when this position is evaluated" (set by the search)
         } else {   // OP_RANDOM
             if (done || turn >= a.max_turn) {
                 if (!a.auto_reset) live = false; else do_reset = true;

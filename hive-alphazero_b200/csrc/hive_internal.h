@@ -1,0 +1,51 @@
+// hive_internal.h -- private to the library: the handle behind hive_env_t and the launch helper the
+// MCTS code shares with the environment code.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/hive_b200.h"
+#include "hive_core.cuh"
+
+struct hive_env {
+    int n = 0, device = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    bool own_stream = false;
+    hive::GameRec* recs = nullptr;
+    uint32_t* legal = nullptr;
+    int32_t* count = nullptr;
+    uint32_t* status = nullptr;
+    uint16_t* planes = nullptr;
+    hive::GameScratch* scratch = nullptr;
+    static constexpr int MAX_SUB = 8;
+    hive::BatchQueues bq[MAX_SUB] = {};
+    int n_sub = 1;                  // the batch is cut into n_sub slices whose kernel chains overlap on side streams
+    int stagger = 1;
+    cudaStream_t sub_stream[MAX_SUB] = {};
+    cudaEvent_t fork_ev = nullptr, join_ev[MAX_SUB] = {}, stage_ev[MAX_SUB] = {};
+    int search_blocks = 0;
+    int32_t* d_actions[2] = {nullptr, nullptr};
+    int act_flip = 0;
+    uint8_t* d_mask = nullptr;
+    uint32_t* hop_lines = nullptr;
+    cudaEvent_t copy_done = nullptr, t0 = nullptr, t1 = nullptr;
+    bool timing = false;
+    long long launches = 0;
+};
+
+
+namespace hive {
+// sets the thread-local error text and returns `code`
+int fail(int code, const std::string& msg);
+// one environment step / evaluation over the whole batch (see hive_env_kernel.cuh for `op`)
+int launch_env(hive_env* h, int op, const int32_t* actions, const uint8_t* mask, uint64_t seed, int max_turn,
+               int auto_reset, int32_t* chosen);
+}  // namespace hive
+
+#define CUDA_TRY(x)                                                                                 \
+    do {                                                                                            \
+        cudaError_t e_ = (x);                                                                       \
+        if (e_ != cudaSuccess) return hive::fail(HIVE_E_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); \
+    } while (0)

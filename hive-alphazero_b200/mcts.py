@@ -1,0 +1,226 @@
+"""Host-side mirror of the reference's search interface (woker/solo_play.py::HivePlayer) on top of
+the batched PUCT kernels (include/hive_b200.h, mcts_*).
+
+* ``MctsBatch``  -- one tree per game of a ``HiveBatch``; searches advance in waves
+                    (descend -> leaf evaluation -> expand/backup).
+* ``HivePlayer`` -- the reference's class: ``action(env) -> (move, [pi, sum_n])`` with the same
+                    hyper-parameters, the same use of ``np.random`` (Dirichlet rows for the root,
+                    the final ``np.random.choice``), driven by a ``GamePlay``.
+"""
+import ctypes
+
+import numpy as np
+
+from . import config as C
+from ._capi import check, lib
+from .env import GamePlay, HiveBatch, _bf16_to_f32
+
+
+class _LeafEnv:
+    """What expand_and_evaluate (solo_play.py:260-278) needs from an env: encode_board()."""
+
+    def __init__(self, planes_hwc):
+        self._p = planes_hwc
+
+    def encode_board(self, player="N"):
+        return self._p
+
+
+class MctsBatch:
+    def __init__(self, batch, sims, edges_per_sim=0):
+        if not isinstance(batch, HiveBatch):
+            raise TypeError("MctsBatch needs a HiveBatch")
+        self.batch, self.n, self.sims = batch, batch.n, int(sims)
+        h = ctypes.c_void_p()
+        check(lib().mcts_create(batch._h, self.sims, int(edges_per_sim), ctypes.byref(h)), "mcts_create")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().mcts_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_params(self, sims=None, max_turn=C.MAX_GAME_LENGTH, noise_seed=0x5EED):
+        sims = self.sims if sims is None else int(sims)
+        check(lib().mcts_set_params(self._h, sims, int(max_turn), int(noise_seed)), "mcts_set_params")
+        self.sims = sims
+
+    def set_root_noise(self, noise):
+        """noise[n][rows][cols] float64 (one Dirichlet row per root visit) or None = device sampling."""
+        if noise is None:
+            check(lib().mcts_set_root_noise_host(self._h, None, 0, 0), "mcts_set_root_noise_host")
+            return
+        noise = np.ascontiguousarray(noise, dtype=np.float64)
+        if noise.ndim != 3 or noise.shape[0] != self.n:
+            raise ValueError("noise must have shape (n_trees, rows, cols)")
+        check(lib().mcts_set_root_noise_host(self._h, noise.ctypes.data, noise.shape[1], noise.shape[2]),
+              "mcts_set_root_noise_host")
+
+    # ---- wave protocol
+    def begin(self, tree_mask=None):
+        m = None if tree_mask is None else np.ascontiguousarray(tree_mask, dtype=np.uint8)
+        check(lib().mcts_begin(self._h, None if m is None else m.ctypes.data), "mcts_begin")
+
+    def descend(self):
+        pending = ctypes.c_int(0)
+        check(lib().mcts_descend(self._h, ctypes.byref(pending)), "mcts_descend")
+        return pending.value
+
+    def expand(self):
+        check(lib().mcts_expand(self._h), "mcts_expand")
+
+    def leaf_planes_host(self):
+        planes = np.empty((self.n, C.STATE_FEATURES * 144), dtype=np.uint16)
+        mask = np.empty(self.n, dtype=np.uint8)
+        check(lib().mcts_leaf_planes_host(self._h, planes.ctypes.data, mask.ctypes.data), "mcts_leaf_planes_host")
+        return planes, mask
+
+    def set_leaf_eval_host(self, policy, value):
+        p = np.ascontiguousarray(policy, dtype=np.float32)
+        v = np.ascontiguousarray(value, dtype=np.float64)
+        check(lib().mcts_set_leaf_eval_host(self._h, p.ctypes.data, v.ctypes.data), "mcts_set_leaf_eval_host")
+
+    @property
+    def dev_leaf_planes(self): return lib().mcts_dev_leaf_planes(self._h)
+    @property
+    def dev_leaf_policy(self): return lib().mcts_dev_leaf_policy(self._h)
+    @property
+    def dev_leaf_value(self): return lib().mcts_dev_leaf_value(self._h)
+    @property
+    def dev_pending_mask(self): return lib().mcts_dev_pending_mask(self._h)
+    @property
+    def launches(self): return lib().mcts_launch_count(self._h)
+
+    def search_host(self, evaluate, tree_mask=None):
+        """Full search with a host evaluator ``evaluate(leaf_env) -> (p float32[1584], v float)`` called
+        once per new position (expand_and_evaluate, solo_play.py:260-278). Returns the number of waves."""
+        self.begin(tree_mask)
+        p = np.zeros((self.n, C.ACTION_SPACE), dtype=np.float32)
+        v = np.zeros(self.n, dtype=np.float64)
+        waves = 0
+        while self.descend() > 0:
+            planes, mask = self.leaf_planes_host()
+            for t in np.nonzero(mask)[0]:
+                hwc = _bf16_to_f32(planes[t]).reshape(C.STATE_FEATURES, 12, 12).transpose(1, 2, 0).astype(np.float64)
+                pt, vt = evaluate(_LeafEnv(hwc))
+                p[t] = np.asarray(pt, dtype=np.float32).reshape(-1)
+                v[t] = float(np.asarray(vt).reshape(-1)[0])
+            self.set_leaf_eval_host(p, v)
+            self.expand()
+            waves += 1
+        return waves
+
+    def search_device(self, evaluate_device, tree_mask=None):
+        """Full search with a device evaluator ``evaluate_device(planes_ptr, policy_ptr, value_ptr,
+        mask_ptr, n)`` (all device pointers) called once per wave."""
+        self.begin(tree_mask)
+        waves = 0
+        while self.descend() > 0:
+            evaluate_device(self.dev_leaf_planes, self.dev_leaf_policy, self.dev_leaf_value, self.dev_pending_mask, self.n)
+            self.expand()
+            waves += 1
+        return waves
+
+    def policy(self):
+        """(pi float64[n,1584], action int32[n], sum_n int32[n]) -- calc_policy + apply_temperature."""
+        pi = np.empty((self.n, C.ACTION_SPACE), dtype=np.float64)
+        action = np.empty(self.n, dtype=np.int32)
+        sum_n = np.empty(self.n, dtype=np.int32)
+        check(lib().mcts_policy_host(self._h, pi.ctypes.data, action.ctypes.data, sum_n.ctypes.data), "mcts_policy_host")
+        return pi, action, sum_n
+
+    def root_stats(self, t, max_edges=256):
+        a = np.zeros(max_edges, dtype=np.int32); n = np.zeros(max_edges, dtype=np.int32)
+        w = np.zeros(max_edges, dtype=np.float64); q = np.zeros(max_edges, dtype=np.float64)
+        p = np.zeros(max_edges, dtype=np.float32); info = np.zeros(6, dtype=np.int32)
+        check(lib().mcts_root_stats_host(self._h, int(t), max_edges, a.ctypes.data, n.ctypes.data, w.ctypes.data,
+                                         q.ctypes.data, p.ctypes.data, info.ctypes.data), "mcts_root_stats_host")
+        k = int(info[0])
+        return dict(action=a[:k], n=n[:k], w=w[:k], q=q[:k], p=p[:k], sum_n=int(info[1]), n_nodes=int(info[2]),
+                    sims_done=int(info[3]), error=int(info[4]), root_selects=int(info[5]))
+
+
+class HivePlayer:
+    """Drop-in for woker/solo_play.py::HivePlayer (sequential search semantics).
+
+    Set ``net`` to a callable ``planes(B,56,12,12 float32 ndarray) -> (p (B,1584), v (B,1))`` or
+    override ``expand_and_evaluate_with_net(env) -> (p, v)`` like the reference's tests do.
+    """
+
+    def __init__(self, pipes=None, reward=False):
+        self.moves = []
+        self.pipe_pool = pipes
+        self.none_queue = True
+        self.net = None
+        self.simulation_num_per_move = C.simulation_num_per_move
+        self.reward = reward
+        self.main_key_state = None
+        self.max_depth = None
+        self._mcts = None
+        self._mcts_key = None
+
+    def reset(self):
+        pass                                   # the device tree is rebuilt by every action()
+
+    def expand_and_evaluate_with_net(self, env):           # solo_play.py:249-258
+        if self.net is None:
+            raise RuntimeError("HivePlayer.net is not set")
+        planes = np.asarray(env.encode_board()).transpose(2, 0, 1)[None].astype(np.float32)
+        p, v = self.net(planes)
+        return np.asarray(p, dtype=np.float32).reshape(-1), float(np.asarray(v).reshape(-1)[0])
+
+    def expand_and_evaluate(self, env):                    # solo_play.py:260-278
+        return self.expand_and_evaluate_with_net(env)
+
+    def _tree_for(self, env):
+        key = (id(env._batch), self.simulation_num_per_move)
+        if self._mcts is None or self._mcts_key != key:
+            if self._mcts is not None:
+                self._mcts.close()
+            self._mcts = MctsBatch(env._batch, self.simulation_num_per_move)
+            self._mcts_key = key
+        return self._mcts
+
+    def action(self, env, non_queue=True):                 # solo_play.py:110-151
+        if not isinstance(env, GamePlay):
+            raise TypeError("HivePlayer.action needs a hive_b200.GamePlay")
+        self.max_depth = env.state.turn
+        self.main_key_state = env.state_key
+        m = self._tree_for(env)
+        sims = self.simulation_num_per_move
+        n_edges = max(len(env.actions()), 1)
+        # the reference draws one Dirichlet row per root visit from the global NumPy stream
+        noise = np.zeros((1, max(sims - 1, 1), max(n_edges, 1)), dtype=np.float64)
+        if len(env.actions()) > 0:
+            for r in range(sims - 1):
+                noise[0, r] = np.random.dirichlet([C.dirichlet_alpha] * n_edges)
+        m.set_root_noise(noise)
+        m.search_host(self.expand_and_evaluate)
+        pi, action, sum_n = m.policy()
+        policy, sum_all = pi[0], float(sum_n[0])
+        p = self.apply_temperature(policy, int(env.state.turn + 1) / 2)
+        my_action = int(np.random.choice(range(C.ACTION_SPACE), p=p))
+        return my_action, [list(policy), sum_all]
+
+    def apply_temperature(self, policy, turn):             # solo_play.py:337-349
+        tau = np.power(C.tau_decay_rate, turn)
+        if tau < 0.1:
+            tau = 0
+        if tau == 0:
+            action = np.argmax(policy)
+            ret = np.zeros(C.ACTION_SPACE)
+            ret[action] = 1.0
+            return ret
+        ret = np.power(policy, 1 / tau)
+        ret /= np.sum(ret)
+        return ret
+
+    def finish_game(self, z):                              # solo_play.py:376-384
+        for move in self.moves:
+            move += [z]

@@ -112,6 +112,46 @@ long long hive_launch_count(const hive_env_t* h);
 int hive_set_timing(hive_env_t* h, int on);
 float hive_last_kernel_ms(hive_env_t* h);
 
+
+/* ------------------------------------------------------------------------------------------
+ * Batched PUCT search -- HivePlayer (woker/solo_play.py:69-385), sequential mode, one tree per
+ * game of `env`.  Bit-exact visit counts given identical network outputs and root noise.
+ * A search runs in waves:
+ *     mcts_begin(m, mask);                                    // HivePlayer.reset + roots = env states
+ *     for (;;) { mcts_descend(m, &pending); if (!pending) break;   // search_my_move down to a new position
+ *                <network on mcts_dev_leaf_planes -> mcts_dev_leaf_policy / mcts_dev_leaf_value>
+ *                mcts_expand(m); }                                 // tree[state].p = p; backup of v
+ *     mcts_policy_host(m, pi, action, sum_n);                 // calc_policy + apply_temperature
+ */
+typedef struct hive_mcts hive_mcts_t;
+/* capacity for `sims` simulations per move (simulation_num_per_move, solo_play.py:23,98);
+ * edges_per_sim <= 0 picks the default edge arena (96 edges per simulation and tree). */
+int mcts_create(hive_env_t* env, int sims, int edges_per_sim, hive_mcts_t** out);
+int mcts_destroy(hive_mcts_t* m);
+int mcts_set_params(hive_mcts_t* m, int sims, int max_turn /*MAX_GAME_LENGTH*/, uint64_t noise_seed);
+/* recorded Dirichlet rows for the root (np.random.dirichlet([0.3]*n_edges), solo_play.py:323), one
+ * row per root visit: noise[n][rows][cols] doubles.  NULL switches back to on-device sampling. */
+int mcts_set_root_noise_host(hive_mcts_t* m, const double* noise, int rows, int cols);
+int mcts_begin(hive_mcts_t* m, const uint8_t* tree_mask /*host, NULL = all*/);
+int mcts_descend(hive_mcts_t* m, int* n_pending /*host, may be NULL*/);
+int mcts_expand(hive_mcts_t* m);
+/* leaf evaluation interface (device): planes bf16 [n][56][144] in, policy float [n][1584] and value
+ * double [n] out; only rows whose pending-mask byte is 1 are read. */
+void* mcts_dev_leaf_planes(hive_mcts_t* m);
+void* mcts_dev_leaf_policy(hive_mcts_t* m);
+void* mcts_dev_leaf_value(hive_mcts_t* m);
+void* mcts_dev_pending_mask(hive_mcts_t* m);
+/* the same through host buffers (expand_and_evaluate, solo_play.py:260-291) */
+int mcts_leaf_planes_host(hive_mcts_t* m, uint16_t* planes_bf16, uint8_t* pending_mask);
+int mcts_set_leaf_eval_host(hive_mcts_t* m, const float* policy, const double* value);
+/* HivePlayer.action's return: pi[n][1584] (float64 like the reference), move, sum N */
+int mcts_policy_host(hive_mcts_t* m, double* pi, int32_t* action, int32_t* sum_n);
+/* root edges of one tree in ascending action order; info[6] = n_edges, sum_n, n_nodes, sims_done,
+ * error (1 node arena, 2 edge arena, 3 depth), root_selects */
+int mcts_root_stats_host(hive_mcts_t* m, int tree, int max_edges, int32_t* action, int32_t* N, double* W, double* Q,
+                         float* P, int32_t* info);
+long long mcts_launch_count(const hive_mcts_t* m);
+
 #ifdef __cplusplus
 }
 #endif

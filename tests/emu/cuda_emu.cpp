@@ -25,7 +25,7 @@ static inline uint64_t next_rand(uint64_t& s) { s ^= s << 13; s ^= s >> 7; s ^= 
 // resolve a warp whose live lanes are all parked at the same warp-level collective
 static void resolve_warp(Block* w, int base, int kind) {
     uint32_t bal = 0, red = 0;
-    for (int l = 0; l < 32; l++) { if (w->in[base + l]) bal |= 1u << l; red |= w->in[base + l]; }
+    for (int l = 0; l < 32; l++) { if (w->in[base + l]) bal |= 1u << l; red |= (uint32_t)w->in[base + l]; }
     for (int l = 0; l < 32; l++) {
         int i = base + l;
         switch (kind) {

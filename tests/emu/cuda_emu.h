@@ -44,7 +44,8 @@ struct Block {
     int nlanes;
     int cur;
     int kind[MAX_LANES];          // collective the lane is parked at (K_NONE = runnable)
-    uint32_t in[MAX_LANES], arg[MAX_LANES], out[MAX_LANES];
+    uint64_t in[MAX_LANES], out[MAX_LANES];
+    uint32_t arg[MAX_LANES];
     bool done[MAX_LANES];
     uint64_t rng;
     long collectives;
@@ -52,13 +53,13 @@ struct Block {
 extern Block* W;
 extern thread_local dim3emu g_threadIdx, g_blockIdx, g_blockDim, g_gridDim;
 
-inline void park(int kind, uint32_t in, uint32_t arg) {
+inline void park(int kind, uint64_t in, uint32_t arg) {
     Block* w = W;
     int l = w->cur;
     w->kind[l] = kind; w->in[l] = in; w->arg[l] = arg;
     swapcontext(&w->ctx[l], &w->sched);
 }
-inline uint32_t result() { return W->out[W->cur]; }
+inline uint64_t result() { return W->out[W->cur]; }
 
 }  // namespace emu
 
@@ -68,13 +69,14 @@ inline uint32_t result() { return W->out[W->cur]; }
 #define gridDim (emu::g_gridDim)
 
 static inline void emu_check_mask(unsigned m) { if (m != 0xffffffffu) { fprintf(stderr, "emu: only full-mask collectives supported\n"); abort(); } }
-static inline int __shfl_sync(unsigned m, int v, int src) { emu_check_mask(m); emu::park(emu::K_SHFL, (uint32_t)v, (uint32_t)src & 31); return (int)emu::result(); }
-static inline uint32_t __shfl_sync(unsigned m, uint32_t v, int src) { emu_check_mask(m); emu::park(emu::K_SHFL, v, (uint32_t)src & 31); return emu::result(); }
-static inline int __shfl_xor_sync(unsigned m, int v, int x) { emu_check_mask(m); emu::park(emu::K_SHFL_XOR, (uint32_t)v, (uint32_t)x); return (int)emu::result(); }
-static inline int __shfl_up_sync(unsigned m, int v, int d) { emu_check_mask(m); emu::park(emu::K_SHFL_UP, (uint32_t)v, (uint32_t)d); return (int)emu::result(); }
-static inline unsigned __ballot_sync(unsigned m, bool p) { emu_check_mask(m); emu::park(emu::K_BALLOT, p ? 1u : 0u, 0); return emu::result(); }
-static inline unsigned __match_any_sync(unsigned m, int v) { emu_check_mask(m); emu::park(emu::K_MATCH, (uint32_t)v, 0); return emu::result(); }
-static inline unsigned __reduce_or_sync(unsigned m, unsigned v) { emu_check_mask(m); emu::park(emu::K_REDOR, v, 0); return emu::result(); }
+template <typename T> static inline uint64_t emu_bits(T v) { uint64_t b = 0; memcpy(&b, &v, sizeof(T)); return b; }
+template <typename T> static inline T emu_unbits(uint64_t b) { T v; memcpy(&v, &b, sizeof(T)); return v; }
+template <typename T> static inline T __shfl_sync(unsigned m, T v, int src) { emu_check_mask(m); emu::park(emu::K_SHFL, emu_bits(v), (uint32_t)src & 31); return emu_unbits<T>(emu::result()); }
+template <typename T> static inline T __shfl_xor_sync(unsigned m, T v, int x) { emu_check_mask(m); emu::park(emu::K_SHFL_XOR, emu_bits(v), (uint32_t)x); return emu_unbits<T>(emu::result()); }
+template <typename T> static inline T __shfl_up_sync(unsigned m, T v, int d) { emu_check_mask(m); emu::park(emu::K_SHFL_UP, emu_bits(v), (uint32_t)d); return emu_unbits<T>(emu::result()); }
+static inline unsigned __ballot_sync(unsigned m, bool p) { emu_check_mask(m); emu::park(emu::K_BALLOT, p ? 1u : 0u, 0); return (unsigned)emu::result(); }
+static inline unsigned __match_any_sync(unsigned m, int v) { emu_check_mask(m); emu::park(emu::K_MATCH, (uint32_t)v, 0); return (unsigned)emu::result(); }
+static inline unsigned __reduce_or_sync(unsigned m, unsigned v) { emu_check_mask(m); emu::park(emu::K_REDOR, v, 0); return (unsigned)emu::result(); }
 static inline void __syncwarp(unsigned m = 0xffffffffu) { emu_check_mask(m); emu::park(emu::K_SYNC, 0, 0); }
 static inline void __syncthreads() { emu::park(emu::K_BAR, 0, 0); }
 
@@ -90,6 +92,8 @@ template <typename T> static inline T __ldg(const T* p) { return *p; }
 static inline uint32_t atomicOr(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
 static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
 static inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; return o; }
+#include <math.h>
+static inline double cospi(double x) { return cos(M_PI * x); }
 
 namespace emu {
 // Run `fn(arg)` as one thread block of `nthreads` threads (multiple of 32), block index `block`.

@@ -16,12 +16,12 @@ NOOP = -2
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, f) for f in ("cuda_emu.cpp", "emu_env.cpp", "cuda_emu.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("cuda_emu.cpp", "emu_env.cpp", "emu_mcts.cpp", "cuda_emu.h")]
     srcs += [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith(".cuh")]
     newest = max(os.path.getmtime(s) for s in srcs)
     if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < newest:
         cpps = [s for s in srcs if s.startswith(_HERE) and s.endswith(".cpp")]
-        subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-o", _LIB] + cpps)
+        subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", _LIB] + cpps)
     return _LIB
 
 
@@ -35,6 +35,20 @@ def lib():
                                   ctypes.c_int, ctypes.c_int, vp, ctypes.c_uint64]
         L.emu_env_run.restype = ctypes.c_int
         L.emu_last_error.restype = ctypes.c_char_p
+        L.emu_mcts_create.restype = vp
+        L.emu_mcts_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.emu_mcts_destroy.argtypes = [vp]
+        L.emu_mcts_set_noise.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int]
+        L.emu_mcts_begin.argtypes = [vp, vp, vp, vp, vp]
+        L.emu_mcts_descend.argtypes = [vp, vp]
+        L.emu_mcts_planes.restype = vp
+        L.emu_mcts_planes.argtypes = [vp]
+        L.emu_mcts_pending_mask.restype = vp
+        L.emu_mcts_pending_mask.argtypes = [vp]
+        L.emu_mcts_set_leaf.argtypes = [vp, vp, vp]
+        L.emu_mcts_expand.argtypes = [vp]
+        L.emu_mcts_finalize.argtypes = [vp, vp, vp, vp]
+        L.emu_mcts_root.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -97,3 +111,73 @@ class EmuBatch:
         """bf16 planes -> (56,144) uint8 values (exact for the small integers involved)."""
         u = self.planes[g].astype(np.uint32) << 16
         return u.view(np.float32).reshape(56, 144).astype(np.uint8)
+
+
+def planes_bf16_to_hwc_f64(bf16_row):
+    """bf16 CHW [56*144] -> (12,12,56) float64, the array GamePlay.encode_board returns."""
+    f = (bf16_row.astype(np.uint32) << 16).view(np.float32).reshape(56, 12, 12)
+    return f.transpose(1, 2, 0).astype(np.float64)
+
+
+class EmuMcts:
+    """Host twin of hive_mcts for the emulator: same wave protocol as the C ABI."""
+
+    def __init__(self, batch, sims, edges_per_sim=96):
+        self.batch, self.n, self.sims = batch, batch.n, sims
+        self._h = lib().emu_mcts_create(self.n, sims, edges_per_sim)
+
+    def __del__(self):
+        try:
+            lib().emu_mcts_destroy(self._h)
+        except Exception:
+            pass
+
+    def set_noise(self, noise):
+        noise = np.ascontiguousarray(noise, dtype=np.float64)
+        assert noise.ndim == 3 and noise.shape[0] == self.n
+        lib().emu_mcts_set_noise(self._h, noise.ctypes.data, noise.shape[1], noise.shape[2])
+
+    def _chk(self, rc):
+        if rc:
+            raise RuntimeError("emulator: " + lib().emu_last_error().decode())
+
+    def search(self, net):
+        """net(planes_hwc_f64) -> (p float32[1584], v float).  Runs all simulations."""
+        self._chk(lib().emu_mcts_begin(self._h, self.batch.recs.ctypes.data, self.batch.legal.ctypes.data,
+                                       self.batch.count.ctypes.data, self.batch.planes.ctypes.data))
+        pending = ctypes.c_int(0)
+        p = np.zeros((self.n, 1584), dtype=np.float32)
+        v = np.zeros(self.n, dtype=np.float64)
+        waves = 0
+        while True:
+            self._chk(lib().emu_mcts_descend(self._h, ctypes.byref(pending)))
+            if pending.value == 0:
+                break
+            planes = np.ctypeslib.as_array(ctypes.cast(lib().emu_mcts_planes(self._h), ctypes.POINTER(ctypes.c_uint16)),
+                                           shape=(self.n, 56 * 144))
+            mask = np.ctypeslib.as_array(ctypes.cast(lib().emu_mcts_pending_mask(self._h), ctypes.POINTER(ctypes.c_uint8)),
+                                         shape=(self.n,))
+            for t in range(self.n):
+                if mask[t]:
+                    p[t], v[t] = net(planes_bf16_to_hwc_f64(planes[t]))
+            lib().emu_mcts_set_leaf(self._h, p.ctypes.data, v.ctypes.data)
+            self._chk(lib().emu_mcts_expand(self._h))
+            waves += 1
+        return waves
+
+    def policy(self):
+        pi = np.zeros((self.n, 1584), dtype=np.float64)
+        action = np.zeros(self.n, dtype=np.int32)
+        sum_n = np.zeros(self.n, dtype=np.int32)
+        self._chk(lib().emu_mcts_finalize(self._h, pi.ctypes.data, action.ctypes.data, sum_n.ctypes.data))
+        return pi, action, sum_n
+
+    def root_stats(self, t, max_edges=256):
+        a = np.zeros(max_edges, dtype=np.int32); n = np.zeros(max_edges, dtype=np.int32)
+        w = np.zeros(max_edges, dtype=np.float64); q = np.zeros(max_edges, dtype=np.float64)
+        p = np.zeros(max_edges, dtype=np.float32); info = np.zeros(6, dtype=np.int32)
+        lib().emu_mcts_root(self._h, t, max_edges, a.ctypes.data, n.ctypes.data, w.ctypes.data, q.ctypes.data,
+                            p.ctypes.data, info.ctypes.data)
+        k = int(info[0])
+        return dict(action=a[:k], n=n[:k], w=w[:k], q=q[:k], p=p[:k], sum_n=int(info[1]), n_nodes=int(info[2]),
+                    sims_done=int(info[3]), error=int(info[4]), root_selects=int(info[5]))

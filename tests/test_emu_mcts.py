@@ -1,0 +1,90 @@
+"""The PUCT search kernels (verbatim device source on the CPU SIMT emulator) against the
+reference's own HivePlayer results (tests/golden/mcts_cases.npz) and the Python MCTS oracle.
+Bar: per-edge N, W, Q, P equal as floats, node count, returned move and policy identical."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle.hive_oracle import OracleEnv
+from oracle.mcts_oracle import MctsOracle, hash_net
+from tests.emu.emu import EmuBatch, EmuMcts
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = np.load(os.path.join(ROOT, "tests", "golden", "mcts_cases.npz"))
+
+
+def _recorded_noise(seed, sims, k, rows=None):
+    np.random.seed(seed)
+    noise = np.zeros((1, sims, 256))
+    for r in range(sims - 1):
+        noise[0, r, :k] = np.random.dirichlet([0.3] * k)
+    return noise
+
+
+@pytest.mark.parametrize("i", range(len(G["seed"])))
+def test_oracle_matches_reference_player(i):
+    env = OracleEnv()
+    for a in G["prefix"][i][:G["n_prefix"][i]]:
+        env.move(int(a))
+    m = MctsOracle(hash_net, int(G["sims"][i]))
+    np.random.seed(int(G["seed"][i]))
+    action, policy, sum_all = m.action(env)
+    acts, n, w, q, p, sum_n, n_nodes = m.root_stats(env)
+    k = G["n_edges"][i]
+    assert acts.tolist() == G["e_action"][i][:k].tolist() and n.tolist() == G["e_n"][i][:k].tolist()
+    assert (w == G["e_w"][i][:k]).all() and (q == G["e_q"][i][:k]).all() and (p == G["e_p"][i][:k]).all()
+    assert sum_n == G["sum_n"][i] and n_nodes == G["n_nodes"][i] and action == G["action"][i]
+    assert (policy == G["policy"][i]).all() and sum_all == G["sum_all"][i]
+
+
+@pytest.mark.parametrize("i", [0, 1, 4, 7, 8, 12, 13])
+def test_kernels_match_reference_player(i):
+    b = EmuBatch(1, sched_seed=i)
+    for a in G["prefix"][i][:G["n_prefix"][i]]:
+        b.step(np.array([a], dtype=np.int32))
+    sims, k = int(G["sims"][i]), int(G["n_edges"][i])
+    m = EmuMcts(b, sims)
+    m.set_noise(_recorded_noise(int(G["seed"][i]), sims, k))
+    m.search(hash_net)
+    st = m.root_stats(0)
+    pi, action, sum_n = m.policy()
+    assert st["error"] == 0 and st["sims_done"] == sims
+    assert st["action"].tolist() == G["e_action"][i][:k].tolist() and st["n"].tolist() == G["e_n"][i][:k].tolist()
+    assert (st["w"] == G["e_w"][i][:k]).all() and (st["q"] == G["e_q"][i][:k]).all() and (st["p"] == G["e_p"][i][:k]).all()
+    assert st["sum_n"] == G["sum_n"][i] and st["n_nodes"] == G["n_nodes"][i]
+    assert action[0] == G["action"][i] and (pi[0] == G["policy"][i]).all() and sum_n[0] == G["sum_n"][i]
+
+
+def test_three_trees_in_one_batch():
+    """Independent trees in one launch (different positions, separate noise) vs the oracle."""
+    n, sims = 3, 24
+    b = EmuBatch(n, sched_seed=77)
+    envs = [OracleEnv() for _ in range(n)]
+    rng = np.random.RandomState(3)
+    for ply in range(9):
+        acts = np.zeros(n, dtype=np.int32)
+        for t, e in enumerate(envs):
+            la = e.actions()
+            acts[t] = la[rng.randint(len(la))] if (len(la) and ply < 3 + 3 * t) else -2
+            if acts[t] != -2:
+                e.move(int(acts[t]))
+        b.step(acts)
+    noise = np.zeros((n, sims, 256))
+    expect = []
+    for t, e in enumerate(envs):
+        k = len(e.actions())
+        np.random.seed(100 + t)
+        o = MctsOracle(hash_net, sims)
+        o.action(e)
+        expect.append(o.root_stats(e))
+        for r, row in enumerate(o.noise_log):
+            noise[t, r, :k] = row
+    m = EmuMcts(b, sims)
+    m.set_noise(noise)
+    m.search(hash_net)
+    for t in range(n):
+        st = m.root_stats(t)
+        acts, nn, w, q, p, sum_n, n_nodes = expect[t]
+        assert st["action"].tolist() == acts.tolist() and st["n"].tolist() == nn.tolist()
+        assert (st["w"] == w).all() and (st["p"] == p).all() and st["n_nodes"] == n_nodes
