@@ -10,5 +10,16 @@ from ._capi import ENV_SYMBOLS, MCTS_SYMBOLS, HiveError, lib
 from .env import GamePlay, HiveBatch, host_pick_actions
 from .mcts import HivePlayer, MctsBatch
 
+
+def __getattr__(name):
+    # torch-dependent parts are imported lazily so that the environment path does not need torch
+    if name in ("HiveNet", "FoldedNet", "LeafEvaluator", "host_net_callable", "device_view"):
+        from . import net
+        return getattr(net, name)
+    if name == "SelfPlayBatch":
+        from .selfplay import SelfPlayBatch
+        return SelfPlayBatch
+    raise AttributeError(name)
+
 __all__ = ["config", "build", "lib", "LIB_PATH", "ENV_SYMBOLS", "HiveError", "GamePlay", "HiveBatch",
            "host_pick_actions", "HivePlayer", "MctsBatch", "MCTS_SYMBOLS"]

@@ -1,0 +1,185 @@
+"""Policy/value network of the hot path (reference: alpha_zero/alpha_net.py:25-95, class ChessNet).
+
+* ``HiveNet``     -- fp32 torch module with the reference's architecture AND parameter names
+                     (``conv.conv1``, ``res_%i.conv1`` ... ``outblock.fc``), so a reference
+                     checkpoint ``{'state_dict': ...}`` (self_play.py:92-96) loads unchanged. It is
+                     the fp32 reference the bf16 path is checked against (tolerance 1e-2).
+* ``FoldedNet``   -- inference form: BatchNorm folded into the convolutions, bf16 weights,
+                     channels-last activations.  forward(planes) -> (p softmax fp32, v tanh fp32).
+* ``LeafEvaluator`` -- glues a FoldedNet to the device buffers of MctsBatch (zero-copy views of the
+                     library's arenas through the CUDA array interface).
+
+The 3x3 trunk convolutions are 98 % of the 6.56 GFLOP/sample; ``FoldedNet`` runs them through the
+library (cuDNN via torch) today -- DESIGN.md tracks the hand-written tcgen05 kernel that replaces
+that call.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import config as C
+
+N_RES = 19
+CH = 256
+BOARD = C.MAX_MAP_FULL                      # 12
+CELLS = BOARD * BOARD                       # 144
+POLICY_CH = 128
+
+
+class _Stem(nn.Module):                     # alpha_net.py:25-34
+    def __init__(self):
+        super().__init__()
+        self.conv1 = nn.Conv2d(C.STATE_FEATURES, CH, 3, stride=1, padding=1)
+        self.bn1 = nn.BatchNorm2d(CH)
+
+    def forward(self, s):
+        return F.relu(self.bn1(self.conv1(s)))
+
+
+class _Residual(nn.Module):                 # alpha_net.py:36-54
+    def __init__(self):
+        super().__init__()
+        self.conv1 = nn.Conv2d(CH, CH, kernel_size=3, stride=1, padding=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(CH)
+        self.conv2 = nn.Conv2d(CH, CH, kernel_size=3, stride=1, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(CH)
+
+    def forward(self, x):
+        out = F.relu(self.bn1(self.conv1(x)))
+        out = self.bn2(self.conv2(out))
+        return F.relu(out + x)
+
+
+class _Heads(nn.Module):                    # alpha_net.py:56-80
+    def __init__(self):
+        super().__init__()
+        self.conv = nn.Conv2d(CH, 1, kernel_size=1)           # value head
+        self.bn = nn.BatchNorm2d(1)
+        self.fc1 = nn.Linear(CELLS, 64)
+        self.fc2 = nn.Linear(64, 1)
+        self.conv1 = nn.Conv2d(CH, POLICY_CH, kernel_size=1)  # policy head
+        self.bn1 = nn.BatchNorm2d(POLICY_CH)
+        self.fc = nn.Linear(CELLS * POLICY_CH, C.ACTION_SPACE)
+
+    def forward(self, s):
+        v = F.relu(self.bn(self.conv(s))).view(-1, CELLS)
+        v = torch.tanh(self.fc2(F.relu(self.fc1(v))))
+        p = F.relu(self.bn1(self.conv1(s))).view(-1, CELLS * POLICY_CH)      # NCHW flatten: c*144 + h*12 + w
+        p = F.log_softmax(self.fc(p), dim=1).exp()
+        return p, v
+
+
+class HiveNet(nn.Module):
+    """fp32 reference network; state_dict-compatible with the reference's ChessNet."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv = _Stem()
+        for i in range(N_RES):
+            setattr(self, "res_%i" % i, _Residual())
+        self.outblock = _Heads()
+
+    def forward(self, s):
+        s = self.conv(s)
+        for i in range(N_RES):
+            s = getattr(self, "res_%i" % i)(s)
+        return self.outblock(s)
+
+
+def _fold(conv_w, conv_b, bn):
+    """conv followed by eval-mode BatchNorm -> one conv (w', b')."""
+    scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    w = conv_w * scale.view(-1, 1, 1, 1)
+    b = bn.bias - bn.running_mean * scale
+    if conv_b is not None:
+        b = b + conv_b * scale
+    return w, b
+
+
+class FoldedNet:
+    """BN-folded bf16 inference network built from a HiveNet (weights frozen at construction)."""
+
+    def __init__(self, net, device="cuda", dtype=torch.bfloat16):
+        net = net.eval()
+        self.device, self.dtype = torch.device(device), dtype
+        with torch.no_grad():
+            def put(w, b):
+                w = w.to(self.device, dtype).contiguous(memory_format=torch.channels_last) if w.dim() == 4 else w.to(self.device, dtype)
+                return w, b.to(self.device, dtype)
+            self.stem = put(*_fold(net.conv.conv1.weight, net.conv.conv1.bias, net.conv.bn1))
+            self.blocks = []
+            for i in range(N_RES):
+                r = getattr(net, "res_%i" % i)
+                self.blocks.append((put(*_fold(r.conv1.weight, None, r.bn1)), put(*_fold(r.conv2.weight, None, r.bn2))))
+            ob = net.outblock
+            self.vconv = put(*_fold(ob.conv.weight, ob.conv.bias, ob.bn))
+            self.pconv = put(*_fold(ob.conv1.weight, ob.conv1.bias, ob.bn1))
+            self.fc1 = (ob.fc1.weight.to(self.device, torch.float32), ob.fc1.bias.to(self.device, torch.float32))
+            self.fc2 = (ob.fc2.weight.to(self.device, torch.float32), ob.fc2.bias.to(self.device, torch.float32))
+            self.fc = (ob.fc.weight.to(self.device, dtype), ob.fc.bias.to(self.device, torch.float32))
+
+    def trunk_weights(self):
+        """[(w (256,Cin,3,3), b (256,)) ...] of the 39 folded 3x3 convolutions, in execution order."""
+        out = [self.stem]
+        for c1, c2 in self.blocks:
+            out += [c1, c2]
+        return out
+
+    @torch.no_grad()
+    def forward(self, planes):
+        """planes (B,56,12,12) bf16/fp32 on the device -> (p (B,1584) fp32, v (B,1) fp32)."""
+        x = planes.to(self.dtype).contiguous(memory_format=torch.channels_last)
+        x = F.relu(F.conv2d(x, self.stem[0], self.stem[1], padding=1))
+        for (w1, b1), (w2, b2) in self.blocks:
+            y = F.relu(F.conv2d(x, w1, b1, padding=1))
+            x = F.relu(F.conv2d(y, w2, b2, padding=1) + x)
+        v = F.relu(F.conv2d(x, self.vconv[0], self.vconv[1])).float().reshape(-1, CELLS)
+        v = torch.tanh(F.linear(F.relu(F.linear(v, *self.fc1)), *self.fc2))
+        p = F.relu(F.conv2d(x, self.pconv[0], self.pconv[1]))
+        p = p.contiguous(memory_format=torch.contiguous_format).reshape(-1, CELLS * POLICY_CH)      # NCHW flatten
+        logits = F.linear(p, self.fc[0]).float() + self.fc[1]
+        return torch.softmax(logits, dim=1), v
+
+    __call__ = forward
+
+
+class _DevArray:
+    """Zero-copy view of a library-owned device arena for torch (CUDA array interface v2)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def device_view(ptr, shape, typestr, device="cuda"):
+    return torch.as_tensor(_DevArray(ptr, shape, typestr), device=device)
+
+
+class LeafEvaluator:
+    """evaluate_device callback for MctsBatch.search_device: planes arena -> policy / value arenas."""
+
+    def __init__(self, folded, max_batch=4096):
+        self.net, self.max_batch = folded, max_batch
+        self.calls = 0
+
+    def __call__(self, planes_ptr, policy_ptr, value_ptr, mask_ptr, n):
+        dev = self.net.device
+        planes = device_view(planes_ptr, (n, C.STATE_FEATURES, BOARD, BOARD), "<u2", dev).view(torch.bfloat16)
+        policy = device_view(policy_ptr, (n, C.ACTION_SPACE), "<f4", dev)
+        value = device_view(value_ptr, (n,), "<f8", dev)
+        for s in range(0, n, self.max_batch):
+            e = min(n, s + self.max_batch)
+            p, v = self.net(planes[s:e])
+            policy[s:e].copy_(p)
+            value[s:e].copy_(v.reshape(-1).double())
+        self.calls += 1
+
+
+def host_net_callable(folded):
+    """planes (B,56,12,12) float32 ndarray -> (p, v) ndarrays; for HivePlayer.net."""
+    def run(planes):
+        x = torch.as_tensor(np.asarray(planes, dtype=np.float32), device=folded.device)
+        p, v = folded(x)
+        return p.float().cpu().numpy(), v.float().cpu().numpy()
+    return run

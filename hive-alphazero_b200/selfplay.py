@@ -1,0 +1,100 @@
+"""Batched self-play on one GPU (reference game loop: woker/self_play_with_train.py:146-219, the
+runnable statement of woker/self_play.py:116-193).
+
+Every game of a ``HiveBatch`` plays with its own tree: per move one batched search
+(``MctsBatch.search_device`` -> ``LeafEvaluator``), then the reference's opening schedule
+(turns with ``error = 0.7 - int(turn+1)/2*0.15 >= 0.1`` sample from ``(1-error)*pi[legal] +
+error*Dir(0.5)``), then one environment step.  Value targets follow the reference: +1/-1 from the
+winner's side, and -1 for BOTH sides when the game is drawn or cut at MAX_GAME_LENGTH
+(self_play_with_train.py:204-216).
+
+For the single-game, RNG-stream-exact drop-in use ``GamePlay`` + ``HivePlayer`` directly.
+"""
+import time
+
+import numpy as np
+
+from . import config as C
+from .env import HiveBatch
+from .mcts import MctsBatch
+
+
+class SelfPlayBatch:
+    def __init__(self, n_games, sims, evaluator, device=0, stream=None, seed=0, collect=False, edges_per_sim=0):
+        self.env = HiveBatch(n_games, device=device, stream=stream)
+        self.mcts = MctsBatch(self.env, sims, edges_per_sim=edges_per_sim)
+        self.mcts.set_root_noise(None)                      # Dirichlet(0.3) rows sampled on the device
+        self.mcts.set_params(sims, C.MAX_GAME_LENGTH, noise_seed=seed * 7919 + 17)
+        self.evaluator = evaluator
+        self.n, self.sims = n_games, sims
+        self.rng = np.random.RandomState(seed)
+        self.collect = collect
+        self.samples = [[] for _ in range(n_games)] if collect else None
+        self.finished = []                                  # (value_white, turn) per finished game
+        self.moves = 0
+        self.waves = 0
+        self.search_calls = 0
+
+    def _choose(self, pi, mcts_action, legal, turn):
+        """The reference's move choice for one game (self_play_with_train.py:169-183)."""
+        if len(legal) == 0:
+            return -1
+        action = int(mcts_action)
+        if turn <= 2:
+            action = int(self.rng.choice(legal))
+        error = 0.7 - int(turn + 1) / 2 * 0.15
+        if error >= 0.1:
+            p = pi[legal]
+            noise = self.rng.dirichlet([0.5] * len(legal))
+            p = (1 - error) * p + error * noise
+            p = p / p.sum()
+            action = int(self.rng.choice(legal, p=p))
+        return action
+
+    def play_moves(self, n_moves, restart_finished=True):
+        """Advance every live game by n_moves plies. Returns dict(moves, seconds, waves)."""
+        t0 = time.perf_counter()
+        moves0, waves0 = self.moves, self.waves
+        for _ in range(n_moves):
+            turn, winner, done = self.env.status()
+            over = (done != 0) | (turn >= C.MAX_GAME_LENGTH)
+            live = ~over
+            self.waves += self.mcts.search_device(self.evaluator, tree_mask=live.astype(np.uint8))
+            self.search_calls += 1
+            pi, mcts_action, _ = self.mcts.policy()
+            legal = self.env.actions()
+            planes = self.env.planes_bf16() if self.collect else None
+            actions = np.full(self.n, C.NOOP, dtype=np.int32)
+            for g in range(self.n):
+                if over[g]:
+                    self._finish(g, int(winner[g]), int(turn[g]))
+                    if restart_finished:
+                        actions[g] = -3                       # HIVE_RESET
+                    continue
+                a = self._choose(pi[g], mcts_action[g], legal[g], int(turn[g]))
+                if self.collect:
+                    self.samples[g].append((planes[g].copy(), pi[g].astype(np.float32), int(turn[g]) % 2))
+                actions[g] = a
+            self.env.step(actions)
+            self.moves += int(live.sum())
+        self.env.sync()
+        return dict(moves=self.moves - moves0, seconds=time.perf_counter() - t0, waves=self.waves - waves0)
+
+    def _finish(self, g, winner, turn):
+        value_white = 1 if winner == 1 else (-1 if winner == 2 else 0)
+        self.finished.append((value_white, turn))
+        if self.collect:
+            data = []
+            counts = {1: 0, 0: 0}
+            for _, _, side_odd in self.samples[g]:
+                counts[side_odd] += 1
+            seen = {1: 0, 0: 0}
+            for planes, pi, side_odd in self.samples[g]:       # side_odd == 1: white to move
+                seen[side_odd] += 1
+                value = value_white if side_odd == 1 else -value_white
+                if value_white == 0:
+                    value = -1                                 # draw / cut game: -1 for both sides
+                data.append((planes, pi, value, (counts[side_odd], seen[side_odd])))
+            self.samples[g] = []
+            self.finished_samples = getattr(self, "finished_samples", [])
+            self.finished_samples.extend(data)

@@ -1,0 +1,74 @@
+"""Network: BN folding is exact in fp32 (CPU); the bf16 device path agrees with the fp32 reference
+architecture within the tolerance BASELINE.json states (1e-2) (GPU)."""
+import numpy as np
+import pytest
+import torch
+
+
+def _randomize_bn(net, seed):
+    g = torch.Generator().manual_seed(seed)
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+            m.running_var.copy_(torch.rand(m.num_features, generator=g) * 0.5 + 0.75)
+            m.weight.data.copy_(torch.rand(m.num_features, generator=g) * 0.5 + 0.75)
+            m.bias.data.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+
+
+def test_state_dict_names_match_reference_layout():
+    import hive_b200
+    net = hive_b200.HiveNet()
+    keys = set(net.state_dict().keys())
+    for k in ("conv.conv1.weight", "conv.conv1.bias", "conv.bn1.running_mean", "res_0.conv1.weight", "res_18.bn2.weight",
+              "outblock.conv.weight", "outblock.fc1.weight", "outblock.fc2.bias", "outblock.conv1.weight", "outblock.fc.weight"):
+        assert k in keys
+    assert net.outblock.fc.weight.shape == (1584, 18432)
+    assert sum(p.numel() for p in net.parameters()) == 51803188
+
+
+def test_bn_folding_is_exact_in_fp32_cpu():
+    import hive_b200
+    torch.manual_seed(0)
+    net = hive_b200.HiveNet().eval()
+    _randomize_bn(net, 1)
+    folded = hive_b200.FoldedNet(net, device="cpu", dtype=torch.float32)
+    x = (torch.rand(2, 56, 12, 12) < 0.1).float()
+    with torch.no_grad():
+        p0, v0 = net(x)
+    p1, v1 = folded(x)
+    assert torch.allclose(p0, p1, atol=2e-6, rtol=1e-4) and torch.allclose(v0, v1, atol=1e-5)
+    assert abs(float(p1.sum(1)[0]) - 1.0) < 1e-5
+
+
+@pytest.mark.gpu
+def test_bf16_device_path_within_1e2_of_fp32_reference():
+    import hive_b200
+    torch.manual_seed(0)
+    net = hive_b200.HiveNet().eval()
+    _randomize_bn(net, 2)
+    b = hive_b200.HiveBatch(64)
+    for _ in range(20):
+        b.step_random(5, 55, True)
+    planes = torch.from_numpy(b.planes().copy())                          # real positions as input
+    with torch.no_grad():
+        p_ref, v_ref = net.cuda()(planes.cuda())
+    folded = hive_b200.FoldedNet(net, device="cuda")
+    p, v = folded(planes.cuda())
+    assert float((p - p_ref).abs().max()) <= 1e-2
+    assert float((v - v_ref).abs().max()) <= 1e-2
+    assert torch.allclose(p.sum(1), torch.ones(64, device="cuda"), atol=1e-3)
+
+
+@pytest.mark.gpu
+def test_selfplay_batch_smoke():
+    import hive_b200
+    torch.manual_seed(0)
+    folded = hive_b200.FoldedNet(hive_b200.HiveNet().eval(), device="cuda")
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        sp = hive_b200.SelfPlayBatch(32, 8, hive_b200.LeafEvaluator(folded), stream=stream.cuda_stream, seed=3, collect=True)
+        r = sp.play_moves(6)
+    assert r["moves"] == 32 * 6 and r["waves"] >= 6 * 7
+    turn, _, _ = sp.env.status()
+    assert (turn == 7).all()
+    assert all(len(s) == 6 for s in sp.samples)
