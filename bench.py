@@ -45,6 +45,10 @@ def parse():
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--max-turn", type=int, default=55)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-selfplay", action="store_true", help="skip the self-play (configs[2]) side measurement")
+    ap.add_argument("--selfplay-games", type=int, default=2048)
+    ap.add_argument("--selfplay-sims", type=int, default=50)
+    ap.add_argument("--selfplay-moves", type=int, default=2)
     return ap.parse_args()
 
 
@@ -174,6 +178,50 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_selfplay(args, hive_b200, torch, dist, rank, world, local_rank, allsum, allmax, barrier):
+    """BASELINE configs[2]: AlphaZero self-play, 50 sims/move, random-init net, 2,048 concurrent games
+    per GPU.  Reports moves/s and sims/s (whole job) and the tensor-pipe utilisation they imply."""
+    import numpy as np
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        tf_peak, tf_src = float(peaks["bf16_tflops_sustained"]), "measured sustained (MEASURED_PEAKS.json)"
+    except Exception:
+        tf_peak, tf_src = 1400.0, "fallback (B200_PROFILING.md ~1.4 PFLOP/s sustained)"
+    torch.manual_seed(0)
+    net = hive_b200.HiveNet().eval().cuda()
+    bcast = 0
+    if dist is not None:
+        from importlib import import_module
+        par = import_module("hive-alphazero_b200.parallel")
+        bcast = par.broadcast_weights(net, src=0)              # NCCL: weights from rank 0
+    folded = hive_b200.FoldedNet(net, device="cuda")
+    stream = torch.cuda.Stream()
+    n, sims = args.selfplay_games, args.selfplay_sims
+    with torch.cuda.stream(stream):
+        sp = hive_b200.SelfPlayBatch(n, sims, hive_b200.LeafEvaluator(folded), device=local_rank,
+                                     stream=stream.cuda_stream, seed=args.seed + rank)
+        sp.play_moves(1)                                       # warm-up move (cuDNN autotune, allocations)
+        barrier()
+        torch.cuda.synchronize()
+        r = sp.play_moves(args.selfplay_moves)
+        torch.cuda.synchronize()
+    barrier()
+    gathered = None
+    if dist is not None:
+        par_rows = torch.from_numpy(np.packbits((sp.env.planes_bf16() != 0).reshape(n, -1), axis=1)[:, :991].copy())
+        gathered = int(par.allgather_samples(par_rows, device="cuda").shape[0])     # NCCL: sample all-gather
+    secs = allmax(r["seconds"])
+    moves = allsum(float(r["moves"]))
+    sims_per_s = moves * sims / secs
+    return {"workload": "configs[2]: AlphaZero self-play, %d sims/move, model_hive net random-init, %d concurrent games per GPU"
+                        % (sims, n),
+            "moves_per_s": moves / secs, "sims_per_s": sims_per_s, "moves": int(moves), "seconds": secs,
+            "waves": int(r["waves"]), "tensor_util": sims_per_s * 6.56e9 / (tf_peak * 1e12 * world),
+            "tensor_peak_tflops": tf_peak, "tensor_peak_source": tf_src,
+            "net": "BN-folded bf16, 3x3 trunk through cuDNN (library) -- hand-written tcgen05 kernel pending",
+            "weights_broadcast_bytes": int(bcast), "samples_allgathered": gathered}
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -299,6 +347,11 @@ def main():
                "sample": "%d full random games (same counter-based policy, from reset to terminal/turn %d) = "
                          "%d env steps in %.1f s on %d threads" % (games, args.max_turn, steps_cpu, dt_cpu, threads)}
 
+    # ------------------------------------------------------------------ self-play side measurement
+    selfplay = None
+    if not args.no_selfplay:
+        selfplay = run_selfplay(args, hive_b200, torch, dist, rank, world, local_rank, allsum, allmax, barrier)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -310,7 +363,7 @@ def main():
                        "cache": "per-GPU working set %.0f MB (state+legal+planes) > 126 MB L2: inputs larger than L2"
                                 % (n * (384 + 200 + 8 + 16128) / 1e6)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks,
+            "clocks": clocks, "selfplay": selfplay,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
