@@ -1,0 +1,243 @@
+// hive_conv_kernel.cuh -- 3x3 convolution (pad 1) over 12x12 boards as an implicit GEMM on the
+// 5th-generation tensor cores (tcgen05 + TMEM), bf16 in / fp32 accumulate / bf16 out, with the
+// folded-BatchNorm bias, the residual add and the ReLU fused into the epilogue.
+// Reference op: alpha_zero/alpha_net.py:29-54 (ConvBlock / ResBlock), 98 % of the network's FLOPs.
+//
+// GEMM view per CTA:  D[128 out-channels][160 pixel slots] += W[128][64 in-ch] * X[160][64 in-ch]^T
+//   * X is the zero-padded board placed ONCE in shared memory by a 5-D TMA box {8 ch, 13, 15, 8
+//     ch-groups, 1 board} starting at pixel (-1,-1) whose out-of-range pixels are zero-filled: rows of
+//     13 slots = one left pad + 12 pixels (the right pad of a row is the left pad of the next one).
+//     The nine filter taps are nine VIEWS of that tile: the K-major no-swizzle operand layout
+//     [ch-group][slot][8 ch] makes "shift by (dy,dx)" a start-address offset of (13*dy+dx)*16 bytes in
+//     the shared-memory descriptor.  Output slot n = 13*y + x; slots with x == 12 (and n >= 156) are
+//     padding columns of D that are never read back (144 of 160 columns are useful).
+//   * W tiles are pre-packed on the host in the operand layout [k-group 8][128 rows][8 ch] (16 KB per
+//     tap and 64-channel chunk) and streamed with 1-D bulk copies.
+//   * CONV_BOARDS_PER_PASS boards share every weight tile (one accumulator each in TMEM); with one board
+//     per pass two CTAs are resident per SM (256 TMEM columns each) so that the epilogue of one
+//     overlaps the MMAs of the other.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocation), warps 2..5 = epilogue.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "umma.cuh"
+
+namespace hive {
+
+constexpr int CONV_OC_TILE = 128;                 // UMMA M
+constexpr int CONV_N = 160;                       // UMMA N (12 rows x 13 slots = 156, rounded to 16)
+constexpr int CONV_PADW = 13;
+constexpr int CONV_PADH = 15;
+constexpr int CONV_PLANE_BYTES = CONV_PADH * CONV_PADW * 16;    // one 8-channel group of a padded board = 3,120 B
+constexpr int CONV_BOARD_BYTES = 8 * CONV_PLANE_BYTES;          // 64 channels = 24,960 B (195 x 128)
+constexpr int CONV_A_BYTES = 8 * CONV_OC_TILE * 16;             // 16,384 B
+#ifndef CONV_BOARDS_PER_PASS
+#define CONV_BOARDS_PER_PASS 1
+#endif
+constexpr int CONV_BOARDS = CONV_BOARDS_PER_PASS;  // boards per weight pass (accumulators in TMEM)
+constexpr int CONV_A_STAGES = CONV_BOARDS == 1 ? 3 : 4;
+constexpr int CONV_B_STAGES = 2;
+constexpr int CONV_CTAS_PER_SM = CONV_BOARDS == 1 ? 2 : 1;   // 1-board CTAs run two per SM: one's epilogue hides under the other's MMAs
+constexpr int CONV_TMEM_COLS = CONV_BOARDS == 1 ? 256 : 512;
+constexpr int CONV_THREADS = 192;
+constexpr int CONV_TAIL_PAD = 0;                  // slot 159 + shift 28 = row 187 < 195: views never leave the tile
+constexpr int CONV_STAGE_STRIDE = 36;             // floats per staging row (32 + 4: keeps 16-byte alignment, spreads banks)
+constexpr int CONV_SMEM_BYTES = CONV_A_STAGES * CONV_A_BYTES + CONV_B_STAGES * CONV_BOARDS * CONV_BOARD_BYTES + CONV_TAIL_PAD +
+                                4 * 16 * CONV_STAGE_STRIDE * 4 + 1024;
+
+struct ConvArgs {
+    const uint8_t* weights;        // [2 halves][9 taps][n_chunks][16 KB] packed operand tiles of this layer
+    const float* bias;             // [256]
+    const __nv_bfloat16* __restrict__ residual; // [B][144][256] or null (never aliases `out`)
+    __nv_bfloat16* __restrict__ out;            // [B][144][256]
+    int n_boards, n_chunks, relu;  // n_chunks = input channels / 64
+};
+
+__device__ __forceinline__ void bulk_load(void* smem, const void* gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(umma::smem_u32(smem)),
+                 "l"(gmem), "r"(bytes), "r"(umma::smem_u32(bar))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(CONV_THREADS, CONV_CTAS_PER_SM) hive_conv3x3_kernel(const __grid_constant__ CUtensorMap in_map, ConvArgs a) {
+    using namespace umma;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + CONV_A_STAGES * CONV_A_BYTES;
+    float* sStage = reinterpret_cast<float*>(sB + CONV_B_STAGES * CONV_BOARDS * CONV_BOARD_BYTES + CONV_TAIL_PAD);   // [4 warps][16][36]
+    __shared__ uint64_t a_full[CONV_A_STAGES], a_empty[CONV_A_STAGES], b_full[CONV_B_STAGES], b_empty[CONV_B_STAGES];
+    __shared__ uint64_t acc_full, acc_empty;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int i = 0; i < CONV_A_STAGES; i++) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < CONV_B_STAGES; i++) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        mbar_init(&acc_full, 1); mbar_init(&acc_empty, 4);
+        mbar_fence_init();
+        tma_prefetch_desc(&in_map);
+    }
+    if (warp == 1) tmem_alloc(&tmem_base, CONV_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base;
+
+    const int n_pairs = (a.n_boards + CONV_BOARDS - 1) / CONV_BOARDS;
+    const int n_items = 2 * n_pairs;                         // (out-channel half, board pair)
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ producer
+        if (lane == 0) {
+            int as = 0, aph = 0, bs = 0, bph = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int half = item & 1, pair = item >> 1;
+                const uint8_t* wbase = a.weights + (size_t)half * 9 * a.n_chunks * CONV_A_BYTES;
+                for (int c = 0; c < a.n_chunks; c++) {
+                    mbar_wait(&b_empty[bs], bph ^ 1);
+                    mbar_expect_tx(&b_full[bs], CONV_BOARDS * CONV_BOARD_BYTES);
+                    for (int j = 0; j < CONV_BOARDS; j++) {
+                        int b = pair * CONV_BOARDS + j;
+                        if (b >= a.n_boards) b = a.n_boards - 1;          // odd tail: reload the last board (result discarded)
+                        tma_load_5d(sB + (bs * CONV_BOARDS + j) * CONV_BOARD_BYTES, &in_map, &b_full[bs], 0, -1, -1, c * 8, b);
+                    }
+                    if (++bs == CONV_B_STAGES) { bs = 0; bph ^= 1; }
+                    for (int t = 0; t < 9; t++) {
+                        mbar_wait(&a_empty[as], aph ^ 1);
+                        mbar_expect_tx(&a_full[as], CONV_A_BYTES);
+                        bulk_load(sA + as * CONV_A_BYTES, wbase + (size_t)(t * a.n_chunks + c) * CONV_A_BYTES, CONV_A_BYTES, &a_full[as]);
+                        if (++as == CONV_A_STAGES) { as = 0; aph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = idesc_bf16(CONV_OC_TILE, CONV_N);
+            int as = 0, aph = 0, bs = 0, bph = 0, accph = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                mbar_wait(&acc_empty, accph ^ 1);
+                tc_fence_after();
+                for (int c = 0; c < a.n_chunks; c++) {
+                    mbar_wait(&b_full[bs], bph);
+                    for (int t = 0; t < 9; t++) {
+                        mbar_wait(&a_full[as], aph);
+                        tc_fence_after();
+                        const uint32_t shift = (uint32_t)((t / 3) * CONV_PADW + (t % 3)) * 16;
+                        const uint32_t a_addr = smem_u32(sA + as * CONV_A_BYTES);
+#pragma unroll
+                        for (int j = 0; j < CONV_BOARDS; j++) {
+                            const uint32_t b_addr = smem_u32(sB + (bs * CONV_BOARDS + j) * CONV_BOARD_BYTES) + shift;
+#pragma unroll
+                            for (int ks = 0; ks < 4; ks++) {
+                                const uint64_t ad = smem_desc(a_addr + 2 * ks * (CONV_OC_TILE * 16), CONV_OC_TILE * 16, 128, 0);
+                                const uint64_t bd = smem_desc(b_addr + 2 * ks * CONV_PLANE_BYTES, CONV_PLANE_BYTES, 128, 0);
+                                mma_bf16(tmem + j * 256, ad, bd, idesc, (c | t | ks) != 0);
+                            }
+                        }
+                        mma_commit(&a_empty[as]);                      // weight stage free when these MMAs retire
+                        if (++as == CONV_A_STAGES) { as = 0; aph ^= 1; }
+                    }
+                    mma_commit(&b_empty[bs]);
+                    if (++bs == CONV_B_STAGES) { bs = 0; bph ^= 1; }
+                }
+                mma_commit(&acc_full);
+                accph ^= 1;
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue (warps 2..5)
+        // TMEM -> registers (thread = out-channel row, 16 pixel slots at a time) -> +bias -> shared staging
+        // [slot][32 ch] -> 16-byte vectors (thread = 8 channels of one slot) -> +residual, ReLU -> bf16 NHWC.
+        const int q = warp & 3;                                    // TMEM lane quarter this warp may read
+        float* stage = sStage + q * 16 * CONV_STAGE_STRIDE;
+        const int sl = lane >> 2, ch8 = (lane & 3) * 8;            // phase-2 role: slots sl and sl+8, channels ch8..ch8+7
+        constexpr int G = CONV_N / 16;
+        constexpr int PF = 4;                                      // residual prefetch distance (groups)
+        int accph = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int half = item & 1, pair = item >> 1;
+            const int oc0 = half * CONV_OC_TILE + q * 32;
+            const float bias = a.bias[oc0 + lane];
+            mbar_wait(&acc_full, accph);
+            accph ^= 1;
+            tc_fence_after();
+            for (int j = 0; j < CONV_BOARDS; j++) {
+                const int b = pair * CONV_BOARDS + j;
+                if (b >= a.n_boards) break;
+                const size_t bbase = (size_t)b * 144 * 256 + oc0 + ch8;
+                // element offset of (group g, k-th slot of this lane) or -1 for a padding slot
+                auto slot_off = [&](int g, int k) -> long long {
+                    const int n = g * 16 + sl + 8 * k, y = n / CONV_PADW, x = n - y * CONV_PADW;
+                    return (x < 12 && y < 12) ? (long long)(bbase + (size_t)(y * 12 + x) * 256) : -1;
+                };
+                uint4 rq[PF][2];
+                if (a.residual) {
+#pragma unroll
+                    for (int g = 0; g < PF; g++)
+#pragma unroll
+                        for (int k = 0; k < 2; k++) {
+                            const long long o = slot_off(g, k);
+                            rq[g][k] = o >= 0 ? *reinterpret_cast<const uint4*>(a.residual + o) : make_uint4(0u, 0u, 0u, 0u);
+                        }
+                }
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    uint32_t v[16];
+                    tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + j * 256 + g * 16, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; i++) stage[i * CONV_STAGE_STRIDE + lane] = __uint_as_float(v[i]) + bias;
+                    __syncwarp();
+#pragma unroll
+                    for (int k = 0; k < 2; k++) {
+                        const long long o = slot_off(g, k);
+                        const float4 f0 = *reinterpret_cast<const float4*>(stage + (sl + 8 * k) * CONV_STAGE_STRIDE + ch8);
+                        const float4 f1 = *reinterpret_cast<const float4*>(stage + (sl + 8 * k) * CONV_STAGE_STRIDE + ch8 + 4);
+                        float r[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+                        if (a.residual) {
+                            const uint4 rv = rq[g % PF][k];
+                            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                            for (int e = 0; e < 4; e++) {
+                                r[2 * e] += __uint_as_float(rw[e] << 16);
+                                r[2 * e + 1] += __uint_as_float(rw[e] & 0xFFFF0000u);
+                            }
+                        }
+                        if (a.relu) {
+#pragma unroll
+                            for (int e = 0; e < 8; e++) r[e] = fmaxf(r[e], 0.f);
+                        }
+                        if (o >= 0) {
+                            uint4 pk;
+                            __nv_bfloat162 h;
+                            h = __floats2bfloat162_rn(r[0], r[1]); pk.x = *reinterpret_cast<uint32_t*>(&h);
+                            h = __floats2bfloat162_rn(r[2], r[3]); pk.y = *reinterpret_cast<uint32_t*>(&h);
+                            h = __floats2bfloat162_rn(r[4], r[5]); pk.z = *reinterpret_cast<uint32_t*>(&h);
+                            h = __floats2bfloat162_rn(r[6], r[7]); pk.w = *reinterpret_cast<uint32_t*>(&h);
+                            *reinterpret_cast<uint4*>(a.out + o) = pk;
+                        }
+                    }
+                    if (a.residual && g + PF < G) {                 // refill the slot just consumed
+#pragma unroll
+                        for (int k = 0; k < 2; k++) {
+                            const long long o = slot_off(g + PF, k);
+                            rq[g % PF][k] = o >= 0 ? *reinterpret_cast<const uint4*>(a.residual + o) : make_uint4(0u, 0u, 0u, 0u);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, CONV_TMEM_COLS);
+}
+
+}  // namespace hive
