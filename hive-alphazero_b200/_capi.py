@@ -14,6 +14,7 @@ ENV_SYMBOLS = [
     "hive_copy_state", "hive_dev_state", "hive_dev_legal", "hive_dev_count", "hive_dev_status", "hive_dev_planes",
     "hive_launch_count", "hive_set_timing", "hive_last_kernel_ms",
 ]
+NET_SYMBOLS = ["net_create", "net_destroy", "net_load_conv_host", "net_trunk_forward", "net_launch_count"]
 MCTS_SYMBOLS = [
     "mcts_create", "mcts_destroy", "mcts_set_params", "mcts_set_root_noise_host", "mcts_begin", "mcts_descend",
     "mcts_expand", "mcts_dev_leaf_planes", "mcts_dev_leaf_policy", "mcts_dev_leaf_value", "mcts_dev_pending_mask",
@@ -79,6 +80,12 @@ def lib():
     L.mcts_root_stats_host.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp]
     L.mcts_launch_count.argtypes = [vp]
     L.mcts_launch_count.restype = ctypes.c_longlong
+    L.net_create.argtypes = [i32, vp, i32, ctypes.POINTER(vp)]
+    L.net_destroy.argtypes = [vp]
+    L.net_load_conv_host.argtypes = [vp, i32, vp, vp, i32]
+    L.net_trunk_forward.argtypes = [vp, vp, i32, ctypes.POINTER(vp)]
+    L.net_launch_count.argtypes = [vp]
+    L.net_launch_count.restype = ctypes.c_longlong
     _lib = L
     return L
 

@@ -32,18 +32,20 @@ constexpr int CONV_PLANE_BYTES = CONV_PADH * CONV_PADW * 16;    // one 8-channel
 constexpr int CONV_BOARD_BYTES = 8 * CONV_PLANE_BYTES;          // 64 channels = 24,960 B (195 x 128)
 constexpr int CONV_A_BYTES = 8 * CONV_OC_TILE * 16;             // 16,384 B
 #ifndef CONV_BOARDS_PER_PASS
-#define CONV_BOARDS_PER_PASS 1
+#define CONV_BOARDS_PER_PASS 2
 #endif
 constexpr int CONV_BOARDS = CONV_BOARDS_PER_PASS;  // boards per weight pass (accumulators in TMEM)
 constexpr int CONV_A_STAGES = CONV_BOARDS == 1 ? 3 : 4;
 constexpr int CONV_B_STAGES = 2;
 constexpr int CONV_CTAS_PER_SM = CONV_BOARDS == 1 ? 2 : 1;   // 1-board CTAs run two per SM: one's epilogue hides under the other's MMAs
 constexpr int CONV_TMEM_COLS = CONV_BOARDS == 1 ? 256 : 512;
-constexpr int CONV_THREADS = 192;
+constexpr int CONV_SLOTS = CONV_BOARDS == 1 ? 1 : 3;          // accumulator slots of CONV_N columns, used round-robin
+constexpr int CONV_EPI_WARPS = CONV_BOARDS == 1 ? 4 : 8;      // epilogue warps (multiple of 4: one per TMEM lane quarter)
+constexpr int CONV_THREADS = 64 + 32 * CONV_EPI_WARPS;
 constexpr int CONV_TAIL_PAD = 0;                  // slot 159 + shift 28 = row 187 < 195: views never leave the tile
 constexpr int CONV_STAGE_STRIDE = 36;             // floats per staging row (32 + 4: keeps 16-byte alignment, spreads banks)
 constexpr int CONV_SMEM_BYTES = CONV_A_STAGES * CONV_A_BYTES + CONV_B_STAGES * CONV_BOARDS * CONV_BOARD_BYTES + CONV_TAIL_PAD +
-                                4 * 16 * CONV_STAGE_STRIDE * 4 + 1024;
+                                CONV_EPI_WARPS * 16 * CONV_STAGE_STRIDE * 4 + 1024;
 
 struct ConvArgs {
     const uint8_t* weights;        // [2 halves][9 taps][n_chunks][16 KB] packed operand tiles of this layer
@@ -67,14 +69,14 @@ __global__ void __launch_bounds__(CONV_THREADS, CONV_CTAS_PER_SM) hive_conv3x3_k
     uint8_t* sB = smem + CONV_A_STAGES * CONV_A_BYTES;
     float* sStage = reinterpret_cast<float*>(sB + CONV_B_STAGES * CONV_BOARDS * CONV_BOARD_BYTES + CONV_TAIL_PAD);   // [4 warps][16][36]
     __shared__ uint64_t a_full[CONV_A_STAGES], a_empty[CONV_A_STAGES], b_full[CONV_B_STAGES], b_empty[CONV_B_STAGES];
-    __shared__ uint64_t acc_full, acc_empty;
+    __shared__ uint64_t acc_full[CONV_SLOTS], acc_empty[CONV_SLOTS];
     __shared__ uint32_t tmem_base;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
         for (int i = 0; i < CONV_A_STAGES; i++) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < CONV_B_STAGES; i++) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        mbar_init(&acc_full, 1); mbar_init(&acc_empty, 4);
+        for (int i = 0; i < CONV_SLOTS; i++) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], CONV_EPI_WARPS); }
         mbar_fence_init();
         tma_prefetch_desc(&in_map);
     }
@@ -116,9 +118,17 @@ __global__ void __launch_bounds__(CONV_THREADS, CONV_CTAS_PER_SM) hive_conv3x3_k
         // ------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             const uint32_t idesc = idesc_bf16(CONV_OC_TILE, CONV_N);
-            int as = 0, aph = 0, bs = 0, bph = 0, accph = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                mbar_wait(&acc_empty, accph ^ 1);
+            int as = 0, aph = 0, bs = 0, bph = 0;
+            uint32_t empty_ph = 0;                                     // bit s: parity of the next wait on acc_empty[s]
+            int k = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, k++) {
+                int slot[CONV_BOARDS];
+#pragma unroll
+                for (int j = 0; j < CONV_BOARDS; j++) {
+                    slot[j] = (CONV_BOARDS * k + j) % CONV_SLOTS;
+                    mbar_wait(&acc_empty[slot[j]], ((empty_ph >> slot[j]) & 1u) ^ 1u);
+                    empty_ph ^= 1u << slot[j];
+                }
                 tc_fence_after();
                 for (int c = 0; c < a.n_chunks; c++) {
                     mbar_wait(&b_full[bs], bph);
@@ -134,7 +144,7 @@ __global__ void __launch_bounds__(CONV_THREADS, CONV_CTAS_PER_SM) hive_conv3x3_k
                             for (int ks = 0; ks < 4; ks++) {
                                 const uint64_t ad = smem_desc(a_addr + 2 * ks * (CONV_OC_TILE * 16), CONV_OC_TILE * 16, 128, 0);
                                 const uint64_t bd = smem_desc(b_addr + 2 * ks * CONV_PLANE_BYTES, CONV_PLANE_BYTES, 128, 0);
-                                mma_bf16(tmem + j * 256, ad, bd, idesc, (c | t | ks) != 0);
+                                mma_bf16(tmem + slot[j] * CONV_N, ad, bd, idesc, (c | t | ks) != 0);
                             }
                         }
                         mma_commit(&a_empty[as]);                      // weight stage free when these MMAs retire
@@ -143,8 +153,8 @@ __global__ void __launch_bounds__(CONV_THREADS, CONV_CTAS_PER_SM) hive_conv3x3_k
                     mma_commit(&b_empty[bs]);
                     if (++bs == CONV_B_STAGES) { bs = 0; bph ^= 1; }
                 }
-                mma_commit(&acc_full);
-                accph ^= 1;
+#pragma unroll
+                for (int j = 0; j < CONV_BOARDS; j++) mma_commit(&acc_full[slot[j]]);
             }
         }
     } else {
@@ -152,25 +162,31 @@ __global__ void __launch_bounds__(CONV_THREADS, CONV_CTAS_PER_SM) hive_conv3x3_k
         // TMEM -> registers (thread = out-channel row, 16 pixel slots at a time) -> +bias -> shared staging
         // [slot][32 ch] -> 16-byte vectors (thread = 8 channels of one slot) -> +residual, ReLU -> bf16 NHWC.
         const int q = warp & 3;                                    // TMEM lane quarter this warp may read
-        float* stage = sStage + q * 16 * CONV_STAGE_STRIDE;
+        const int ew = warp - 2;                                   // epilogue warp index 0..CONV_EPI_WARPS-1
+        constexpr int SETS = CONV_EPI_WARPS / 4;                   // warp sets sharing a board: each takes G/SETS column groups
+        const int set = ew >> 2;
+        float* stage = sStage + ew * 16 * CONV_STAGE_STRIDE;
         const int sl = lane >> 2, ch8 = (lane & 3) * 8;            // phase-2 role: slots sl and sl+8, channels ch8..ch8+7
-        constexpr int G = CONV_N / 16;
-        constexpr int PF = 4;                                      // residual prefetch distance (groups)
-        int accph = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        constexpr int G = CONV_N / 16 / SETS;                      // column groups per warp
+        constexpr int PF = 4 < G ? 4 : G;                          // residual prefetch distance (groups)
+        uint32_t full_ph = 0;
+        int it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
             const int half = item & 1, pair = item >> 1;
             const int oc0 = half * CONV_OC_TILE + q * 32;
             const float bias = a.bias[oc0 + lane];
-            mbar_wait(&acc_full, accph);
-            accph ^= 1;
-            tc_fence_after();
             for (int j = 0; j < CONV_BOARDS; j++) {
+                const int slot = (CONV_BOARDS * it + j) % CONV_SLOTS;
+                mbar_wait(&acc_full[slot], (full_ph >> slot) & 1u);
+                full_ph ^= 1u << slot;
+                tc_fence_after();
                 const int b = pair * CONV_BOARDS + j;
-                if (b >= a.n_boards) break;
+                const int g0 = set * G;                                // first column group of this warp
+                if (b < a.n_boards) {
                 const size_t bbase = (size_t)b * 144 * 256 + oc0 + ch8;
                 // element offset of (group g, k-th slot of this lane) or -1 for a padding slot
-                auto slot_off = [&](int g, int k) -> long long {
-                    const int n = g * 16 + sl + 8 * k, y = n / CONV_PADW, x = n - y * CONV_PADW;
+                auto slot_off = [&](int g, int k) -> long long {      // g counts from this warp's first group
+                    const int n = (g0 + g) * 16 + sl + 8 * k, y = n / CONV_PADW, x = n - y * CONV_PADW;
                     return (x < 12 && y < 12) ? (long long)(bbase + (size_t)(y * 12 + x) * 256) : -1;
                 };
                 uint4 rq[PF][2];
@@ -186,7 +202,7 @@ __global__ void __launch_bounds__(CONV_THREADS, CONV_CTAS_PER_SM) hive_conv3x3_k
 #pragma unroll
                 for (int g = 0; g < G; g++) {
                     uint32_t v[16];
-                    tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + j * 256 + g * 16, v);
+                    tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + slot * CONV_N + (g0 + g) * 16, v);
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 16; i++) stage[i * CONV_STAGE_STRIDE + lane] = __uint_as_float(v[i]) + bias;
@@ -229,10 +245,12 @@ __global__ void __launch_bounds__(CONV_THREADS, CONV_CTAS_PER_SM) hive_conv3x3_k
                     }
                     __syncwarp();
                 }
+                }
+                // this board's accumulator is drained: hand its TMEM slot back to the MMA issuer
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[slot]);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty);
         }
     }
     tc_fence_before();

@@ -9,10 +9,14 @@
 * ``LeafEvaluator`` -- glues a FoldedNet to the device buffers of MctsBatch (zero-copy views of the
                      library's arenas through the CUDA array interface).
 
-The 3x3 trunk convolutions are 98 % of the 6.56 GFLOP/sample; ``FoldedNet`` runs them through the
-library (cuDNN via torch) today -- DESIGN.md tracks the hand-written tcgen05 kernel that replaces
-that call.
+The 3x3 trunk convolutions are 98 % of the 6.56 GFLOP/sample: ``TensorCoreTrunk`` runs them in the
+hand-written tcgen05 kernel of csrc/hive_conv_kernel.cuh (``net_*`` entry points of the C ABI);
+the two small heads are plain library GEMMs / 1x1 convolutions through torch.  ``FoldedNet`` uses
+the trunk kernel whenever it is attached (``attach_trunk``) and falls back to nothing: without it
+``forward`` runs the same math through torch only when ``trunk="torch"`` is requested explicitly
+(the reference path for parity tests).
 """
+import ctypes
 import numpy as np
 import torch
 import torch.nn as nn
@@ -97,12 +101,56 @@ def _fold(conv_w, conv_b, bn):
     return w, b
 
 
+class TensorCoreTrunk:
+    """The 39 folded 3x3 convolutions on the tensor cores (net_create / net_load_conv_host /
+    net_trunk_forward)."""
+
+    def __init__(self, folded_fp32, device_index, stream_ptr, max_boards):
+        from ._capi import check, lib
+        self._lib, self._check = lib(), check
+        h = ctypes.c_void_p()
+        check(self._lib.net_create(int(device_index), stream_ptr, int(max_boards), ctypes.byref(h)), "net_create")
+        self._h, self.max_boards = h, int(max_boards)
+        for layer, (w, b) in enumerate(folded_fp32):
+            w = np.ascontiguousarray(w.detach().float().cpu().numpy())
+            b = np.ascontiguousarray(b.detach().float().cpu().numpy())
+            check(self._lib.net_load_conv_host(h, layer, w.ctypes.data, b.ctypes.data, w.shape[1]), "net_load_conv_host")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.net_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def forward_ptr(self, planes_ptr, n_boards):
+        """planes_ptr: device bf16 [n][56][144].  Returns the device pointer of [n][144][256] bf16 NHWC."""
+        out = ctypes.c_void_p()
+        self._check(self._lib.net_trunk_forward(self._h, planes_ptr, int(n_boards), ctypes.byref(out)), "net_trunk_forward")
+        return out.value
+
+    @property
+    def launches(self):
+        return self._lib.net_launch_count(self._h)
+
+
 class FoldedNet:
     """BN-folded bf16 inference network built from a HiveNet (weights frozen at construction)."""
 
     def __init__(self, net, device="cuda", dtype=torch.bfloat16):
         net = net.eval()
         self.device, self.dtype = torch.device(device), dtype
+        self.trunk = None
+        with torch.no_grad():
+            folded = [_fold(net.conv.conv1.weight, net.conv.conv1.bias, net.conv.bn1)]
+            for i in range(N_RES):
+                r = getattr(net, "res_%i" % i)
+                folded += [_fold(r.conv1.weight, None, r.bn1), _fold(r.conv2.weight, None, r.bn2)]
+            self._folded_fp32 = [(w.detach().float().cpu(), b.detach().float().cpu()) for w, b in folded]
         with torch.no_grad():
             def put(w, b):
                 w = w.to(self.device, dtype).contiguous(memory_format=torch.channels_last) if w.dim() == 4 else w.to(self.device, dtype)
@@ -126,14 +174,43 @@ class FoldedNet:
             out += [c1, c2]
         return out
 
-    @torch.no_grad()
-    def forward(self, planes):
-        """planes (B,56,12,12) bf16/fp32 on the device -> (p (B,1584) fp32, v (B,1) fp32)."""
+    def attach_trunk(self, stream_ptr=None, max_boards=4096):
+        """Create the tensor-core trunk on this net's device; kernels are queued on `stream_ptr`
+        (a cudaStream_t as int; None = the legacy default stream)."""
+        if self.device.type != "cuda":
+            raise RuntimeError("the tensor-core trunk needs a CUDA device (there is no CPU fallback)")
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.trunk = TensorCoreTrunk(self._folded_fp32, idx, stream_ptr, max_boards)
+        return self
+
+    def _trunk_torch(self, planes):
         x = planes.to(self.dtype).contiguous(memory_format=torch.channels_last)
         x = F.relu(F.conv2d(x, self.stem[0], self.stem[1], padding=1))
         for (w1, b1), (w2, b2) in self.blocks:
             y = F.relu(F.conv2d(x, w1, b1, padding=1))
             x = F.relu(F.conv2d(y, w2, b2, padding=1) + x)
+        return x
+
+    def _trunk_tc(self, planes):
+        """planes: contiguous bf16 (B,56,12,12) on the device."""
+        n = planes.shape[0]
+        outs = []
+        for s in range(0, n, self.trunk.max_boards):
+            e = min(n, s + self.trunk.max_boards)
+            ptr = self.trunk.forward_ptr(planes[s:e].data_ptr(), e - s)
+            nhwc = device_view(ptr, (e - s, BOARD, BOARD, CH), "<u2", self.device).view(torch.bfloat16)
+            outs.append(nhwc if n <= self.trunk.max_boards else nhwc.clone())
+        x = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+        return x.permute(0, 3, 1, 2)                         # NCHW view over NHWC memory (= channels_last)
+
+    @torch.no_grad()
+    def forward(self, planes, trunk=None):
+        """planes (B,56,12,12) bf16/fp32 on the device -> (p (B,1584) fp32, v (B,1) fp32).
+        trunk: None = the tensor-core kernel if attached else torch; "torch" forces the library path."""
+        if self.trunk is not None and trunk != "torch":
+            x = self._trunk_tc(planes.to(self.dtype).contiguous())
+        else:
+            x = self._trunk_torch(planes)
         v = F.relu(F.conv2d(x, self.vconv[0], self.vconv[1])).float().reshape(-1, CELLS)
         v = torch.tanh(F.linear(F.relu(F.linear(v, *self.fc1)), *self.fc2))
         p = F.relu(F.conv2d(x, self.pconv[0], self.pconv[1]))

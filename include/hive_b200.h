@@ -152,6 +152,23 @@ int mcts_root_stats_host(hive_mcts_t* m, int tree, int max_edges, int32_t* actio
                          float* P, int32_t* info);
 long long mcts_launch_count(const hive_mcts_t* m);
 
+/* ------------------------------------------------------------------------------------------
+ * Network trunk on the tensor cores -- the 39 3x3 convolutions of ChessNet
+ * (alpha_zero/alpha_net.py:25-54: ConvBlock + 19 ResBlocks, 98 % of the 6.56 GFLOP per position),
+ * bf16 tcgen05 implicit GEMM with folded BatchNorm, residual add and ReLU fused.  The two small
+ * heads (alpha_net.py:56-80) stay with the caller (plain library GEMMs).
+ */
+typedef struct hive_net hive_net_t;
+int net_create(int device, void* stream, int max_boards, hive_net_t** out);
+int net_destroy(hive_net_t* n);
+/* layer 0 = stem (cin 56); 1+2i / 2+2i = conv1 / conv2 of residual block i (cin 256).
+ * w [256][cin][3][3] fp32 with BatchNorm folded, bias [256] fp32 (host pointers). */
+int net_load_conv_host(hive_net_t* n, int layer, const float* w, const float* bias, int cin);
+/* planes: device bf16 [n_boards][56][144]; *out_nhwc: device bf16 [n_boards][144][256], valid until the
+ * next call.  Stream-ordered on the handle's stream. */
+int net_trunk_forward(hive_net_t* n, const uint16_t* planes_chw_dev, int n_boards, uint16_t** out_nhwc);
+long long net_launch_count(const hive_net_t* n);
+
 #ifdef __cplusplus
 }
 #endif

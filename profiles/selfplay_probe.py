@@ -5,14 +5,17 @@ import hive_b200
 n = int(sys.argv[1]); sims = int(sys.argv[2]); moves = int(sys.argv[3])
 torch.manual_seed(0)
 folded = hive_b200.FoldedNet(hive_b200.HiveNet().eval(), device="cuda")
+stream = torch.cuda.Stream()
+if len(sys.argv) > 4 and sys.argv[4] == "tc":
+    folded.attach_trunk(stream_ptr=stream.cuda_stream, max_boards=n)
 # pure net throughput
 x = torch.zeros(n, 56, 12, 12, device="cuda", dtype=torch.bfloat16)
-for _ in range(3): folded(x)
-torch.cuda.synchronize(); t0 = time.perf_counter()
-for _ in range(5): folded(x)
-torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 5
-print("net fwd batch", n, "ms", dt * 1e3, "TFLOP/s", n * 6.56e9 / dt / 1e12, flush=True)
-stream = torch.cuda.Stream()
+with torch.cuda.stream(stream):
+    for _ in range(3): folded(x)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(5): folded(x)
+    torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 5
+print("net fwd batch", n, "trunk", "tcgen05" if folded.trunk else "cudnn", "ms", dt * 1e3, "TFLOP/s", n * 6.56e9 / dt / 1e12, flush=True)
 with torch.cuda.stream(stream):
     sp = hive_b200.SelfPlayBatch(n, sims, hive_b200.LeafEvaluator(folded), stream=stream.cuda_stream, seed=1)
     sp.play_moves(1)

@@ -72,3 +72,31 @@ def test_selfplay_batch_smoke():
     turn, _, _ = sp.env.status()
     assert (turn == 7).all()
     assert all(len(s) == 6 for s in sp.samples)
+
+
+@pytest.mark.gpu
+def test_tensor_core_trunk_matches_references():
+    """tcgen05 trunk kernel: within 1e-2 of the fp32 reference architecture on p and v, and close to the
+    library bf16 path layer for layer (same folded weights)."""
+    import hive_b200
+    torch.manual_seed(0)
+    net = hive_b200.HiveNet().eval()
+    _randomize_bn(net, 3)
+    b = hive_b200.HiveBatch(67)                                            # odd count: exercises the tail pair
+    for _ in range(25):
+        b.step_random(9, 55, True)
+    planes = torch.from_numpy(b.planes().copy()).cuda()
+    with torch.no_grad():
+        p_ref, v_ref = net.cuda()(planes)
+    folded = hive_b200.FoldedNet(net, device="cuda")
+    p_lib, v_lib = folded(planes, trunk="torch")
+    x_lib = folded._trunk_torch(planes).float()
+    folded.attach_trunk(stream_ptr=torch.cuda.current_stream().cuda_stream, max_boards=128)
+    x_tc = folded._trunk_tc(planes.to(torch.bfloat16).contiguous()).float()
+    torch.cuda.synchronize()
+    scale = float(x_lib.abs().max())
+    assert float((x_tc - x_lib).abs().max()) <= 0.05 * scale + 0.05          # 39 layers of bf16 rounding
+    p, v = folded(planes)
+    assert float((p - p_ref).abs().max()) <= 1e-2 and float((v - v_ref).abs().max()) <= 1e-2
+    assert float((p - p_lib).abs().max()) <= 1e-2
+    assert folded.trunk.launches >= 40
