@@ -12,9 +12,9 @@
 The 3x3 trunk convolutions are 98 % of the 6.56 GFLOP/sample: ``TensorCoreTrunk`` runs them in the
 hand-written tcgen05 kernel of csrc/hive_conv_kernel.cuh (``net_*`` entry points of the C ABI);
 the two small heads are plain library GEMMs / 1x1 convolutions through torch.  ``FoldedNet`` uses
-the trunk kernel whenever it is attached (``attach_trunk``) and falls back to nothing: without it
-``forward`` runs the same math through torch only when ``trunk="torch"`` is requested explicitly
-(the reference path for parity tests).
+the trunk kernel once it is attached (``attach_trunk``); ``forward(..., trunk="torch")`` runs the
+same folded weights through the library instead (the comparison path of the parity tests and the
+only path on a machine without a GPU).
 """
 import ctypes
 import numpy as np
