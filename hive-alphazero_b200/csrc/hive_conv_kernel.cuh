@@ -168,7 +168,8 @@ __global__ void __launch_bounds__(CONV_THREADS, CONV_CTAS_PER_SM) hive_conv3x3_k
         float* stage = sStage + ew * 16 * CONV_STAGE_STRIDE;
         const int sl = lane >> 2, ch8 = (lane & 3) * 8;            // phase-2 role: slots sl and sl+8, channels ch8..ch8+7
         constexpr int G = CONV_N / 16 / SETS;                      // column groups per warp
-        constexpr int PF = 4 < G ? 4 : G;                          // residual prefetch distance (groups)
+        constexpr int CH = 5;                                      // column groups held in registers at a time
+        static_assert(G % CH == 0, "column groups per warp must be a multiple of the register chunk");
         uint32_t full_ph = 0;
         int it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
@@ -177,79 +178,84 @@ __global__ void __launch_bounds__(CONV_THREADS, CONV_CTAS_PER_SM) hive_conv3x3_k
             const float bias = a.bias[oc0 + lane];
             for (int j = 0; j < CONV_BOARDS; j++) {
                 const int slot = (CONV_BOARDS * it + j) % CONV_SLOTS;
-                mbar_wait(&acc_full[slot], (full_ph >> slot) & 1u);
-                full_ph ^= 1u << slot;
-                tc_fence_after();
                 const int b = pair * CONV_BOARDS + j;
+                const bool valid = b < a.n_boards;
                 const int g0 = set * G;                                // first column group of this warp
-                if (b < a.n_boards) {
-                const size_t bbase = (size_t)b * 144 * 256 + oc0 + ch8;
+                const size_t bbase = (size_t)(valid ? b : 0) * 144 * 256 + oc0 + ch8;
                 // element offset of (group g, k-th slot of this lane) or -1 for a padding slot
                 auto slot_off = [&](int g, int k) -> long long {      // g counts from this warp's first group
                     const int n = (g0 + g) * 16 + sl + 8 * k, y = n / CONV_PADW, x = n - y * CONV_PADW;
-                    return (x < 12 && y < 12) ? (long long)(bbase + (size_t)(y * 12 + x) * 256) : -1;
+                    return (valid && x < 12 && y < 12) ? (long long)(bbase + (size_t)(y * 12 + x) * 256) : -1;
                 };
-                uint4 rq[PF][2];
-                if (a.residual) {
 #pragma unroll
-                    for (int g = 0; g < PF; g++)
+                for (int c0 = 0; c0 < G; c0 += CH) {
+                    // residual rows of this chunk are requested BEFORE the accumulator is awaited, so their
+                    // latency hides under the MMAs that are still running
+                    uint4 rq[CH][2];
+                    if (a.residual) {
+#pragma unroll
+                        for (int g = 0; g < CH; g++)
+#pragma unroll
+                            for (int k = 0; k < 2; k++) {
+                                const long long o = slot_off(c0 + g, k);
+                                rq[g][k] = o >= 0 ? *reinterpret_cast<const uint4*>(a.residual + o) : make_uint4(0u, 0u, 0u, 0u);
+                            }
+                    }
+                    if (c0 == 0) {
+                        mbar_wait(&acc_full[slot], (full_ph >> slot) & 1u);
+                        full_ph ^= 1u << slot;
+                        tc_fence_after();
+                    }
+                    // all TMEM reads of the chunk in flight at once, one wait
+                    uint32_t v[CH][16];
+#pragma unroll
+                    for (int g = 0; g < CH; g++)
+                        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + slot * CONV_N + (g0 + c0 + g) * 16, v[g]);
+                    tmem_ld_wait();
+                    if (c0 + CH >= G) {
+                        // the accumulator now lives in registers: hand the TMEM slot back to the MMA issuer
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_empty[slot]);
+                    }
+                    if (!valid) continue;
+#pragma unroll
+                    for (int g = 0; g < CH; g++) {
+#pragma unroll
+                        for (int i = 0; i < 16; i++) stage[i * CONV_STAGE_STRIDE + lane] = __uint_as_float(v[g][i]) + bias;
+                        __syncwarp();
 #pragma unroll
                         for (int k = 0; k < 2; k++) {
-                            const long long o = slot_off(g, k);
-                            rq[g][k] = o >= 0 ? *reinterpret_cast<const uint4*>(a.residual + o) : make_uint4(0u, 0u, 0u, 0u);
-                        }
-                }
+                            const long long o = slot_off(c0 + g, k);
+                            const float4 f0 = *reinterpret_cast<const float4*>(stage + (sl + 8 * k) * CONV_STAGE_STRIDE + ch8);
+                            const float4 f1 = *reinterpret_cast<const float4*>(stage + (sl + 8 * k) * CONV_STAGE_STRIDE + ch8 + 4);
+                            float r[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+                            if (a.residual) {
+                                const uint4 rv = rq[g][k];
+                                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
-                for (int g = 0; g < G; g++) {
-                    uint32_t v[16];
-                    tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + slot * CONV_N + (g0 + g) * 16, v);
-                    tmem_ld_wait();
+                                for (int e = 0; e < 4; e++) {
+                                    r[2 * e] += __uint_as_float(rw[e] << 16);
+                                    r[2 * e + 1] += __uint_as_float(rw[e] & 0xFFFF0000u);
+                                }
+                            }
+                            if (a.relu) {
 #pragma unroll
-                    for (int i = 0; i < 16; i++) stage[i * CONV_STAGE_STRIDE + lane] = __uint_as_float(v[i]) + bias;
-                    __syncwarp();
-#pragma unroll
-                    for (int k = 0; k < 2; k++) {
-                        const long long o = slot_off(g, k);
-                        const float4 f0 = *reinterpret_cast<const float4*>(stage + (sl + 8 * k) * CONV_STAGE_STRIDE + ch8);
-                        const float4 f1 = *reinterpret_cast<const float4*>(stage + (sl + 8 * k) * CONV_STAGE_STRIDE + ch8 + 4);
-                        float r[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
-                        if (a.residual) {
-                            const uint4 rv = rq[g % PF][k];
-                            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                            for (int e = 0; e < 4; e++) {
-                                r[2 * e] += __uint_as_float(rw[e] << 16);
-                                r[2 * e + 1] += __uint_as_float(rw[e] & 0xFFFF0000u);
+                                for (int e = 0; e < 8; e++) r[e] = fmaxf(r[e], 0.f);
+                            }
+                            if (o >= 0) {
+                                uint4 pk;
+                                __nv_bfloat162 h;
+                                h = __floats2bfloat162_rn(r[0], r[1]); pk.x = *reinterpret_cast<uint32_t*>(&h);
+                                h = __floats2bfloat162_rn(r[2], r[3]); pk.y = *reinterpret_cast<uint32_t*>(&h);
+                                h = __floats2bfloat162_rn(r[4], r[5]); pk.z = *reinterpret_cast<uint32_t*>(&h);
+                                h = __floats2bfloat162_rn(r[6], r[7]); pk.w = *reinterpret_cast<uint32_t*>(&h);
+                                *reinterpret_cast<uint4*>(a.out + o) = pk;
                             }
                         }
-                        if (a.relu) {
-#pragma unroll
-                            for (int e = 0; e < 8; e++) r[e] = fmaxf(r[e], 0.f);
-                        }
-                        if (o >= 0) {
-                            uint4 pk;
-                            __nv_bfloat162 h;
-                            h = __floats2bfloat162_rn(r[0], r[1]); pk.x = *reinterpret_cast<uint32_t*>(&h);
-                            h = __floats2bfloat162_rn(r[2], r[3]); pk.y = *reinterpret_cast<uint32_t*>(&h);
-                            h = __floats2bfloat162_rn(r[4], r[5]); pk.z = *reinterpret_cast<uint32_t*>(&h);
-                            h = __floats2bfloat162_rn(r[6], r[7]); pk.w = *reinterpret_cast<uint32_t*>(&h);
-                            *reinterpret_cast<uint4*>(a.out + o) = pk;
-                        }
+                        __syncwarp();
                     }
-                    if (a.residual && g + PF < G) {                 // refill the slot just consumed
-#pragma unroll
-                        for (int k = 0; k < 2; k++) {
-                            const long long o = slot_off(g + PF, k);
-                            rq[g % PF][k] = o >= 0 ? *reinterpret_cast<const uint4*>(a.residual + o) : make_uint4(0u, 0u, 0u, 0u);
-                        }
-                    }
-                    __syncwarp();
                 }
-                }
-                // this board's accumulator is drained: hand its TMEM slot back to the MMA issuer
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[slot]);
             }
         }
     }
