@@ -306,40 +306,54 @@ def main():
                 "env_steps_per_launch": env_steps / max(launches, 1), "launch_us": launch_s * 1e6}
 
     # ------------------------------------------------------------------ e2e (host buffers)
+    # The same 16,384 games driven from the host through the C ABI: every step reads legal masks,
+    # counts and status D2H into pinned memory, picks the actions on the host (hive_host_pick_actions,
+    # the twin of the device policy) and sends them H2D.  The batch is cut in two halves on two
+    # streams so that the host works on one half while the GPU steps the other.
     k_e2e = min(args.steps, 1500)
-    mask_h = torch.empty((n, 25), dtype=torch.int64).pin_memory()
-    count_h = torch.empty(n, dtype=torch.int32).pin_memory()
-    status_h = torch.empty(n, dtype=torch.int32).pin_memory()
-    actions_h = torch.empty(n, dtype=torch.int32).pin_memory()
-    mask_np, count_np = mask_h.numpy().view(np.uint64), count_h.numpy()
-    status_np, actions_np = status_h.numpy().view(np.uint32), actions_h.numpy()
-    _, episodes = batch.counters()
-    episodes = episodes.copy()
+    halves = []
+    for hi, cnt in enumerate((n // 2, n - n // 2)):
+        st = torch.cuda.Stream()
+        hb = hive_b200.HiveBatch(cnt, device=local_rank, stream=st.cuda_stream)
+        mask_h = torch.empty((cnt, 25), dtype=torch.int64).pin_memory()
+        count_h = torch.empty(cnt, dtype=torch.int32).pin_memory()
+        status_h = torch.empty(cnt, dtype=torch.int32).pin_memory()
+        actions_h = torch.empty(cnt, dtype=torch.int32).pin_memory()
+        halves.append(dict(b=hb, st=st, mask_h=mask_h, count_h=count_h, status_h=status_h, actions_h=actions_h,
+                           mask=mask_h.numpy().view(np.uint64), count=count_h.numpy(), status=status_h.numpy().view(np.uint32),
+                           actions=actions_h.numpy(), episodes=np.zeros(cnt, dtype=np.uint32), seed=seed + 77 * (hi + 1)))
 
-    def e2e_step():
-        batch.legal_into(mask_h.data_ptr(), count_h.data_ptr())        # D2H 200 B + 4 B per game
-        batch.status_packed_into(status_h.data_ptr())                  # D2H 4 B per game
-        hive_b200.host_pick_actions(mask_np, count_np, status_np, episodes, seed, args.max_turn, actions_np)
-        batch.step_ptr(actions_h.data_ptr())                           # H2D 4 B per game + kernel
+    def e2e_half(h):
+        h["b"].legal_into(h["mask_h"].data_ptr(), h["count_h"].data_ptr())          # D2H 200 B + 4 B per game
+        h["b"].status_packed_into(h["status_h"].data_ptr())                          # D2H 4 B per game
+        hive_b200.host_pick_actions(h["mask"], h["count"], h["status"], h["episodes"], h["seed"], args.max_turn, h["actions"])
+        h["b"].step_ptr(h["actions_h"].data_ptr())                                   # H2D 4 B per game + kernels
 
-    for _ in range(3):
-        e2e_step()
-    batch.sync()
-    s0 = int(batch.counters()[0].astype(np.int64).sum())
+    for _ in range(5):
+        for h in halves:
+            e2e_half(h)
+    for h in halves:
+        h["b"].sync()
+    s0 = sum(int(h["b"].counters()[0].astype(np.int64).sum()) for h in halves)
     barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(k_e2e):
-        e2e_step()
-    batch.legal_into(mask_h.data_ptr(), count_h.data_ptr())            # the last step's result
+        for h in halves:
+            e2e_half(h)
+    for h in halves:
+        h["b"].legal_into(h["mask_h"].data_ptr(), h["count_h"].data_ptr())           # the last step's result
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     barrier()
-    e2e_steps = int(batch.counters()[0].astype(np.int64).sum()) - s0
+    e2e_steps = sum(int(h["b"].counters()[0].astype(np.int64).sum()) for h in halves) - s0
     e2e_value = allsum(float(e2e_steps)) / allmax(dt)
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": (200 + 4 + 4) * n,
-           "steps": k_e2e, "note": "per-GPU bytes per kernel launch; host picks actions with the C-ABI twin "
-           "of the device policy; planes stay in HBM for the net"}
+           "steps": k_e2e, "note": "per-GPU bytes per step of all 16,384 games; two 8,192-game halves on two streams, host "
+           "picks actions (C-ABI twin of the device policy, host worker pool) for one half while the GPU steps the other; "
+           "planes stay in HBM for the net"}
+    for h in halves:
+        h["b"].close()
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N=1)
     cpu = None

@@ -14,7 +14,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 
 # per-file flags: the search mirrors the reference's IEEE operation order, so no FMA contraction there
-EXTRA_FLAGS = {"hive_mcts.cu": ["--fmad=false"]}
+EXTRA_FLAGS = {"hive_mcts.cu": ["--fmad=false"], "hive_env.cu": ["-Xcompiler", "-mpopcnt"]}
 
 
 def sources():

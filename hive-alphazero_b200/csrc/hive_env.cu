@@ -11,7 +11,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <condition_variable>
+#include <functional>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -302,11 +305,9 @@ static inline uint64_t host_splitmix64(uint64_t x) {
     return x ^ (x >> 31);
 }
 
-int hive_host_pick_actions(int n, const uint64_t* mask, const int32_t* count, const uint32_t* packed_status,
-                           uint32_t* episodes, uint64_t seed, int max_turn, int32_t* actions) {
-    if (n <= 0 || !mask || !count || !packed_status || !episodes || !actions)
-        return fail(HIVE_E_ARG, "hive_host_pick_actions: bad arguments");
-    for (int g = 0; g < n; g++) {
+static void pick_range(int g0, int g1, int n, const uint64_t* mask, const int32_t* count, const uint32_t* packed_status,
+                       uint32_t* episodes, uint64_t seed, int max_turn, int32_t* actions) {
+    for (int g = g0; g < g1; g++) {
         const uint32_t st = packed_status[g];
         const int turn = st & 0xFF, done = (st >> 16) & 0xFF;
         if (done || turn >= max_turn) { actions[g] = HIVE_RESET; episodes[g]++; continue; }
@@ -327,6 +328,82 @@ int hive_host_pick_actions(int n, const uint64_t* mask, const int32_t* count, co
         }
         actions[g] = a;
     }
+}
+
+// A small persistent worker pool for the host-side policy twin (the caller's thread takes a share too).
+namespace {
+struct PickPool {
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::function<void(int)> job;          // job(part)
+    int parts = 0, next = 0, pending = 0;
+    uint64_t epoch = 0;
+    bool stop = false;
+    explicit PickPool(int nthreads) {
+        for (int i = 0; i < nthreads; i++)
+            workers.emplace_back([this] {
+                uint64_t seen = 0;
+                for (;;) {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv_work.wait(lk, [&] { return stop || (epoch != seen && next < parts); });
+                    if (stop) return;
+                    while (next < parts) {
+                        const int part = next++;
+                        lk.unlock();
+                        job(part);
+                        lk.lock();
+                        if (--pending == 0) cv_done.notify_all();
+                    }
+                    seen = epoch;
+                }
+            });
+    }
+    ~PickPool() {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv_work.notify_all();
+        for (auto& t : workers) t.join();
+    }
+    void run(int nparts, std::function<void(int)> f) {
+        std::unique_lock<std::mutex> lk(mu);
+        job = std::move(f); parts = nparts; next = 0; pending = nparts; epoch++;
+        cv_work.notify_all();
+        while (next < parts) {               // the calling thread works too
+            const int part = next++;
+            lk.unlock();
+            job(part);
+            lk.lock();
+            --pending;
+        }
+        cv_done.wait(lk, [&] { return pending == 0; });
+    }
+};
+PickPool* pick_pool() {
+    static PickPool* pool = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        unsigned hc = std::thread::hardware_concurrency();
+        int nt = hc > 2 ? (int)(hc < 16 ? hc : 16) - 1 : 0;
+        const char* e = getenv("HIVE_B200_HOST_THREADS");
+        if (e) nt = atoi(e) - 1;
+        if (nt < 0) nt = 0;
+        pool = new PickPool(nt);
+    });
+    return pool;
+}
+}  // namespace
+
+int hive_host_pick_actions(int n, const uint64_t* mask, const int32_t* count, const uint32_t* packed_status,
+                           uint32_t* episodes, uint64_t seed, int max_turn, int32_t* actions) {
+    if (n <= 0 || !mask || !count || !packed_status || !episodes || !actions)
+        return fail(HIVE_E_ARG, "hive_host_pick_actions: bad arguments");
+    const int chunk = 512;
+    const int parts = (n + chunk - 1) / chunk;
+    if (parts <= 1) { pick_range(0, n, n, mask, count, packed_status, episodes, seed, max_turn, actions); return 0; }
+    pick_pool()->run(parts, [=](int part) {
+        const int g0 = part * chunk, g1 = g0 + chunk < n ? g0 + chunk : n;
+        pick_range(g0, g1, n, mask, count, packed_status, episodes, seed, max_turn, actions);
+    });
     return 0;
 }
 
