@@ -324,11 +324,14 @@ def main():
                            actions=actions_h.numpy(), episodes=np.zeros(cnt, dtype=np.uint32), seed=seed + 77 * (hi + 1)))
 
     def e2e_half(h):
-        h["b"].legal_into(h["mask_h"].data_ptr(), h["count_h"].data_ptr())          # D2H 200 B + 4 B per game
-        h["b"].status_packed_into(h["status_h"].data_ptr())                          # D2H 4 B per game
+        h["b"].sync()                                                                # results of this half's last step are in host memory
         hive_b200.host_pick_actions(h["mask"], h["count"], h["status"], h["episodes"], h["seed"], args.max_turn, h["actions"])
-        h["b"].step_ptr(h["actions_h"].data_ptr())                                   # H2D 4 B per game + kernels
+        # H2D 4 B/game -> kernels -> D2H (200 + 4 + 4) B/game, all queued; the other half is handled meanwhile
+        h["b"].step_async_ptr(h["actions_h"].data_ptr(), h["mask_h"].data_ptr(), h["count_h"].data_ptr(), h["status_h"].data_ptr())
 
+    for h in halves:
+        h["b"].legal_into(h["mask_h"].data_ptr(), h["count_h"].data_ptr())
+        h["b"].status_packed_into(h["status_h"].data_ptr())
     for _ in range(5):
         for h in halves:
             e2e_half(h)
@@ -342,7 +345,7 @@ def main():
         for h in halves:
             e2e_half(h)
     for h in halves:
-        h["b"].legal_into(h["mask_h"].data_ptr(), h["count_h"].data_ptr())           # the last step's result
+        h["b"].sync()                                                                # the last step's results have landed
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     barrier()

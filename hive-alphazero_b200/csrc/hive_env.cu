@@ -243,6 +243,21 @@ int hive_step_host(hive_env_t* h, const int32_t* actions) {
     return rc;
 }
 
+int hive_step_host_async(hive_env_t* h, const int32_t* actions, uint64_t* mask, int32_t* count, uint32_t* packed_status) {
+    if (check(h)) return HIVE_E_HANDLE;
+    if (!actions) return fail(HIVE_E_ARG, "hive_step_host_async: null actions");
+    CUDA_TRY(cudaSetDevice(h->device));
+    int32_t* d = h->d_actions[h->act_flip];
+    h->act_flip ^= 1;
+    CUDA_TRY(cudaMemcpyAsync(d, actions, (size_t)h->n * 4, cudaMemcpyHostToDevice, h->stream));
+    int rc = launch_env(h, OP_STEP, d, nullptr, 0, 0, 0, nullptr);
+    if (rc) return rc;
+    if (mask) CUDA_TRY(cudaMemcpyAsync(mask, h->legal, (size_t)h->n * LEGAL_WORDS * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (count) CUDA_TRY(cudaMemcpyAsync(count, h->count, (size_t)h->n * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (packed_status) CUDA_TRY(cudaMemcpyAsync(packed_status, h->status, (size_t)h->n * 4, cudaMemcpyDeviceToHost, h->stream));
+    return 0;
+}
+
 int hive_step_random(hive_env_t* h, uint64_t seed, int max_turn, int auto_reset, int32_t* chosen_dev) {
     if (check(h)) return HIVE_E_HANDLE;
     if (max_turn < 1 || max_turn > 250) return fail(HIVE_E_ARG, "hive_step_random: max_turn out of range");

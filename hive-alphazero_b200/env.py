@@ -59,6 +59,10 @@ class HiveBatch:
         """Same, from a raw host pointer (e.g. pinned memory)."""
         check(lib().hive_step_host(self._h, host_ptr), "hive_step_host")
 
+    def step_async_ptr(self, actions_ptr, mask_ptr, count_ptr, status_ptr):
+        """Queue H2D(actions) -> step -> D2H(results) without waiting (pinned host pointers)."""
+        check(lib().hive_step_host_async(self._h, actions_ptr, mask_ptr, count_ptr, status_ptr), "hive_step_host_async")
+
     def step_device(self, actions_dev_ptr):
         check(lib().hive_step(self._h, actions_dev_ptr), "hive_step")
 

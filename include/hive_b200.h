@@ -60,6 +60,10 @@ int hive_reset(hive_env_t* h, const uint8_t* game_mask);
  * the new side to move and encode its 56 planes. */
 int hive_step_host(hive_env_t* h, const int32_t* actions);          /* host int32[n] */
 int hive_step(hive_env_t* h, const int32_t* actions_dev);           /* device int32[n] */
+/* Fully asynchronous form for pipelined callers: queues the H2D copy of `actions`, the step and the
+ * D2H copies of the new legal masks / counts / packed status (any may be NULL) on the handle's
+ * stream and returns at once.  All buffers should be pinned and must stay untouched until hive_sync. */
+int hive_step_host_async(hive_env_t* h, const int32_t* actions, uint64_t* mask, int32_t* count, uint32_t* packed_status);
 
 /* On-device rollout policy of the benchmark (SURVEY 8d Config 2): a = A[x % len(A)],
  * x = splitmix64(seed ^ game_id<<32 ^ turn), game_id = slot + n_games*episode; pass when A is
