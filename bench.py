@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--max-turn", type=int, default=55)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunk", type=int, default=50, help="rollout steps per CUDA-graph launch (1 = one launch per step)")
     ap.add_argument("--no-selfplay", action="store_true", help="skip the self-play (configs[2]) side measurement")
     ap.add_argument("--selfplay-games", type=int, default=2048)
     ap.add_argument("--selfplay-sims", type=int, default=50)
@@ -273,6 +274,8 @@ def main():
     # ------------------------------------------------------------------ resident (device-timed)
     for _ in range(max(args.warmup, 3)):
         batch.step_random(seed, args.max_turn, True)
+    if args.chunk > 1:
+        batch.step_random_multi(seed, min(args.chunk, args.steps), args.max_turn, True)      # graph capture + one replay, untimed
     batch.sync()
     steps0 = int(batch.counters()[0].astype(np.int64).sum())
     launches0 = batch.launches
@@ -282,8 +285,14 @@ def main():
     barrier()
     torch.cuda.synchronize()
     ev0.record(stream)
-    for _ in range(args.steps):
-        batch.step_random(seed, args.max_turn, True)
+    done_steps = 0
+    while done_steps < args.steps:                      # EXACTLY args.steps steps, in graph launches of <= chunk steps
+        c = min(args.chunk, args.steps - done_steps)
+        if c > 1:
+            batch.step_random_multi(seed, c, args.max_turn, True)
+        else:
+            batch.step_random(seed, args.max_turn, True)
+        done_steps += c
     ev1.record(stream)
     torch.cuda.synchronize()
     barrier()
@@ -379,6 +388,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic (random-legal-move games from reset, "
             "counter-based splitmix64 policy; planes emitted as bf16)",
             "config": {"workload": WORKLOAD, "games_per_gpu": n, "max_turn": args.max_turn, "auto_reset": True,
+                       "steps_per_graph_launch": args.chunk,
                        "parallelism": "games sharded %d-way, no data-path collective" % world,
                        "cache": "per-GPU working set %.0f MB (state+legal+planes) > 126 MB L2: inputs larger than L2"
                                 % (n * (384 + 200 + 8 + 16128) / 1e6)},

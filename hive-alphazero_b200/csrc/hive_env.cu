@@ -23,7 +23,7 @@
 #include "hive_internal.h"
 
 #ifndef HIVE_DEFAULT_SLICES
-#define HIVE_DEFAULT_SLICES 4
+#define HIVE_DEFAULT_SLICES 8
 #endif
 
 using namespace hive;
@@ -52,9 +52,46 @@ namespace hive {
 
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
+static int launch_env_kernels(hive_env* h, int op, const int32_t* actions, const uint8_t* mask, uint64_t seed, int max_turn,
+                              int auto_reset, int32_t* chosen, int repeat = 1);
+
 int launch_env(hive_env* h, int op, const int32_t* actions, const uint8_t* mask, uint64_t seed, int max_turn,
                int auto_reset, int32_t* chosen) {
     if (h->timing) CUDA_TRY(cudaEventRecord(h->t0, h->stream));
+    // (host-driven steps alternate between two staging buffers, so they would never hit the cache)
+    const bool graphable = h->use_graph && (op == OP_RANDOM || (op == OP_STEP && actions != h->d_actions[0] && actions != h->d_actions[1]));
+    if (!graphable) {
+        int rc = launch_env_kernels(h, op, actions, mask, seed, max_turn, auto_reset, chosen);
+        if (rc) return rc;
+    } else {
+        hive_env::StepGraph& g = h->graph;
+        const bool hit = g.exec && g.op == op && g.actions == actions && g.mask == mask && g.chosen == chosen && g.seed == seed &&
+                         g.max_turn == max_turn && g.auto_reset == auto_reset;
+        if (!hit) {
+            if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+            cudaGraph_t graph = nullptr;
+            CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
+            const long long l0 = h->launches;
+            int rc = launch_env_kernels(h, op, actions, mask, seed, max_turn, auto_reset, chosen);
+            cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+            h->launches = l0;
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (e != cudaSuccess) return fail(HIVE_E_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+            e = cudaGraphInstantiate(&g.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) { g.exec = nullptr; return fail(HIVE_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+            g.op = op; g.actions = actions; g.mask = mask; g.chosen = chosen; g.seed = seed; g.max_turn = max_turn; g.auto_reset = auto_reset;
+        }
+        CUDA_TRY(cudaGraphLaunch(g.exec, h->stream));
+        const int S = h->n_sub;
+        h->launches += 4 * S;
+    }
+    if (h->timing) CUDA_TRY(cudaEventRecord(h->t1, h->stream));
+    return 0;
+}
+
+static int launch_env_kernels(hive_env* h, int op, const int32_t* actions, const uint8_t* mask, uint64_t seed, int max_turn,
+                              int auto_reset, int32_t* chosen, int repeat) {
     const int S = h->n_sub;
     // slices are multiples of GROUP games so that CTAs never straddle two slices
     const int per = ((h->n + S - 1) / S + GROUP - 1) / GROUP * GROUP;
@@ -82,19 +119,20 @@ int launch_env(hive_env* h, int op, const int32_t* actions, const uint8_t* mask,
             // compute-bound kernels of one slice run under the memory-bound encode of another
             if (h->stagger && s > 0) CUDA_TRY(cudaStreamWaitEvent(st, h->stage_ev[s - 1], 0));
         }
-        hive_analyse_kernel<<<groups, GROUP * 32, 0, st>>>(a);
-        if (S > 1 && h->stagger) CUDA_TRY(cudaEventRecord(h->stage_ev[s], st));
-        hive_flood_kernel<<<sblocks, SEARCH_THREADS, 0, st>>>(a);
-        hive_moves_kernel<<<sblocks, SEARCH_THREADS, 0, st>>>(a);
-        hive_encode_kernel<<<enc_blocks, HIVE_ENCODE_WARPS * 32, 0, st>>>(a);
+        for (int rep = 0; rep < repeat; rep++) {
+            hive_analyse_kernel<<<groups, GROUP * 32, 0, st>>>(a);
+            if (S > 1 && h->stagger && rep == 0) CUDA_TRY(cudaEventRecord(h->stage_ev[s], st));
+            hive_flood_kernel<<<sblocks, SEARCH_THREADS, 0, st>>>(a);
+            hive_moves_kernel<<<sblocks, SEARCH_THREADS, 0, st>>>(a);
+            hive_encode_kernel<<<enc_blocks, HIVE_ENCODE_WARPS * 32, 0, st>>>(a);
+        }
         CUDA_TRY(cudaGetLastError());
         if (S > 1) {
             CUDA_TRY(cudaEventRecord(h->join_ev[s], st));
             CUDA_TRY(cudaStreamWaitEvent(h->stream, h->join_ev[s], 0));
         }
-        h->launches += 4;
+        h->launches += 4 * repeat;
     }
-    if (h->timing) CUDA_TRY(cudaEventRecord(h->t1, h->stream));
     return 0;
 }
 
@@ -143,6 +181,8 @@ int hive_create(int n_games, int device, void* stream, hive_env_t** out) {
         h->n_sub = S;
         const char* g = getenv("HIVE_B200_STAGGER");
         h->stagger = g ? atoi(g) : 0;
+        const char* ug = getenv("HIVE_B200_GRAPH");
+        h->use_graph = ug ? atoi(ug) : 1;
     }
     CUDA_TRY(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
     for (int s = 0; s < h->n_sub; s++) {
@@ -181,6 +221,8 @@ int hive_destroy(hive_env_t* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    if (h->graph.exec) cudaGraphExecDestroy(h->graph.exec);
+    if (h->multi_graph.exec) cudaGraphExecDestroy(h->multi_graph.exec);
     cudaFree(h->recs); cudaFree(h->legal); cudaFree(h->count); cudaFree(h->status); cudaFree(h->planes); cudaFree(h->scratch);
     for (int s = 0; s < h->n_sub; s++) {
         cudaFree(h->bq[s].counters); cudaFree(h->bq[s].flood);
@@ -263,6 +305,37 @@ int hive_step_random(hive_env_t* h, uint64_t seed, int max_turn, int auto_reset,
     if (max_turn < 1 || max_turn > 250) return fail(HIVE_E_ARG, "hive_step_random: max_turn out of range");
     CUDA_TRY(cudaSetDevice(h->device));
     return launch_env(h, OP_RANDOM, nullptr, nullptr, seed, max_turn, auto_reset, chosen_dev);
+}
+
+// n_steps consecutive rollout steps as ONE CUDA graph: inside the graph every slice of the batch runs its
+// own chain of n_steps x (analyse, flood, moves, encode), so the memory-bound encode of one slice
+// overlaps the issue-bound kernels of the others across step boundaries.
+int hive_step_random_multi(hive_env_t* h, uint64_t seed, int max_turn, int auto_reset, int n_steps) {
+    if (check(h)) return HIVE_E_HANDLE;
+    if (max_turn < 1 || max_turn > 250 || n_steps < 1 || n_steps > 4096) return fail(HIVE_E_ARG, "hive_step_random_multi: bad arguments");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (h->timing) CUDA_TRY(cudaEventRecord(h->t0, h->stream));
+    hive_env::StepGraph& g = h->multi_graph;
+    const bool hit = g.exec && g.seed == seed && g.max_turn == max_turn && g.auto_reset == auto_reset && g.op == n_steps;
+    if (!hit) {
+        if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+        cudaGraph_t graph = nullptr;
+        CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
+        const long long l0 = h->launches;
+        int rc = launch_env_kernels(h, OP_RANDOM, nullptr, nullptr, seed, max_turn, auto_reset, nullptr, n_steps);
+        cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+        h->launches = l0;
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess) return fail(HIVE_E_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { g.exec = nullptr; return fail(HIVE_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+        g.op = n_steps; g.seed = seed; g.max_turn = max_turn; g.auto_reset = auto_reset;
+    }
+    CUDA_TRY(cudaGraphLaunch(g.exec, h->stream));
+    h->launches += 4LL * h->n_sub * n_steps;
+    if (h->timing) CUDA_TRY(cudaEventRecord(h->t1, h->stream));
+    return 0;
 }
 
 int hive_legal_host(hive_env_t* h, uint64_t* mask, int32_t* count) {

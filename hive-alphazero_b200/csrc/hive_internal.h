@@ -26,6 +26,10 @@ struct hive_env {
     cudaStream_t sub_stream[MAX_SUB] = {};
     cudaEvent_t fork_ev = nullptr, join_ev[MAX_SUB] = {}, stage_ev[MAX_SUB] = {};
     int search_blocks = 0;
+    // the step of the resident rollout loop is replayed from a CUDA graph (same arguments every step)
+    struct StepGraph { int op = -1; const void* actions = nullptr; const void* mask = nullptr; void* chosen = nullptr;
+                       uint64_t seed = 0; int max_turn = 0, auto_reset = 0; cudaGraphExec_t exec = nullptr; } graph, multi_graph;
+    int use_graph = 1;
     int32_t* d_actions[2] = {nullptr, nullptr};
     int act_flip = 0;
     uint8_t* d_mask = nullptr;

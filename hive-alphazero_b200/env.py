@@ -70,6 +70,11 @@ class HiveBatch:
         check(lib().hive_step_random(self._h, seed, max_turn, 1 if auto_reset else 0, chosen_dev_ptr),
               "hive_step_random")
 
+    def step_random_multi(self, seed, n_steps, max_turn=C.MAX_GAME_LENGTH, auto_reset=True):
+        """n_steps rollout steps as one CUDA graph launch."""
+        check(lib().hive_step_random_multi(self._h, seed, max_turn, 1 if auto_reset else 0, int(n_steps)),
+              "hive_step_random_multi")
+
     def sync(self):
         check(lib().hive_sync(self._h), "hive_sync")
 

@@ -71,6 +71,9 @@ int hive_step_host_async(hive_env_t* h, const int32_t* actions, uint64_t* mask, 
  * MAX_GAME_LENGTH cut of self_play.py:162) is reset instead of stepped.  `chosen_dev` (optional,
  * device int32[n]) receives the action taken (HIVE_NOOP for a reset / idle slot). */
 int hive_step_random(hive_env_t* h, uint64_t seed, int max_turn, int auto_reset, int32_t* chosen_dev);
+/* n_steps consecutive hive_step_random steps replayed as one CUDA graph (the slices of the batch run
+ * their step chains independently inside it, so kernels of different steps overlap). */
+int hive_step_random_multi(hive_env_t* h, uint64_t seed, int max_turn, int auto_reset, int n_steps);
 
 /* GamePlay.actions() (env_hive.py:182): bit a of mask[g] set <=> action a legal; count = len. */
 int hive_legal_host(hive_env_t* h, uint64_t* mask /*[n][25]*/, int32_t* count /*[n]*/);

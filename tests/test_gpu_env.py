@@ -192,3 +192,20 @@ def test_host_policy_twin_matches_device_policy(hb):
     assert (m1 == m2).all() and (c1 == c2).all()
     assert (dev.planes_bf16() == host.planes_bf16()).all()
     assert [a.tolist() for a in dev.status()] == [a.tolist() for a in host.status()]
+
+
+def test_multi_step_graph_equals_single_steps(hb):
+    """hive_step_random_multi (one CUDA graph, slices free-running across steps) == the same number of
+    hive_step_random calls."""
+    n, seed = 4096, 4242
+    a, b = hb.HiveBatch(n), hb.HiveBatch(n)
+    for _ in range(3):
+        a.step_random_multi(seed, 37)
+        for _ in range(37):
+            b.step_random(seed, 55, True)
+    m1, c1 = a.legal_mask()
+    m2, c2 = b.legal_mask()
+    assert (m1 == m2).all() and (c1 == c2).all()
+    assert (a.planes_bf16() == b.planes_bf16()).all()
+    assert [x.tolist() for x in a.status()] == [x.tolist() for x in b.status()]
+    assert [x.tolist() for x in a.counters()] == [x.tolist() for x in b.counters()]
