@@ -55,6 +55,7 @@ struct __align__(16) WarpScratch {
     uint32_t hist[2][4][2][5];     // 320 B, 16-byte aligned
     uint32_t planes[N_PLANE][5];   // bit boards of the 56 planes (plane 31 unused: it is the turn)
     uint32_t legal[LEGAL_WORDS + 2];
+    uint32_t qn[12];               // queen neighbours in tile.adjacent_tiles order: cell | rank<<8 | empty<<12 (white 0..5, black 6..11)
 };
 static_assert(sizeof(WarpScratch) % 16 == 0, "WarpScratch must keep 16-byte alignment in arrays");
 static_assert(offsetof(WarpScratch, hist) % 16 == 0 && offsetof(WarpScratch, legal) % 8 == 0, "vector access alignment");
@@ -262,8 +263,8 @@ __device__ __forceinline__ int piece_type_of(int k) {
     return (k == 0) ? T_QUEEN : (k <= 2) ? T_BEETLE : (k <= 4) ? T_SPIDER : (k <= 7) ? T_HOPPER : T_ANT;
 }
 
-__device__ __forceinline__ void eval_analyse(GameScratch& gs, GroupQueues& q, int game_slot, int lane, int cell, int level,
-                                             int turn, bool push_history, int prev_winner) {
+__device__ __forceinline__ void eval_analyse(GameScratch& gs, GroupQueues& q, uint32_t* occ_s, int game_slot, int lane, int cell,
+                                             int level, int turn, bool push_history, int prev_winner) {
     const int side = (turn & 1) ? 0 : 1;                 // game_state.py:58-62
     const bool valid = lane < N_PIECE;
     const int color = lane >= 11 ? 1 : 0;
@@ -288,10 +289,12 @@ __device__ __forceinline__ void eval_analyse(GameScratch& gs, GroupQueues& q, in
     const bool ownq_on = (side == 0 ? cq_w : cq_b) != HAND;
     const unsigned in_hand = __ballot_sync(FULL, own && !on_board);
 
+    if (lane < 5) occ_s[lane] = occ.w[lane];             // per-warp shared copy for the random-access ring tests
+    __syncwarp();
     uint32_t ring = 0;                                   // occupancy of the six neighbours
     if (on_board) {
 #pragma unroll
-        for (int i = 0; i < 6; i++) ring |= (uint32_t)bb_test(occ, cell_nbr(cell, i)) << i;
+        for (int i = 0; i < 6; i++) ring |= (uint32_t)words_test(occ_s, cell_nbr(cell, i)) << i;
     }
 
     // turn gates shared by every candidate of a piece (move_checker.py:38-55)
@@ -481,7 +484,6 @@ __device__ __forceinline__ EvalResult eval_encode(WarpScratch& sm, const GameScr
     const bool top = (info >> 12) & 1u;
     const uint32_t ring = (info >> 16) & 63u;
     const bool pinned = (gs.head[1] >> lane) & 1u;
-    const int cq_own = side == 0 ? cq_w : cq_b, cq_opp = side == 0 ? cq_b : cq_w;
 
     {   // zero the scratch outputs: planes (1120 B) and legal (208 B) are contiguous and 16-byte aligned
         uint4* pz = reinterpret_cast<uint4*>(&sm.planes[0][0]);
@@ -527,6 +529,18 @@ __device__ __forceinline__ EvalResult eval_encode(WarpScratch& sm, const GameScr
     res.done = ws || bs;
     res.winner = (ws && bs) ? prev_winner : ws ? 2 : bs ? 1 : prev_winner;
 
+    {   // neighbours of both queens, ranked in tile.adjacent_tiles order (board_tiles order: q descending, then
+        // r ascending; tile.py:111-123): lanes 0..5 white queen, 6..11 black queen
+        const int which = lane >= 6 ? 1 : 0, qcell = which ? cq_b : cq_w;
+        const bool use = lane < 12 && qcell != HAND;
+        const int nb = use ? cell_nbr(qcell, lane - 6 * which) : 0;
+        const int key = (11 - nb / 12) * 12 + nb % 12;
+        int rank = 0;
+#pragma unroll
+        for (int t = 0; t < 6; t++) rank += __shfl_sync(FULL, key, which * 6 + t) < key;
+        if (lane < 12) sm.qn[lane] = use ? ((uint32_t)nb | ((uint32_t)rank << 8) | ((uint32_t)!words_test(gs.occ, nb) << 12)) : 0u;
+    }
+    __syncwarp();
     if (on_board) {
         const uint32_t bit = 1u << (cell & 31); const int wi = cell >> 5;
         sm.planes[(own ? 0 : 12) + k][wi] = bit;                          // 0-10 / 12-22
@@ -540,20 +554,15 @@ __device__ __forceinline__ EvalResult eval_encode(WarpScratch& sm, const GameScr
                 if ((ring >> i) & 1u) { int c = cell_nbr(cell, i); atomicOr(&sm.planes[own ? 32 : 33][c >> 5], 1u << (c & 31)); }
         }
         // 44+j: opponent pieces able to reach the j-th empty neighbour of the own queen;
-        // 50+j: own on-board pieces whose action list holds the j-th empty neighbour of the opponent queen.
-        // j follows tile.adjacent_tiles order = board_tiles order: q descending, then r ascending.
-        const int qc = own ? cq_opp : cq_own;      // own pieces look at the opponent queen and vice versa
-        if (qc != HAND && bb_any(mv)) {
-            int nb[6], key[6];
-#pragma unroll
-            for (int i = 0; i < 6; i++) { nb[i] = cell_nbr(qc, i); key[i] = (11 - nb[i] / 12) * 12 + nb[i] % 12; }
+        // 50+j: own on-board pieces whose action list holds the j-th empty neighbour of the opponent queen
+        // (every piece looks at the queen of the other colour; table built once per game above).
+        if (bb_any(mv)) {
+            const uint32_t* tbl = &sm.qn[(1 - color) * 6];
 #pragma unroll
             for (int i = 0; i < 6; i++) {
-                if (words_test(gs.occ, nb[i]) || !bb_test(mv, nb[i])) continue;
-                int j = 0;
-#pragma unroll
-                for (int t = 0; t < 6; t++) j += key[t] < key[i];
-                atomicOr(&sm.planes[(own ? 50 : 44) + j][wi], bit);
+                const uint32_t e = tbl[i];
+                if (((e >> 12) & 1u) && words_test(gs.moves[lane], (int)(e & 0xFFu)))
+                    atomicOr(&sm.planes[(own ? 50 : 44) + ((e >> 8) & 7u)][wi], bit);
             }
         }
     }
@@ -582,15 +591,18 @@ __device__ __forceinline__ EvalResult eval_encode(WarpScratch& sm, const GameScr
 // ------------------------------------------------------------------------------------------
 // Expand the 56 bit planes to bf16 CHW [56][144] (16,128 B) with coalesced 16-byte stores.
 // `lut` = 16 x uint2 in shared memory: nibble -> four bf16 {0,1} values.
-__device__ __forceinline__ void fill_bf16_lut(uint2* lut, int t) {
-    if (t < 16) {
-        uint2 v;
+// `lut` = 256 x uint4 in shared memory: byte of eight {0,1} cells -> eight bf16 values.
+__device__ __forceinline__ void fill_bf16_lut(uint4* lut, int t) {
+    if (t < 256) {
+        uint4 v;
         v.x = ((t & 1) ? 0x3F80u : 0u) | ((t & 2) ? 0x3F800000u : 0u);
         v.y = ((t & 4) ? 0x3F80u : 0u) | ((t & 8) ? 0x3F800000u : 0u);
+        v.z = ((t & 16) ? 0x3F80u : 0u) | ((t & 32) ? 0x3F800000u : 0u);
+        v.w = ((t & 64) ? 0x3F80u : 0u) | ((t & 128) ? 0x3F800000u : 0u);
         lut[t] = v;
     }
 }
-__device__ __forceinline__ void store_planes_bf16(const WarpScratch& sm, const uint2* lut, int lane, int turn,
+__device__ __forceinline__ void store_planes_bf16(const WarpScratch& sm, const uint4* lut, int lane, int turn,
                                                   uint16_t* __restrict__ out) {
     const uint8_t* bytes = reinterpret_cast<const uint8_t*>(&sm.planes[0][0]);   // 20 B per plane, 18 used
     // bf16(turn): turn <= 255 is exact in bf16 (8 significant bits)
@@ -604,9 +616,7 @@ __device__ __forceinline__ void store_planes_bf16(const WarpScratch& sm, const u
     uint4* o = reinterpret_cast<uint4*>(out) + half * 18 + j;
 #pragma unroll
     for (int i = 0; i < N_PLANE / 2; i++) {
-        const uint32_t x = b[i * 40];
-        const uint2 lo = lut[x & 15u], hi = lut[x >> 4];
-        uint4 v = make_uint4(lo.x, lo.y, hi.x, hi.y);
+        uint4 v = lut[b[i * 40]];
         if (i == 15 && half) v = turn4;                         // plane 31 = the turn number
         o[i * 36] = v;
     }
@@ -616,9 +626,7 @@ __device__ __forceinline__ void store_planes_bf16(const WarpScratch& sm, const u
         const int u = lane + 32 * i;
         if (u < 2 * N_PLANE) {
             const int p = u >> 1, jj = 16 + (u & 1);
-            const uint32_t x = bytes[p * 20 + jj];
-            const uint2 lo = lut[x & 15u], hi = lut[x >> 4];
-            uint4 v = make_uint4(lo.x, lo.y, hi.x, hi.y);
+            uint4 v = lut[bytes[p * 20 + jj]];
             if (p == 31) v = turn4;
             reinterpret_cast<uint4*>(out)[p * 18 + jj] = v;
         }

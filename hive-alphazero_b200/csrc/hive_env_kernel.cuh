@@ -40,6 +40,7 @@ struct EnvArgs {
 // ---- kernel 1: decode the operation, apply the action, analyse the new position (warp <-> game)
 __global__ void __launch_bounds__(GROUP * 32) hive_analyse_kernel(EnvArgs a) {
     __shared__ GroupQueues q;
+    __shared__ uint32_t occ_s[GROUP][8];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.x * GROUP + warp;
     if (tid < 5) (&q.n_flood)[tid] = 0;
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(GROUP * 32) hive_analyse_kernel(EnvArgs a) {
             __syncwarp();
             if (lane < N_PIECE) { rec->cell[lane] = (uint8_t)cell; rec->level[lane] = (uint8_t)level; }
             if (lane == 0) { hw[12] = episode; hw[13] = steps; }
-            eval_analyse(a.scratch[g], q, warp, lane, cell, level, turn, push, winner);
+            eval_analyse(a.scratch[g], q, occ_s[warp], warp, lane, cell, level, turn, push, winner);
         } else if (lane == 0) {
             a.scratch[g].head[2] = 0;                           // not evaluated in this launch
         }
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hive_moves_kernel(EnvArgs a) {
 // ---- kernel 4: legal mask, planes, history, terminal test, outputs (warp <-> game)
 __global__ void __launch_bounds__(HIVE_ENCODE_WARPS * 32) hive_encode_kernel(EnvArgs a) {
     __shared__ WarpScratch scratch[HIVE_ENCODE_WARPS];
-    __shared__ uint2 bf16_lut[16];
+    __shared__ uint4 bf16_lut[256];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.x * HIVE_ENCODE_WARPS + warp;
     fill_bf16_lut(bf16_lut, tid);
