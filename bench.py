@@ -309,7 +309,21 @@ def main():
     per_launch_bytes = BYTES_PER_ENV_STEP * env_steps / max(launches, 1)
     launch_s = ms * 1e-3 / max(launches, 1)
     achieved = per_launch_bytes / launch_s / 1e9
+    # the step is ~96 % writes (16,128 + 200 of 17,094 B): a write-only stream reaches far less than the
+    # copy figure the contract's denominator is; measure it here for context (torch fill of 1 GiB)
+    wbuf = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
+    for _ in range(2):
+        wbuf.zero_()
+    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0.record()
+    for _ in range(5):
+        wbuf.zero_()
+    w1.record()
+    torch.cuda.synchronize()
+    write_only = 5 * (1 << 30) / (w0.elapsed_time(w1) * 1e-3) / 1e9
+    del wbuf
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "write_only_stream_gbs": write_only, "frac_of_write_only_stream": achieved / write_only,
                 "traffic": ncu_traffic(), "kernel": "hive_env_kernel", "peak_source": peak_src,
                 "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP,
                 "env_steps_per_launch": env_steps / max(launches, 1), "launch_us": launch_s * 1e6}
