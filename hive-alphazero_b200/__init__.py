@@ -16,9 +16,12 @@ def __getattr__(name):
     if name in ("HiveNet", "FoldedNet", "LeafEvaluator", "host_net_callable", "device_view"):
         from . import net
         return getattr(net, name)
-    if name == "SelfPlayBatch":
-        from .selfplay import SelfPlayBatch
-        return SelfPlayBatch
+    if name in ("SelfPlayBatch", "write_play_file", "sample_to_reference_row"):
+        from . import selfplay
+        return getattr(selfplay, name)
+    if name == "EvaluatorMatch":
+        from .evaluator import EvaluatorMatch
+        return EvaluatorMatch
     raise AttributeError(name)
 
 __all__ = ["config", "build", "lib", "LIB_PATH", "ENV_SYMBOLS", "HiveError", "GamePlay", "HiveBatch",

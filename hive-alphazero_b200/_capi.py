@@ -17,7 +17,7 @@ ENV_SYMBOLS = [
 NET_SYMBOLS = ["net_create", "net_destroy", "net_load_conv_host", "net_trunk_forward", "net_launch_count"]
 MCTS_SYMBOLS = [
     "mcts_create", "mcts_destroy", "mcts_set_params", "mcts_set_root_noise_host", "mcts_begin", "mcts_descend",
-    "mcts_expand", "mcts_dev_leaf_planes", "mcts_dev_leaf_policy", "mcts_dev_leaf_value", "mcts_dev_pending_mask",
+    "mcts_expand", "mcts_pending_host", "mcts_dev_leaf_planes", "mcts_dev_leaf_policy", "mcts_dev_leaf_value", "mcts_dev_pending_mask",
     "mcts_leaf_planes_host", "mcts_set_leaf_eval_host", "mcts_policy_host", "mcts_root_stats_host", "mcts_launch_count",
 ]
 
@@ -73,6 +73,7 @@ def lib():
     L.mcts_begin.argtypes = [vp, vp]
     L.mcts_descend.argtypes = [vp, vp]
     L.mcts_expand.argtypes = [vp]
+    L.mcts_pending_host.argtypes = [vp, vp]
     for name in ("mcts_dev_leaf_planes", "mcts_dev_leaf_policy", "mcts_dev_leaf_value", "mcts_dev_pending_mask"):
         getattr(L, name).argtypes = [vp]
         getattr(L, name).restype = vp

@@ -147,7 +147,13 @@ extern "C" {
 const char* hive_last_error(void) { return g_err.c_str(); }
 int hive_abi_version(void) { return 1; }
 
-int hive_create(int n_games, int device, void* stream, hive_env_t** out) {
+int hive_create(int n_games, int device, void* stream, hive_env_t** out) { return hive::create_env(n_games, device, stream, 0, out); }
+
+}  // extern "C"
+
+// slices <= 0: HIVE_B200_SLICES / the default; the search's working batch asks for 1 (its evaluations are
+// not graph-replayed, so fewer launches win)
+int hive::create_env(int n_games, int device, void* stream, int slices, hive_env** out) {
     if (!out || n_games <= 0) return fail(HIVE_E_ARG, "hive_create: bad arguments");
     *out = nullptr;
     int ndev = 0;
@@ -174,7 +180,7 @@ int hive_create(int n_games, int device, void* stream, hive_env_t** out) {
     CUDA_TRY(cudaMalloc(&h->scratch, n * sizeof(GameScratch)));
     {
         const char* e = getenv("HIVE_B200_SLICES");
-        int S = e ? atoi(e) : HIVE_DEFAULT_SLICES;
+        int S = slices > 0 ? slices : (e ? atoi(e) : HIVE_DEFAULT_SLICES);
         if (S < 1) S = 1;
         if (S > hive_env::MAX_SUB) S = hive_env::MAX_SUB;
         while (S > 1 && n_games < S * GROUP * 8) S--;         // small batches are not worth slicing
@@ -216,6 +222,8 @@ int hive_create(int n_games, int device, void* stream, hive_env_t** out) {
     *out = h;
     return 0;
 }
+
+extern "C" {
 
 int hive_destroy(hive_env_t* h) {
     if (!h) return 0;

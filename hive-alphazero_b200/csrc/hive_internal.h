@@ -41,6 +41,8 @@ struct hive_env {
 
 
 namespace hive {
+// hive_create with an explicit slice count (<= 0: default)
+int create_env(int n_games, int device, void* stream, int slices, hive_env** out);
 // sets the thread-local error text and returns `code`
 int fail(int code, const std::string& msg);
 // one environment step / evaluation over the whole batch (see hive_env_kernel.cuh for `op`)

@@ -59,7 +59,7 @@ int mcts_create(hive_env_t* env, int sims, int edges_per_sim, hive_mcts_t** out)
     CUDA_TRY(cudaSetDevice(env->device));
     hive_mcts* m = new hive_mcts();
     m->env = env; m->n = env->n; m->sims = sims;
-    int rc = hive_create(env->n, env->device, env->stream, &m->sim);     // same stream: strict ordering
+    int rc = create_env(env->n, env->device, env->stream, 1, &m->sim);   // same stream: strict ordering; one slice
     if (rc) { delete m; return rc; }
     m->node_cap = sims + 1;
     if (edges_per_sim <= 0) edges_per_sim = 96;
@@ -197,6 +197,15 @@ int mcts_set_leaf_eval_host(hive_mcts_t* m, const float* policy, const double* v
     CUDA_TRY(cudaMemcpyAsync(m->leaf_p, policy, (size_t)m->n * 1584 * 4, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(m->leaf_v, value, (size_t)m->n * 8, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int mcts_pending_host(hive_mcts_t* m, int* n_pending) {
+    if (check(m)) return HIVE_E_HANDLE;
+    if (!n_pending) return fail(HIVE_E_ARG, "mcts_pending_host: null output");
+    CUDA_TRY(cudaSetDevice(m->env->device));
+    CUDA_TRY(cudaMemcpyAsync(n_pending, m->pending, 4, cudaMemcpyDeviceToHost, m->env->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->env->stream));
     return 0;
 }
 

@@ -417,7 +417,9 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_finalize_kernel(MctsArgs
         const int oi = __shfl_xor_sync(FULL, bi, o);
         if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
     }
-    if (lane == 0) { a.out_action[t] = bi; a.out_sum_n[t] = (int)sum; }
+    // a root without legal actions holds only the pass edge: the batched driver passes (-1); the policy
+    // vector keeps the reference's policy[-1] quirk
+    if (lane == 0) { a.out_action[t] = nd.n_legal > 0 ? bi : -1; a.out_sum_n[t] = (int)sum; }
 }
 
 }  // namespace hive

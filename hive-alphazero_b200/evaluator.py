@@ -1,0 +1,60 @@
+"""New-vs-best evaluator match (reference: woker/evaluation.py:128-310 and hive-report.pdf p.6;
+BASELINE configs[4]): two networks play each other with colours split evenly, the first four plies
+are uniformly random, afterwards every side moves by its own PUCT search; wins are tallied per net.
+Games are independent, one tree per game, both nets evaluated as batched leaf inference.
+"""
+import time
+
+import numpy as np
+
+from . import config as C
+from .env import HiveBatch
+from .mcts import MctsBatch
+
+
+class EvaluatorMatch:
+    def __init__(self, n_games, sims, eval_new, eval_best, device=0, stream=None, seed=0, random_plies=4):
+        self.env = HiveBatch(n_games, device=device, stream=stream)
+        self.mcts = MctsBatch(self.env, sims)
+        self.mcts.set_root_noise(None)
+        self.mcts.set_params(sims, C.MAX_GAME_LENGTH, noise_seed=seed * 104729 + 5)
+        self.eval_new, self.eval_best = eval_new, eval_best
+        self.n, self.sims, self.random_plies = n_games, sims, random_plies
+        self.rng = np.random.RandomState(seed)
+        self.new_is_white = np.arange(n_games) < n_games // 2          # colours split evenly
+        self.moves = 0
+        self.waves = 0
+
+    def play(self, max_plies=C.MAX_GAME_LENGTH):
+        """Play every game to the end (or max_plies).  Returns the tally and timing."""
+        t0 = time.perf_counter()
+        for _ in range(max_plies):
+            turn, winner, done = self.env.status()
+            over = (done != 0) | (turn >= C.MAX_GAME_LENGTH)
+            live = ~over
+            if not live.any():
+                break
+            actions = np.full(self.n, C.NOOP, dtype=np.int32)
+            t = int(turn[live][0])                                       # all live games are at the same ply
+            if t <= self.random_plies:                                   # evaluation.py:169-170,187-188
+                legal = self.env.actions()
+                for g in np.nonzero(live)[0]:
+                    actions[g] = int(self.rng.choice(legal[g])) if len(legal[g]) else -1
+            else:
+                white_to_move = (t % 2) == 1
+                new_moves = live & (self.new_is_white == white_to_move)
+                best_moves = live & ~new_moves
+                for mask, ev in ((new_moves, self.eval_new), (best_moves, self.eval_best)):
+                    if mask.any():
+                        self.waves += self.mcts.search_device(ev, tree_mask=mask.astype(np.uint8))
+                        a = self.mcts.actions()
+                        actions[mask] = a[mask]
+            self.env.step(actions)
+            self.moves += int(live.sum())
+        self.env.sync()
+        turn, winner, done = self.env.status()
+        white_won, black_won = winner == 1, winner == 2
+        new_wins = int((white_won & self.new_is_white).sum() + (black_won & ~self.new_is_white).sum())
+        best_wins = int((white_won & ~self.new_is_white).sum() + (black_won & self.new_is_white).sum())
+        return dict(games=self.n, new_wins=new_wins, best_wins=best_wins, draws=self.n - new_wins - best_wins,
+                    moves=self.moves, waves=self.waves, seconds=time.perf_counter() - t0)

@@ -118,14 +118,27 @@ class MctsBatch:
 
     def search_device(self, evaluate_device, tree_mask=None):
         """Full search with a device evaluator ``evaluate_device(planes_ptr, policy_ptr, value_ptr,
-        mask_ptr, n)`` (all device pointers) called once per wave."""
+        mask_ptr, n)`` (all device pointers) called once per wave.  Every wave finishes at least one
+        simulation of every unfinished tree, so `sims` waves always suffice: the loop runs without
+        reading anything back and checks once at the end."""
         self.begin(tree_mask)
         waves = 0
-        while self.descend() > 0:
+        for _ in range(self.sims):
+            check(lib().mcts_descend(self._h, None), "mcts_descend")
+            evaluate_device(self.dev_leaf_planes, self.dev_leaf_policy, self.dev_leaf_value, self.dev_pending_mask, self.n)
+            self.expand()
+            waves += 1
+        while self.descend() > 0:                            # normally returns 0 at once
             evaluate_device(self.dev_leaf_planes, self.dev_leaf_policy, self.dev_leaf_value, self.dev_pending_mask, self.n)
             self.expand()
             waves += 1
         return waves
+
+    def actions(self):
+        """Only the chosen moves (int32[n]) -- skips the 12.7 KB/tree policy read-back."""
+        action = np.empty(self.n, dtype=np.int32)
+        check(lib().mcts_policy_host(self._h, None, action.ctypes.data, None), "mcts_policy_host")
+        return action
 
     def policy(self):
         """(pi float64[n,1584], action int32[n], sum_n int32[n]) -- calc_policy + apply_temperature."""

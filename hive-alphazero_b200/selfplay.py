@@ -10,6 +10,9 @@ winner's side, and -1 for BOTH sides when the game is drawn or cut at MAX_GAME_L
 
 For the single-game, RNG-stream-exact drop-in use ``GamePlay`` + ``HivePlayer`` directly.
 """
+import datetime
+import json
+import os
 import time
 
 import numpy as np
@@ -61,20 +64,31 @@ class SelfPlayBatch:
             live = ~over
             self.waves += self.mcts.search_device(self.evaluator, tree_mask=live.astype(np.uint8))
             self.search_calls += 1
-            pi, mcts_action, _ = self.mcts.policy()
-            legal = self.env.actions()
-            planes = self.env.planes_bf16() if self.collect else None
+            # after the opening (error < 0.1 from turn 7 on) the move is the search's own choice: no need to
+            # read policies or legal lists back unless samples are being collected
+            fast = (not self.collect) and bool((turn[live] > 6).all()) if live.any() else True
             actions = np.full(self.n, C.NOOP, dtype=np.int32)
-            for g in range(self.n):
-                if over[g]:
-                    self._finish(g, int(winner[g]), int(turn[g]))
+            if fast:
+                mcts_action = self.mcts.actions()
+                actions[live] = mcts_action[live]
+                for g in np.nonzero(over)[0]:
+                    self._finish(int(g), int(winner[g]), int(turn[g]))
                     if restart_finished:
-                        actions[g] = -3                       # HIVE_RESET
-                    continue
-                a = self._choose(pi[g], mcts_action[g], legal[g], int(turn[g]))
-                if self.collect:
-                    self.samples[g].append((planes[g].copy(), pi[g].astype(np.float32), int(turn[g]) % 2))
-                actions[g] = a
+                        actions[g] = -3
+            else:
+                pi, mcts_action, _ = self.mcts.policy()
+                legal = self.env.actions()
+                planes = self.env.planes_bf16() if self.collect else None
+                for g in range(self.n):
+                    if over[g]:
+                        self._finish(g, int(winner[g]), int(turn[g]))
+                        if restart_finished:
+                            actions[g] = -3                       # HIVE_RESET
+                        continue
+                    a = self._choose(pi[g], mcts_action[g], legal[g], int(turn[g]))
+                    if self.collect:
+                        self.samples[g].append((planes[g].copy(), pi[g].astype(np.float32), int(turn[g]) % 2))
+                    actions[g] = a
             self.env.step(actions)
             self.moves += int(live.sum())
         self.env.sync()
@@ -98,3 +112,22 @@ class SelfPlayBatch:
             self.samples[g] = []
             self.finished_samples = getattr(self, "finished_samples", [])
             self.finished_samples.extend(data)
+
+
+def sample_to_reference_row(planes_bf16, pi, value, lens):
+    """One finished sample in the reference's on-disk form (self_play.py:160,190):
+    [planes 12x12x56 nested list, pi[1584], value, [game_len_for_side, move_idx_for_side]]."""
+    f = (np.asarray(planes_bf16, dtype=np.uint16).astype(np.uint32) << 16).view(np.float32).reshape(C.STATE_FEATURES, 12, 12)
+    hwc = f.transpose(1, 2, 0).astype(np.float64)
+    return [hwc.tolist(), [float(x) for x in pi], int(value), [int(lens[0]), int(lens[1])]]
+
+
+def write_play_file(samples, directory="."):
+    """Flush samples like SelfPlayWorker.flush_buffer (self_play.py:100-112, sl.py:49-60):
+    ``play_%Y%m%d-%H%M%S.%f.json`` holding the list of rows.  Returns the path."""
+    os.makedirs(directory, exist_ok=True)
+    game_id = datetime.datetime.now().strftime("%Y%m%d-%H%M%S.%f")
+    path = os.path.join(directory, "play_%s.json" % game_id)
+    with open(path, "wt") as f:
+        json.dump([sample_to_reference_row(*s) for s in samples], f)
+    return path

@@ -142,6 +142,8 @@ int mcts_set_root_noise_host(hive_mcts_t* m, const double* noise, int rows, int 
 int mcts_begin(hive_mcts_t* m, const uint8_t* tree_mask /*host, NULL = all*/);
 int mcts_descend(hive_mcts_t* m, int* n_pending /*host, may be NULL*/);
 int mcts_expand(hive_mcts_t* m);
+/* number of trees that asked for an evaluation in the last mcts_descend (synchronises) */
+int mcts_pending_host(hive_mcts_t* m, int* n_pending);
 /* leaf evaluation interface (device): planes bf16 [n][56][144] in, policy float [n][1584] and value
  * double [n] out; only rows whose pending-mask byte is 1 are read. */
 void* mcts_dev_leaf_planes(hive_mcts_t* m);

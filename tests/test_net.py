@@ -100,3 +100,30 @@ def test_tensor_core_trunk_matches_references():
     assert float((p - p_ref).abs().max()) <= 1e-2 and float((v - v_ref).abs().max()) <= 1e-2
     assert float((p - p_lib).abs().max()) <= 1e-2
     assert folded.trunk.launches >= 40
+
+
+@pytest.mark.gpu
+def test_selfplay_samples_and_evaluator_match(tmp_path):
+    """Row f1/f3: finished games produce the reference's sample rows (value -1 for both sides on a cut
+    game); the evaluator match plays two nets with split colours and tallies wins."""
+    import json
+    import hive_b200
+    torch.manual_seed(0)
+    net_a = hive_b200.HiveNet().eval()
+    torch.manual_seed(1)
+    net_b = hive_b200.HiveNet().eval()
+    stream = torch.cuda.Stream()
+    fa = hive_b200.FoldedNet(net_a, device="cuda").attach_trunk(stream_ptr=stream.cuda_stream, max_boards=64)
+    fb = hive_b200.FoldedNet(net_b, device="cuda").attach_trunk(stream_ptr=stream.cuda_stream, max_boards=64)
+    with torch.cuda.stream(stream):
+        sp = hive_b200.SelfPlayBatch(8, 4, hive_b200.LeafEvaluator(fa), stream=stream.cuda_stream, seed=5, collect=True)
+        sp.play_moves(56)                                    # every game reaches the turn-55 cut (or ends) and is flushed
+        assert len(sp.finished) >= 8 and len(sp.finished_samples) >= 8 * 50
+        planes, pi, value, lens = sp.finished_samples[0]
+        assert value in (-1, 1) and lens[1] == 1 and abs(float(pi.sum()) - 1.0) < 1e-5
+        path = hive_b200.write_play_file(sp.finished_samples[:3], str(tmp_path))
+        rows = json.load(open(path))
+        assert len(rows) == 3 and len(rows[0][0]) == 12 and len(rows[0][0][0][0]) == 56 and len(rows[0][1]) == 1584
+        ev = hive_b200.EvaluatorMatch(16, 4, hive_b200.LeafEvaluator(fa), hive_b200.LeafEvaluator(fb), stream=stream.cuda_stream, seed=2)
+        r = ev.play()
+    assert r["games"] == 16 and r["new_wins"] + r["best_wins"] + r["draws"] == 16 and r["moves"] > 16 * 20
