@@ -118,6 +118,8 @@ __global__ void __launch_bounds__(CONV_THREADS, CONV_CTAS_PER_SM) hive_conv3x3_k
         // ------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             const uint32_t idesc = idesc_bf16(CONV_OC_TILE, CONV_N);
+            const uint64_t a_desc0 = smem_desc(smem_u32(sA), CONV_OC_TILE * 16, 128, 0);     // LBO = k-group stride, SBO = 8 rows
+            const uint64_t b_desc0 = smem_desc(smem_u32(sB), CONV_PLANE_BYTES, 128, 0);
             int as = 0, aph = 0, bs = 0, bph = 0;
             uint32_t empty_ph = 0;                                     // bit s: parity of the next wait on acc_empty[s]
             int k = 0;
@@ -132,20 +134,20 @@ __global__ void __launch_bounds__(CONV_THREADS, CONV_CTAS_PER_SM) hive_conv3x3_k
                 tc_fence_after();
                 for (int c = 0; c < a.n_chunks; c++) {
                     mbar_wait(&b_full[bs], bph);
+#pragma unroll
                     for (int t = 0; t < 9; t++) {
                         mbar_wait(&a_full[as], aph);
                         tc_fence_after();
-                        const uint32_t shift = (uint32_t)((t / 3) * CONV_PADW + (t % 3)) * 16;
-                        const uint32_t a_addr = smem_u32(sA + as * CONV_A_BYTES);
+                        // descriptors differ only in their 14-bit start-address field: add to the low word
+                        const uint32_t kShift = (uint32_t)((t / 3) * CONV_PADW + (t % 3));              // 16-byte units (constant after unrolling)
+                        const uint64_t a_lo = a_desc0 + (uint64_t)((uint32_t)(as * CONV_A_BYTES) >> 4);
 #pragma unroll
                         for (int j = 0; j < CONV_BOARDS; j++) {
-                            const uint32_t b_addr = smem_u32(sB + (bs * CONV_BOARDS + j) * CONV_BOARD_BYTES) + shift;
+                            const uint64_t b_lo = b_desc0 + (uint64_t)(((uint32_t)((bs * CONV_BOARDS + j) * CONV_BOARD_BYTES) >> 4) + kShift);
 #pragma unroll
-                            for (int ks = 0; ks < 4; ks++) {
-                                const uint64_t ad = smem_desc(a_addr + 2 * ks * (CONV_OC_TILE * 16), CONV_OC_TILE * 16, 128, 0);
-                                const uint64_t bd = smem_desc(b_addr + 2 * ks * CONV_PLANE_BYTES, CONV_PLANE_BYTES, 128, 0);
-                                mma_bf16(tmem + slot[j] * CONV_N, ad, bd, idesc, (c | t | ks) != 0);
-                            }
+                            for (int ks = 0; ks < 4; ks++)
+                                mma_bf16(tmem + slot[j] * CONV_N, a_lo + (uint64_t)(ks * ((2 * CONV_OC_TILE * 16) >> 4)),
+                                         b_lo + (uint64_t)(ks * ((2 * CONV_PLANE_BYTES) >> 4)), idesc, (c | t | ks) != 0);
                         }
                         mma_commit(&a_empty[as]);                      // weight stage free when these MMAs retire
                         if (++as == CONV_A_STAGES) { as = 0; aph ^= 1; }
