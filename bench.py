@@ -304,11 +304,22 @@ def main():
     env_steps_all = allsum(float(env_steps))
     value = env_steps_all / (ms_max * 1e-3)
 
-    # roofline of the dominant (only) kernel, this rank
+    # roofline, this rank.  One "launch" of the hot path = one step = analyse -> flood -> moves -> encode over
+    # the whole batch (cut into slices inside one CUDA graph); algorithmic bytes as in SURVEY 8d / DESIGN.md.
     peak, peak_src = measured_peak()
-    per_launch_bytes = BYTES_PER_ENV_STEP * env_steps / max(launches, 1)
-    launch_s = ms * 1e-3 / max(launches, 1)
+    n_steps = max(args.steps, 1)
+    per_launch_bytes = BYTES_PER_ENV_STEP * env_steps / n_steps
+    launch_s = ms * 1e-3 / n_steps
     achieved = per_launch_bytes / launch_s / 1e9
+    # the dominant kernel alone (hive_encode_kernel writes planes + legal mask + count/status + history):
+    # timed live with events between the four kernels of un-sliced steps
+    prof = [batch.profile_step(seed, args.max_turn) for _ in range(12)][2:]
+    kms = {k: sum(p[k] for p in prof) / len(prof) for k in prof[0]}
+    enc_bytes = (16128 + 198 + 8 + 384) * (env_steps / n_steps)
+    dominant = {"kernel": "hive_encode_kernel", "share_of_step": kms["encode"] / sum(kms.values()), "launch_us": kms["encode"] * 1e3,
+                "algorithmic_bytes_per_env_step": 16128 + 198 + 8 + 384, "achieved": enc_bytes / (kms["encode"] * 1e-3) / 1e9,
+                "per_kernel_us": {k: v * 1e3 for k, v in kms.items()}}
+    dominant["frac"] = dominant["achieved"] / peak
     # the step is ~96 % writes (16,128 + 200 of 17,094 B): a write-only stream reaches far less than the
     # copy figure the contract's denominator is; measure it here for context (torch fill of 1 GiB)
     wbuf = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
@@ -324,9 +335,10 @@ def main():
     del wbuf
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "write_only_stream_gbs": write_only, "frac_of_write_only_stream": achieved / write_only,
-                "traffic": ncu_traffic(), "kernel": "hive_env_kernel", "peak_source": peak_src,
-                "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP,
-                "env_steps_per_launch": env_steps / max(launches, 1), "launch_us": launch_s * 1e6}
+                "traffic": ncu_traffic(), "kernel": "env step = hive_analyse + hive_flood + hive_moves + hive_encode kernels",
+                "peak_source": peak_src, "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP,
+                "env_steps_per_launch": env_steps / n_steps, "launch_us": launch_s * 1e6,
+                "kernels_per_step": launches / n_steps, "dominant_kernel": dominant}
 
     # ------------------------------------------------------------------ e2e (host buffers)
     # The same 16,384 games driven from the host through the C ABI: every step reads legal masks,

@@ -346,6 +346,46 @@ int hive_step_random_multi(hive_env_t* h, uint64_t seed, int max_turn, int auto_
     return 0;
 }
 
+// One rollout step with CUDA events between the four kernels (whole batch as one slice, no graph):
+// ms[0..3] = analyse, flood, moves, encode.  For bench.py's per-kernel roofline; it advances the games.
+int hive_profile_step(hive_env_t* h, uint64_t seed, int max_turn, float* ms) {
+    if (check(h)) return HIVE_E_HANDLE;
+    if (!ms || max_turn < 1 || max_turn > 250) return fail(HIVE_E_ARG, "hive_profile_step: bad arguments");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaEvent_t ev[5];
+    for (int i = 0; i < 5; i++) CUDA_TRY(cudaEventCreate(&ev[i]));
+    EnvArgs a;
+    a.recs = h->recs; a.legal = h->legal; a.count = h->count; a.status = h->status; a.planes = h->planes;
+    a.actions = nullptr; a.mask = nullptr; a.chosen = nullptr; a.hop_lines = h->hop_lines;
+    a.seed = seed; a.n = h->n; a.op = OP_RANDOM; a.max_turn = max_turn; a.auto_reset = 1; a.g_offset = 0; a.n_total = h->n;
+    a.scratch = h->scratch;
+    // slice 0's queues are sized for a slice: use a whole-batch set allocated on the fly
+    BatchQueues q;
+    const size_t n = (size_t)h->n;
+    CUDA_TRY(cudaMalloc(&q.counters, 32)); CUDA_TRY(cudaMemsetAsync(q.counters, 0, 32, h->stream));
+    CUDA_TRY(cudaMalloc(&q.flood, n * N_PIECE * 4));
+    for (int c = 0; c < 4; c++) CUDA_TRY(cudaMalloc(&q.mv[c], n * 6 * 4));
+    a.bq = q;
+    const int groups = (h->n + GROUP - 1) / GROUP, enc_blocks = (h->n + HIVE_ENCODE_WARPS - 1) / HIVE_ENCODE_WARPS;
+    CUDA_TRY(cudaEventRecord(ev[0], h->stream));
+    hive_analyse_kernel<<<groups, GROUP * 32, 0, h->stream>>>(a);
+    CUDA_TRY(cudaEventRecord(ev[1], h->stream));
+    hive_flood_kernel<<<h->search_blocks, SEARCH_THREADS, 0, h->stream>>>(a);
+    CUDA_TRY(cudaEventRecord(ev[2], h->stream));
+    hive_moves_kernel<<<h->search_blocks, SEARCH_THREADS, 0, h->stream>>>(a);
+    CUDA_TRY(cudaEventRecord(ev[3], h->stream));
+    hive_encode_kernel<<<enc_blocks, HIVE_ENCODE_WARPS * 32, 0, h->stream>>>(a);
+    CUDA_TRY(cudaEventRecord(ev[4], h->stream));
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < 4; i++) CUDA_TRY(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+    for (int i = 0; i < 5; i++) cudaEventDestroy(ev[i]);
+    cudaFree(q.counters); cudaFree(q.flood);
+    for (int c = 0; c < 4; c++) cudaFree(q.mv[c]);
+    h->launches += 4;
+    return 0;
+}
+
 int hive_legal_host(hive_env_t* h, uint64_t* mask, int32_t* count) {
     if (check(h)) return HIVE_E_HANDLE;
     CUDA_TRY(cudaSetDevice(h->device));

@@ -160,6 +160,12 @@ class HiveBatch:
     @property
     def launches(self): return lib().hive_launch_count(self._h)
 
+    def profile_step(self, seed, max_turn=C.MAX_GAME_LENGTH):
+        """One rollout step timed kernel by kernel: dict(analyse, flood, moves, encode) in ms."""
+        ms = (ctypes.c_float * 4)()
+        check(lib().hive_profile_step(self._h, seed, max_turn, ms), "hive_profile_step")
+        return dict(zip(("analyse", "flood", "moves", "encode"), [float(x) for x in ms]))
+
     def set_timing(self, on): check(lib().hive_set_timing(self._h, 1 if on else 0), "hive_set_timing")
     def last_kernel_ms(self): return float(lib().hive_last_kernel_ms(self._h))
 
