@@ -160,3 +160,47 @@ if __name__ == "__main__":
         r = rollout(s)
         print(s, r["transcript"][:8].tolist(), r["legal_sum"],
               transcript_hash(r["transcript"]), "%.1fs" % (time.time() - t0))
+
+
+def inject(turn, cells, levels):
+    """Build a reference GamePlay holding an arbitrary position (history empty, no pending push):
+    pieces are taken from their inventory tiles and stacked bottom-up, then the same tail as
+    GamePlay.move (frontier with the turn-2 rule, state_key, pre_actions, make_state_value) is run."""
+    env = new_env()
+    keys = list(env.white_pieces_set.keys())
+    for lvl in range(5):
+        for p in range(22):
+            if cells[p] == 255 or levels[p] != lvl:
+                continue
+            pset = env.white_pieces_set if p < 11 else env.black_pieces_set
+            key = keys[p % 11]
+            inv_tile, _, piece = pset[key]
+            inv_tile.remove_piece()
+            tile = env.board_matrix[int(cells[p]) // 12, int(cells[p]) % 12]
+            assert len(tile.pieces) == lvl
+            tile.add_piece(piece)
+            pset[key] = [tile, lvl, piece]
+    env.state.turn = int(turn)
+    env.next_move_tiles = []
+    state_key = ""
+    for tile in env.state.board_tiles:
+        if tile.axial_coords != (99, 99):
+            if tile.has_pieces():
+                for adj in tile.adjacent_tiles:
+                    if not adj.has_pieces() and adj not in env.next_move_tiles:
+                        if env.state.turn == 2:
+                            if adj.core_index == ('M', '13'):
+                                env.next_move_tiles.append(adj)
+                        else:
+                            env.next_move_tiles.append(adj)
+                for piece in tile.pieces:
+                    state_key += env.pieces_keys[piece]
+            else:
+                state_key += "."
+    state_key += str(env.state.player())
+    env.state_key = state_key
+    env.history_white, env.history_black = [], []
+    env.add_history = False
+    env.encoded_action = env.pre_actions()
+    env.state_final = env.make_state_value()
+    return env
