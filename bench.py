@@ -202,10 +202,11 @@ def run_selfplay(args, hive_b200, torch, dist, rank, world, local_rank, allsum, 
     with torch.cuda.stream(stream):
         sp = hive_b200.SelfPlayBatch(n, sims, hive_b200.LeafEvaluator(folded), device=local_rank,
                                      stream=stream.cuda_stream, seed=args.seed + rank)
-        sp.play_moves(1)                                       # warm-up move (cuDNN autotune, allocations)
+        sp.play_moves(1)                                       # warm-up move (autotune, allocations): turn 1 -> 2
         barrier()
         torch.cuda.synchronize()
-        r = sp.play_moves(args.selfplay_moves)
+        r_open = sp.play_moves(5)                              # turns 2..6: the reference's opening schedule (policy read-back + noise mix)
+        r = sp.play_moves(args.selfplay_moves)                 # turns 7..: the search's own move, nothing but the action comes back
         torch.cuda.synchronize()
     barrier()
     gathered = None
@@ -215,9 +216,12 @@ def run_selfplay(args, hive_b200, torch, dist, rank, world, local_rank, allsum, 
     secs = allmax(r["seconds"])
     moves = allsum(float(r["moves"]))
     sims_per_s = moves * sims / secs
+    open_moves, open_secs = allsum(float(r_open["moves"])), allmax(r_open["seconds"])
     return {"workload": "configs[2]: AlphaZero self-play, %d sims/move, model_hive net random-init, %d concurrent games per GPU"
                         % (sims, n),
             "moves_per_s": moves / secs, "sims_per_s": sims_per_s, "moves": int(moves), "seconds": secs,
+            "opening_moves_per_s": open_moves / open_secs, "opening_moves": int(open_moves),
+            "full_game_moves_per_s_estimate": 54.0 / (5.0 / (open_moves / open_secs) + 49.0 / (moves / secs)),
             "waves": int(r["waves"]), "tensor_util": sims_per_s * 6.56e9 / (tf_peak * 1e12 * world),
             "tensor_peak_tflops": tf_peak, "tensor_peak_source": tf_src,
             "net": "BN-folded bf16; 39 trunk 3x3 convs = hand-written tcgen05 implicit GEMM (TMA halo tile, TMEM "

@@ -54,6 +54,33 @@ class SelfPlayBatch:
             action = int(self.rng.choice(legal, p=p))
         return action
 
+    def _choose_batch(self, pi, mcts_action, legal_bits, count, turn):
+        """The reference's move choice (self_play_with_train.py:169-183) for every game at once:
+        turns with error >= 0.1 sample from (1-error)*pi[legal] + error*Dir(0.5) (normalised)."""
+        n = len(turn)
+        chosen = np.asarray(mcts_action, dtype=np.int32).copy()
+        chosen[count == 0] = -1
+        error = 0.7 - ((turn + 1).astype(np.int64)).astype(np.float64) / 2 * 0.15
+        noisy = (error >= 0.1) & (count > 0)
+        if noisy.any():
+            idx = np.nonzero(noisy)[0]
+            rows, cols = np.nonzero(legal_bits[idx])                          # sparse legal entries, sorted by row
+            m = len(idx)
+            gam = self.rng.gamma(0.5, 1.0, size=len(rows))                    # Dirichlet(0.5) over each row's legal entries
+            noise = gam / np.bincount(rows, weights=gam, minlength=m)[rows]
+            e = error[idx][rows]
+            p = (1 - e) * pi[idx[rows], cols] + e * noise
+            p /= np.bincount(rows, weights=p, minlength=m)[rows]
+            cum = np.cumsum(p)
+            ends = np.cumsum(np.bincount(rows, minlength=m))                   # one past the last entry of each row
+            starts = ends - np.bincount(rows, minlength=m)
+            base = np.where(starts > 0, cum[np.maximum(starts - 1, 0)], 0.0)
+            target = base + self.rng.random_sample(m) * (cum[ends - 1] - base)
+            pos = np.minimum(np.maximum(np.searchsorted(cum, target, side="left"), starts), ends - 1)
+            pick = cols[pos]
+            chosen[idx] = pick
+        return chosen
+
     def play_moves(self, n_moves, restart_finished=True):
         """Advance every live game by n_moves plies. Returns dict(moves, seconds, waves)."""
         t0 = time.perf_counter()
@@ -77,18 +104,18 @@ class SelfPlayBatch:
                         actions[g] = -3
             else:
                 pi, mcts_action, _ = self.mcts.policy()
-                legal = self.env.actions()
+                mask, count = self.env.legal_mask()
+                legal_bits = np.unpackbits(mask.view(np.uint8), axis=1, bitorder="little")[:, :C.ACTION_SPACE].astype(bool)
                 planes = self.env.planes_bf16() if self.collect else None
-                for g in range(self.n):
-                    if over[g]:
-                        self._finish(g, int(winner[g]), int(turn[g]))
-                        if restart_finished:
-                            actions[g] = -3                       # HIVE_RESET
-                        continue
-                    a = self._choose(pi[g], mcts_action[g], legal[g], int(turn[g]))
-                    if self.collect:
+                chosen = self._choose_batch(pi, mcts_action, legal_bits, count, turn)
+                for g in np.nonzero(over)[0]:
+                    self._finish(int(g), int(winner[g]), int(turn[g]))
+                    if restart_finished:
+                        actions[g] = -3                           # HIVE_RESET
+                actions[live] = chosen[live]
+                if self.collect:
+                    for g in np.nonzero(live)[0]:
                         self.samples[g].append((planes[g].copy(), pi[g].astype(np.float32), int(turn[g]) % 2))
-                    actions[g] = a
             self.env.step(actions)
             self.moves += int(live.sum())
         self.env.sync()

@@ -20,4 +20,9 @@ with torch.cuda.stream(stream):
     sp = hive_b200.SelfPlayBatch(n, sims, hive_b200.LeafEvaluator(folded), stream=stream.cuda_stream, seed=1)
     sp.play_moves(1)
     r = sp.play_moves(moves)
+    print(json.dumps(dict(phase='opening', n=n, sims=sims, **r, moves_per_s=r['moves'] / r['seconds'])), flush=True)
+    for _ in range(6):
+        sp.env.step_random(3, 55, False)            # leave the opening schedule (turn > 6)
+    sp.play_moves(1)
+    r = sp.play_moves(moves)
 print(json.dumps(dict(n=n, sims=sims, **r, moves_per_s=r["moves"] / r["seconds"], sims_per_s=r["moves"] * sims / r["seconds"])))
