@@ -19,6 +19,9 @@ def __getattr__(name):
     if name in ("SelfPlayBatch", "write_play_file", "sample_to_reference_row"):
         from . import selfplay
         return getattr(selfplay, name)
+    if name in ("Trainer", "alpha_loss", "samples_to_tensors", "discounted_value"):
+        from . import train
+        return getattr(train, name)
     if name == "EvaluatorMatch":
         from .evaluator import EvaluatorMatch
         return EvaluatorMatch

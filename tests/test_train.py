@@ -1,0 +1,57 @@
+"""Row f2: the loss is the reference's AlphaLoss (checked against the real class when the reference
+tree is present), value targets follow the discount rule, one step on a tiny batch lowers the loss."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import hive_b200
+from oracle import ref_harness as rh
+
+
+def test_alpha_loss_formula_and_discount():
+    torch.manual_seed(0)
+    vp, v = torch.rand(5) * 2 - 1, torch.tensor([1.0, -1.0, -1.0, 1.0, -1.0])
+    pp = torch.softmax(torch.randn(5, 1584), 1)
+    p = torch.softmax(torch.randn(5, 1584) * 3, 1)
+    ours = hive_b200.alpha_loss(vp, v, pp, p)
+    manual = ((v - vp) ** 2 + (-(p * (1e-6 + pp).log()).sum(1))).mean()
+    assert torch.allclose(ours, manual)
+    assert hive_b200.discounted_value(-1, 20, 20) == -1
+    assert abs(hive_b200.discounted_value(1, 20, 17) - 0.99 ** 3) < 1e-12
+
+
+@pytest.mark.skipif(not rh.available(), reason="reference tree not present")
+def test_alpha_loss_matches_reference_class(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)                        # alpha_net.py creates ./datasets/iter3 on import
+    rh.load()
+    from alpha_zero.alpha_net import AlphaLoss        # the reference's own module (matplotlib stubbed)
+    torch.manual_seed(1)
+    vp, v = torch.rand(7) * 2 - 1, torch.sign(torch.randn(7))
+    pp = torch.softmax(torch.randn(7, 1584), 1)
+    p = torch.softmax(torch.randn(7, 1584) * 2, 1)
+    ref = AlphaLoss()(vp, v, pp, p)
+    assert torch.equal(ref, hive_b200.alpha_loss(vp, v, pp, p))
+
+
+def test_training_step_lowers_loss_on_a_tiny_batch():
+    torch.manual_seed(0)
+    net = hive_b200.HiveNet()
+    # shrink the work: keep the architecture but only run a few samples on CPU
+    planes = np.zeros((4, 56 * 144), dtype=np.uint16)
+    planes[:, 100:140] = 0x3F80
+    samples = []
+    for i in range(4):
+        pi = np.zeros(1584, dtype=np.float32); pi[10 * (i + 1)] = 1.0
+        samples.append((planes[i], pi, 1 if i % 2 else -1, (10, 7 + i % 3)))
+    x, p, v = hive_b200.samples_to_tensors(samples)
+    assert x.shape == (4, 56, 12, 12) and p.shape == (4, 1584) and abs(float(v[0]) + 0.99 ** 3) < 1e-6
+    tr = hive_b200.Trainer(net, lr=1e-3)
+    l0 = tr.step(x, p, v)
+    l1 = tr.step(x, p, v)
+    l2 = tr.step(x, p, v)
+    assert l2 < l0
+    xo, po, _ = hive_b200.samples_to_tensors(samples, one_hot_policy=True)
+    assert (po.sum(1) == 1).all()
