@@ -13,7 +13,7 @@ from .mcts import HivePlayer, MctsBatch
 
 def __getattr__(name):
     # torch-dependent parts are imported lazily so that the environment path does not need torch
-    if name in ("HiveNet", "FoldedNet", "LeafEvaluator", "host_net_callable", "device_view"):
+    if name in ("HiveNet", "FoldedNet", "LeafEvaluator", "SplitEvaluator", "host_net_callable", "device_view"):
         from . import net
         return getattr(net, name)
     if name in ("SelfPlayBatch", "write_play_file", "sample_to_reference_row"):

@@ -10,6 +10,7 @@ import numpy as np
 from . import config as C
 from .env import HiveBatch
 from .mcts import MctsBatch
+from .net import SplitEvaluator
 
 
 class EvaluatorMatch:
@@ -41,14 +42,13 @@ class EvaluatorMatch:
                 for g in np.nonzero(live)[0]:
                     actions[g] = int(self.rng.choice(legal[g])) if len(legal[g]) else -1
             else:
+                # one search for all games: the half where the new net is to move is evaluated by the new
+                # net, the other half by the best net (rows are ordered new-is-white first)
                 white_to_move = (t % 2) == 1
-                new_moves = live & (self.new_is_white == white_to_move)
-                best_moves = live & ~new_moves
-                for mask, ev in ((new_moves, self.eval_new), (best_moves, self.eval_best)):
-                    if mask.any():
-                        self.waves += self.mcts.search_device(ev, tree_mask=mask.astype(np.uint8))
-                        a = self.mcts.actions()
-                        actions[mask] = a[mask]
+                first, second = (self.eval_new, self.eval_best) if white_to_move else (self.eval_best, self.eval_new)
+                self.waves += self.mcts.search_device(SplitEvaluator(first, second, self.n // 2), tree_mask=live.astype(np.uint8))
+                a = self.mcts.actions()
+                actions[live] = a[live]
             self.env.step(actions)
             self.moves += int(live.sum())
         self.env.sync()

@@ -253,6 +253,22 @@ class LeafEvaluator:
         self.calls += 1
 
 
+class SplitEvaluator:
+    """Two networks in one search: rows [0, split) are evaluated by `first`, rows [split, n) by `second`
+    (the evaluator match keeps the games where the new net plays white in the first half)."""
+
+    def __init__(self, first, second, split):
+        self.first, self.second, self.split = first, second, int(split)
+
+    def __call__(self, planes_ptr, policy_ptr, value_ptr, mask_ptr, n):
+        k = self.split
+        if k > 0:
+            self.first(planes_ptr, policy_ptr, value_ptr, mask_ptr, k)
+        if n > k:
+            self.second(planes_ptr + k * C.STATE_FEATURES * CELLS * 2, policy_ptr + k * C.ACTION_SPACE * 4,
+                        value_ptr + k * 8, mask_ptr + k, n - k)
+
+
 def host_net_callable(folded):
     """planes (B,56,12,12) float32 ndarray -> (p, v) ndarrays; for HivePlayer.net."""
     def run(planes):
