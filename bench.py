@@ -201,7 +201,8 @@ def run_selfplay(args, hive_b200, torch, dist, rank, world, local_rank, allsum, 
     folded.attach_trunk(stream_ptr=stream.cuda_stream, max_boards=n)     # tcgen05 implicit-GEMM trunk (csrc/hive_conv_kernel.cuh)
     with torch.cuda.stream(stream):
         sp = hive_b200.SelfPlayBatch(n, sims, hive_b200.LeafEvaluator(folded), device=local_rank,
-                                     stream=stream.cuda_stream, seed=args.seed + rank)
+                                     stream=stream.cuda_stream, seed=args.seed + rank,
+                                     wave_graph=hive_b200.WaveGraph(stream))     # one search wave = one CUDA graph replay
         sp.play_moves(1)                                       # warm-up move (autotune, allocations): turn 1 -> 2
         barrier()
         torch.cuda.synchronize()

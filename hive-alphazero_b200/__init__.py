@@ -8,7 +8,7 @@ from . import config
 from ._build import LIB_PATH, build
 from ._capi import ENV_SYMBOLS, MCTS_SYMBOLS, HiveError, lib
 from .env import GamePlay, HiveBatch, host_pick_actions
-from .mcts import HivePlayer, MctsBatch
+from .mcts import HivePlayer, MctsBatch, WaveGraph
 
 
 def __getattr__(name):
@@ -28,4 +28,4 @@ def __getattr__(name):
     raise AttributeError(name)
 
 __all__ = ["config", "build", "lib", "LIB_PATH", "ENV_SYMBOLS", "HiveError", "GamePlay", "HiveBatch",
-           "host_pick_actions", "HivePlayer", "MctsBatch", "MCTS_SYMBOLS"]
+           "host_pick_actions", "HivePlayer", "MctsBatch", "WaveGraph", "MCTS_SYMBOLS"]

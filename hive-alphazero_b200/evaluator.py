@@ -14,7 +14,7 @@ from .net import SplitEvaluator
 
 
 class EvaluatorMatch:
-    def __init__(self, n_games, sims, eval_new, eval_best, device=0, stream=None, seed=0, random_plies=4):
+    def __init__(self, n_games, sims, eval_new, eval_best, device=0, stream=None, seed=0, random_plies=4, torch_stream=None):
         self.env = HiveBatch(n_games, device=device, stream=stream)
         self.mcts = MctsBatch(self.env, sims)
         self.mcts.set_root_noise(None)
@@ -25,6 +25,12 @@ class EvaluatorMatch:
         self.new_is_white = np.arange(n_games) < n_games // 2          # colours split evenly
         self.moves = 0
         self.waves = 0
+        # two wave graphs (white to move / black to move differ in which net evaluates which half)
+        self._graphs = None
+        if torch_stream is not None:
+            from .mcts import WaveGraph
+            self._graphs = {True: WaveGraph(torch_stream), False: WaveGraph(torch_stream)}
+        self._evals = {True: SplitEvaluator(eval_new, eval_best, n_games // 2), False: SplitEvaluator(eval_best, eval_new, n_games // 2)}
 
     def play(self, max_plies=C.MAX_GAME_LENGTH):
         """Play every game to the end (or max_plies).  Returns the tally and timing."""
@@ -45,8 +51,8 @@ class EvaluatorMatch:
                 # one search for all games: the half where the new net is to move is evaluated by the new
                 # net, the other half by the best net (rows are ordered new-is-white first)
                 white_to_move = (t % 2) == 1
-                first, second = (self.eval_new, self.eval_best) if white_to_move else (self.eval_best, self.eval_new)
-                self.waves += self.mcts.search_device(SplitEvaluator(first, second, self.n // 2), tree_mask=live.astype(np.uint8))
+                g = self._graphs[white_to_move] if self._graphs else None
+                self.waves += self.mcts.search_device(self._evals[white_to_move], tree_mask=live.astype(np.uint8), graph=g)
                 a = self.mcts.actions()
                 actions[live] = a[live]
             self.env.step(actions)

@@ -116,18 +116,27 @@ class MctsBatch:
             waves += 1
         return waves
 
-    def search_device(self, evaluate_device, tree_mask=None):
+    def search_device(self, evaluate_device, tree_mask=None, graph=None):
         """Full search with a device evaluator ``evaluate_device(planes_ptr, policy_ptr, value_ptr,
         mask_ptr, n)`` (all device pointers) called once per wave.  Every wave finishes at least one
         simulation of every unfinished tree, so `sims` waves always suffice: the loop runs without
-        reading anything back and checks once at the end."""
+        reading anything back and checks once at the end.
+
+        graph: a ``WaveGraph`` (see below) replays one captured wave instead of re-issuing its ~60
+        launches from Python every time -- worthwhile when a wave is short (small batches)."""
         self.begin(tree_mask)
         waves = 0
-        for _ in range(self.sims):
-            check(lib().mcts_descend(self._h, None), "mcts_descend")
-            evaluate_device(self.dev_leaf_planes, self.dev_leaf_policy, self.dev_leaf_value, self.dev_pending_mask, self.n)
-            self.expand()
-            waves += 1
+        if graph is not None:
+            graph.ensure(self, evaluate_device, tree_mask is not None)
+            for _ in range(self.sims):
+                graph.replay()
+            waves += self.sims
+        else:
+            for _ in range(self.sims):
+                check(lib().mcts_descend(self._h, None), "mcts_descend")
+                evaluate_device(self.dev_leaf_planes, self.dev_leaf_policy, self.dev_leaf_value, self.dev_pending_mask, self.n)
+                self.expand()
+                waves += 1
         while self.descend() > 0:                            # normally returns 0 at once
             evaluate_device(self.dev_leaf_planes, self.dev_leaf_policy, self.dev_leaf_value, self.dev_pending_mask, self.n)
             self.expand()
@@ -157,6 +166,38 @@ class MctsBatch:
         k = int(info[0])
         return dict(action=a[:k], n=n[:k], w=w[:k], q=q[:k], p=p[:k], sum_n=int(info[1]), n_nodes=int(info[2]),
                     sims_done=int(info[3]), error=int(info[4]), root_selects=int(info[5]))
+
+
+class WaveGraph:
+    """One search wave (descend -> leaf evaluation by the environment kernels -> network -> expand) captured
+    once as a CUDA graph on the stream shared by the library handles and torch, then replayed.  All buffers of
+    a wave are fixed arenas, so the captured launches stay valid for every wave of every search of this tree
+    batch with this evaluator."""
+
+    def __init__(self, torch_stream):
+        import torch
+        self._torch, self.stream = torch, torch_stream
+        self.g, self.key = None, None
+
+    def ensure(self, mcts, evaluate_device, masked):
+        key = (id(mcts), id(evaluate_device), bool(masked), mcts.sims)
+        if self.g is not None and self.key == key:
+            return
+        torch = self._torch
+        # one eager wave first: lets torch pick its algorithms / allocate outside the capture
+        check(lib().mcts_descend(mcts._h, None), "mcts_descend")
+        evaluate_device(mcts.dev_leaf_planes, mcts.dev_leaf_policy, mcts.dev_leaf_value, mcts.dev_pending_mask, mcts.n)
+        mcts.expand()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=self.stream, capture_error_mode="relaxed"):
+            check(lib().mcts_descend(mcts._h, None), "mcts_descend")
+            evaluate_device(mcts.dev_leaf_planes, mcts.dev_leaf_policy, mcts.dev_leaf_value, mcts.dev_pending_mask, mcts.n)
+            mcts.expand()
+        self.g, self.key = g, key
+
+    def replay(self):
+        self.g.replay()
 
 
 class HivePlayer:

@@ -23,12 +23,13 @@ from .mcts import MctsBatch
 
 
 class SelfPlayBatch:
-    def __init__(self, n_games, sims, evaluator, device=0, stream=None, seed=0, collect=False, edges_per_sim=0):
+    def __init__(self, n_games, sims, evaluator, device=0, stream=None, seed=0, collect=False, edges_per_sim=0, wave_graph=None):
         self.env = HiveBatch(n_games, device=device, stream=stream)
         self.mcts = MctsBatch(self.env, sims, edges_per_sim=edges_per_sim)
         self.mcts.set_root_noise(None)                      # Dirichlet(0.3) rows sampled on the device
         self.mcts.set_params(sims, C.MAX_GAME_LENGTH, noise_seed=seed * 7919 + 17)
         self.evaluator = evaluator
+        self.wave_graph = wave_graph                        # optional mcts.WaveGraph: replay captured waves
         self.n, self.sims = n_games, sims
         self.rng = np.random.RandomState(seed)
         self.collect = collect
@@ -89,7 +90,7 @@ class SelfPlayBatch:
             turn, winner, done = self.env.status()
             over = (done != 0) | (turn >= C.MAX_GAME_LENGTH)
             live = ~over
-            self.waves += self.mcts.search_device(self.evaluator, tree_mask=live.astype(np.uint8))
+            self.waves += self.mcts.search_device(self.evaluator, tree_mask=live.astype(np.uint8), graph=self.wave_graph)
             self.search_calls += 1
             # after the opening (error < 0.1 from turn 7 on) the move is the search's own choice: no need to
             # read policies or legal lists back unless samples are being collected

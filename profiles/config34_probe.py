@@ -30,7 +30,8 @@ bytes_b = par.broadcast_weights(net, src=0)
 start, cnt = par.shard_games(8192, world, rank)
 folded = hive_b200.FoldedNet(net, device="cuda").attach_trunk(stream_ptr=stream.cuda_stream, max_boards=max(cnt, 1024))
 with torch.cuda.stream(stream):
-    sp = hive_b200.SelfPlayBatch(cnt, 250, hive_b200.LeafEvaluator(folded), device=lr, stream=stream.cuda_stream, seed=100 + rank)
+    sp = hive_b200.SelfPlayBatch(cnt, 250, hive_b200.LeafEvaluator(folded), device=lr, stream=stream.cuda_stream, seed=100 + rank,
+                                 wave_graph=hive_b200.WaveGraph(stream))
     for _ in range(7): sp.env.step_random(5 + rank, 55, False)
     barrier(); torch.cuda.synchronize()
     r = sp.play_moves(moves3)
@@ -50,7 +51,7 @@ par.broadcast_weights(net_b, src=0)
 folded_b = hive_b200.FoldedNet(net_b, device="cuda").attach_trunk(stream_ptr=stream.cuda_stream, max_boards=1024)
 with torch.cuda.stream(stream):
     ev = hive_b200.EvaluatorMatch(1024, 500, hive_b200.LeafEvaluator(folded), hive_b200.LeafEvaluator(folded_b), device=lr,
-                                  stream=stream.cuda_stream, seed=7 + rank)
+                                  stream=stream.cuda_stream, seed=7 + rank, torch_stream=stream)
     barrier(); torch.cuda.synchronize()
     r = ev.play(max_plies=5)                                   # 4 random plies + one searched ply
     torch.cuda.synchronize()

@@ -17,7 +17,8 @@ with torch.cuda.stream(stream):
     torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 5
 print("net fwd batch", n, "trunk", "tcgen05" if folded.trunk else "cudnn", "ms", dt * 1e3, "TFLOP/s", n * 6.56e9 / dt / 1e12, flush=True)
 with torch.cuda.stream(stream):
-    sp = hive_b200.SelfPlayBatch(n, sims, hive_b200.LeafEvaluator(folded), stream=stream.cuda_stream, seed=1)
+    wg = hive_b200.WaveGraph(stream) if (len(sys.argv) > 5 and sys.argv[5] == 'graph') else None
+    sp = hive_b200.SelfPlayBatch(n, sims, hive_b200.LeafEvaluator(folded), stream=stream.cuda_stream, seed=1, wave_graph=wg)
     sp.play_moves(1)
     r = sp.play_moves(moves)
     print(json.dumps(dict(phase='opening', n=n, sims=sims, **r, moves_per_s=r['moves'] / r['seconds'])), flush=True)
