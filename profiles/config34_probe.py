@@ -33,6 +33,7 @@ with torch.cuda.stream(stream):
     sp = hive_b200.SelfPlayBatch(cnt, 250, hive_b200.LeafEvaluator(folded), device=lr, stream=stream.cuda_stream, seed=100 + rank,
                                  wave_graph=hive_b200.WaveGraph(stream))
     for _ in range(7): sp.env.step_random(5 + rank, 55, False)
+    sp.play_moves(1)                                          # warm-up move: autotune, graph capture, allocations
     barrier(); torch.cuda.synchronize()
     r = sp.play_moves(moves3)
     torch.cuda.synchronize()
@@ -52,10 +53,13 @@ folded_b = hive_b200.FoldedNet(net_b, device="cuda").attach_trunk(stream_ptr=str
 with torch.cuda.stream(stream):
     ev = hive_b200.EvaluatorMatch(1024, 500, hive_b200.LeafEvaluator(folded), hive_b200.LeafEvaluator(folded_b), device=lr,
                                   stream=stream.cuda_stream, seed=7 + rank, torch_stream=stream)
+    ev.play(max_plies=5)                                       # 4 random plies + one searched ply (warm-up)
     barrier(); torch.cuda.synchronize()
-    r = ev.play(max_plies=5)                                   # 4 random plies + one searched ply
+    r0 = ev.waves
+    r = ev.play(max_plies=2)                                   # two searched plies (one by each colour), timed
+    r["waves"] = ev.waves - r0
     torch.cuda.synchronize()
-searched = 1024.0
+searched = 2 * 1024.0
 secs, moves = allmax(r["seconds"]), allsum(searched)
 if rank == 0:
     print(json.dumps(dict(config="configs[4]: evaluator match 500 sims/move, 1024 games per GPU on %d B200" % world,
