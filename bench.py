@@ -301,7 +301,6 @@ def main():
     ev1.record(stream)
     torch.cuda.synchronize()
     barrier()
-    clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
     launches = batch.launches - launches0
     env_steps = int(batch.counters()[0].astype(np.int64).sum()) - steps0
@@ -397,6 +396,7 @@ def main():
            "planes stay in HBM for the net"}
     for h in halves:
         h["b"].close()
+    clocks = sampler.stop()                       # sampled over both timed regions (resident rollout + host-driven e2e)
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N=1)
     cpu = None

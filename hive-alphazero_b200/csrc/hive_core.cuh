@@ -1,14 +1,17 @@
-// hive_core.cuh -- warp-per-game Hive position evaluator for sm_100a.
+// hive_core.cuh -- device building blocks of the Hive position evaluator for sm_100a.
 //
-// One warp owns one game.  Lane p (0..21) owns piece p (white Q,B0,B1,S0,S1,G0,G1,G2,A0,A1,A2
-// then the same for black -- reference order, inventory_frame.py:47-99 / env_hive.py:71-87);
-// every lane keeps whole 144-cell boards in registers as a linear bit string (cell = q*12+r,
-// 5 x u32), so translating a board along one of the six torus directions (tile.py:111-123) is a
-// handful of funnel shifts and no shuffles.  Board-wide facts (occupancy, colour masks) are
-// OR-reduced across lanes with REDUX (__reduce_or_sync), stack heights come from
-// __match_any_sync, the per-piece searches (one-hive flood, Ant flood, 3-step Spider walk,
-// Grasshopper line flood) run concurrently in the lanes that own such a piece, and results are
-// combined into the dense 1584-bit legal mask and the 56 network planes in shared memory.
+// Boards are whole 144-cell bit strings held in registers (cell = q*12+r, 5 x u32), so translating a
+// board along one of the six torus directions (tile.py:111-123) is a handful of funnel shifts and no
+// shuffles.  A position is evaluated in three stages (kernels in hive_env_kernel.cuh):
+//   analyse -- one warp per game, lane p (0..21) owns piece p (white Q,B0,B1,S0,S1,G0,G1,G2,A0,A1,A2
+//              then the same for black: reference order, inventory_frame.py:47-99 / env_hive.py:71-87).
+//              Board-wide facts (occupancy, colour masks) are OR-reduced across lanes with REDUX
+//              (__reduce_or_sync), stack heights come from __match_any_sync; pieces that need a one-hive
+//              flood or a move search are queued.
+//   search  -- one thread per queued piece, warps homogeneous in piece type: one-hive flood, Ant flood
+//              over slide gates, exact 3-step Spider walk, Grasshopper line flood, Queen/Beetle ring logic.
+//   encode  -- one warp per game again: dense 1584-bit legal mask and the 56 network planes assembled in
+//              shared memory and written as bf16 with 16-byte stores.
 //
 // What is computed is exactly what the reference computes in GamePlay.move()'s tail
 // (hive_engine/env_hive.py:170-171): pre_actions() (env_hive.py:196-304, move_checker.py:9-55,
