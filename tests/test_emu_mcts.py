@@ -88,3 +88,53 @@ def test_three_trees_in_one_batch():
         acts, nn, w, q, p, sum_n, n_nodes = expect[t]
         assert st["action"].tolist() == acts.tolist() and st["n"].tolist() == nn.tolist()
         assert (st["w"] == w).all() and (st["p"] == p).all() and st["n_nodes"] == n_nodes
+
+
+# ---- searches from injected positions (pass-edge roots, tall stacks): reference results in mcts_injected.npz
+GI = np.load(os.path.join(ROOT, "tests", "golden", "mcts_injected.npz"))
+EP = np.load(os.path.join(ROOT, "tests", "golden", "edge_positions.npz"))
+
+
+def _check_injected(j, st, pi, action, sum_n):
+    k = int(GI["n_edges"][j])
+    assert st["action"].tolist() == GI["e_action"][j][:k].tolist() and st["n"].tolist() == GI["e_n"][j][:k].tolist()
+    assert (st["w"] == GI["e_w"][j][:k]).all() and (st["p"] == GI["e_p"][j][:k]).all()
+    assert st["sum_n"] == GI["sum_n"][j] and st["n_nodes"] == GI["n_nodes"][j]
+    assert (pi == GI["policy"][j]).all() and int(np.argmax(pi)) == GI["action"][j] and sum_n == GI["sum_n"][j]
+
+
+def test_fixture_has_pass_edge_roots():
+    assert int((GI["e_action"][:, 0] == -1).sum()) >= 1
+
+
+@pytest.mark.parametrize("j", range(len(GI["seed"])))
+def test_oracle_on_injected_roots(j):
+    i = int(GI["edge_index"][j])
+    env = OracleEnv()
+    env.load(int(EP["turn"][i]), EP["cells"][i], EP["levels"][i])
+    m = MctsOracle(hash_net, int(GI["sims"][j]))
+    np.random.seed(int(GI["seed"][j]))
+    action, policy, sum_all = m.action(env)
+    acts, n, w, q, p, sum_n, n_nodes = m.root_stats(env)
+    _check_injected(j, dict(action=acts, n=n, w=w, p=p, sum_n=sum_n, n_nodes=n_nodes), policy, action, sum_n)
+    assert action == GI["action"][j]
+
+
+@pytest.mark.parametrize("j", range(len(GI["seed"])))
+def test_kernels_on_injected_roots(j):
+    i = int(GI["edge_index"][j])
+    b = EmuBatch(1, sched_seed=40 + j)
+    b.load(0, int(EP["turn"][i]), EP["cells"][i], EP["levels"][i])
+    sims, k = int(GI["sims"][j]), max(int(EP["n_legal"][i]), 1)
+    m = EmuMcts(b, sims)
+    noise = np.zeros((1, sims, 256))
+    if EP["n_legal"][i] > 0:
+        np.random.seed(int(GI["seed"][j]))
+        for r in range(sims - 1):
+            noise[0, r, :k] = np.random.dirichlet([0.3] * k)
+    m.set_noise(noise)
+    m.search(hash_net)
+    st = m.root_stats(0)
+    pi, action, sum_n = m.policy()
+    assert st["error"] == 0
+    _check_injected(j, st, pi[0], action[0], sum_n[0])

@@ -95,3 +95,28 @@ def test_device_noise_search_runs_and_is_consistent(hb):
         assert st["action"].tolist() == legal[t].tolist()            # root edges == legal actions
         assert st["n"].sum() == sims - 1 and abs(pi[t].sum() - 1.0) < 1e-9
         assert action[t] in legal[t]
+
+
+GI = np.load(os.path.join(ROOT, "tests", "golden", "mcts_injected.npz"))
+EP = np.load(os.path.join(ROOT, "tests", "golden", "edge_positions.npz"))
+
+
+@pytest.mark.parametrize("j", range(len(GI["seed"])))
+def test_facade_on_injected_roots_incl_pass_edge(hb, j):
+    """Roots without legal actions (pass edge -1, policy[-1] quirk) and tall-stack roots, searched by the real
+    reference from injected positions."""
+    from oracle.mcts_oracle import hash_net
+    i = int(GI["edge_index"][j])
+    env = hb.GamePlay()
+    env.load_position(int(EP["turn"][i]), EP["cells"][i], EP["levels"][i])
+    pl = hb.HivePlayer()
+    pl.none_queue = False
+    pl.simulation_num_per_move = int(GI["sims"][j])
+    pl.expand_and_evaluate_with_net = lambda e: hash_net(e.encode_board())
+    np.random.seed(int(GI["seed"][j]))
+    action, (policy, sum_all) = pl.action(env)
+    st = pl._mcts.root_stats(0)
+    k = int(GI["n_edges"][j])
+    assert st["error"] == 0 and st["action"].tolist() == GI["e_action"][j][:k].tolist()
+    assert st["n"].tolist() == GI["e_n"][j][:k].tolist() and (st["w"] == GI["e_w"][j][:k]).all() and (st["p"] == GI["e_p"][j][:k]).all()
+    assert st["n_nodes"] == GI["n_nodes"][j] and action == GI["action"][j] and (np.array(policy) == GI["policy"][j]).all()
