@@ -324,19 +324,11 @@ def main():
                 "algorithmic_bytes_per_env_step": 16128 + 198 + 8 + 384, "achieved": enc_bytes / (kms["encode"] * 1e-3) / 1e9,
                 "per_kernel_us": {k: v * 1e3 for k, v in kms.items()}}
     dominant["frac"] = dominant["achieved"] / peak
-    # the step is ~96 % writes (16,128 + 200 of 17,094 B): a write-only stream reaches far less than the
-    # copy figure the contract's denominator is; measure it here for context (torch fill of 1 GiB)
-    wbuf = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
-    for _ in range(2):
-        wbuf.zero_()
-    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    w0.record()
-    for _ in range(5):
-        wbuf.zero_()
-    w1.record()
-    torch.cuda.synchronize()
-    write_only = 5 * (1 << 30) / (w0.elapsed_time(w1) * 1e-3) / 1e9
-    del wbuf
+    # the step is ~96 % writes (16,128 + 200 of 17,094 B): next to the contract's copy figure, report what a
+    # write-only stream over the same planes arena reaches on this GPU (own 16-byte-store kernel, nothing read)
+    write_only = batch.probe_write_stream(20)
+    batch.step_random(seed, args.max_turn, True)       # planes hold real data again
+    batch.sync()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "write_only_stream_gbs": write_only, "frac_of_write_only_stream": achieved / write_only,
                 "traffic": ncu_traffic(), "kernel": "env step = hive_analyse + hive_flood + hive_moves + hive_encode kernels",

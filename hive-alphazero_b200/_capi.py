@@ -12,7 +12,7 @@ ENV_SYMBOLS = [
     "hive_reset", "hive_step_host", "hive_step", "hive_step_host_async", "hive_step_random", "hive_step_random_multi", "hive_legal_host", "hive_encode_host",
     "hive_status_host", "hive_status_packed_host", "hive_host_pick_actions", "hive_counters_host", "hive_state_key", "hive_load_state", "hive_dump_state",
     "hive_copy_state", "hive_dev_state", "hive_dev_legal", "hive_dev_count", "hive_dev_status", "hive_dev_planes",
-    "hive_launch_count", "hive_profile_step", "hive_set_timing", "hive_last_kernel_ms",
+    "hive_launch_count", "hive_profile_step", "hive_probe_write_stream", "hive_set_timing", "hive_last_kernel_ms",
 ]
 NET_SYMBOLS = ["net_create", "net_destroy", "net_load_conv_host", "net_trunk_forward", "net_launch_count"]
 MCTS_SYMBOLS = [
@@ -64,6 +64,7 @@ def lib():
     L.hive_launch_count.restype = ctypes.c_longlong
     L.hive_set_timing.argtypes = [vp, i32]
     L.hive_profile_step.argtypes = [vp, u64, i32, vp]
+    L.hive_probe_write_stream.argtypes = [vp, i32, vp]
     L.hive_last_kernel_ms.argtypes = [vp]
     L.hive_last_kernel_ms.restype = ctypes.c_float
     f64p, dbl = vp, ctypes.c_double

@@ -23,6 +23,7 @@
 #endif
 #include <stddef.h>
 #include <stdint.h>
+#include <string.h>
 
 namespace hive {
 
@@ -59,6 +60,8 @@ struct __align__(16) WarpScratch {
     uint32_t planes[N_PLANE][5];   // bit boards of the 56 planes (plane 31 unused: it is the turn)
     uint32_t legal[LEGAL_WORDS + 2];
     uint32_t qn[12];               // queen neighbours in tile.adjacent_tiles order: cell | rank<<8 | empty<<12 (white 0..5, black 6..11)
+    uint32_t moves[N_PIECE][5];    // the per-piece sets of GameScratch, staged so that other lanes can index them
+    uint32_t occ[6];
 };
 static_assert(sizeof(WarpScratch) % 16 == 0, "WarpScratch must keep 16-byte alignment in arrays");
 static_assert(offsetof(WarpScratch, hist) % 16 == 0 && offsetof(WarpScratch, legal) % 8 == 0, "vector access alignment");
@@ -470,8 +473,29 @@ __device__ __forceinline__ void eval_moves(GameScratch& gs, int p, const uint32_
 
 // encode: legal mask + all 56 planes (env_hive.py:287-304, 320-447) into shared
 // memory, history push, terminal test.  "own" = side to move.
-__device__ __forceinline__ EvalResult eval_encode(WarpScratch& sm, const GameScratch& gs, int lane) {
-    const uint32_t head = gs.head[0], flags = gs.head[2];
+// Everything the encode step reads of a game's GameScratch, fetched by encode_fetch with all loads issued
+// back to back (one L2 round trip; the profile of the first version showed five serial ones).
+struct EncodeIn {
+    uint4 head;                    // GameScratch::head
+    uint32_t info;                 // info[lane] (HAND for lanes >= 22)
+    BB mv;                         // moves[lane]
+    uint32_t occ_w, own_w, opp_w;  // word `lane` of the three boards (lanes 0..4)
+};
+__device__ __forceinline__ EncodeIn encode_fetch(const GameScratch& gs, int lane) {
+    EncodeIn in;
+    in.head = *reinterpret_cast<const uint4*>(gs.head);
+    const int l = lane < N_PIECE ? lane : 0, w = lane < 5 ? lane : 0;
+    in.info = gs.info[l];
+#pragma unroll
+    for (int i = 0; i < 5; i++) in.mv.w[i] = gs.moves[l][i];
+    in.occ_w = gs.occ[w]; in.own_w = gs.own_all[w]; in.opp_w = gs.opp_all[w];
+    if (lane >= N_PIECE) { in.info = (uint32_t)HAND; in.mv = bb_zero(); }
+    if (lane >= 5) in.occ_w = in.own_w = in.opp_w = 0;
+    return in;
+}
+
+__device__ __forceinline__ EvalResult eval_encode(WarpScratch& sm, const EncodeIn& in, int lane) {
+    const uint32_t head = in.head.x, flags = in.head.z;
     const int turn = head & 0xFF, cq_w = (head >> 8) & 0xFF, cq_b = (head >> 16) & 0xFF;
     const bool push_history = (flags >> 1) & 1u;
     const int prev_winner = (flags >> 8) & 0xFF;
@@ -481,12 +505,12 @@ __device__ __forceinline__ EvalResult eval_encode(WarpScratch& sm, const GameScr
     const int k = lane - 11 * color;
     const int type = piece_type_of(k);
     const bool own = valid && (color == side);
-    const uint32_t info = valid ? gs.info[lane] : (uint32_t)HAND;
+    const uint32_t info = in.info;
     const int cell = info & 0xFF, level = (info >> 13) & 7;
     const bool on_board = valid && cell != HAND;
     const bool top = (info >> 12) & 1u;
     const uint32_t ring = (info >> 16) & 63u;
-    const bool pinned = (gs.head[1] >> lane) & 1u;
+    const bool pinned = (in.head.y >> lane) & 1u;
 
     {   // zero the scratch outputs: planes (1120 B) and legal (208 B) are contiguous and 16-byte aligned
         uint4* pz = reinterpret_cast<uint4*>(&sm.planes[0][0]);
@@ -494,13 +518,13 @@ __device__ __forceinline__ EvalResult eval_encode(WarpScratch& sm, const GameScr
 #pragma unroll
         for (int i = 0; i < 3; i++) { const int t = lane + 32 * i; if (t < (N_PLANE * 20 + (LEGAL_WORDS + 2) * 4) / 16) pz[t] = z; }
     }
-    BB mv = bb_zero();
+    const BB mv = in.mv;
+    const uint32_t occ_w = in.occ_w, own_w = in.own_w, opp_w = in.opp_w;
     if (valid) {
 #pragma unroll
-        for (int i = 0; i < 5; i++) mv.w[i] = gs.moves[lane][i];
+        for (int i = 0; i < 5; i++) sm.moves[lane][i] = mv.w[i];
     }
-    uint32_t occ_w = 0, own_w = 0, opp_w = 0;
-    if (lane < 5) { occ_w = gs.occ[lane]; own_w = gs.own_all[lane]; opp_w = gs.opp_all[lane]; }
+    if (lane < 5) sm.occ[lane] = occ_w;
     __syncwarp();
 
     // dense legal mask a = cell*11 + k: the 11 own pieces x 5 board words are 55 work items spread
@@ -511,7 +535,7 @@ __device__ __forceinline__ EvalResult eval_encode(WarpScratch& sm, const GameScr
         const int item = lane + 32 * r;
         if (item < 55) {
             const int kk = item / 5, w = item - kk * 5;
-            uint32_t m = gs.moves[side * 11 + kk][w];
+            uint32_t m = sm.moves[side * 11 + kk][w];
             n_mine += __popc(m);
             while (m) {
                 const int b = __ffs(m) - 1; m &= m - 1;
@@ -541,7 +565,7 @@ __device__ __forceinline__ EvalResult eval_encode(WarpScratch& sm, const GameScr
         int rank = 0;
 #pragma unroll
         for (int t = 0; t < 6; t++) rank += __shfl_sync(FULL, key, which * 6 + t) < key;
-        if (lane < 12) sm.qn[lane] = use ? ((uint32_t)nb | ((uint32_t)rank << 8) | ((uint32_t)!words_test(gs.occ, nb) << 12)) : 0u;
+        if (lane < 12) sm.qn[lane] = use ? ((uint32_t)nb | ((uint32_t)rank << 8) | ((uint32_t)!words_test(sm.occ, nb) << 12)) : 0u;
     }
     __syncwarp();
     if (on_board) {
@@ -564,7 +588,7 @@ __device__ __forceinline__ EvalResult eval_encode(WarpScratch& sm, const GameScr
 #pragma unroll
             for (int i = 0; i < 6; i++) {
                 const uint32_t e = tbl[i];
-                if (((e >> 12) & 1u) && words_test(gs.moves[lane], (int)(e & 0xFFu)))
+                if (((e >> 12) & 1u) && words_test(sm.moves[lane], (int)(e & 0xFFu)))
                     atomicOr(&sm.planes[(own ? 50 : 44) + ((e >> 8) & 7u)][wi], bit);
             }
         }
@@ -612,6 +636,22 @@ __device__ __forceinline__ void store_planes_bf16(const WarpScratch& sm, const u
     const uint32_t tb = __float_as_uint((float)turn) >> 16;
     const uint32_t tt = tb | (tb << 16);
     const uint4 turn4 = make_uint4(tt, tt, tt, tt);
+#ifndef HIVE_STORE_SPLIT
+    // the game's 16,128 B are one flat run of 1008 16-byte chunks; chunk u = 18*plane + byte.  Every warp
+    // instruction writes 512 contiguous bytes (lane = u mod 32), plane/byte advance incrementally.
+    int p = lane / 18, j = lane - 18 * p;
+    uint4* o = reinterpret_cast<uint4*>(out) + lane;
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        if (i < 31 || lane < 16) {
+            uint4 v = lut[bytes[p * 20 + j]];
+            if (p == 31) v = turn4;                                 // plane 31 = the turn number
+            o[i * 32] = v;
+        }
+        j += 14; p += 1;                                            // u += 32 = 18 + 14
+        if (j >= 18) { j -= 18; p += 1; }
+    }
+#else
     // main part: half-warp h writes bytes 0..15 of plane 2i+h (16 chunks = 256 contiguous bytes);
     // every address is base + compile-time offset.
     const int half = lane >> 4, j = lane & 15;
@@ -633,6 +673,73 @@ __device__ __forceinline__ void store_planes_bf16(const WarpScratch& sm, const u
             if (p == 31) v = turn4;
             reinterpret_cast<uint4*>(out)[p * 18 + jj] = v;
         }
+    }
+#endif
+}
+
+// ------------------------------------------------------------------------------------------
+// Plane store through the TMA: a warp expands its game's bit planes into a small bf16 staging ring in
+// shared memory (STAGE_PLANES planes at a time) and lane 0 hands every filled stage to the bulk-copy
+// engine (cp.async.bulk shared -> global).  The 16 KB per game leave the SM without occupying the
+// load/store queue the position evaluation of the other warps needs for its shared-memory traffic.
+#ifndef HIVE_STAGE_PLANES
+#define HIVE_STAGE_PLANES 7
+#endif
+#ifndef HIVE_STAGE_BUFS
+#define HIVE_STAGE_BUFS 2
+#endif
+constexpr int STAGE_PLANES = HIVE_STAGE_PLANES, STAGE_BUFS = HIVE_STAGE_BUFS;
+constexpr int STAGE_CHUNKS = STAGE_PLANES * 18, STAGE_BYTES = STAGE_CHUNKS * 16, N_STAGE = N_PLANE / STAGE_PLANES;
+static_assert(N_PLANE % STAGE_PLANES == 0 && N_STAGE % STAGE_BUFS == 0 && STAGE_BYTES % 16 == 0, "stages tile the 56 planes");
+
+__device__ __forceinline__ void fence_proxy_async_smem() {
+#ifndef HIVE_EMU
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void bulk_store_s2g(void* dst, const void* src_smem, uint32_t bytes) {
+#ifdef HIVE_EMU
+    memcpy(dst, src_smem, bytes);
+#else
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(dst), "r"((uint32_t)__cvta_generic_to_shared(src_smem)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#endif
+}
+template <int PENDING>
+__device__ __forceinline__ void bulk_wait_read() {      // at most PENDING of this thread's bulk stores still read shared memory
+#ifndef HIVE_EMU
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING) : "memory");
+#endif
+}
+
+__device__ __forceinline__ void store_planes_bulk(const WarpScratch& sm, const uint4* lut, uint4* stage, int lane, int turn,
+                                                  uint16_t* __restrict__ out) {
+    const uint8_t* bytes = reinterpret_cast<const uint8_t*>(&sm.planes[0][0]);   // 20 B per plane, 18 used
+    const uint32_t tb = __float_as_uint((float)turn) >> 16;     // bf16(turn): turn <= 255 is exact
+    const uint32_t tt = tb | (tb << 16);
+    const uint4 turn4 = make_uint4(tt, tt, tt, tt);
+    const int p0 = lane / 18, j0 = lane - 18 * p0;
+#pragma unroll
+    for (int q = 0; q < N_STAGE; q++) {
+        uint4* buf = stage + (q % STAGE_BUFS) * STAGE_CHUNKS;
+        // the stage that used this buffer last (of this game or of the warp's previous game) has left shared memory
+        if (lane == 0) bulk_wait_read<STAGE_BUFS - 1>();
+        __syncwarp();
+        int p = q * STAGE_PLANES + p0, j = j0;                  // chunk u = lane + 32 i of the stage = 18 * plane + byte
+#pragma unroll
+        for (int i = 0; i < (STAGE_CHUNKS + 31) / 32; i++) {
+            if ((i + 1) * 32 <= STAGE_CHUNKS || lane + 32 * i < STAGE_CHUNKS) {
+                uint4 v = lut[bytes[p * 20 + j]];
+                if (p == 31) v = turn4;                         // plane 31 = the turn number
+                buf[lane + 32 * i] = v;
+            }
+            j += 14; p += 1;                                    // u += 32 = 18 + 14
+            if (j >= 18) { j -= 18; p += 1; }
+        }
+        fence_proxy_async_smem();                               // generic-proxy writes -> visible to the bulk-copy engine
+        __syncwarp();
+        if (lane == 0) bulk_store_s2g(reinterpret_cast<uint8_t*>(out) + q * STAGE_BYTES, buf, STAGE_BYTES);
     }
 }
 

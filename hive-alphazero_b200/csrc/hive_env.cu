@@ -90,29 +90,52 @@ int launch_env(hive_env* h, int op, const int32_t* actions, const uint8_t* mask,
     return 0;
 }
 
+static EnvArgs slice_args(hive_env* h, int s, int per, int op, const int32_t* actions, const uint8_t* mask, uint64_t seed, int max_turn,
+                          int auto_reset, int32_t* chosen) {
+    const int off = s * per;
+    const int cnt = (off + per <= h->n) ? per : h->n - off;
+    EnvArgs a;
+    a.recs = h->recs + off; a.legal = h->legal + (size_t)off * LEGAL_WORDS; a.count = h->count + off;
+    a.status = h->status + off; a.planes = h->planes + (size_t)off * HIVE_PLANES_ELEMS;
+    a.actions = actions ? actions + off : nullptr; a.mask = mask ? mask + off : nullptr;
+    a.chosen = chosen ? chosen + off : nullptr; a.hop_lines = h->hop_lines;
+    a.seed = seed; a.n = cnt > 0 ? cnt : 0; a.op = op; a.max_turn = max_turn; a.auto_reset = auto_reset;
+    a.g_offset = off; a.n_total = h->n;
+    a.scratch = h->scratch + off; a.bq = h->bq[s];
+    return a;
+}
+static void launch_search_part(hive_env* h, const EnvArgs& a, cudaStream_t st) {     // analyse -> flood -> moves
+    int sblocks = (int)(((long long)a.n * N_PIECE + SEARCH_THREADS - 1) / SEARCH_THREADS);
+    if (sblocks > h->search_blocks) sblocks = h->search_blocks;
+    hive_analyse_kernel<<<(a.n + GROUP - 1) / GROUP, GROUP * 32, 0, st>>>(a);
+    hive_flood_kernel<<<sblocks, SEARCH_THREADS, 0, st>>>(a);
+    hive_moves_kernel<<<sblocks, SEARCH_THREADS, 0, st>>>(a);
+}
+// One warp per game by default.  HIVE_B200_ENC_CTAS > 0 caps the grid (the kernel's warps then walk over several
+// games): all encode launches that run at the same time (`concurrent` slices) share that many CTAs per SM.
+static void launch_encode_part(hive_env* h, const EnvArgs& a, cudaStream_t st, int concurrent) {
+    int blocks = (a.n + HIVE_ENCODE_WARPS - 1) / HIVE_ENCODE_WARPS;
+    if (h->enc_ctas_per_sm > 0) {
+        int cap = h->sm_count * h->enc_ctas_per_sm / (concurrent > 0 ? concurrent : 1);
+        if (cap < 1) cap = 1;
+        if (blocks > cap) blocks = cap;
+    }
+    hive_encode_kernel<<<blocks, HIVE_ENCODE_WARPS * 32, ENCODE_STAGE_BYTES, st>>>(a);
+}
+
 static int launch_env_kernels(hive_env* h, int op, const int32_t* actions, const uint8_t* mask, uint64_t seed, int max_turn,
                               int auto_reset, int32_t* chosen, int repeat) {
-    const int S = h->n_sub;
+    // launches the host issues one by one (not graph replays) are launch-bound: they use at most host_slices slices
+    cudaStreamCaptureStatus cap_state = cudaStreamCaptureStatusNone;
+    CUDA_TRY(cudaStreamIsCapturing(h->stream, &cap_state));
+    const int S = (cap_state == cudaStreamCaptureStatusActive || h->n_sub < h->host_slices) ? h->n_sub : h->host_slices;
     // slices are multiples of GROUP games so that CTAs never straddle two slices
     const int per = ((h->n + S - 1) / S + GROUP - 1) / GROUP * GROUP;
     if (S > 1) CUDA_TRY(cudaEventRecord(h->fork_ev, h->stream));
     for (int s = 0; s < S; s++) {
-        const int off = s * per;
-        const int cnt = (off + per <= h->n) ? per : h->n - off;
-        if (cnt <= 0) break;
+        const EnvArgs a = slice_args(h, s, per, op, actions, mask, seed, max_turn, auto_reset, chosen);
+        if (a.n <= 0) break;
         cudaStream_t st = (S > 1) ? h->sub_stream[s] : h->stream;
-        EnvArgs a;
-        a.recs = h->recs + off; a.legal = h->legal + (size_t)off * LEGAL_WORDS; a.count = h->count + off;
-        a.status = h->status + off; a.planes = h->planes + (size_t)off * HIVE_PLANES_ELEMS;
-        a.actions = actions ? actions + off : nullptr; a.mask = mask ? mask + off : nullptr;
-        a.chosen = chosen ? chosen + off : nullptr; a.hop_lines = h->hop_lines;
-        a.seed = seed; a.n = cnt; a.op = op; a.max_turn = max_turn; a.auto_reset = auto_reset;
-        a.g_offset = off; a.n_total = h->n;
-        a.scratch = h->scratch + off; a.bq = h->bq[s];
-        const int groups = (cnt + GROUP - 1) / GROUP;
-        const int enc_blocks = (cnt + HIVE_ENCODE_WARPS - 1) / HIVE_ENCODE_WARPS;
-        int sblocks = (int)(((long long)cnt * N_PIECE + SEARCH_THREADS - 1) / SEARCH_THREADS);
-        if (sblocks > h->search_blocks) sblocks = h->search_blocks;
         if (S > 1) {
             CUDA_TRY(cudaStreamWaitEvent(st, h->fork_ev, 0));
             // stagger: slice s starts analysing when slice s-1 has finished analysing, so that the
@@ -120,11 +143,13 @@ static int launch_env_kernels(hive_env* h, int op, const int32_t* actions, const
             if (h->stagger && s > 0) CUDA_TRY(cudaStreamWaitEvent(st, h->stage_ev[s - 1], 0));
         }
         for (int rep = 0; rep < repeat; rep++) {
-            hive_analyse_kernel<<<groups, GROUP * 32, 0, st>>>(a);
+            hive_analyse_kernel<<<(a.n + GROUP - 1) / GROUP, GROUP * 32, 0, st>>>(a);
             if (S > 1 && h->stagger && rep == 0) CUDA_TRY(cudaEventRecord(h->stage_ev[s], st));
+            int sblocks = (int)(((long long)a.n * N_PIECE + SEARCH_THREADS - 1) / SEARCH_THREADS);
+            if (sblocks > h->search_blocks) sblocks = h->search_blocks;
             hive_flood_kernel<<<sblocks, SEARCH_THREADS, 0, st>>>(a);
             hive_moves_kernel<<<sblocks, SEARCH_THREADS, 0, st>>>(a);
-            hive_encode_kernel<<<enc_blocks, HIVE_ENCODE_WARPS * 32, 0, st>>>(a);
+            launch_encode_part(h, a, st, S);
         }
         CUDA_TRY(cudaGetLastError());
         if (S > 1) {
@@ -143,6 +168,26 @@ int check(const hive_env* h) { return h && h->n > 0 ? 0 : fail(HIVE_E_HANDLE, "b
 }  // namespace
 
 extern "C" {
+
+#ifdef HIVE_TRACE
+// experiment builds only: per-CTA timeline of the four kernels (records of 32 bytes, see TraceRec)
+int hive_trace_start(int cap) {
+    TraceRec* buf = nullptr;
+    unsigned zero = 0, ucap = (unsigned)cap;
+    if (cudaMalloc(&buf, (size_t)cap * sizeof(TraceRec)) != cudaSuccess) return -1;
+    cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf)); cudaMemcpyToSymbol(g_trace_n, &zero, 4); cudaMemcpyToSymbol(g_trace_cap, &ucap, 4);
+    return 0;
+}
+int hive_trace_read(void* host, int cap) {
+    TraceRec* buf = nullptr; unsigned n = 0;
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(&buf, g_trace, sizeof(buf)); cudaMemcpyFromSymbol(&n, g_trace_n, 4);
+    if ((int)n > cap) n = cap;
+    cudaMemcpy(host, buf, (size_t)n * sizeof(TraceRec), cudaMemcpyDeviceToHost);
+    TraceRec* none = nullptr; cudaMemcpyToSymbol(g_trace, &none, sizeof(none)); cudaFree(buf);
+    return (int)n;
+}
+#endif
 
 const char* hive_last_error(void) { return g_err.c_str(); }
 int hive_abi_version(void) { return 1; }
@@ -172,6 +217,8 @@ int hive::create_env(int n_games, int device, void* stream, int slices, hive_env
     CUDA_TRY(cudaEventCreate(&h->t0));
     CUDA_TRY(cudaEventCreate(&h->t1));
     const size_t n = (size_t)n_games;
+    if (ENCODE_STAGE_BYTES > 0)     // static + dynamic shared memory of the encode kernel exceeds the 48 KB default
+        CUDA_TRY(cudaFuncSetAttribute(hive_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ENCODE_STAGE_BYTES));
     CUDA_TRY(cudaMalloc(&h->recs, n * sizeof(GameRec)));
     CUDA_TRY(cudaMalloc(&h->legal, n * LEGAL_WORDS * 4));
     CUDA_TRY(cudaMalloc(&h->count, n * 4));
@@ -185,24 +232,32 @@ int hive::create_env(int n_games, int device, void* stream, int slices, hive_env
         if (S > hive_env::MAX_SUB) S = hive_env::MAX_SUB;
         while (S > 1 && n_games < S * GROUP * 8) S--;         // small batches are not worth slicing
         h->n_sub = S;
+        const char* ec = getenv("HIVE_B200_ENC_CTAS");
+        h->enc_ctas_per_sm = ec && atoi(ec) > 0 ? atoi(ec) : 0;      // 0 = no cap (one warp per game); > 0 only for experiments
+        const char* hs = getenv("HIVE_B200_HOST_SLICES");
+        h->host_slices = hs && atoi(hs) > 0 ? atoi(hs) : 2;
         const char* g = getenv("HIVE_B200_STAGGER");
         h->stagger = g ? atoi(g) : 0;
         const char* ug = getenv("HIVE_B200_GRAPH");
         h->use_graph = ug ? atoi(ug) : 1;
     }
     CUDA_TRY(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
+    // a slice's work queues hold the largest slice any launch mode cuts (host-issued steps use fewer, larger slices)
+    const int min_slices = h->n_sub < h->host_slices ? h->n_sub : h->host_slices;
+    const size_t qgames = (n + min_slices - 1) / min_slices + 2 * GROUP;
     for (int s = 0; s < h->n_sub; s++) {
         CUDA_TRY(cudaStreamCreateWithFlags(&h->sub_stream[s], cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&h->join_ev[s], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&h->stage_ev[s], cudaEventDisableTiming));
         CUDA_TRY(cudaMalloc(&h->bq[s].counters, 8 * 4));
         CUDA_TRY(cudaMemsetAsync(h->bq[s].counters, 0, 8 * 4, h->stream));
-        CUDA_TRY(cudaMalloc(&h->bq[s].flood, n * N_PIECE * 4 / h->n_sub + GROUP * N_PIECE * 4));
-        for (int c = 0; c < 4; c++) CUDA_TRY(cudaMalloc(&h->bq[s].mv[c], n * 6 * 4 / h->n_sub + GROUP * 6 * 4));
+        CUDA_TRY(cudaMalloc(&h->bq[s].flood, qgames * N_PIECE * 4));
+        for (int c = 0; c < 4; c++) CUDA_TRY(cudaMalloc(&h->bq[s].mv[c], qgames * 6 * 4));
     }
     {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        h->sm_count = sms;
         const long long want = ((long long)n * N_PIECE + SEARCH_THREADS - 1) / SEARCH_THREADS;
         const long long cap = (long long)sms * 16;                 // 16 x 128-thread CTAs fill an SM
         h->search_blocks = (int)(want < cap ? want : cap);
@@ -366,7 +421,7 @@ int hive_profile_step(hive_env_t* h, uint64_t seed, int max_turn, float* ms) {
     CUDA_TRY(cudaMalloc(&q.flood, n * N_PIECE * 4));
     for (int c = 0; c < 4; c++) CUDA_TRY(cudaMalloc(&q.mv[c], n * 6 * 4));
     a.bq = q;
-    const int groups = (h->n + GROUP - 1) / GROUP, enc_blocks = (h->n + HIVE_ENCODE_WARPS - 1) / HIVE_ENCODE_WARPS;
+    const int groups = (h->n + GROUP - 1) / GROUP;
     CUDA_TRY(cudaEventRecord(ev[0], h->stream));
     hive_analyse_kernel<<<groups, GROUP * 32, 0, h->stream>>>(a);
     CUDA_TRY(cudaEventRecord(ev[1], h->stream));
@@ -374,7 +429,7 @@ int hive_profile_step(hive_env_t* h, uint64_t seed, int max_turn, float* ms) {
     CUDA_TRY(cudaEventRecord(ev[2], h->stream));
     hive_moves_kernel<<<h->search_blocks, SEARCH_THREADS, 0, h->stream>>>(a);
     CUDA_TRY(cudaEventRecord(ev[3], h->stream));
-    hive_encode_kernel<<<enc_blocks, HIVE_ENCODE_WARPS * 32, 0, h->stream>>>(a);
+    launch_encode_part(h, a, h->stream, 1);
     CUDA_TRY(cudaEventRecord(ev[4], h->stream));
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -384,6 +439,33 @@ int hive_profile_step(hive_env_t* h, uint64_t seed, int max_turn, float* ms) {
     for (int c = 0; c < 4; c++) cudaFree(q.mv[c]);
     h->launches += 4;
     return 0;
+}
+
+// Measurement aid for the roofline: a write-only stream over the planes arena (16-byte stores, one per thread,
+// nothing read) -- the ceiling of a kernel that, like the step, only writes.  GB/s over `reps` launches.
+__global__ void hive_write_stream_kernel(uint4* __restrict__ dst, size_t n_vec, uint32_t tag) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_vec) dst[i] = make_uint4(tag, tag ^ (uint32_t)i, tag + 2, threadIdx.x);
+}
+int hive_probe_write_stream(hive_env_t* h, int reps, double* gbs) {
+    if (check(h)) return HIVE_E_HANDLE;
+    if (!gbs || reps < 1) return fail(HIVE_E_ARG, "hive_probe_write_stream: bad arguments");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t n_vec = (size_t)h->n * HIVE_PLANES_ELEMS * 2 / 16;
+    const unsigned blocks = (unsigned)((n_vec + 255) / 256);
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+    for (int i = 0; i < 2; i++) hive_write_stream_kernel<<<blocks, 256, 0, h->stream>>>(reinterpret_cast<uint4*>(h->planes), n_vec, 1u);
+    CUDA_TRY(cudaEventRecord(e0, h->stream));
+    for (int i = 0; i < reps; i++) hive_write_stream_kernel<<<blocks, 256, 0, h->stream>>>(reinterpret_cast<uint4*>(h->planes), n_vec, 2u + i);
+    CUDA_TRY(cudaEventRecord(e1, h->stream));
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *gbs = (double)n_vec * 16.0 * reps / (ms * 1e-3) / 1e9;
+    return 0;    // the planes arena now holds the probe pattern: step or reset the batch before reading planes
 }
 
 int hive_legal_host(hive_env_t* h, uint64_t* mask, int32_t* count) {

@@ -18,6 +18,11 @@ namespace hive {
 #ifndef HIVE_ENCODE_WARPS
 #define HIVE_ENCODE_WARPS 8                        // games per CTA of the encode kernel
 #endif
+#ifndef HIVE_STORE_STG
+constexpr int ENCODE_STAGE_BYTES = HIVE_ENCODE_WARPS * STAGE_BUFS * STAGE_BYTES;   // dynamic shared memory of the encode kernel
+#else
+constexpr int ENCODE_STAGE_BYTES = 0;
+#endif
 enum Op { OP_RESET = 0, OP_STEP = 1, OP_EVAL = 2, OP_RANDOM = 3, OP_INIT = 4 };   // INIT = first reset, zeroes the counters
 
 struct EnvArgs {
@@ -37,10 +42,36 @@ struct EnvArgs {
     int g_offset, n_total;   // this launch covers games [g_offset, g_offset+n) of a batch of n_total (pointers are pre-offset)
 };
 
+// ---- optional per-CTA timeline (builds with -DHIVE_TRACE only; profiles/trace_probe.py reads it)
+#ifdef HIVE_TRACE
+struct TraceRec { unsigned long long t0, t1; uint32_t sm, kernel, g_offset, block; };
+__device__ TraceRec* g_trace;
+__device__ unsigned int g_trace_n, g_trace_cap;
+__device__ __forceinline__ unsigned long long trace_now() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+struct TraceScope {
+    TraceRec* r;
+    __device__ TraceScope(int kernel, int g_offset) : r(nullptr) {
+        if (threadIdx.x == 0 && g_trace) {
+            const unsigned i = atomicAdd(&g_trace_n, 1u);
+            if (i < g_trace_cap) {
+                r = g_trace + i;
+                uint32_t sm; asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
+                r->sm = sm; r->kernel = kernel; r->g_offset = g_offset; r->block = blockIdx.x; r->t1 = 0; r->t0 = trace_now();
+            }
+        }
+    }
+    __device__ ~TraceScope() { if (r) r->t1 = trace_now(); }
+};
+#define HIVE_TRACE_SCOPE(k, a) TraceScope trace_scope_(k, (a).g_offset)
+#else
+#define HIVE_TRACE_SCOPE(k, a)
+#endif
+
 // ---- kernel 1: decode the operation, apply the action, analyse the new position (warp <-> game)
-__global__ void __launch_bounds__(GROUP * 32) hive_analyse_kernel(EnvArgs a) {
+__global__ void __launch_bounds__(GROUP * 32, 4) hive_analyse_kernel(EnvArgs a) {
     __shared__ GroupQueues q;
     __shared__ uint32_t occ_s[GROUP][8];
+    HIVE_TRACE_SCOPE(0, a);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.x * GROUP + warp;
     if (tid < 5) (&q.n_flood)[tid] = 0;
@@ -132,6 +163,7 @@ __global__ void __launch_bounds__(GROUP * 32) hive_analyse_kernel(EnvArgs a) {
 // ---- kernel 2: one-hive floods over the batch-wide flood queue (thread <-> queued piece)
 constexpr int SEARCH_THREADS = 128;
 __global__ void __launch_bounds__(SEARCH_THREADS) hive_flood_kernel(EnvArgs a) {
+    HIVE_TRACE_SCOPE(1, a);
     const int lane = threadIdx.x & 31;
     const int nf = (int)a.bq.counters[0];
     const int stride = gridDim.x * SEARCH_THREADS;
@@ -165,6 +197,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hive_flood_kernel(EnvArgs a) {
 
 // ---- kernel 3: move searches, warps homogeneous in piece type (thread <-> queued piece)
 __global__ void __launch_bounds__(SEARCH_THREADS) hive_moves_kernel(EnvArgs a) {
+    HIVE_TRACE_SCOPE(2, a);
     // move classes start at warp boundaries so that warps stay homogeneous
     const int n0 = (int)a.bq.counters[1], n1 = (int)a.bq.counters[2], n2 = (int)a.bq.counters[3], n3 = (int)a.bq.counters[4];
     const int s1 = (n0 + 31) & ~31, s2 = s1 + ((n1 + 31) & ~31), s3 = s2 + ((n2 + 31) & ~31), total = s3 + n3;
@@ -183,33 +216,53 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hive_moves_kernel(EnvArgs a) {
 }
 
 // ---- kernel 4: legal mask, planes, history, terminal test, outputs (warp <-> game)
-__global__ void __launch_bounds__(HIVE_ENCODE_WARPS * 32) hive_encode_kernel(EnvArgs a) {
+__global__ void __launch_bounds__(HIVE_ENCODE_WARPS * 32, 6) hive_encode_kernel(EnvArgs a) {
     __shared__ WarpScratch scratch[HIVE_ENCODE_WARPS];
     __shared__ uint4 bf16_lut[256];
+#ifndef HIVE_STORE_STG
+#ifdef HIVE_EMU
+    __shared__ uint4 stage_ring[ENCODE_STAGE_BYTES / 16];
+#else
+    extern __shared__ __align__(128) uint4 stage_ring[];
+#endif
+#endif
+    HIVE_TRACE_SCOPE(3, a);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = blockIdx.x * HIVE_ENCODE_WARPS + warp;
     fill_bf16_lut(bf16_lut, tid);
     if (blockIdx.x == 0 && tid < 8) a.bq.counters[tid] = 0;     // the queues are consumed: reset for the next step
     __syncthreads();
-    if (g >= a.n) return;
-    const GameScratch& gs = a.scratch[g];
-    if (!(gs.head[2] & 1u)) return;
     WarpScratch& sm = scratch[warp];
-    GameRec* rec = a.recs + g;
-    if (lane < 20) reinterpret_cast<uint4*>(&sm.hist[0][0][0][0])[lane] = reinterpret_cast<const uint4*>(rec->hist)[lane];
-    __syncwarp();
-    const EvalResult r = eval_encode(sm, gs, lane);
-    const int turn = gs.head[0] & 0xFF;
-    if (lane == 0) {
-        uint32_t* w = reinterpret_cast<uint32_t*>(rec);
-        const uint32_t st = (uint32_t)turn | ((uint32_t)r.winner << 8) | ((uint32_t)r.done << 16);
-        w[11] = st; w[14] = (uint32_t)r.n_legal;
-        a.count[g] = r.n_legal;
-        a.status[g] = st;
+    // persistent: the grid is capped (hive_env.cu) so that every CTA is resident from the start and other
+    // kernels can be placed beside it; a warp walks over its games
+    for (int g = blockIdx.x * HIVE_ENCODE_WARPS + warp; g < a.n; g += gridDim.x * HIVE_ENCODE_WARPS) {
+        // every global read of this game is issued before the first use (also for games this launch skips)
+        GameRec* rec = a.recs + g;
+        const EncodeIn in = encode_fetch(a.scratch[g], lane);
+        const uint4 h4 = reinterpret_cast<const uint4*>(rec->hist)[lane < 20 ? lane : 0];
+        __syncwarp();                                           // the previous game's planes have been expanded
+        if (lane < 20) reinterpret_cast<uint4*>(&sm.hist[0][0][0][0])[lane] = h4;    // consumed before the skip test: keeps the load up here
+        if (!(in.head.z & 1u)) continue;
+        __syncwarp();
+        const EvalResult r = eval_encode(sm, in, lane);
+        const int turn = in.head.x & 0xFF;
+        if (lane == 0) {
+            uint32_t* w = reinterpret_cast<uint32_t*>(rec);
+            const uint32_t st = (uint32_t)turn | ((uint32_t)r.winner << 8) | ((uint32_t)r.done << 16);
+            w[11] = st; w[14] = (uint32_t)r.n_legal;
+            a.count[g] = r.n_legal;
+            a.status[g] = st;
+        }
+        if (lane < 20) reinterpret_cast<uint4*>(rec->hist)[lane] = reinterpret_cast<const uint4*>(&sm.hist[0][0][0][0])[lane];
+        if (lane < 25) reinterpret_cast<uint2*>(a.legal + (size_t)g * LEGAL_WORDS)[lane] = reinterpret_cast<const uint2*>(sm.legal)[lane];
+#ifndef HIVE_STORE_STG
+        store_planes_bulk(sm, bf16_lut, stage_ring + warp * (STAGE_BUFS * STAGE_CHUNKS), lane, turn, a.planes + (size_t)g * HIVE_PLANES_ELEMS);
+#else
+        store_planes_bf16(sm, bf16_lut, lane, turn, a.planes + (size_t)g * HIVE_PLANES_ELEMS);
+#endif
     }
-    if (lane < 20) reinterpret_cast<uint4*>(rec->hist)[lane] = reinterpret_cast<const uint4*>(&sm.hist[0][0][0][0])[lane];
-    if (lane < 25) reinterpret_cast<uint2*>(a.legal + (size_t)g * LEGAL_WORDS)[lane] = reinterpret_cast<const uint2*>(sm.legal)[lane];
-    store_planes_bf16(sm, bf16_lut, lane, turn, a.planes + (size_t)g * HIVE_PLANES_ELEMS);
+#ifndef HIVE_STORE_STG
+    if (lane == 0) bulk_wait_read<0>();                         // shared memory must outlive the copy engine's reads
+#endif
 }
 
 }  // namespace hive

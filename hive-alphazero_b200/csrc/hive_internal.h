@@ -19,10 +19,12 @@ struct hive_env {
     uint32_t* status = nullptr;
     uint16_t* planes = nullptr;
     hive::GameScratch* scratch = nullptr;
-    static constexpr int MAX_SUB = 8;
+    static constexpr int MAX_SUB = 16;
     hive::BatchQueues bq[MAX_SUB] = {};
     int n_sub = 1;                  // the batch is cut into n_sub slices whose kernel chains overlap on side streams
     int stagger = 1;
+    int sm_count = 148, enc_ctas_per_sm = 4;   // the persistent encode kernels together keep this many CTAs per SM
+    int host_slices = 2;            // slices of a step the host launches kernel by kernel (graph replays use n_sub)
     cudaStream_t sub_stream[MAX_SUB] = {};
     cudaEvent_t fork_ev = nullptr, join_ev[MAX_SUB] = {}, stage_ev[MAX_SUB] = {};
     int search_blocks = 0;

@@ -166,6 +166,12 @@ class HiveBatch:
         check(lib().hive_profile_step(self._h, seed, max_turn, ms), "hive_profile_step")
         return dict(zip(("analyse", "flood", "moves", "encode"), [float(x) for x in ms]))
 
+    def probe_write_stream(self, reps=20):
+        """GB/s of a write-only stream over this batch's planes arena (roofline aid; clobbers the planes)."""
+        g = ctypes.c_double()
+        check(lib().hive_probe_write_stream(self._h, reps, ctypes.byref(g)), "hive_probe_write_stream")
+        return g.value
+
     def set_timing(self, on): check(lib().hive_set_timing(self._h, 1 if on else 0), "hive_set_timing")
     def last_kernel_ms(self): return float(lib().hive_last_kernel_ms(self._h))
 

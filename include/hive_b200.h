@@ -119,6 +119,9 @@ long long hive_launch_count(const hive_env_t* h);
 /* one rollout step with events between its four kernels: ms[4] = analyse, flood, moves, encode */
 int hive_profile_step(hive_env_t* h, uint64_t seed, int max_turn, float* ms);
 int hive_set_timing(hive_env_t* h, int on);
+/* Roofline aid: GB/s of a write-only stream (16-byte stores, nothing read) over this batch's planes arena,
+ * averaged over `reps` launches.  Overwrites the planes arena with a probe pattern. */
+int hive_probe_write_stream(hive_env_t* h, int reps, double* gbs);
 float hive_last_kernel_ms(hive_env_t* h);
 
 

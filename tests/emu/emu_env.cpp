@@ -61,7 +61,9 @@ int emu_env_run(void* recs, uint32_t* legal, int32_t* count, uint32_t* status, u
         int rc = emu::run_block(k_moves, &a, b, SEARCH_THREADS, sched_seed + 1500 + (uint64_t)b);
         if (rc) return rc;
     }
-    const int enc_blocks = (n + HIVE_ENCODE_WARPS - 1) / HIVE_ENCODE_WARPS;
+    int enc_blocks = (n + HIVE_ENCODE_WARPS - 1) / HIVE_ENCODE_WARPS;
+    if (enc_blocks > 2) enc_blocks = 2;     // capped grid: warps walk over several games like the persistent launch on the GPU
+    emu::g_gridDim.x = enc_blocks;
     for (int b = 0; b < enc_blocks; b++) {
         int rc = emu::run_block(k_encode, &a, b, HIVE_ENCODE_WARPS * 32, sched_seed + 2000 + (uint64_t)b);
         if (rc) return rc;
