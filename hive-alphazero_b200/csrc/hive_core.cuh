@@ -31,7 +31,11 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int HAND = 255;
 constexpr int N_PIECE = 22;
 constexpr int N_PLANE = 56;
+constexpr int N_PLANE_C = 56;
 constexpr int LEGAL_WORDS = 50;      // 1584 bits -> 49.5 u32 (25 u64)
+// bit-plane record handed from the encode kernel to the plane-store kernel: 56 planes x 5 words; the slot of
+// plane 31 (the turn plane holds no bits) carries the turn in word 0 and "evaluated in this launch" in word 1
+constexpr int BITS_WORDS = N_PLANE_C * 5, BITS_TURN = 31 * 5, BITS_LIVE = 31 * 5 + 1;
 constexpr int START_CELL = 6 * 12 + 6;   // tile.py:156,188 Start_Tile
 constexpr int TURN2_CELL = 5 * 12 + 6;   // core_index ('M','13'), env_hive.py:157-159
 
@@ -616,8 +620,6 @@ __device__ __forceinline__ EvalResult eval_encode(WarpScratch& sm, const EncodeI
 }
 
 // ------------------------------------------------------------------------------------------
-// Expand the 56 bit planes to bf16 CHW [56][144] (16,128 B) with coalesced 16-byte stores.
-// `lut` = 16 x uint2 in shared memory: nibble -> four bf16 {0,1} values.
 // `lut` = 256 x uint4 in shared memory: byte of eight {0,1} cells -> eight bf16 values.
 __device__ __forceinline__ void fill_bf16_lut(uint4* lut, int t) {
     if (t < 256) {
@@ -629,54 +631,6 @@ __device__ __forceinline__ void fill_bf16_lut(uint4* lut, int t) {
         lut[t] = v;
     }
 }
-__device__ __forceinline__ void store_planes_bf16(const WarpScratch& sm, const uint4* lut, int lane, int turn,
-                                                  uint16_t* __restrict__ out) {
-    const uint8_t* bytes = reinterpret_cast<const uint8_t*>(&sm.planes[0][0]);   // 20 B per plane, 18 used
-    // bf16(turn): turn <= 255 is exact in bf16 (8 significant bits)
-    const uint32_t tb = __float_as_uint((float)turn) >> 16;
-    const uint32_t tt = tb | (tb << 16);
-    const uint4 turn4 = make_uint4(tt, tt, tt, tt);
-#ifndef HIVE_STORE_SPLIT
-    // the game's 16,128 B are one flat run of 1008 16-byte chunks; chunk u = 18*plane + byte.  Every warp
-    // instruction writes 512 contiguous bytes (lane = u mod 32), plane/byte advance incrementally.
-    int p = lane / 18, j = lane - 18 * p;
-    uint4* o = reinterpret_cast<uint4*>(out) + lane;
-#pragma unroll
-    for (int i = 0; i < 32; i++) {
-        if (i < 31 || lane < 16) {
-            uint4 v = lut[bytes[p * 20 + j]];
-            if (p == 31) v = turn4;                                 // plane 31 = the turn number
-            o[i * 32] = v;
-        }
-        j += 14; p += 1;                                            // u += 32 = 18 + 14
-        if (j >= 18) { j -= 18; p += 1; }
-    }
-#else
-    // main part: half-warp h writes bytes 0..15 of plane 2i+h (16 chunks = 256 contiguous bytes);
-    // every address is base + compile-time offset.
-    const int half = lane >> 4, j = lane & 15;
-    const uint8_t* b = bytes + half * 20 + j;
-    uint4* o = reinterpret_cast<uint4*>(out) + half * 18 + j;
-#pragma unroll
-    for (int i = 0; i < N_PLANE / 2; i++) {
-        uint4 v = lut[b[i * 40]];
-        if (i == 15 && half) v = turn4;                         // plane 31 = the turn number
-        o[i * 36] = v;
-    }
-    // tail: bytes 16,17 of every plane (112 chunks)
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int u = lane + 32 * i;
-        if (u < 2 * N_PLANE) {
-            const int p = u >> 1, jj = 16 + (u & 1);
-            uint4 v = lut[bytes[p * 20 + jj]];
-            if (p == 31) v = turn4;
-            reinterpret_cast<uint4*>(out)[p * 18 + jj] = v;
-        }
-    }
-#endif
-}
-
 // ------------------------------------------------------------------------------------------
 // Plane store through the TMA: a warp expands its game's bit planes into a small bf16 staging ring in
 // shared memory (STAGE_PLANES planes at a time) and lane 0 hands every filled stage to the bulk-copy
@@ -701,8 +655,12 @@ __device__ __forceinline__ void bulk_store_s2g(void* dst, const void* src_smem, 
 #ifdef HIVE_EMU
     memcpy(dst, src_smem, bytes);
 #else
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                 ::"l"(dst), "r"((uint32_t)__cvta_generic_to_shared(src_smem)), "r"(bytes) : "memory");
+    // the planes are a pure output stream: mark their lines evict-first so that they do not push the step's small
+    // working set (records, scratch, queues, legal masks) out of the L2
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 ::"l"(dst), "r"((uint32_t)__cvta_generic_to_shared(src_smem)), "r"(bytes), "l"(policy) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 #endif
 }
@@ -713,9 +671,9 @@ __device__ __forceinline__ void bulk_wait_read() {      // at most PENDING of th
 #endif
 }
 
-__device__ __forceinline__ void store_planes_bulk(const WarpScratch& sm, const uint4* lut, uint4* stage, int lane, int turn,
+// `bytes`: the game's bit planes in shared memory, 20 B per plane of which 18 are used
+__device__ __forceinline__ void store_planes_bulk(const uint8_t* bytes, const uint4* lut, uint4* stage, int lane, int turn,
                                                   uint16_t* __restrict__ out) {
-    const uint8_t* bytes = reinterpret_cast<const uint8_t*>(&sm.planes[0][0]);   // 20 B per plane, 18 used
     const uint32_t tb = __float_as_uint((float)turn) >> 16;     // bf16(turn): turn <= 255 is exact
     const uint32_t tt = tb | (tb << 16);
     const uint4 turn4 = make_uint4(tt, tt, tt, tt);

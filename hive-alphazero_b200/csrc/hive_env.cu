@@ -84,7 +84,7 @@ int launch_env(hive_env* h, int op, const int32_t* actions, const uint8_t* mask,
         }
         CUDA_TRY(cudaGraphLaunch(g.exec, h->stream));
         const int S = h->n_sub;
-        h->launches += 4 * S;
+        h->launches += 5 * S;
     }
     if (h->timing) CUDA_TRY(cudaEventRecord(h->t1, h->stream));
     return 0;
@@ -104,25 +104,52 @@ static EnvArgs slice_args(hive_env* h, int s, int per, int op, const int32_t* ac
     a.scratch = h->scratch + off; a.bq = h->bq[s];
     return a;
 }
-static void launch_search_part(hive_env* h, const EnvArgs& a, cudaStream_t st) {     // analyse -> flood -> moves
-    int sblocks = (int)(((long long)a.n * N_PIECE + SEARCH_THREADS - 1) / SEARCH_THREADS);
-    if (sblocks > h->search_blocks) sblocks = h->search_blocks;
-    hive_analyse_kernel<<<(a.n + GROUP - 1) / GROUP, GROUP * 32, 0, st>>>(a);
-    hive_flood_kernel<<<sblocks, SEARCH_THREADS, 0, st>>>(a);
-    hive_moves_kernel<<<sblocks, SEARCH_THREADS, 0, st>>>(a);
+static void launch_encode_part(const EnvArgs& a, cudaStream_t st) {
+    hive_encode_kernel<<<(a.n + HIVE_ENCODE_WARPS - 1) / HIVE_ENCODE_WARPS, HIVE_ENCODE_WARPS * 32, 0, st>>>(a);
 }
-// One warp per game by default.  HIVE_B200_ENC_CTAS > 0 caps the grid (the kernel's warps then walk over several
-// games): all encode launches that run at the same time (`concurrent` slices) share that many CTAs per SM.
-static void launch_encode_part(hive_env* h, const EnvArgs& a, cudaStream_t st, int concurrent) {
-    int blocks = (a.n + HIVE_ENCODE_WARPS - 1) / HIVE_ENCODE_WARPS;
-    if (h->enc_ctas_per_sm > 0) {
-        int cap = h->sm_count * h->enc_ctas_per_sm / (concurrent > 0 ? concurrent : 1);
+// The plane-store kernel is persistent: the store launches that run at the same time (`concurrent` slices) share
+// store_ctas_per_sm CTAs per SM, so each grid is resident at once and never queues in front of other kernels.
+static void launch_planes_part(hive_env* h, const EnvArgs& a, cudaStream_t st, int concurrent) {
+    int blocks = (a.n + HIVE_STORE_WARPS - 1) / HIVE_STORE_WARPS;
+    if (concurrent > 0) {                                      // 0: alone on the GPU (profiling), one warp per game
+        int cap = h->sm_count * h->store_ctas_per_sm / concurrent;
         if (cap < 1) cap = 1;
         if (blocks > cap) blocks = cap;
     }
-    hive_encode_kernel<<<blocks, HIVE_ENCODE_WARPS * 32, ENCODE_STAGE_BYTES, st>>>(a);
+    hive_planes_kernel<<<blocks, HIVE_STORE_WARPS * 32, STORE_STAGE_BYTES, st>>>(a);
 }
 
+// `repeat` steps of one slice: analyse -> flood -> moves -> encode on stream `st`, and the plane store of every step on
+// stream `ss`, so that it runs beside the next step's kernels (the bit planes it reads are double-buffered; step k+2's
+// encode waits for step k's store).  With st != ss the chain ends joined on `st`.
+static int launch_slice_chain(hive_env* h, int s, EnvArgs a, cudaStream_t st, cudaStream_t ss, int concurrent, int repeat) {
+    const bool side = st != ss;
+    for (int rep = 0; rep < repeat; rep++) {
+        a.bits = h->bits[rep & 1] + (size_t)a.g_offset * BITS_WORDS;
+        hive_analyse_kernel<<<(a.n + GROUP - 1) / GROUP, GROUP * 32, 0, st>>>(a);
+        int sblocks = (int)(((long long)a.n * N_PIECE + SEARCH_THREADS - 1) / SEARCH_THREADS);
+        if (sblocks > h->search_blocks) sblocks = h->search_blocks;
+        hive_flood_kernel<<<sblocks, SEARCH_THREADS, 0, st>>>(a);
+        hive_moves_kernel<<<sblocks, SEARCH_THREADS, 0, st>>>(a);
+        if (side && rep >= 2) CUDA_TRY(cudaStreamWaitEvent(st, h->stored_ev[s][rep & 1], 0));    // this bit-plane buffer is free again
+        launch_encode_part(a, st);
+        if (side) {
+            CUDA_TRY(cudaEventRecord(h->encoded_ev[s], st));
+            CUDA_TRY(cudaStreamWaitEvent(ss, h->encoded_ev[s], 0));
+        }
+        launch_planes_part(h, a, ss, concurrent);
+        if (side) CUDA_TRY(cudaEventRecord(h->stored_ev[s][rep & 1], ss));
+    }
+    if (side) {
+        CUDA_TRY(cudaStreamWaitEvent(st, h->stored_ev[s][(repeat - 1) & 1], 0));
+        if (repeat > 1) CUDA_TRY(cudaStreamWaitEvent(st, h->stored_ev[s][repeat & 1], 0));
+    }
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 5 * repeat;
+    return 0;
+}
+
+// One or `repeat` steps of the whole batch: every slice's chain on its own pair of streams, joined into h->stream.
 static int launch_env_kernels(hive_env* h, int op, const int32_t* actions, const uint8_t* mask, uint64_t seed, int max_turn,
                               int auto_reset, int32_t* chosen, int repeat) {
     // launches the host issues one by one (not graph replays) are launch-bound: they use at most host_slices slices
@@ -131,32 +158,19 @@ static int launch_env_kernels(hive_env* h, int op, const int32_t* actions, const
     const int S = (cap_state == cudaStreamCaptureStatusActive || h->n_sub < h->host_slices) ? h->n_sub : h->host_slices;
     // slices are multiples of GROUP games so that CTAs never straddle two slices
     const int per = ((h->n + S - 1) / S + GROUP - 1) / GROUP * GROUP;
-    if (S > 1) CUDA_TRY(cudaEventRecord(h->fork_ev, h->stream));
+    const bool side = S > 1 || repeat > 1;                 // side streams in use (else everything goes down h->stream)
+    if (side) CUDA_TRY(cudaEventRecord(h->fork_ev, h->stream));
     for (int s = 0; s < S; s++) {
         const EnvArgs a = slice_args(h, s, per, op, actions, mask, seed, max_turn, auto_reset, chosen);
         if (a.n <= 0) break;
-        cudaStream_t st = (S > 1) ? h->sub_stream[s] : h->stream;
-        if (S > 1) {
-            CUDA_TRY(cudaStreamWaitEvent(st, h->fork_ev, 0));
-            // stagger: slice s starts analysing when slice s-1 has finished analysing, so that the
-            // compute-bound kernels of one slice run under the memory-bound encode of another
-            if (h->stagger && s > 0) CUDA_TRY(cudaStreamWaitEvent(st, h->stage_ev[s - 1], 0));
-        }
-        for (int rep = 0; rep < repeat; rep++) {
-            hive_analyse_kernel<<<(a.n + GROUP - 1) / GROUP, GROUP * 32, 0, st>>>(a);
-            if (S > 1 && h->stagger && rep == 0) CUDA_TRY(cudaEventRecord(h->stage_ev[s], st));
-            int sblocks = (int)(((long long)a.n * N_PIECE + SEARCH_THREADS - 1) / SEARCH_THREADS);
-            if (sblocks > h->search_blocks) sblocks = h->search_blocks;
-            hive_flood_kernel<<<sblocks, SEARCH_THREADS, 0, st>>>(a);
-            hive_moves_kernel<<<sblocks, SEARCH_THREADS, 0, st>>>(a);
-            launch_encode_part(h, a, st, S);
-        }
-        CUDA_TRY(cudaGetLastError());
-        if (S > 1) {
+        cudaStream_t st = side ? h->sub_stream[s] : h->stream, ss = side ? h->store_stream[s] : h->stream;
+        if (side) CUDA_TRY(cudaStreamWaitEvent(st, h->fork_ev, 0));
+        int rc = launch_slice_chain(h, s, a, st, ss, S, repeat);
+        if (rc) return rc;
+        if (side) {
             CUDA_TRY(cudaEventRecord(h->join_ev[s], st));
             CUDA_TRY(cudaStreamWaitEvent(h->stream, h->join_ev[s], 0));
         }
-        h->launches += 4 * repeat;
     }
     return 0;
 }
@@ -217,8 +231,12 @@ int hive::create_env(int n_games, int device, void* stream, int slices, hive_env
     CUDA_TRY(cudaEventCreate(&h->t0));
     CUDA_TRY(cudaEventCreate(&h->t1));
     const size_t n = (size_t)n_games;
-    if (ENCODE_STAGE_BYTES > 0)     // static + dynamic shared memory of the encode kernel exceeds the 48 KB default
-        CUDA_TRY(cudaFuncSetAttribute(hive_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ENCODE_STAGE_BYTES));
+    // static + dynamic shared memory of the plane-store kernel exceeds the 48 KB default
+    CUDA_TRY(cudaFuncSetAttribute(hive_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STORE_STAGE_BYTES));
+    for (int b = 0; b < 2; b++) {
+        CUDA_TRY(cudaMalloc(&h->bits[b], n * BITS_WORDS * 4));
+        CUDA_TRY(cudaMemsetAsync(h->bits[b], 0, n * BITS_WORDS * 4, h->stream));
+    }
     CUDA_TRY(cudaMalloc(&h->recs, n * sizeof(GameRec)));
     CUDA_TRY(cudaMalloc(&h->legal, n * LEGAL_WORDS * 4));
     CUDA_TRY(cudaMalloc(&h->count, n * 4));
@@ -232,12 +250,10 @@ int hive::create_env(int n_games, int device, void* stream, int slices, hive_env
         if (S > hive_env::MAX_SUB) S = hive_env::MAX_SUB;
         while (S > 1 && n_games < S * GROUP * 8) S--;         // small batches are not worth slicing
         h->n_sub = S;
-        const char* ec = getenv("HIVE_B200_ENC_CTAS");
-        h->enc_ctas_per_sm = ec && atoi(ec) > 0 ? atoi(ec) : 0;      // 0 = no cap (one warp per game); > 0 only for experiments
+        const char* ec = getenv("HIVE_B200_STORE_CTAS");
+        h->store_ctas_per_sm = ec && atoi(ec) > 0 ? atoi(ec) : 2;
         const char* hs = getenv("HIVE_B200_HOST_SLICES");
         h->host_slices = hs && atoi(hs) > 0 ? atoi(hs) : 2;
-        const char* g = getenv("HIVE_B200_STAGGER");
-        h->stagger = g ? atoi(g) : 0;
         const char* ug = getenv("HIVE_B200_GRAPH");
         h->use_graph = ug ? atoi(ug) : 1;
     }
@@ -247,8 +263,10 @@ int hive::create_env(int n_games, int device, void* stream, int slices, hive_env
     const size_t qgames = (n + min_slices - 1) / min_slices + 2 * GROUP;
     for (int s = 0; s < h->n_sub; s++) {
         CUDA_TRY(cudaStreamCreateWithFlags(&h->sub_stream[s], cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->store_stream[s], cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&h->join_ev[s], cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&h->stage_ev[s], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->encoded_ev[s], cudaEventDisableTiming));
+        for (int b = 0; b < 2; b++) CUDA_TRY(cudaEventCreateWithFlags(&h->stored_ev[s][b], cudaEventDisableTiming));
         CUDA_TRY(cudaMalloc(&h->bq[s].counters, 8 * 4));
         CUDA_TRY(cudaMemsetAsync(h->bq[s].counters, 0, 8 * 4, h->stream));
         CUDA_TRY(cudaMalloc(&h->bq[s].flood, qgames * N_PIECE * 4));
@@ -286,13 +304,15 @@ int hive_destroy(hive_env_t* h) {
     cudaStreamSynchronize(h->stream);
     if (h->graph.exec) cudaGraphExecDestroy(h->graph.exec);
     if (h->multi_graph.exec) cudaGraphExecDestroy(h->multi_graph.exec);
-    cudaFree(h->recs); cudaFree(h->legal); cudaFree(h->count); cudaFree(h->status); cudaFree(h->planes); cudaFree(h->scratch);
+    cudaFree(h->recs); cudaFree(h->legal); cudaFree(h->count); cudaFree(h->status); cudaFree(h->planes); cudaFree(h->scratch); cudaFree(h->bits[0]); cudaFree(h->bits[1]);
     for (int s = 0; s < h->n_sub; s++) {
         cudaFree(h->bq[s].counters); cudaFree(h->bq[s].flood);
         for (int c = 0; c < 4; c++) cudaFree(h->bq[s].mv[c]);
         if (h->sub_stream[s]) cudaStreamDestroy(h->sub_stream[s]);
+        if (h->store_stream[s]) cudaStreamDestroy(h->store_stream[s]);
+        if (h->encoded_ev[s]) cudaEventDestroy(h->encoded_ev[s]);
+        for (int b = 0; b < 2; b++) if (h->stored_ev[s][b]) cudaEventDestroy(h->stored_ev[s][b]);
         if (h->join_ev[s]) cudaEventDestroy(h->join_ev[s]);
-        if (h->stage_ev[s]) cudaEventDestroy(h->stage_ev[s]);
     }
     if (h->fork_ev) cudaEventDestroy(h->fork_ev);
     cudaFree(h->d_actions[0]); cudaFree(h->d_actions[1]); cudaFree(h->d_mask); cudaFree(h->hop_lines);
@@ -396,24 +416,24 @@ int hive_step_random_multi(hive_env_t* h, uint64_t seed, int max_turn, int auto_
         g.op = n_steps; g.seed = seed; g.max_turn = max_turn; g.auto_reset = auto_reset;
     }
     CUDA_TRY(cudaGraphLaunch(g.exec, h->stream));
-    h->launches += 4LL * h->n_sub * n_steps;
+    h->launches += 5LL * h->n_sub * n_steps;
     if (h->timing) CUDA_TRY(cudaEventRecord(h->t1, h->stream));
     return 0;
 }
 
 // One rollout step with CUDA events between the four kernels (whole batch as one slice, no graph):
-// ms[0..3] = analyse, flood, moves, encode.  For bench.py's per-kernel roofline; it advances the games.
+// ms[0..4] = analyse, flood, moves, encode, planes.  For bench.py's per-kernel roofline; it advances the games.
 int hive_profile_step(hive_env_t* h, uint64_t seed, int max_turn, float* ms) {
     if (check(h)) return HIVE_E_HANDLE;
     if (!ms || max_turn < 1 || max_turn > 250) return fail(HIVE_E_ARG, "hive_profile_step: bad arguments");
     CUDA_TRY(cudaSetDevice(h->device));
-    cudaEvent_t ev[5];
-    for (int i = 0; i < 5; i++) CUDA_TRY(cudaEventCreate(&ev[i]));
+    cudaEvent_t ev[6];
+    for (int i = 0; i < 6; i++) CUDA_TRY(cudaEventCreate(&ev[i]));
     EnvArgs a;
     a.recs = h->recs; a.legal = h->legal; a.count = h->count; a.status = h->status; a.planes = h->planes;
     a.actions = nullptr; a.mask = nullptr; a.chosen = nullptr; a.hop_lines = h->hop_lines;
     a.seed = seed; a.n = h->n; a.op = OP_RANDOM; a.max_turn = max_turn; a.auto_reset = 1; a.g_offset = 0; a.n_total = h->n;
-    a.scratch = h->scratch;
+    a.scratch = h->scratch; a.bits = h->bits[0];
     // slice 0's queues are sized for a slice: use a whole-batch set allocated on the fly
     BatchQueues q;
     const size_t n = (size_t)h->n;
@@ -429,15 +449,17 @@ int hive_profile_step(hive_env_t* h, uint64_t seed, int max_turn, float* ms) {
     CUDA_TRY(cudaEventRecord(ev[2], h->stream));
     hive_moves_kernel<<<h->search_blocks, SEARCH_THREADS, 0, h->stream>>>(a);
     CUDA_TRY(cudaEventRecord(ev[3], h->stream));
-    launch_encode_part(h, a, h->stream, 1);
+    launch_encode_part(a, h->stream);
     CUDA_TRY(cudaEventRecord(ev[4], h->stream));
+    launch_planes_part(h, a, h->stream, 0);                    // alone on the GPU: uncapped
+    CUDA_TRY(cudaEventRecord(ev[5], h->stream));
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    for (int i = 0; i < 4; i++) CUDA_TRY(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
-    for (int i = 0; i < 5; i++) cudaEventDestroy(ev[i]);
+    for (int i = 0; i < 5; i++) CUDA_TRY(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+    for (int i = 0; i < 6; i++) cudaEventDestroy(ev[i]);
     cudaFree(q.counters); cudaFree(q.flood);
     for (int c = 0; c < 4; c++) cudaFree(q.mv[c]);
-    h->launches += 4;
+    h->launches += 5;
     return 0;
 }
 

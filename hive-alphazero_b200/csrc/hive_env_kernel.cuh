@@ -18,11 +18,6 @@ namespace hive {
 #ifndef HIVE_ENCODE_WARPS
 #define HIVE_ENCODE_WARPS 8                        // games per CTA of the encode kernel
 #endif
-#ifndef HIVE_STORE_STG
-constexpr int ENCODE_STAGE_BYTES = HIVE_ENCODE_WARPS * STAGE_BUFS * STAGE_BYTES;   // dynamic shared memory of the encode kernel
-#else
-constexpr int ENCODE_STAGE_BYTES = 0;
-#endif
 enum Op { OP_RESET = 0, OP_STEP = 1, OP_EVAL = 2, OP_RANDOM = 3, OP_INIT = 4 };   // INIT = first reset, zeroes the counters
 
 struct EnvArgs {
@@ -32,6 +27,7 @@ struct EnvArgs {
     uint32_t* status;      // [n] turn | winner<<8 | done<<16
     uint16_t* planes;      // [n][56*144] bf16
     GameScratch* scratch;  // [n] kernel-to-kernel intermediates (L2 resident)
+    uint32_t* bits;        // [n][BITS_WORDS] bit planes, encode kernel -> plane-store kernel (this step's buffer of two)
     BatchQueues bq;        // batch-wide work queues
     const int32_t* actions;
     const uint8_t* mask;
@@ -215,54 +211,89 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hive_moves_kernel(EnvArgs a) {
     }
 }
 
-// ---- kernel 4: legal mask, planes, history, terminal test, outputs (warp <-> game)
+// ---- kernel 4: legal mask, bit planes, history, terminal test, small outputs (warp <-> game).  Everything the
+// next step needs is written here; the 16 KB of bf16 planes per game are left to kernel 5, which runs on its own
+// stream beside the next step's kernels.
 __global__ void __launch_bounds__(HIVE_ENCODE_WARPS * 32, 6) hive_encode_kernel(EnvArgs a) {
     __shared__ WarpScratch scratch[HIVE_ENCODE_WARPS];
+    HIVE_TRACE_SCOPE(3, a);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = blockIdx.x * HIVE_ENCODE_WARPS + warp;
+    if (blockIdx.x == 0 && tid < 8) a.bq.counters[tid] = 0;     // the queues are consumed: reset for the next step
+    if (g >= a.n) return;
+    // every global read of this game is issued before the first use (also for games this launch skips)
+    GameRec* rec = a.recs + g;
+    const EncodeIn in = encode_fetch(a.scratch[g], lane);
+    const uint4 h4 = reinterpret_cast<const uint4*>(rec->hist)[lane < 20 ? lane : 0];
+    WarpScratch& sm = scratch[warp];
+    uint32_t* bits = a.bits + (size_t)g * BITS_WORDS;
+    if (lane < 20) reinterpret_cast<uint4*>(&sm.hist[0][0][0][0])[lane] = h4;    // consumed before the exit test: keeps the load up here
+    if (!(in.head.z & 1u)) {
+        if (lane == 0) bits[BITS_LIVE] = 0u;                    // the plane store leaves this game's planes alone
+        return;
+    }
+    __syncwarp();
+    const EvalResult r = eval_encode(sm, in, lane);
+    const int turn = in.head.x & 0xFF;
+    if (lane == 0) {
+        uint32_t* w = reinterpret_cast<uint32_t*>(rec);
+        const uint32_t st = (uint32_t)turn | ((uint32_t)r.winner << 8) | ((uint32_t)r.done << 16);
+        w[11] = st; w[14] = (uint32_t)r.n_legal;
+        a.count[g] = r.n_legal;
+        a.status[g] = st;
+        sm.planes[31][0] = (uint32_t)turn; sm.planes[31][1] = 1u;
+    }
+    if (lane < 20) reinterpret_cast<uint4*>(rec->hist)[lane] = reinterpret_cast<const uint4*>(&sm.hist[0][0][0][0])[lane];
+    if (lane < 25) reinterpret_cast<uint2*>(a.legal + (size_t)g * LEGAL_WORDS)[lane] = reinterpret_cast<const uint2*>(sm.legal)[lane];
+    __syncwarp();
+    {   // 1120 B of bit planes -> L2 (70 x 16 B)
+        const uint4* src = reinterpret_cast<const uint4*>(&sm.planes[0][0]);
+        uint4* dst = reinterpret_cast<uint4*>(bits);
+#pragma unroll
+        for (int i = 0; i < 3; i++) { const int t = lane + 32 * i; if (t < BITS_WORDS / 4) dst[t] = src[t]; }
+    }
+}
+
+// ---- kernel 5: bit planes -> bf16 CHW planes [56][144] per game, through the TMA (persistent: the grid is capped in
+// hive_env.cu so that every CTA is resident at once and other kernels are placed beside it; a warp walks over games)
+#ifndef HIVE_STORE_WARPS
+#define HIVE_STORE_WARPS 8
+#endif
+constexpr int STORE_STAGE_BYTES = HIVE_STORE_WARPS * STAGE_BUFS * STAGE_BYTES;     // dynamic shared memory
+__global__ void __launch_bounds__(HIVE_STORE_WARPS * 32) hive_planes_kernel(EnvArgs a) {
     __shared__ uint4 bf16_lut[256];
-#ifndef HIVE_STORE_STG
+    __shared__ __align__(16) uint32_t planes_s[HIVE_STORE_WARPS][BITS_WORDS];
 #ifdef HIVE_EMU
-    __shared__ uint4 stage_ring[ENCODE_STAGE_BYTES / 16];
+    __shared__ uint4 stage_ring[STORE_STAGE_BYTES / 16];
 #else
     extern __shared__ __align__(128) uint4 stage_ring[];
 #endif
-#endif
-    HIVE_TRACE_SCOPE(3, a);
+    HIVE_TRACE_SCOPE(4, a);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     fill_bf16_lut(bf16_lut, tid);
-    if (blockIdx.x == 0 && tid < 8) a.bq.counters[tid] = 0;     // the queues are consumed: reset for the next step
     __syncthreads();
-    WarpScratch& sm = scratch[warp];
-    // persistent: the grid is capped (hive_env.cu) so that every CTA is resident from the start and other
-    // kernels can be placed beside it; a warp walks over its games
-    for (int g = blockIdx.x * HIVE_ENCODE_WARPS + warp; g < a.n; g += gridDim.x * HIVE_ENCODE_WARPS) {
-        // every global read of this game is issued before the first use (also for games this launch skips)
-        GameRec* rec = a.recs + g;
-        const EncodeIn in = encode_fetch(a.scratch[g], lane);
-        const uint4 h4 = reinterpret_cast<const uint4*>(rec->hist)[lane < 20 ? lane : 0];
+    constexpr int NV = BITS_WORDS / 4;                           // 70 uint4 per game
+    const int g_first = blockIdx.x * HIVE_STORE_WARPS + warp, g_stride = gridDim.x * HIVE_STORE_WARPS;
+    uint4 v[3];
+    auto fetch = [&](int g) {
+        const uint4* src = reinterpret_cast<const uint4*>(a.bits + (size_t)g * BITS_WORDS);
+#pragma unroll
+        for (int i = 0; i < 3; i++) { const int t = lane + 32 * i; v[i] = src[t < NV ? t : 0]; }
+    };
+    if (g_first < a.n) fetch(g_first);
+    uint32_t* mine = planes_s[warp];
+    for (int g = g_first; g < a.n; g += g_stride) {
         __syncwarp();                                           // the previous game's planes have been expanded
-        if (lane < 20) reinterpret_cast<uint4*>(&sm.hist[0][0][0][0])[lane] = h4;    // consumed before the skip test: keeps the load up here
-        if (!(in.head.z & 1u)) continue;
+#pragma unroll
+        for (int i = 0; i < 3; i++) { const int t = lane + 32 * i; if (t < NV) reinterpret_cast<uint4*>(mine)[t] = v[i]; }
         __syncwarp();
-        const EvalResult r = eval_encode(sm, in, lane);
-        const int turn = in.head.x & 0xFF;
-        if (lane == 0) {
-            uint32_t* w = reinterpret_cast<uint32_t*>(rec);
-            const uint32_t st = (uint32_t)turn | ((uint32_t)r.winner << 8) | ((uint32_t)r.done << 16);
-            w[11] = st; w[14] = (uint32_t)r.n_legal;
-            a.count[g] = r.n_legal;
-            a.status[g] = st;
-        }
-        if (lane < 20) reinterpret_cast<uint4*>(rec->hist)[lane] = reinterpret_cast<const uint4*>(&sm.hist[0][0][0][0])[lane];
-        if (lane < 25) reinterpret_cast<uint2*>(a.legal + (size_t)g * LEGAL_WORDS)[lane] = reinterpret_cast<const uint2*>(sm.legal)[lane];
-#ifndef HIVE_STORE_STG
-        store_planes_bulk(sm, bf16_lut, stage_ring + warp * (STAGE_BUFS * STAGE_CHUNKS), lane, turn, a.planes + (size_t)g * HIVE_PLANES_ELEMS);
-#else
-        store_planes_bf16(sm, bf16_lut, lane, turn, a.planes + (size_t)g * HIVE_PLANES_ELEMS);
-#endif
+        const uint32_t live = mine[BITS_LIVE], turn = mine[BITS_TURN];
+        if (g + g_stride < a.n) fetch(g + g_stride);            // next game's bit planes arrive during the expansion
+        if (live)
+            store_planes_bulk(reinterpret_cast<const uint8_t*>(mine), bf16_lut, stage_ring + warp * (STAGE_BUFS * STAGE_CHUNKS), lane,
+                              (int)turn, a.planes + (size_t)g * HIVE_PLANES_ELEMS);
     }
-#ifndef HIVE_STORE_STG
     if (lane == 0) bulk_wait_read<0>();                         // shared memory must outlive the copy engine's reads
-#endif
 }
 
 }  // namespace hive

@@ -19,14 +19,15 @@ struct hive_env {
     uint32_t* status = nullptr;
     uint16_t* planes = nullptr;
     hive::GameScratch* scratch = nullptr;
+    uint32_t* bits[2] = {nullptr, nullptr};   // bit planes, encode kernel -> plane-store kernel (double-buffered over steps)
     static constexpr int MAX_SUB = 16;
     hive::BatchQueues bq[MAX_SUB] = {};
     int n_sub = 1;                  // the batch is cut into n_sub slices whose kernel chains overlap on side streams
-    int stagger = 1;
-    int sm_count = 148, enc_ctas_per_sm = 4;   // the persistent encode kernels together keep this many CTAs per SM
+    int sm_count = 148, store_ctas_per_sm = 2;   // the persistent plane-store kernels together keep this many CTAs per SM
     int host_slices = 2;            // slices of a step the host launches kernel by kernel (graph replays use n_sub)
-    cudaStream_t sub_stream[MAX_SUB] = {};
-    cudaEvent_t fork_ev = nullptr, join_ev[MAX_SUB] = {}, stage_ev[MAX_SUB] = {};
+    cudaStream_t sub_stream[MAX_SUB] = {}, store_stream[MAX_SUB] = {};
+    cudaEvent_t encoded_ev[MAX_SUB] = {}, stored_ev[MAX_SUB][2] = {};
+    cudaEvent_t fork_ev = nullptr, join_ev[MAX_SUB] = {};
     int search_blocks = 0;
     // the step of the resident rollout loop is replayed from a CUDA graph (same arguments every step)
     struct StepGraph { int op = -1; const void* actions = nullptr; const void* mask = nullptr; void* chosen = nullptr;

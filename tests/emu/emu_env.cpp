@@ -25,6 +25,7 @@ static void k_analyse(void* p) { hive_analyse_kernel(*(EnvArgs*)p); }
 static void k_flood(void* p) { hive_flood_kernel(*(EnvArgs*)p); }
 static void k_moves(void* p) { hive_moves_kernel(*(EnvArgs*)p); }
 static void k_encode(void* p) { hive_encode_kernel(*(EnvArgs*)p); }
+static void k_planes(void* p) { hive_planes_kernel(*(EnvArgs*)p); }
 
 extern "C" {
 
@@ -44,7 +45,9 @@ int emu_env_run(void* recs, uint32_t* legal, int32_t* count, uint32_t* status, u
     if ((int)scratch.size() < n) scratch.resize(n);
     if ((int)qflood.size() < n * N_PIECE) qflood.resize(n * N_PIECE);
     for (int c = 0; c < 4; c++) if ((int)qmv[c].size() < n * 6) qmv[c].resize(n * 6);
-    a.scratch = scratch.data();
+    static std::vector<uint32_t> bits;
+    if ((int)bits.size() < n * BITS_WORDS) bits.resize((size_t)n * BITS_WORDS);
+    a.scratch = scratch.data(); a.bits = bits.data();
     a.bq.counters = counters.data(); a.bq.flood = qflood.data();
     for (int c = 0; c < 4; c++) a.bq.mv[c] = qmv[c].data();
     for (int b = 0; b < groups; b++) {
@@ -61,11 +64,17 @@ int emu_env_run(void* recs, uint32_t* legal, int32_t* count, uint32_t* status, u
         int rc = emu::run_block(k_moves, &a, b, SEARCH_THREADS, sched_seed + 1500 + (uint64_t)b);
         if (rc) return rc;
     }
-    int enc_blocks = (n + HIVE_ENCODE_WARPS - 1) / HIVE_ENCODE_WARPS;
-    if (enc_blocks > 2) enc_blocks = 2;     // capped grid: warps walk over several games like the persistent launch on the GPU
+    const int enc_blocks = (n + HIVE_ENCODE_WARPS - 1) / HIVE_ENCODE_WARPS;
     emu::g_gridDim.x = enc_blocks;
     for (int b = 0; b < enc_blocks; b++) {
         int rc = emu::run_block(k_encode, &a, b, HIVE_ENCODE_WARPS * 32, sched_seed + 2000 + (uint64_t)b);
+        if (rc) return rc;
+    }
+    int store_blocks = (n + HIVE_STORE_WARPS - 1) / HIVE_STORE_WARPS;
+    if (store_blocks > 2) store_blocks = 2;     // capped grid: warps walk over several games like the persistent launch on the GPU
+    emu::g_gridDim.x = store_blocks;
+    for (int b = 0; b < store_blocks; b++) {
+        int rc = emu::run_block(k_planes, &a, b, HIVE_STORE_WARPS * 32, sched_seed + 3000 + (uint64_t)b);
         if (rc) return rc;
     }
     return 0;
