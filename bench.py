@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--selfplay-games", type=int, default=2048)
     ap.add_argument("--selfplay-sims", type=int, default=50)
     ap.add_argument("--selfplay-moves", type=int, default=2)
+    ap.add_argument("--e2e-parts", type=int, default=3, help="host-driven path: pipelined parts of the batch (each on its own stream)")
     return ap.parse_args()
 
 
@@ -344,7 +345,8 @@ def main():
     # streams so that the host works on one half while the GPU steps the other.
     k_e2e = min(args.steps, 1500)
     halves = []
-    for hi, cnt in enumerate((n // 2, n - n // 2)):
+    parts = max(1, args.e2e_parts)
+    for hi, cnt in enumerate([n // parts + (1 if i < n % parts else 0) for i in range(parts)]):
         st = torch.cuda.Stream()
         hb = hive_b200.HiveBatch(cnt, device=local_rank, stream=st.cuda_stream)
         mask_h = torch.empty((cnt, 25), dtype=torch.int64).pin_memory()
@@ -384,9 +386,10 @@ def main():
     e2e_steps = sum(int(h["b"].counters()[0].astype(np.int64).sum()) for h in halves) - s0
     e2e_value = allsum(float(e2e_steps)) / allmax(dt)
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": (200 + 4 + 4) * n,
-           "steps": k_e2e, "note": "per-GPU bytes per step of all 16,384 games; two 8,192-game halves on two streams, host "
-           "picks actions (C-ABI twin of the device policy, host worker pool) for one half while the GPU steps the other; "
-           "planes stay in HBM for the net"}
+           "steps": k_e2e, "parts": parts,
+           "note": "per-GPU bytes per step of all %d games; %d pipelined parts of the batch on their own streams, host "
+           "picks actions (C-ABI twin of the device policy, host worker pool) for one part while the GPU steps the others; "
+           "planes stay in HBM for the net" % (n, parts)}
     for h in halves:
         h["b"].close()
     clocks = sampler.stop()                       # sampled over both timed regions (resident rollout + host-driven e2e)

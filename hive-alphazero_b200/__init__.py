@@ -22,6 +22,9 @@ def __getattr__(name):
     if name in ("Trainer", "alpha_loss", "samples_to_tensors", "discounted_value"):
         from . import train
         return getattr(train, name)
+    if name in ("get_buffer", "get_buffers", "IngestResult", "record_action", "decode_piece"):
+        from . import ingest
+        return getattr(ingest, name)
     if name == "EvaluatorMatch":
         from .evaluator import EvaluatorMatch
         return EvaluatorMatch

@@ -637,7 +637,7 @@ __device__ __forceinline__ void fill_bf16_lut(uint4* lut, int t) {
 // engine (cp.async.bulk shared -> global).  The 16 KB per game leave the SM without occupying the
 // load/store queue the position evaluation of the other warps needs for its shared-memory traffic.
 #ifndef HIVE_STAGE_PLANES
-#define HIVE_STAGE_PLANES 7
+#define HIVE_STAGE_PLANES 28
 #endif
 #ifndef HIVE_STAGE_BUFS
 #define HIVE_STAGE_BUFS 2
@@ -671,29 +671,52 @@ __device__ __forceinline__ void bulk_wait_read() {      // at most PENDING of th
 #endif
 }
 
-// `bytes`: the game's bit planes in shared memory, 20 B per plane of which 18 are used
-__device__ __forceinline__ void store_planes_bulk(const uint8_t* bytes, const uint4* lut, uint4* stage, int lane, int turn,
+// `bytes`: the game's bit planes in shared memory, 20 B per plane of which 18 are used.
+// A stage covers STAGE_PLANES planes = STAGE_PLANES*20 source bytes; lane l looks at source bytes l, l+32, ... of
+// the stage.  Which plane and byte that is, whether it is one of the two padding bytes, and the 16-byte chunk of the
+// staging buffer its eight bf16 values go to are the same for every stage and every game, so they are worked out
+// once per call (SRC_ROUNDS offsets kept in registers) and the inner loop is: byte load at an immediate offset,
+// LUT row load, 16-byte store.
+constexpr int STAGE_SRC_BYTES = STAGE_PLANES * 20, SRC_ROUNDS = (STAGE_SRC_BYTES + 31) / 32;
+constexpr int TURN_STAGE = 31 / STAGE_PLANES, TURN_CHUNK0 = (31 % STAGE_PLANES) * 18;   // plane 31 = the turn number
+// `lut_s`: the LUT's shared-window address, read back from memory by the caller so that it stays in a register (ptxas
+// otherwise re-materialises the window base -- S2R + LEA -- in front of every LUT load).
+__device__ __forceinline__ void store_planes_bulk(const uint8_t* bytes, const uint4* lut, uint32_t lut_s, uint4* stage, int lane, int turn,
                                                   uint16_t* __restrict__ out) {
     const uint32_t tb = __float_as_uint((float)turn) >> 16;     // bf16(turn): turn <= 255 is exact
     const uint32_t tt = tb | (tb << 16);
     const uint4 turn4 = make_uint4(tt, tt, tt, tt);
-    const int p0 = lane / 18, j0 = lane - 18 * p0;
+    int dst[SRC_ROUNDS];                                        // chunk of the stage buffer, -1: padding byte / past the stage
+#pragma unroll
+    for (int i = 0; i < SRC_ROUNDS; i++) {
+        const int sb = lane + 32 * i, pl = sb / 20, j = sb - 20 * pl;
+        dst[i] = (sb < STAGE_SRC_BYTES && j < 18) ? pl * 18 + j : -1;
+    }
+    const uint8_t* mine = bytes + lane;
+#ifdef HIVE_EMU
+    (void)lut_s;
+#endif
 #pragma unroll
     for (int q = 0; q < N_STAGE; q++) {
         uint4* buf = stage + (q % STAGE_BUFS) * STAGE_CHUNKS;
         // the stage that used this buffer last (of this game or of the warp's previous game) has left shared memory
         if (lane == 0) bulk_wait_read<STAGE_BUFS - 1>();
         __syncwarp();
-        int p = q * STAGE_PLANES + p0, j = j0;                  // chunk u = lane + 32 i of the stage = 18 * plane + byte
 #pragma unroll
-        for (int i = 0; i < (STAGE_CHUNKS + 31) / 32; i++) {
-            if ((i + 1) * 32 <= STAGE_CHUNKS || lane + 32 * i < STAGE_CHUNKS) {
-                uint4 v = lut[bytes[p * 20 + j]];
-                if (p == 31) v = turn4;                         // plane 31 = the turn number
-                buf[lane + 32 * i] = v;
+        for (int i = 0; i < SRC_ROUNDS; i++)
+            if (dst[i] >= 0) {
+#ifdef HIVE_EMU
+                buf[dst[i]] = lut[mine[q * STAGE_SRC_BYTES + 32 * i]];
+#else
+                const uint32_t byte = mine[q * STAGE_SRC_BYTES + 32 * i];
+                uint4 v;
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(lut_s + byte * 16u));
+                buf[dst[i]] = v;
+#endif
             }
-            j += 14; p += 1;                                    // u += 32 = 18 + 14
-            if (j >= 18) { j -= 18; p += 1; }
+        if (q == TURN_STAGE) {                                  // plane 31 holds the turn number, not bits
+            __syncwarp();                                       // (its chunks were written by other lanes above)
+            if (lane < 18) buf[TURN_CHUNK0 + lane] = turn4;
         }
         fence_proxy_async_smem();                               // generic-proxy writes -> visible to the bulk-copy engine
         __syncwarp();
@@ -720,10 +743,18 @@ __device__ __forceinline__ int select_kth_action(const uint32_t* words, int lane
     const int owner = __ffs(hit) - 1;
     int ans = -1;
     if (lane == owner) {
-        int r = kth - (incl - c);
-        uint64_t m = ((uint64_t)w1 << 32) | w0;
-        for (int i = 0; i < r; i++) m &= m - 1;
-        ans = lane * 64 + __ffsll((long long)m) - 1;
+        // r-th set bit of the 64-bit mask w1:w0 by halving on popcounts (a clear-lowest-bit loop here was compiled
+        // into a 64-bit division for its trip count)
+        int r = kth - (incl - c), pos = 0;
+        uint32_t w = w0;
+        const int c0 = __popc(w0);
+        if (r >= c0) { r -= c0; w = w1; pos = 32; }
+#pragma unroll
+        for (int h = 16; h > 0; h >>= 1) {
+            const int t = __popc(w & ((1u << h) - 1u));
+            if (r >= t) { r -= t; w >>= h; pos += h; }
+        }
+        ans = lane * 64 + pos;
     }
     return __shfl_sync(FULL, ans, owner < 0 ? 0 : owner);
 }

@@ -11,6 +11,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -53,7 +55,7 @@ namespace hive {
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
 static int launch_env_kernels(hive_env* h, int op, const int32_t* actions, const uint8_t* mask, uint64_t seed, int max_turn,
-                              int auto_reset, int32_t* chosen, int repeat = 1);
+                              int auto_reset, int32_t* chosen, int repeat = 1, int force_slices = 0);
 
 int launch_env(hive_env* h, int op, const int32_t* actions, const uint8_t* mask, uint64_t seed, int max_turn,
                int auto_reset, int32_t* chosen) {
@@ -151,11 +153,12 @@ static int launch_slice_chain(hive_env* h, int s, EnvArgs a, cudaStream_t st, cu
 
 // One or `repeat` steps of the whole batch: every slice's chain on its own pair of streams, joined into h->stream.
 static int launch_env_kernels(hive_env* h, int op, const int32_t* actions, const uint8_t* mask, uint64_t seed, int max_turn,
-                              int auto_reset, int32_t* chosen, int repeat) {
+                              int auto_reset, int32_t* chosen, int repeat, int force_slices) {
     // launches the host issues one by one (not graph replays) are launch-bound: they use at most host_slices slices
     cudaStreamCaptureStatus cap_state = cudaStreamCaptureStatusNone;
     CUDA_TRY(cudaStreamIsCapturing(h->stream, &cap_state));
-    const int S = (cap_state == cudaStreamCaptureStatusActive || h->n_sub < h->host_slices) ? h->n_sub : h->host_slices;
+    int S = (cap_state == cudaStreamCaptureStatusActive || h->n_sub < h->host_slices) ? h->n_sub : h->host_slices;
+    if (force_slices > 0) S = force_slices < h->n_sub ? force_slices : h->n_sub;
     // slices are multiples of GROUP games so that CTAs never straddle two slices
     const int per = ((h->n + S - 1) / S + GROUP - 1) / GROUP * GROUP;
     const bool side = S > 1 || repeat > 1;                 // side streams in use (else everything goes down h->stream)
@@ -254,12 +257,16 @@ int hive::create_env(int n_games, int device, void* stream, int slices, hive_env
         h->store_ctas_per_sm = ec && atoi(ec) > 0 ? atoi(ec) : 2;
         const char* hs = getenv("HIVE_B200_HOST_SLICES");
         h->host_slices = hs && atoi(hs) > 0 ? atoi(hs) : 2;
+        const char* as = getenv("HIVE_B200_ASYNC_SLICES");
+        h->async_slices = as && atoi(as) > 0 ? atoi(as) : 4;
+        if (h->async_slices > h->n_sub) h->async_slices = h->n_sub;
         const char* ug = getenv("HIVE_B200_GRAPH");
         h->use_graph = ug ? atoi(ug) : 1;
     }
     CUDA_TRY(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
     // a slice's work queues hold the largest slice any launch mode cuts (host-issued steps use fewer, larger slices)
-    const int min_slices = h->n_sub < h->host_slices ? h->n_sub : h->host_slices;
+    int min_slices = h->n_sub < h->host_slices ? h->n_sub : h->host_slices;
+    if (h->async_slices < min_slices) min_slices = h->async_slices;
     const size_t qgames = (n + min_slices - 1) / min_slices + 2 * GROUP;
     for (int s = 0; s < h->n_sub; s++) {
         CUDA_TRY(cudaStreamCreateWithFlags(&h->sub_stream[s], cudaStreamNonBlocking));
@@ -304,6 +311,7 @@ int hive_destroy(hive_env_t* h) {
     cudaStreamSynchronize(h->stream);
     if (h->graph.exec) cudaGraphExecDestroy(h->graph.exec);
     if (h->multi_graph.exec) cudaGraphExecDestroy(h->multi_graph.exec);
+    if (h->host_graph.exec) cudaGraphExecDestroy(h->host_graph.exec);
     cudaFree(h->recs); cudaFree(h->legal); cudaFree(h->count); cudaFree(h->status); cudaFree(h->planes); cudaFree(h->scratch); cudaFree(h->bits[0]); cudaFree(h->bits[1]);
     for (int s = 0; s < h->n_sub; s++) {
         cudaFree(h->bq[s].counters); cudaFree(h->bq[s].flood);
@@ -368,19 +376,68 @@ int hive_step_host(hive_env_t* h, const int32_t* actions) {
     return rc;
 }
 
-int hive_step_host_async(hive_env_t* h, const int32_t* actions, uint64_t* mask, int32_t* count, uint32_t* packed_status) {
-    if (check(h)) return HIVE_E_HANDLE;
-    if (!actions) return fail(HIVE_E_ARG, "hive_step_host_async: null actions");
-    CUDA_TRY(cudaSetDevice(h->device));
-    int32_t* d = h->d_actions[h->act_flip];
-    h->act_flip ^= 1;
+// true if `p` is page-locked host memory (cudaHostAlloc / cudaHostRegister): only such buffers can be the
+// endpoints of copy nodes in a captured graph
+static bool is_pinned_host(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// H2D actions -> the step's kernels -> D2H results, queued on h->stream
+static int queue_host_step(hive_env* h, int32_t* d, const int32_t* actions, uint64_t* mask, int32_t* count, uint32_t* packed_status,
+                           int slices) {
     CUDA_TRY(cudaMemcpyAsync(d, actions, (size_t)h->n * 4, cudaMemcpyHostToDevice, h->stream));
-    int rc = launch_env(h, OP_STEP, d, nullptr, 0, 0, 0, nullptr);
+    int rc = slices > 0 ? launch_env_kernels(h, OP_STEP, d, nullptr, 0, 0, 0, nullptr, 1, slices)
+                        : launch_env(h, OP_STEP, d, nullptr, 0, 0, 0, nullptr);
     if (rc) return rc;
     if (mask) CUDA_TRY(cudaMemcpyAsync(mask, h->legal, (size_t)h->n * LEGAL_WORDS * 4, cudaMemcpyDeviceToHost, h->stream));
     if (count) CUDA_TRY(cudaMemcpyAsync(count, h->count, (size_t)h->n * 4, cudaMemcpyDeviceToHost, h->stream));
     if (packed_status) CUDA_TRY(cudaMemcpyAsync(packed_status, h->status, (size_t)h->n * 4, cudaMemcpyDeviceToHost, h->stream));
     return 0;
+}
+
+// The host-driven step.  A caller that steps from the same page-locked buffers every time (the normal loop: one
+// set of pinned staging buffers per handle) gets the whole sequence -- action upload, the five kernels of every
+// slice with their fork/join events, the three result downloads -- replayed as ONE CUDA graph launch: the host
+// thread then spends a few microseconds per step instead of ~30 driver calls, which is what bounded this path.
+int hive_step_host_async(hive_env_t* h, const int32_t* actions, uint64_t* mask, int32_t* count, uint32_t* packed_status) {
+    if (check(h)) return HIVE_E_HANDLE;
+    if (!actions) return fail(HIVE_E_ARG, "hive_step_host_async: null actions");
+    CUDA_TRY(cudaSetDevice(h->device));
+    hive_env::HostGraph& g = h->host_graph;
+    const bool same = g.exec && g.actions == actions && g.mask == mask && g.count == count && g.status == packed_status;
+    if (!same && h->use_graph) {
+        // a second call with the same buffers builds the graph; one-off callers stay on the plain path
+        const bool repeat_caller = g.seen_actions == actions && g.seen_mask == mask && g.seen_count == count && g.seen_status == packed_status;
+        g.seen_actions = actions; g.seen_mask = mask; g.seen_count = count; g.seen_status = packed_status;
+        if (repeat_caller && is_pinned_host(actions) && (!mask || is_pinned_host(mask)) && (!count || is_pinned_host(count)) &&
+            (!packed_status || is_pinned_host(packed_status))) {
+            if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+            cudaGraph_t graph = nullptr;
+            CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
+            const long long l0 = h->launches;
+            int rc = queue_host_step(h, h->d_actions[0], actions, mask, count, packed_status, h->async_slices);
+            g.launches = (int)(h->launches - l0);
+            h->launches = l0;
+            cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (e != cudaSuccess) return fail(HIVE_E_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+            e = cudaGraphInstantiate(&g.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) { g.exec = nullptr; return fail(HIVE_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+            g.actions = actions; g.mask = mask; g.count = count; g.status = packed_status;
+        }
+    }
+    if (g.exec && g.actions == actions && g.mask == mask && g.count == count && g.status == packed_status) {
+        CUDA_TRY(cudaGraphLaunch(g.exec, h->stream));
+        h->launches += g.launches;
+        return 0;
+    }
+    // stream-ordered on h->stream, so one device-side action buffer would do; the two alternate with hive_step_host's
+    int32_t* d = h->d_actions[h->act_flip];
+    h->act_flip ^= 1;
+    return queue_host_step(h, d, actions, mask, count, packed_status, 0);
 }
 
 int hive_step_random(hive_env_t* h, uint64_t seed, int max_turn, int auto_reset, int32_t* chosen_dev) {
@@ -571,51 +628,84 @@ static void pick_range(int g0, int g1, int n, const uint64_t* mask, const int32_
 }
 
 // A small persistent worker pool for the host-side policy twin (the caller's thread takes a share too).
+// The host-driven loop calls it every few tens of microseconds, far below the wake-up latency of a sleeping
+// thread, so idle workers first spin on the ticket word (HIVE_B200_HOST_SPIN_US, default 200 us) and only then
+// block on the condition variable.  ticket = epoch<<40 | parts<<20 | next: a part is claimed by a CAS on the
+// whole word, so a worker late from the previous job can never claim (or skip) a part of the next one.
 namespace {
 struct PickPool {
     std::vector<std::thread> workers;
     std::mutex mu;
-    std::condition_variable cv_work, cv_done;
-    std::function<void(int)> job;          // job(part)
-    int parts = 0, next = 0, pending = 0;
-    uint64_t epoch = 0;
-    bool stop = false;
+    std::condition_variable cv_work;
+    std::function<void(int)> job;          // job(part); written by run() before the ticket is published
+    std::atomic<uint64_t> ticket{0};
+    std::atomic<int> pending{0}, sleepers{0};
+    std::atomic<bool> stop{false};
+    long spin_ns = 200000;
+    static uint64_t epoch_of(uint64_t t) { return t >> 40; }
+    static int parts_of(uint64_t t) { return (int)((t >> 20) & 0xFFFFF); }
+    static int next_of(uint64_t t) { return (int)(t & 0xFFFFF); }
+    // claims and runs parts of the job published as epoch `e` until none is left
+    void drain(uint64_t e) {
+        uint64_t t = ticket.load(std::memory_order_acquire);
+        for (;;) {
+            if (epoch_of(t) != e || next_of(t) >= parts_of(t)) return;
+            if (ticket.compare_exchange_weak(t, t + 1, std::memory_order_acq_rel, std::memory_order_acquire)) {
+                job(next_of(t));
+                pending.fetch_sub(1, std::memory_order_acq_rel);
+                t = ticket.load(std::memory_order_acquire);
+            }
+        }
+    }
     explicit PickPool(int nthreads) {
+        const char* e = getenv("HIVE_B200_HOST_SPIN_US");
+        if (e) spin_ns = atol(e) * 1000L;
         for (int i = 0; i < nthreads; i++)
             workers.emplace_back([this] {
                 uint64_t seen = 0;
                 for (;;) {
-                    std::unique_lock<std::mutex> lk(mu);
-                    cv_work.wait(lk, [&] { return stop || (epoch != seen && next < parts); });
-                    if (stop) return;
-                    while (next < parts) {
-                        const int part = next++;
-                        lk.unlock();
-                        job(part);
-                        lk.lock();
-                        if (--pending == 0) cv_done.notify_all();
+                    // wait for a new epoch: spin first, then sleep
+                    const auto t0 = std::chrono::steady_clock::now();
+                    uint64_t t;
+                    int polls = 0;
+                    while (epoch_of(t = ticket.load(std::memory_order_acquire)) == seen && !stop.load(std::memory_order_relaxed)) {
+#if defined(__x86_64__) || defined(__i386__)
+                        __builtin_ia32_pause();
+#endif
+                        if ((++polls & 255) == 0 &&
+                            std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count() > spin_ns) {
+                            std::unique_lock<std::mutex> lk(mu);
+                            sleepers.fetch_add(1);
+                            cv_work.wait(lk, [&] { return stop.load() || epoch_of(ticket.load(std::memory_order_acquire)) != seen; });
+                            sleepers.fetch_sub(1);
+                        }
                     }
-                    seen = epoch;
+                    if (stop.load()) return;
+                    seen = epoch_of(t);
+                    drain(seen);
                 }
             });
     }
     ~PickPool() {
-        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        { std::lock_guard<std::mutex> lk(mu); stop.store(true); }
         cv_work.notify_all();
         for (auto& t : workers) t.join();
     }
+    // one caller at a time (the library's handles are single-owner; calls from several threads serialise here)
+    std::mutex run_mu;
     void run(int nparts, std::function<void(int)> f) {
-        std::unique_lock<std::mutex> lk(mu);
-        job = std::move(f); parts = nparts; next = 0; pending = nparts; epoch++;
-        cv_work.notify_all();
-        while (next < parts) {               // the calling thread works too
-            const int part = next++;
-            lk.unlock();
-            job(part);
-            lk.lock();
-            --pending;
+        std::lock_guard<std::mutex> serial(run_mu);
+        job = std::move(f);
+        pending.store(nparts, std::memory_order_relaxed);
+        const uint64_t e = (epoch_of(ticket.load(std::memory_order_relaxed)) + 1) & 0xFFFFFF;
+        ticket.store((e << 40) | ((uint64_t)nparts << 20), std::memory_order_release);
+        if (sleepers.load(std::memory_order_acquire) > 0) { std::lock_guard<std::mutex> lk(mu); cv_work.notify_all(); }
+        drain(e);                            // the calling thread works too
+        while (pending.load(std::memory_order_acquire) > 0) {
+#if defined(__x86_64__) || defined(__i386__)
+            __builtin_ia32_pause();
+#endif
         }
-        cv_done.wait(lk, [&] { return pending == 0; });
     }
 };
 PickPool* pick_pool() {

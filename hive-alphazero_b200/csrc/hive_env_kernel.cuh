@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(HIVE_ENCODE_WARPS * 32, 6) hive_encode_kernel(
 // ---- kernel 5: bit planes -> bf16 CHW planes [56][144] per game, through the TMA (persistent: the grid is capped in
 // hive_env.cu so that every CTA is resident at once and other kernels are placed beside it; a warp walks over games)
 #ifndef HIVE_STORE_WARPS
-#define HIVE_STORE_WARPS 8
+#define HIVE_STORE_WARPS 4
 #endif
 constexpr int STORE_STAGE_BYTES = HIVE_STORE_WARPS * STAGE_BUFS * STAGE_BYTES;     // dynamic shared memory
 __global__ void __launch_bounds__(HIVE_STORE_WARPS * 32) hive_planes_kernel(EnvArgs a) {
@@ -270,8 +270,13 @@ __global__ void __launch_bounds__(HIVE_STORE_WARPS * 32) hive_planes_kernel(EnvA
 #endif
     HIVE_TRACE_SCOPE(4, a);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    fill_bf16_lut(bf16_lut, tid);
+    for (int t = tid; t < 256; t += HIVE_STORE_WARPS * 32) fill_bf16_lut(bf16_lut, t);
+    __shared__ uint32_t lut_addr;
+#ifndef HIVE_EMU
+    if (tid == 0) lut_addr = (uint32_t)__cvta_generic_to_shared(bf16_lut);
+#endif
     __syncthreads();
+    const uint32_t lut_s = *reinterpret_cast<volatile uint32_t*>(&lut_addr);
     constexpr int NV = BITS_WORDS / 4;                           // 70 uint4 per game
     const int g_first = blockIdx.x * HIVE_STORE_WARPS + warp, g_stride = gridDim.x * HIVE_STORE_WARPS;
     uint4 v[3];
@@ -290,7 +295,7 @@ __global__ void __launch_bounds__(HIVE_STORE_WARPS * 32) hive_planes_kernel(EnvA
         const uint32_t live = mine[BITS_LIVE], turn = mine[BITS_TURN];
         if (g + g_stride < a.n) fetch(g + g_stride);            // next game's bit planes arrive during the expansion
         if (live)
-            store_planes_bulk(reinterpret_cast<const uint8_t*>(mine), bf16_lut, stage_ring + warp * (STAGE_BUFS * STAGE_CHUNKS), lane,
+            store_planes_bulk(reinterpret_cast<const uint8_t*>(mine), bf16_lut, lut_s, stage_ring + warp * (STAGE_BUFS * STAGE_CHUNKS), lane,
                               (int)turn, a.planes + (size_t)g * HIVE_PLANES_ELEMS);
     }
     if (lane == 0) bulk_wait_read<0>();                         // shared memory must outlive the copy engine's reads

@@ -32,6 +32,12 @@ struct hive_env {
     // the step of the resident rollout loop is replayed from a CUDA graph (same arguments every step)
     struct StepGraph { int op = -1; const void* actions = nullptr; const void* mask = nullptr; void* chosen = nullptr;
                        uint64_t seed = 0; int max_turn = 0, auto_reset = 0; cudaGraphExec_t exec = nullptr; } graph, multi_graph;
+    // the host-driven step (hive_step_host_async) from one fixed set of page-locked buffers: upload, kernels and
+    // downloads replayed as one graph
+    struct HostGraph { const void* actions = nullptr; const void* mask = nullptr; const void* count = nullptr; const void* status = nullptr;
+                       const void* seen_actions = nullptr; const void* seen_mask = nullptr; const void* seen_count = nullptr;
+                       const void* seen_status = nullptr; int launches = 0; cudaGraphExec_t exec = nullptr; } host_graph;
+    int async_slices = 4;           // slices of a graph-replayed host-driven step
     int use_graph = 1;
     int32_t* d_actions[2] = {nullptr, nullptr};
     int act_flip = 0;

@@ -209,3 +209,41 @@ def test_multi_step_graph_equals_single_steps(hb):
     assert (a.planes_bf16() == b.planes_bf16()).all()
     assert [x.tolist() for x in a.status()] == [x.tolist() for x in b.status()]
     assert [x.tolist() for x in a.counters()] == [x.tolist() for x in b.counters()]
+
+
+def test_async_host_step_graph_replay_matches_device_policy(hb):
+    """hive_step_host_async from one fixed set of page-locked buffers (replayed as one CUDA graph from the second
+    call on) == hive_step_random; the same loop from pageable buffers (plain path) gives the same games."""
+    import torch
+    n, seed = 4096, 99
+    dev, pinned, pageable = hb.HiveBatch(n), hb.HiveBatch(n), hb.HiveBatch(n)
+
+    def buffers(pin):
+        t = [torch.empty((n, 25), dtype=torch.int64), torch.empty(n, dtype=torch.int32), torch.empty(n, dtype=torch.int32),
+             torch.empty(n, dtype=torch.int32)]
+        return [x.pin_memory() for x in t] if pin else t
+
+    runs = []
+    for b, pin in ((pinned, True), (pageable, False)):
+        mask_h, count_h, status_h, actions_h = buffers(pin)
+        mask, count = mask_h.numpy().view(np.uint64), count_h.numpy()
+        status, actions = status_h.numpy().view(np.uint32), actions_h.numpy()
+        episodes = np.zeros(n, dtype=np.uint32)
+        b.legal_into(mask_h.data_ptr(), count_h.data_ptr())
+        b.status_packed_into(status_h.data_ptr())
+        for _ in range(70):
+            b.sync()
+            hb.host_pick_actions(mask, count, status, episodes, seed, 55, actions)
+            b.step_async_ptr(actions_h.data_ptr(), mask_h.data_ptr(), count_h.data_ptr(), status_h.data_ptr())
+        b.sync()
+        runs.append((mask.copy(), count.copy(), status.copy()))
+    for _ in range(70):
+        dev.step_random(seed, max_turn=55, auto_reset=True)
+    m1, c1 = dev.legal_mask()
+    for b, (mask, count, status) in zip((pinned, pageable), runs):
+        m2, c2 = b.legal_mask()
+        assert (m1 == m2).all() and (c1 == c2).all()
+        assert (mask == m2).all() and (count == c2).all()          # what the step downloaded == the device arrays
+        assert (dev.planes_bf16() == b.planes_bf16()).all()
+        assert [a.tolist() for a in dev.status()] == [a.tolist() for a in b.status()]
+        assert [x.tolist() for x in dev.counters()] == [x.tolist() for x in b.counters()]
