@@ -106,8 +106,20 @@ static EnvArgs slice_args(hive_env* h, int s, int per, int op, const int32_t* ac
     a.scratch = h->scratch + off; a.bq = h->bq[s];
     return a;
 }
-static void launch_encode_part(const EnvArgs& a, cudaStream_t st) {
-    hive_encode_kernel<<<(a.n + HIVE_ENCODE_WARPS - 1) / HIVE_ENCODE_WARPS, HIVE_ENCODE_WARPS * 32, 0, st>>>(a);
+// Launch of one kernel of a slice's chain.  `pdl`: programmatic stream serialization -- the grid may be made resident
+// while its predecessor in the stream still runs (its CTAs wait in chain_wait_then_release), which takes the launch
+// latency (7 us per dependent kernel in the v8 trace, 4 per step) off the chain's critical path.
+static cudaError_t launch_chain_kernel(void (*kernel)(EnvArgs), int blocks, int threads, cudaStream_t st, bool pdl, const EnvArgs& a) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, a);
+}
+static cudaError_t launch_encode_part(const EnvArgs& a, cudaStream_t st, bool pdl = false) {
+    return launch_chain_kernel(hive_encode_kernel, (a.n + HIVE_ENCODE_WARPS - 1) / HIVE_ENCODE_WARPS, HIVE_ENCODE_WARPS * 32, st, pdl, a);
 }
 // The plane-store kernel is persistent: the store launches that run at the same time (`concurrent` slices) share
 // store_ctas_per_sm CTAs per SM, so each grid is resident at once and never queues in front of other kernels.
@@ -128,18 +140,20 @@ static int launch_slice_chain(hive_env* h, int s, EnvArgs a, cudaStream_t st, cu
     const bool side = st != ss;
     for (int rep = 0; rep < repeat; rep++) {
         a.bits = h->bits[rep & 1] + (size_t)a.g_offset * BITS_WORDS;
-        hive_analyse_kernel<<<(a.n + GROUP - 1) / GROUP, GROUP * 32, 0, st>>>(a);
+        const int pdl = h->pdl_mask;                            // bit 0 analyse, 1 flood, 2 moves, 3 encode
+        CUDA_TRY(launch_chain_kernel(hive_analyse_kernel, (a.n + GROUP - 1) / GROUP, GROUP * 32, st, (pdl & 1) && rep > 0, a));
         int sblocks = (int)(((long long)a.n * N_PIECE + SEARCH_THREADS - 1) / SEARCH_THREADS);
         if (sblocks > h->search_blocks) sblocks = h->search_blocks;
-        hive_flood_kernel<<<sblocks, SEARCH_THREADS, 0, st>>>(a);
-        hive_moves_kernel<<<sblocks, SEARCH_THREADS, 0, st>>>(a);
-        if (side && rep >= 2) CUDA_TRY(cudaStreamWaitEvent(st, h->stored_ev[s][rep & 1], 0));    // this bit-plane buffer is free again
-        launch_encode_part(a, st);
+        CUDA_TRY(launch_chain_kernel(hive_flood_kernel, sblocks, SEARCH_THREADS, st, pdl & 2, a));
+        CUDA_TRY(launch_chain_kernel(hive_moves_kernel, sblocks, SEARCH_THREADS, st, pdl & 4, a));
+        const bool waits_store = side && rep >= 2;
+        if (waits_store) CUDA_TRY(cudaStreamWaitEvent(st, h->stored_ev[s][rep & 1], 0));    // this bit-plane buffer is free again
+        CUDA_TRY(launch_encode_part(a, st, (pdl & 8) && (!waits_store || (pdl & 16))));
         if (side) {
             CUDA_TRY(cudaEventRecord(h->encoded_ev[s], st));
             CUDA_TRY(cudaStreamWaitEvent(ss, h->encoded_ev[s], 0));
         }
-        launch_planes_part(h, a, ss, concurrent);
+        if (!h->skip_planes) launch_planes_part(h, a, ss, concurrent);
         if (side) CUDA_TRY(cudaEventRecord(h->stored_ev[s][rep & 1], ss));
     }
     if (side) {
@@ -260,6 +274,11 @@ int hive::create_env(int n_games, int device, void* stream, int slices, hive_env
         const char* as = getenv("HIVE_B200_ASYNC_SLICES");
         h->async_slices = as && atoi(as) > 0 ? atoi(as) : 4;
         if (h->async_slices > h->n_sub) h->async_slices = h->n_sub;
+        h->skip_planes = getenv("HIVE_B200_EXPERIMENT_SKIP_PLANES") != nullptr;   // measurement aid: the step without its plane store
+        const char* pm = getenv("HIVE_B200_PDL");
+        h->pdl_mask = pm ? atoi(pm) : 0;
+        const char* sg = getenv("HIVE_B200_SPLIT_GRAPHS");
+        h->split_graphs = sg ? atoi(sg) : 1;
         const char* ug = getenv("HIVE_B200_GRAPH");
         h->use_graph = ug ? atoi(ug) : 1;
     }
@@ -310,7 +329,8 @@ int hive_destroy(hive_env_t* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     if (h->graph.exec) cudaGraphExecDestroy(h->graph.exec);
-    if (h->multi_graph.exec) cudaGraphExecDestroy(h->multi_graph.exec);
+    if (h->multi_graph.exec && h->multi_graph.exec != h->slice_exec[0]) cudaGraphExecDestroy(h->multi_graph.exec);
+    for (int s = 0; s < hive_env::MAX_SUB; s++) if (h->slice_exec[s]) cudaGraphExecDestroy(h->slice_exec[s]);
     if (h->host_graph.exec) cudaGraphExecDestroy(h->host_graph.exec);
     cudaFree(h->recs); cudaFree(h->legal); cudaFree(h->count); cudaFree(h->status); cudaFree(h->planes); cudaFree(h->scratch); cudaFree(h->bits[0]); cudaFree(h->bits[1]);
     for (int s = 0; s < h->n_sub; s++) {
@@ -457,22 +477,59 @@ int hive_step_random_multi(hive_env_t* h, uint64_t seed, int max_turn, int auto_
     if (h->timing) CUDA_TRY(cudaEventRecord(h->t0, h->stream));
     hive_env::StepGraph& g = h->multi_graph;
     const bool hit = g.exec && g.seed == seed && g.max_turn == max_turn && g.auto_reset == auto_reset && g.op == n_steps;
+    const int S = h->n_sub;
+    const bool split = h->split_graphs && S > 1;
     if (!hit) {
-        if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
-        cudaGraph_t graph = nullptr;
-        CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
+        if (g.exec && g.exec != h->slice_exec[0]) cudaGraphExecDestroy(g.exec);
+        g.exec = nullptr;
+        for (int s = 0; s < hive_env::MAX_SUB; s++) if (h->slice_exec[s]) { cudaGraphExecDestroy(h->slice_exec[s]); h->slice_exec[s] = nullptr; }
         const long long l0 = h->launches;
-        int rc = launch_env_kernels(h, OP_RANDOM, nullptr, nullptr, seed, max_turn, auto_reset, nullptr, n_steps);
-        cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
-        h->launches = l0;
-        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-        if (e != cudaSuccess) return fail(HIVE_E_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
-        e = cudaGraphInstantiate(&g.exec, graph, 0);
-        cudaGraphDestroy(graph);
-        if (e != cudaSuccess) { g.exec = nullptr; return fail(HIVE_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+        if (!split) {
+            cudaGraph_t graph = nullptr;
+            CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
+            int rc = launch_env_kernels(h, OP_RANDOM, nullptr, nullptr, seed, max_turn, auto_reset, nullptr, n_steps);
+            cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+            h->launches = l0;
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (e != cudaSuccess) return fail(HIVE_E_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+            e = cudaGraphInstantiate(&g.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) { g.exec = nullptr; return fail(HIVE_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+        } else {
+            // One graph PER SLICE, each launched into its own stream.  The nodes of a single graph holding all
+            // slices are issued level by level (all analyse kernels, then all floods, ...: profiles/README.md,
+            // v8 trace), which lines the slices' phases up and leaves the SMs to one kernel type at a time;
+            // separate graphs are separate launch queues, so the chains drift apart and their phases mix.
+            const int per = ((h->n + S - 1) / S + GROUP - 1) / GROUP * GROUP;
+            for (int s = 0; s < S; s++) {
+                const EnvArgs a = slice_args(h, s, per, OP_RANDOM, nullptr, nullptr, seed, max_turn, auto_reset, nullptr);
+                if (a.n <= 0) break;
+                cudaGraph_t graph = nullptr;
+                CUDA_TRY(cudaStreamBeginCapture(h->sub_stream[s], cudaStreamCaptureModeRelaxed));
+                int rc = launch_slice_chain(h, s, a, h->sub_stream[s], h->store_stream[s], S, n_steps);
+                cudaError_t e = cudaStreamEndCapture(h->sub_stream[s], &graph);
+                if (rc) { h->launches = l0; if (graph) cudaGraphDestroy(graph); return rc; }
+                if (e != cudaSuccess) { h->launches = l0; return fail(HIVE_E_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e)); }
+                e = cudaGraphInstantiate(&h->slice_exec[s], graph, 0);
+                cudaGraphDestroy(graph);
+                if (e != cudaSuccess) { h->slice_exec[s] = nullptr; h->launches = l0; return fail(HIVE_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+            }
+            h->launches = l0;
+            g.exec = h->slice_exec[0];       // marks the cache valid (owned through slice_exec)
+        }
         g.op = n_steps; g.seed = seed; g.max_turn = max_turn; g.auto_reset = auto_reset;
     }
-    CUDA_TRY(cudaGraphLaunch(g.exec, h->stream));
+    if (!split) {
+        CUDA_TRY(cudaGraphLaunch(g.exec, h->stream));
+    } else {
+        CUDA_TRY(cudaEventRecord(h->fork_ev, h->stream));
+        for (int s = 0; s < S && h->slice_exec[s]; s++) {
+            CUDA_TRY(cudaStreamWaitEvent(h->sub_stream[s], h->fork_ev, 0));
+            CUDA_TRY(cudaGraphLaunch(h->slice_exec[s], h->sub_stream[s]));
+            CUDA_TRY(cudaEventRecord(h->join_ev[s], h->sub_stream[s]));
+            CUDA_TRY(cudaStreamWaitEvent(h->stream, h->join_ev[s], 0));
+        }
+    }
     h->launches += 5LL * h->n_sub * n_steps;
     if (h->timing) CUDA_TRY(cudaEventRecord(h->t1, h->stream));
     return 0;
@@ -506,7 +563,7 @@ int hive_profile_step(hive_env_t* h, uint64_t seed, int max_turn, float* ms) {
     CUDA_TRY(cudaEventRecord(ev[2], h->stream));
     hive_moves_kernel<<<h->search_blocks, SEARCH_THREADS, 0, h->stream>>>(a);
     CUDA_TRY(cudaEventRecord(ev[3], h->stream));
-    launch_encode_part(a, h->stream);
+    CUDA_TRY(launch_encode_part(a, h->stream));
     CUDA_TRY(cudaEventRecord(ev[4], h->stream));
     launch_planes_part(h, a, h->stream, 0);                    // alone on the GPU: uncapped
     CUDA_TRY(cudaEventRecord(ev[5], h->stream));
@@ -727,10 +784,14 @@ int hive_host_pick_actions(int n, const uint64_t* mask, const int32_t* count, co
                            uint32_t* episodes, uint64_t seed, int max_turn, int32_t* actions) {
     if (n <= 0 || !mask || !count || !packed_status || !episodes || !actions)
         return fail(HIVE_E_ARG, "hive_host_pick_actions: bad arguments");
-    const int chunk = 512;
+    if (n <= 512) { pick_range(0, n, n, mask, count, packed_status, episodes, seed, max_turn, actions); return 0; }
+    // one chunk per thread of the pool (a fixed 512-game chunk left most of the 16 threads idle on a 5,461-game part)
+    PickPool* pool = pick_pool();
+    const int threads = (int)pool->workers.size() + 1;
+    int chunk = (n + threads - 1) / threads;
+    if (chunk < 128) chunk = 128;
     const int parts = (n + chunk - 1) / chunk;
-    if (parts <= 1) { pick_range(0, n, n, mask, count, packed_status, episodes, seed, max_turn, actions); return 0; }
-    pick_pool()->run(parts, [=](int part) {
+    pool->run(parts, [=](int part) {
         const int g0 = part * chunk, g1 = g0 + chunk < n ? g0 + chunk : n;
         pick_range(g0, g1, n, mask, count, packed_status, episodes, seed, max_turn, actions);
     });

@@ -63,10 +63,23 @@ struct TraceScope {
 #define HIVE_TRACE_SCOPE(k, a)
 #endif
 
+// Programmatic dependent launch (hive_env.cu launches the kernels of a slice's chain with
+// cudaLaunchAttributeProgrammaticStreamSerialization): a kernel's CTAs may become resident while the kernel before it in
+// the stream is still running; they wait here until that grid has completed and its writes are visible, and only then
+// let their own dependent start launching (so at most one kernel of a chain is pre-launched).  Without the launch
+// attribute both instructions return at once.
+__device__ __forceinline__ void chain_wait_then_release() {
+#ifndef HIVE_EMU
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
 // ---- kernel 1: decode the operation, apply the action, analyse the new position (warp <-> game)
 __global__ void __launch_bounds__(GROUP * 32, 4) hive_analyse_kernel(EnvArgs a) {
     __shared__ GroupQueues q;
     __shared__ uint32_t occ_s[GROUP][8];
+    chain_wait_then_release();
     HIVE_TRACE_SCOPE(0, a);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.x * GROUP + warp;
@@ -159,6 +172,7 @@ __global__ void __launch_bounds__(GROUP * 32, 4) hive_analyse_kernel(EnvArgs a) 
 // ---- kernel 2: one-hive floods over the batch-wide flood queue (thread <-> queued piece)
 constexpr int SEARCH_THREADS = 128;
 __global__ void __launch_bounds__(SEARCH_THREADS) hive_flood_kernel(EnvArgs a) {
+    chain_wait_then_release();
     HIVE_TRACE_SCOPE(1, a);
     const int lane = threadIdx.x & 31;
     const int nf = (int)a.bq.counters[0];
@@ -193,6 +207,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hive_flood_kernel(EnvArgs a) {
 
 // ---- kernel 3: move searches, warps homogeneous in piece type (thread <-> queued piece)
 __global__ void __launch_bounds__(SEARCH_THREADS) hive_moves_kernel(EnvArgs a) {
+    chain_wait_then_release();
     HIVE_TRACE_SCOPE(2, a);
     // move classes start at warp boundaries so that warps stay homogeneous
     const int n0 = (int)a.bq.counters[1], n1 = (int)a.bq.counters[2], n2 = (int)a.bq.counters[3], n3 = (int)a.bq.counters[4];
@@ -216,6 +231,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hive_moves_kernel(EnvArgs a) {
 // stream beside the next step's kernels.
 __global__ void __launch_bounds__(HIVE_ENCODE_WARPS * 32, 6) hive_encode_kernel(EnvArgs a) {
     __shared__ WarpScratch scratch[HIVE_ENCODE_WARPS];
+    chain_wait_then_release();
     HIVE_TRACE_SCOPE(3, a);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.x * HIVE_ENCODE_WARPS + warp;

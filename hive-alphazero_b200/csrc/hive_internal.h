@@ -38,6 +38,10 @@ struct hive_env {
                        const void* seen_actions = nullptr; const void* seen_mask = nullptr; const void* seen_count = nullptr;
                        const void* seen_status = nullptr; int launches = 0; cudaGraphExec_t exec = nullptr; } host_graph;
     int async_slices = 4;           // slices of a graph-replayed host-driven step
+    cudaGraphExec_t slice_exec[MAX_SUB] = {};   // multi-step rollout: one graph per slice, each on its own stream
+    bool skip_planes = false;       // measurement aid (HIVE_B200_EXPERIMENT_SKIP_PLANES): results are then incomplete
+    int split_graphs = 1;
+    int pdl_mask = 0;               // HIVE_B200_PDL: programmatic dependent launch per chain kernel, off by default (measured: no gain) (bit 0 analyse .. 3 encode; 16: also when encode waits on a store event)
     int use_graph = 1;
     int32_t* d_actions[2] = {nullptr, nullptr};
     int act_flip = 0;

@@ -62,7 +62,9 @@ int hive_step_host(hive_env_t* h, const int32_t* actions);          /* host int3
 int hive_step(hive_env_t* h, const int32_t* actions_dev);           /* device int32[n] */
 /* Fully asynchronous form for pipelined callers: queues the H2D copy of `actions`, the step and the
  * D2H copies of the new legal masks / counts / packed status (any may be NULL) on the handle's
- * stream and returns at once.  All buffers should be pinned and must stay untouched until hive_sync. */
+ * stream and returns at once.  All buffers should be pinned and must stay untouched until hive_sync.
+ * From the second call with the same set of page-locked buffers on, the whole sequence (upload, the kernels of
+ * every slice, downloads) is replayed as one CUDA graph launch; pageable buffers stay on the plain path. */
 int hive_step_host_async(hive_env_t* h, const int32_t* actions, uint64_t* mask, int32_t* count, uint32_t* packed_status);
 
 /* On-device rollout policy of the benchmark (SURVEY 8d Config 2): a = A[x % len(A)],

@@ -9,7 +9,7 @@ from hive_b200 import _capi
 out, steps = sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 10
 L = _capi.lib()
 b = hive_b200.HiveBatch(16384)
-for _ in range(30):
+for _ in range(140):                      # positions of every age
     b.step_random(7, 55, True)
 b.step_random_multi(7, steps, 55, True)
 b.step_random_multi(7, steps, 55, True)
