@@ -358,7 +358,7 @@ def main():
                            actions=actions_h.numpy(), episodes=np.zeros(cnt, dtype=np.uint32), seed=seed + 77 * (hi + 1)))
 
     def e2e_half(h):
-        h["b"].sync()                                                                # results of this half's last step are in host memory
+        h["b"].wait_results()                                                        # this part's last downloads have landed (its planes may still be in flight)
         hive_b200.host_pick_actions(h["mask"], h["count"], h["status"], h["episodes"], h["seed"], args.max_turn, h["actions"])
         # H2D 4 B/game -> kernels -> D2H (200 + 4 + 4) B/game, all queued; the other half is handled meanwhile
         h["b"].step_async_ptr(h["actions_h"].data_ptr(), h["mask_h"].data_ptr(), h["count_h"].data_ptr(), h["status_h"].data_ptr())

@@ -55,7 +55,7 @@ namespace hive {
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
 static int launch_env_kernels(hive_env* h, int op, const int32_t* actions, const uint8_t* mask, uint64_t seed, int max_turn,
-                              int auto_reset, int32_t* chosen, int repeat = 1, int force_slices = 0);
+                              int auto_reset, int32_t* chosen, int repeat = 1, int force_slices = 0, int* deferred_stores = nullptr);
 
 int launch_env(hive_env* h, int op, const int32_t* actions, const uint8_t* mask, uint64_t seed, int max_turn,
                int auto_reset, int32_t* chosen) {
@@ -136,7 +136,10 @@ static void launch_planes_part(hive_env* h, const EnvArgs& a, cudaStream_t st, i
 // `repeat` steps of one slice: analyse -> flood -> moves -> encode on stream `st`, and the plane store of every step on
 // stream `ss`, so that it runs beside the next step's kernels (the bit planes it reads are double-buffered; step k+2's
 // encode waits for step k's store).  With st != ss the chain ends joined on `st`.
-static int launch_slice_chain(hive_env* h, int s, EnvArgs a, cudaStream_t st, cudaStream_t ss, int concurrent, int repeat) {
+// `defer_store_join` (single steps only): `st` is NOT joined with the plane store; the caller joins
+// stored_ev[s][0] itself, after whatever it wants to run beside the store (the result downloads of the host-driven step).
+static int launch_slice_chain(hive_env* h, int s, EnvArgs a, cudaStream_t st, cudaStream_t ss, int concurrent, int repeat,
+                              bool defer_store_join = false) {
     const bool side = st != ss;
     for (int rep = 0; rep < repeat; rep++) {
         a.bits = h->bits[rep & 1] + (size_t)a.g_offset * BITS_WORDS;
@@ -156,7 +159,7 @@ static int launch_slice_chain(hive_env* h, int s, EnvArgs a, cudaStream_t st, cu
         if (!h->skip_planes) launch_planes_part(h, a, ss, concurrent);
         if (side) CUDA_TRY(cudaEventRecord(h->stored_ev[s][rep & 1], ss));
     }
-    if (side) {
+    if (side && !(defer_store_join && repeat == 1)) {
         CUDA_TRY(cudaStreamWaitEvent(st, h->stored_ev[s][(repeat - 1) & 1], 0));
         if (repeat > 1) CUDA_TRY(cudaStreamWaitEvent(st, h->stored_ev[s][repeat & 1], 0));
     }
@@ -166,8 +169,10 @@ static int launch_slice_chain(hive_env* h, int s, EnvArgs a, cudaStream_t st, cu
 }
 
 // One or `repeat` steps of the whole batch: every slice's chain on its own pair of streams, joined into h->stream.
+// `deferred_stores` (repeat == 1): if given, h->stream is joined with the encode kernels only and *deferred_stores
+// receives the number of slices whose plane store (stored_ev[s][0]) the caller still has to join.
 static int launch_env_kernels(hive_env* h, int op, const int32_t* actions, const uint8_t* mask, uint64_t seed, int max_turn,
-                              int auto_reset, int32_t* chosen, int repeat, int force_slices) {
+                              int auto_reset, int32_t* chosen, int repeat, int force_slices, int* deferred_stores) {
     // launches the host issues one by one (not graph replays) are launch-bound: they use at most host_slices slices
     cudaStreamCaptureStatus cap_state = cudaStreamCaptureStatusNone;
     CUDA_TRY(cudaStreamIsCapturing(h->stream, &cap_state));
@@ -176,18 +181,21 @@ static int launch_env_kernels(hive_env* h, int op, const int32_t* actions, const
     // slices are multiples of GROUP games so that CTAs never straddle two slices
     const int per = ((h->n + S - 1) / S + GROUP - 1) / GROUP * GROUP;
     const bool side = S > 1 || repeat > 1;                 // side streams in use (else everything goes down h->stream)
+    const bool defer = deferred_stores && side && repeat == 1 && !h->skip_planes;
+    if (deferred_stores) *deferred_stores = 0;
     if (side) CUDA_TRY(cudaEventRecord(h->fork_ev, h->stream));
     for (int s = 0; s < S; s++) {
         const EnvArgs a = slice_args(h, s, per, op, actions, mask, seed, max_turn, auto_reset, chosen);
         if (a.n <= 0) break;
         cudaStream_t st = side ? h->sub_stream[s] : h->stream, ss = side ? h->store_stream[s] : h->stream;
         if (side) CUDA_TRY(cudaStreamWaitEvent(st, h->fork_ev, 0));
-        int rc = launch_slice_chain(h, s, a, st, ss, S, repeat);
+        int rc = launch_slice_chain(h, s, a, st, ss, S, repeat, defer);
         if (rc) return rc;
         if (side) {
             CUDA_TRY(cudaEventRecord(h->join_ev[s], st));
             CUDA_TRY(cudaStreamWaitEvent(h->stream, h->join_ev[s], 0));
         }
+        if (defer) *deferred_stores = s + 1;
     }
     return 0;
 }
@@ -283,6 +291,7 @@ int hive::create_env(int n_games, int device, void* stream, int slices, hive_env
         h->use_graph = ug ? atoi(ug) : 1;
     }
     CUDA_TRY(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->results_ev, cudaEventDisableTiming));
     // a slice's work queues hold the largest slice any launch mode cuts (host-issued steps use fewer, larger slices)
     int min_slices = h->n_sub < h->host_slices ? h->n_sub : h->host_slices;
     if (h->async_slices < min_slices) min_slices = h->async_slices;
@@ -343,6 +352,7 @@ int hive_destroy(hive_env_t* h) {
         if (h->join_ev[s]) cudaEventDestroy(h->join_ev[s]);
     }
     if (h->fork_ev) cudaEventDestroy(h->fork_ev);
+    if (h->results_ev) cudaEventDestroy(h->results_ev);
     cudaFree(h->d_actions[0]); cudaFree(h->d_actions[1]); cudaFree(h->d_mask); cudaFree(h->hop_lines);
     if (h->copy_done) cudaEventDestroy(h->copy_done);
     if (h->t0) cudaEventDestroy(h->t0);
@@ -404,16 +414,23 @@ static bool is_pinned_host(const void* p) {
     return at.type == cudaMemoryTypeHost;
 }
 
-// H2D actions -> the step's kernels -> D2H results, queued on h->stream
+// H2D actions -> the step's kernels -> D2H results, queued on h->stream.  The downloads need the encode kernels only:
+// they are queued BEFORE the join with the plane stores, and results_ev is recorded behind them, so that
+// hive_wait_results returns while the 16 KB/game of planes are still being written (hive_sync waits for those too).
 static int queue_host_step(hive_env* h, int32_t* d, const int32_t* actions, uint64_t* mask, int32_t* count, uint32_t* packed_status,
                            int slices) {
     CUDA_TRY(cudaMemcpyAsync(d, actions, (size_t)h->n * 4, cudaMemcpyHostToDevice, h->stream));
-    int rc = slices > 0 ? launch_env_kernels(h, OP_STEP, d, nullptr, 0, 0, 0, nullptr, 1, slices)
-                        : launch_env(h, OP_STEP, d, nullptr, 0, 0, 0, nullptr);
+    int deferred = 0;
+    int rc = launch_env_kernels(h, OP_STEP, d, nullptr, 0, 0, 0, nullptr, 1, slices > 0 ? slices : h->host_slices, &deferred);
     if (rc) return rc;
     if (mask) CUDA_TRY(cudaMemcpyAsync(mask, h->legal, (size_t)h->n * LEGAL_WORDS * 4, cudaMemcpyDeviceToHost, h->stream));
     if (count) CUDA_TRY(cudaMemcpyAsync(count, h->count, (size_t)h->n * 4, cudaMemcpyDeviceToHost, h->stream));
     if (packed_status) CUDA_TRY(cudaMemcpyAsync(packed_status, h->status, (size_t)h->n * 4, cudaMemcpyDeviceToHost, h->stream));
+    cudaStreamCaptureStatus cap_state = cudaStreamCaptureStatusNone;
+    CUDA_TRY(cudaStreamIsCapturing(h->stream, &cap_state));
+    CUDA_TRY(cudaEventRecordWithFlags(h->results_ev, h->stream,
+                                      cap_state == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault));
+    for (int s = 0; s < deferred; s++) CUDA_TRY(cudaStreamWaitEvent(h->stream, h->stored_ev[s][0], 0));
     return 0;
 }
 
@@ -458,6 +475,13 @@ int hive_step_host_async(hive_env_t* h, const int32_t* actions, uint64_t* mask, 
     int32_t* d = h->d_actions[h->act_flip];
     h->act_flip ^= 1;
     return queue_host_step(h, d, actions, mask, count, packed_status, 0);
+}
+
+int hive_wait_results(hive_env_t* h) {
+    if (check(h)) return HIVE_E_HANDLE;
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaEventSynchronize(h->results_ev));
+    return 0;
 }
 
 int hive_step_random(hive_env_t* h, uint64_t seed, int max_turn, int auto_reset, int32_t* chosen_dev) {

@@ -28,6 +28,7 @@ struct hive_env {
     cudaStream_t sub_stream[MAX_SUB] = {}, store_stream[MAX_SUB] = {};
     cudaEvent_t encoded_ev[MAX_SUB] = {}, stored_ev[MAX_SUB][2] = {};
     cudaEvent_t fork_ev = nullptr, join_ev[MAX_SUB] = {};
+    cudaEvent_t results_ev = nullptr;   // behind the result downloads of the last hive_step_host_async (hive_wait_results)
     int search_blocks = 0;
     // the step of the resident rollout loop is replayed from a CUDA graph (same arguments every step)
     struct StepGraph { int op = -1; const void* actions = nullptr; const void* mask = nullptr; void* chosen = nullptr;

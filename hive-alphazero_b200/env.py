@@ -63,6 +63,10 @@ class HiveBatch:
         """Queue H2D(actions) -> step -> D2H(results) without waiting (pinned host pointers)."""
         check(lib().hive_step_host_async(self._h, actions_ptr, mask_ptr, count_ptr, status_ptr), "hive_step_host_async")
 
+    def wait_results(self):
+        """Blocks until the downloads of the last step_async_ptr have landed (the planes may still be in flight)."""
+        check(lib().hive_wait_results(self._h), "hive_wait_results")
+
     def step_device(self, actions_dev_ptr):
         check(lib().hive_step(self._h, actions_dev_ptr), "hive_step")
 

@@ -66,6 +66,10 @@ int hive_step(hive_env_t* h, const int32_t* actions_dev);           /* device in
  * From the second call with the same set of page-locked buffers on, the whole sequence (upload, the kernels of
  * every slice, downloads) is replayed as one CUDA graph launch; pageable buffers stay on the plain path. */
 int hive_step_host_async(hive_env_t* h, const int32_t* actions, uint64_t* mask, int32_t* count, uint32_t* packed_status);
+/* Blocks until the downloads of the last hive_step_host_async have landed in the caller's buffers.  The step's
+ * 16 KB/game of planes may still be in flight (they stay in HBM for the network; hive_sync waits for them too), so a
+ * host loop that only needs masks / counts / status picks its next actions beside the plane store. */
+int hive_wait_results(hive_env_t* h);
 
 /* On-device rollout policy of the benchmark (SURVEY 8d Config 2): a = A[x % len(A)],
  * x = splitmix64(seed ^ game_id<<32 ^ turn), game_id = slot + n_games*episode; pass when A is

@@ -232,7 +232,7 @@ def test_async_host_step_graph_replay_matches_device_policy(hb):
         b.legal_into(mask_h.data_ptr(), count_h.data_ptr())
         b.status_packed_into(status_h.data_ptr())
         for _ in range(70):
-            b.sync()
+            b.wait_results()                                   # downloads landed; the plane store may still run
             hb.host_pick_actions(mask, count, status, episodes, seed, 55, actions)
             b.step_async_ptr(actions_h.data_ptr(), mask_h.data_ptr(), count_h.data_ptr(), status_h.data_ptr())
         b.sync()
