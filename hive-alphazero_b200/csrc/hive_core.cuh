@@ -90,7 +90,11 @@ static_assert(sizeof(GameScratch) == 656, "GameScratch layout");
 // Work queues.  The analyse kernel first collects the items of its 16 games in shared memory
 // (GroupQueues), then reserves a slice of the batch-wide queues with one atomic per class and CTA.
 // item = game<<6 | piece<<1 | wants_moves
-constexpr int GROUP = 16;          // games per CTA of the analyse kernel
+#ifndef HIVE_GROUP
+#define HIVE_GROUP 8
+#endif
+constexpr int GROUP = HIVE_GROUP;  // games per CTA of the analyse kernel (<= 16: queue items carry the slot in 4 bits)
+static_assert(GROUP >= 1 && GROUP <= 16, "GROUP");
 struct __align__(16) GroupQueues {
     uint32_t n_flood;
     uint32_t n_mv[4];              // move classes: 0 Ant, 1 Grasshopper, 2 Spider, 3 Queen/Beetle

@@ -76,7 +76,7 @@ __device__ __forceinline__ void chain_wait_then_release() {
 }
 
 // ---- kernel 1: decode the operation, apply the action, analyse the new position (warp <-> game)
-__global__ void __launch_bounds__(GROUP * 32, 4) hive_analyse_kernel(EnvArgs a) {
+__global__ void __launch_bounds__(GROUP * 32, 64 / GROUP) hive_analyse_kernel(EnvArgs a) {
     __shared__ GroupQueues q;
     __shared__ uint32_t occ_s[GROUP][8];
     chain_wait_then_release();
@@ -276,7 +276,10 @@ __global__ void __launch_bounds__(HIVE_ENCODE_WARPS * 32, 6) hive_encode_kernel(
 #define HIVE_STORE_WARPS 4
 #endif
 constexpr int STORE_STAGE_BYTES = HIVE_STORE_WARPS * STAGE_BUFS * STAGE_BYTES;     // dynamic shared memory
-__global__ void __launch_bounds__(HIVE_STORE_WARPS * 32) hive_planes_kernel(EnvArgs a) {
+#ifndef HIVE_STORE_MIN_CTAS
+#define HIVE_STORE_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(HIVE_STORE_WARPS * 32, HIVE_STORE_MIN_CTAS) hive_planes_kernel(EnvArgs a) {
     __shared__ uint4 bf16_lut[256];
     __shared__ __align__(16) uint32_t planes_s[HIVE_STORE_WARPS][BITS_WORDS];
 #ifdef HIVE_EMU
