@@ -271,6 +271,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    if world > 1:
+        # the ranks of one box share its host cores: give the host policy pool of every rank its share
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except AttributeError:
+            cores = os.cpu_count() or 1
+        os.environ.setdefault("HIVE_B200_HOST_THREADS", str(max(1, min(16, cores // world))))
     hive_b200.build()
     n = args.games
     stream = torch.cuda.Stream()
@@ -386,7 +393,7 @@ def main():
     e2e_steps = sum(int(h["b"].counters()[0].astype(np.int64).sum()) for h in halves) - s0
     e2e_value = allsum(float(e2e_steps)) / allmax(dt)
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": (200 + 4 + 4) * n,
-           "steps": k_e2e, "parts": parts,
+           "steps": k_e2e, "parts": parts, "host_threads_per_rank": int(os.environ.get("HIVE_B200_HOST_THREADS", min(16, os.cpu_count() or 1))),
            "note": "per-GPU bytes per step of all %d games; %d pipelined parts of the batch on their own streams, host "
            "picks actions (C-ABI twin of the device policy, host worker pool) for one part while the GPU steps the others; "
            "planes stay in HBM for the net" % (n, parts)}
