@@ -299,13 +299,14 @@ def main():
     torch.cuda.synchronize()
     ev0.record(stream)
     done_steps = 0
-    while done_steps < args.steps:                      # EXACTLY args.steps steps, in graph launches of <= chunk steps
-        c = min(args.chunk, args.steps - done_steps)
-        if c > 1:
-            batch.step_random_multi(seed, c, args.max_turn, True)
-        else:
+    full = min(args.chunk, args.steps)                  # the multi-step graph captured during warm-up
+    while done_steps < args.steps:                      # EXACTLY args.steps steps: graph launches of `full` steps, then single steps
+        if full > 1 and args.steps - done_steps >= full:
+            batch.step_random_multi(seed, full, args.max_turn, True)
+            done_steps += full
+        else:                                           # (a shorter multi-step graph would be captured inside the timed region)
             batch.step_random(seed, args.max_turn, True)
-        done_steps += c
+            done_steps += 1
     ev1.record(stream)
     torch.cuda.synchronize()
     barrier()
