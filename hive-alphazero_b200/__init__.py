@@ -19,7 +19,7 @@ def __getattr__(name):
     if name in ("SelfPlayBatch", "write_play_file", "sample_to_reference_row"):
         from . import selfplay
         return getattr(selfplay, name)
-    if name in ("Trainer", "alpha_loss", "samples_to_tensors", "discounted_value"):
+    if name in ("Trainer", "alpha_loss", "samples_to_tensors", "discounted_value", "load_play_file", "load_play_files", "rows_to_tensors"):
         from . import train
         return getattr(train, name)
     if name in ("get_buffer", "get_buffers", "IngestResult", "record_action", "decode_piece"):

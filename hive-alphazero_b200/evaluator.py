@@ -62,5 +62,10 @@ class EvaluatorMatch:
         white_won, black_won = winner == 1, winner == 2
         new_wins = int((white_won & self.new_is_white).sum() + (black_won & ~self.new_is_white).sum())
         best_wins = int((white_won & ~self.new_is_white).sum() + (black_won & self.new_is_white).sum())
+        # what the reference's evaluation worker prints every 10 games (evaluation.py:76-88): mean game length and the
+        # share of distinct final positions (state_key) among the games played
+        keys = [self.env.state_key(g) for g in range(self.n)]
         return dict(games=self.n, new_wins=new_wins, best_wins=best_wins, draws=self.n - new_wins - best_wins,
+                    white_win_rate=float(white_won.mean()), mean_game_len=float(np.mean(turn)),
+                    distinct_final_positions=len(set(keys)) / self.n,
                     moves=self.moves, waves=self.waves, seconds=time.perf_counter() - t0)

@@ -41,6 +41,38 @@ def samples_to_tensors(samples, one_hot_policy=False):
     return (torch.from_numpy(np.stack(xs)), torch.from_numpy(np.stack(ps)), torch.tensor(vs, dtype=torch.float32))
 
 
+def load_play_file(path):
+    """optimize.py:42-65 ``load_data``: one ``play_*.json`` file (rows ``[planes 12x12x56, policy[1584], value,
+    [game_len_for_side, step]]``, what ``write_play_file`` / the reference's workers write) -> list of
+    ``[state (12,12,56) float64 ndarray, policy float32[1584], discounted value]``."""
+    import json
+    with open(path, "rt") as f:
+        data = json.load(f)
+    out = []
+    for state, policy, value, game_lens in data:
+        out.append([np.array(state), np.array(policy, dtype=np.float32), discounted_value(value, game_lens[0], game_lens[1])])
+    return out
+
+
+def load_play_files(directory=".", pattern="play_*.json"):
+    """All play files of a directory in name order (optimize.py:26-40,68-100), concatenated."""
+    import glob
+    import os
+    rows = []
+    for path in sorted(glob.glob(os.path.join(directory, pattern))):
+        rows.extend(load_play_file(path))
+    return rows
+
+
+def rows_to_tensors(rows):
+    """Rows of ``load_play_file`` -> (states (B,56,12,12) f32, policies (B,1584) f32, values (B,) f32) for ``Trainer``:
+    the HWC planes are moved to the CHW layout the net takes (api_hive.py:61-62, alpha_net.py:140-147)."""
+    xs = np.stack([np.asarray(r[0], dtype=np.float32).transpose(2, 0, 1) for r in rows])
+    ps = np.stack([np.asarray(r[1], dtype=np.float32) for r in rows])
+    vs = np.asarray([r[2] for r in rows], dtype=np.float32)
+    return torch.from_numpy(xs), torch.from_numpy(ps), torch.from_numpy(vs)
+
+
 class Trainer:
     """Adam(lr=1e-3) + MultiStepLR([100,200,300,400], 0.2) as alpha_net.py:121-123."""
 

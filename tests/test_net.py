@@ -127,3 +127,4 @@ def test_selfplay_samples_and_evaluator_match(tmp_path):
         ev = hive_b200.EvaluatorMatch(16, 4, hive_b200.LeafEvaluator(fa), hive_b200.LeafEvaluator(fb), stream=stream.cuda_stream, seed=2)
         r = ev.play()
     assert r["games"] == 16 and r["new_wins"] + r["best_wins"] + r["draws"] == 16 and r["moves"] > 16 * 20
+    assert 0 < r["distinct_final_positions"] <= 1 and 20 < r["mean_game_len"] <= 55 and 0 <= r["white_win_rate"] <= 1

@@ -55,3 +55,22 @@ def test_training_step_lowers_loss_on_a_tiny_batch():
     assert l2 < l0
     xo, po, _ = hive_b200.samples_to_tensors(samples, one_hot_policy=True)
     assert (po.sum(1) == 1).all()
+
+
+def test_play_file_round_trip_matches_sample_tensors(tmp_path):
+    """write_play_file (self_play.py:100-112 format) -> load_play_file (optimize.py:42-65) gives the same training
+    tensors as the in-memory path, including the value discount 0.99 ** (game_len - step)."""
+    rng = np.random.RandomState(3)
+    samples = []
+    for i in range(5):
+        planes = np.where(rng.rand(56 * 144) < 0.05, 0x3F80, 0).astype(np.uint16)
+        planes.reshape(56, 144)[31] = (np.float32(7 + i).view(np.uint32) >> 16).astype(np.uint16)     # turn plane
+        pi = rng.rand(1584).astype(np.float32); pi /= pi.sum()
+        samples.append((planes, pi, 1 if i % 2 else -1, (12, 8 + i)))
+    path = hive_b200.write_play_file(samples, str(tmp_path))
+    rows = hive_b200.load_play_file(path)
+    assert len(rows) == 5 and rows[0][0].shape == (12, 12, 56) and rows[0][1].dtype == np.float32
+    assert abs(rows[0][2] - (-1) * 0.99 ** 4) < 1e-12 and rows[4][2] == -1          # step 12 of 12: raw value
+    x1, p1, v1 = hive_b200.rows_to_tensors(hive_b200.load_play_files(str(tmp_path)))
+    x0, p0, v0 = hive_b200.samples_to_tensors(samples)
+    assert torch.equal(x0, x1) and torch.allclose(p0, p1, atol=1e-7) and torch.allclose(v0, v1, atol=1e-6)
