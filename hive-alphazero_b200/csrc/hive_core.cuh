@@ -36,6 +36,9 @@ constexpr int LEGAL_WORDS = 50;      // 1584 bits -> 49.5 u32 (25 u64)
 // bit-plane record handed from the encode kernel to the plane-store kernel: 56 planes x 5 words; the slot of
 // plane 31 (the turn plane holds no bits) carries the turn in word 0 and "evaluated in this launch" in word 1
 constexpr int BITS_WORDS = N_PLANE_C * 5, BITS_TURN = 31 * 5, BITS_LIVE = 31 * 5 + 1;
+// constant geometry tables behind EnvArgs::hop_lines (built on the host by hive_tables.h): is_straight_line masks,
+// per-cell neighbour ranks (3 bits per direction) and per-cell neighbour cells (six bytes in two words)
+constexpr int GEO_HOP = 0, GEO_RANK = 144 * 5, GEO_NBR = GEO_RANK + 144, GEO_WORDS = GEO_NBR + 288;
 constexpr int START_CELL = 6 * 12 + 6;   // tile.py:156,188 Start_Tile
 constexpr int TURN2_CELL = 5 * 12 + 6;   // core_index ('M','13'), env_hive.py:157-159
 
@@ -278,7 +281,8 @@ __device__ __forceinline__ int piece_type_of(int k) {
 }
 
 __device__ __forceinline__ void eval_analyse(GameScratch& gs, GroupQueues& q, uint32_t* occ_s, int game_slot, int lane, int cell,
-                                             int level, int turn, bool push_history, int prev_winner) {
+                                             int level, int turn, bool push_history, int prev_winner,
+                                             const uint32_t* __restrict__ geo) {
     const int side = (turn & 1) ? 0 : 1;                 // game_state.py:58-62
     const bool valid = lane < N_PIECE;
     const int color = lane >= 11 ? 1 : 0;
@@ -305,10 +309,11 @@ __device__ __forceinline__ void eval_analyse(GameScratch& gs, GroupQueues& q, ui
 
     if (lane < 5) occ_s[lane] = occ.w[lane];             // per-warp shared copy for the random-access ring tests
     __syncwarp();
-    uint32_t ring = 0;                                   // occupancy of the six neighbours
+    uint32_t ring = 0;                                   // occupancy of the six neighbours (cells from the GEO_NBR table)
     if (on_board) {
+        const uint32_t n03 = __ldg(geo + GEO_NBR + 2 * cell), n45 = __ldg(geo + GEO_NBR + 2 * cell + 1);
 #pragma unroll
-        for (int i = 0; i < 6; i++) ring |= (uint32_t)words_test(occ_s, cell_nbr(cell, i)) << i;
+        for (int i = 0; i < 6; i++) ring |= (uint32_t)words_test(occ_s, (int)(((i < 4 ? n03 : n45) >> (8 * (i & 3))) & 0xFFu)) << i;
     }
 
     // turn gates shared by every candidate of a piece (move_checker.py:38-55)
@@ -502,7 +507,7 @@ __device__ __forceinline__ EncodeIn encode_fetch(const GameScratch& gs, int lane
     return in;
 }
 
-__device__ __forceinline__ EvalResult eval_encode(WarpScratch& sm, const EncodeIn& in, int lane) {
+__device__ __forceinline__ EvalResult eval_encode(WarpScratch& sm, const EncodeIn& in, int lane, const uint32_t* __restrict__ geo) {
     const uint32_t head = in.head.x, flags = in.head.z;
     const int turn = head & 0xFF, cq_w = (head >> 8) & 0xFF, cq_b = (head >> 16) & 0xFF;
     const bool push_history = (flags >> 1) & 1u;
@@ -565,15 +570,18 @@ __device__ __forceinline__ EvalResult eval_encode(WarpScratch& sm, const EncodeI
     res.winner = (ws && bs) ? prev_winner : ws ? 2 : bs ? 1 : prev_winner;
 
     {   // neighbours of both queens, ranked in tile.adjacent_tiles order (board_tiles order: q descending, then
-        // r ascending; tile.py:111-123): lanes 0..5 white queen, 6..11 black queen
-        const int which = lane >= 6 ? 1 : 0, qcell = which ? cq_b : cq_w;
+        // r ascending; tile.py:111-123; cells and ranks from the GEO tables): lanes 0..5 white queen, 6..11 black queen.
+        // The occupied ones are planes 32 (own queen) / 33 (opponent queen).
+        const int which = lane >= 6 ? 1 : 0, qcell = which ? cq_b : cq_w, dir = lane - 6 * which;
         const bool use = lane < 12 && qcell != HAND;
-        const int nb = use ? cell_nbr(qcell, lane - 6 * which) : 0;
-        const int key = (11 - nb / 12) * 12 + nb % 12;
-        int rank = 0;
-#pragma unroll
-        for (int t = 0; t < 6; t++) rank += __shfl_sync(FULL, key, which * 6 + t) < key;
-        if (lane < 12) sm.qn[lane] = use ? ((uint32_t)nb | ((uint32_t)rank << 8) | ((uint32_t)!words_test(sm.occ, nb) << 12)) : 0u;
+        uint32_t nb = 0, rank = 0;
+        if (use) {
+            nb = (__ldg(geo + GEO_NBR + 2 * qcell + (dir >> 2)) >> (8 * (dir & 3))) & 0xFFu;
+            rank = (__ldg(geo + GEO_RANK + qcell) >> (3 * dir)) & 7u;
+        }
+        const bool empty = use && !words_test(sm.occ, (int)nb);
+        if (lane < 12) sm.qn[lane] = use ? (nb | (rank << 8) | ((uint32_t)empty << 12)) : 0u;
+        if (use && !empty) atomicOr(&sm.planes[which == side ? 32 : 33][nb >> 5], 1u << (nb & 31));
     }
     __syncwarp();
     if (on_board) {
@@ -583,11 +591,6 @@ __device__ __forceinline__ EvalResult eval_encode(WarpScratch& sm, const EncodeI
             atomicOr(&sm.planes[(own ? 24 : 27) + level - 2][wi], bit);
         // 34: own pieces without a legal action; 35: opponent pieces covered or pinned
         if (!top || (own ? !bb_any(mv) : pinned)) atomicOr(&sm.planes[own ? 34 : 35][wi], bit);
-        if (type == T_QUEEN) {                                            // 32 / 33
-#pragma unroll
-            for (int i = 0; i < 6; i++)
-                if ((ring >> i) & 1u) { int c = cell_nbr(cell, i); atomicOr(&sm.planes[own ? 32 : 33][c >> 5], 1u << (c & 31)); }
-        }
         // 44+j: opponent pieces able to reach the j-th empty neighbour of the own queen;
         // 50+j: own on-board pieces whose action list holds the j-th empty neighbour of the opponent queen
         // (every piece looks at the queen of the other colour; table built once per game above).

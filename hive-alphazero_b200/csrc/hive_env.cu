@@ -23,6 +23,7 @@
 #include "../../include/hive_b200.h"
 #include "hive_env_kernel.cuh"
 #include "hive_internal.h"
+#include "hive_tables.h"
 
 #ifndef HIVE_DEFAULT_SLICES
 #define HIVE_DEFAULT_SLICES 8
@@ -34,19 +35,6 @@ namespace {
 
 // ------------------------------------------------------------------------------------------
 thread_local std::string g_err;
-
-// move_checker.py:249-265 on raw (non-modular) deltas, as 144 masks of 144 bits
-void build_hop_lines(std::vector<uint32_t>& t) {
-    t.assign(144 * 5, 0);
-    for (int o = 0; o < 144; o++)
-        for (int x = 0; x < 144; x++) {
-            int q1 = o / 12, r1 = o % 12, q2 = x / 12, r2 = x % 12;
-            int d1 = q1 - q2, d2 = 12 - d1, dx = d1 < d2 ? d1 : d2;
-            d1 = r1 - r2; d2 = 12 - d1;
-            int dy = d1 < d2 ? d1 : d2;
-            if (q1 == q2 || r1 == r2 || dy == dx) t[o * 5 + (x >> 5)] |= 1u << (x & 31);
-        }
-}
 
 }  // namespace
 
@@ -318,9 +306,9 @@ int hive::create_env(int n_games, int device, void* stream, int slices, hive_env
     CUDA_TRY(cudaMalloc(&h->d_actions[0], n * 4));
     CUDA_TRY(cudaMalloc(&h->d_actions[1], n * 4));
     CUDA_TRY(cudaMalloc(&h->d_mask, n));
-    CUDA_TRY(cudaMalloc(&h->hop_lines, 144 * 5 * 4));
+    CUDA_TRY(cudaMalloc(&h->hop_lines, GEO_WORDS * 4));       // hop lines + neighbour rank / neighbour cell tables (hive_tables.h)
     std::vector<uint32_t> lines;
-    build_hop_lines(lines);
+    build_geometry_tables(lines);
     CUDA_TRY(cudaMemcpyAsync(h->hop_lines, lines.data(), lines.size() * 4, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemsetAsync(h->recs, 0, n * sizeof(GameRec), h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));

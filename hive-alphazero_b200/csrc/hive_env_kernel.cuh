@@ -32,7 +32,7 @@ struct EnvArgs {
     const int32_t* actions;
     const uint8_t* mask;
     int32_t* chosen;
-    const uint32_t* hop_lines;
+    const uint32_t* hop_lines;   // GEO_* tables (hive_core.cuh): hop lines, neighbour ranks, neighbour cells
     uint64_t seed;
     int n, op, max_turn, auto_reset;
     int g_offset, n_total;   // this launch covers games [g_offset, g_offset+n) of a batch of n_total (pointers are pre-offset)
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(GROUP * 32, 64 / GROUP) hive_analyse_kernel(En
             __syncwarp();
             if (lane < N_PIECE) { rec->cell[lane] = (uint8_t)cell; rec->level[lane] = (uint8_t)level; }
             if (lane == 0) { hw[12] = episode; hw[13] = steps; }
-            eval_analyse(a.scratch[g], q, occ_s[warp], warp, lane, cell, level, turn, push, winner);
+            eval_analyse(a.scratch[g], q, occ_s[warp], warp, lane, cell, level, turn, push, winner, a.hop_lines);
         } else if (lane == 0) {
             a.scratch[g].head[2] = 0;                           // not evaluated in this launch
         }
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(HIVE_ENCODE_WARPS * 32, 6) hive_encode_kernel(
         return;
     }
     __syncwarp();
-    const EvalResult r = eval_encode(sm, in, lane);
+    const EvalResult r = eval_encode(sm, in, lane, a.hop_lines);
     const int turn = in.head.x & 0xFF;
     if (lane == 0) {
         uint32_t* w = reinterpret_cast<uint32_t*>(rec);

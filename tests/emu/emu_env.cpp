@@ -4,21 +4,13 @@
 #include "cuda_emu.h"
 #include <vector>
 #include "../../hive-alphazero_b200/csrc/hive_env_kernel.cuh"
+#include "../../hive-alphazero_b200/csrc/hive_tables.h"
 
 using namespace hive;
 
 static std::vector<uint32_t> g_lines;
 static void build_lines() {
-    if (!g_lines.empty()) return;
-    g_lines.assign(144 * 5, 0);
-    for (int o = 0; o < 144; o++)
-        for (int x = 0; x < 144; x++) {
-            int q1 = o / 12, r1 = o % 12, q2 = x / 12, r2 = x % 12;
-            int d1 = q1 - q2, d2 = 12 - d1, dx = d1 < d2 ? d1 : d2;
-            d1 = r1 - r2; d2 = 12 - d1;
-            int dy = d1 < d2 ? d1 : d2;
-            if (q1 == q2 || r1 == r2 || dy == dx) g_lines[o * 5 + (x >> 5)] |= 1u << (x & 31);
-        }
+    if (g_lines.empty()) build_geometry_tables(g_lines);
 }
 
 static void k_analyse(void* p) { hive_analyse_kernel(*(EnvArgs*)p); }
