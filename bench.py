@@ -363,13 +363,16 @@ def main():
         actions_h = torch.empty(cnt, dtype=torch.int32).pin_memory()
         halves.append(dict(b=hb, st=st, mask_h=mask_h, count_h=count_h, status_h=status_h, actions_h=actions_h,
                            mask=mask_h.numpy().view(np.uint64), count=count_h.numpy(), status=status_h.numpy().view(np.uint32),
-                           actions=actions_h.numpy(), episodes=np.zeros(cnt, dtype=np.uint32), seed=seed + 77 * (hi + 1)))
+                           actions=actions_h.numpy(), episodes=np.zeros(cnt, dtype=np.uint32), seed=seed + 77 * (hi + 1), n=cnt))
+        h = halves[-1]                                  # raw addresses once: the loop below runs every ~40 us
+        h["p"] = (mask_h.data_ptr(), count_h.data_ptr(), status_h.data_ptr(), h["episodes"].ctypes.data, actions_h.data_ptr())
 
     def e2e_half(h):
         h["b"].wait_results()                                                        # this part's last downloads have landed (its planes may still be in flight)
-        hive_b200.host_pick_actions(h["mask"], h["count"], h["status"], h["episodes"], h["seed"], args.max_turn, h["actions"])
-        # H2D 4 B/game -> kernels -> D2H (200 + 4 + 4) B/game, all queued; the other half is handled meanwhile
-        h["b"].step_async_ptr(h["actions_h"].data_ptr(), h["mask_h"].data_ptr(), h["count_h"].data_ptr(), h["status_h"].data_ptr())
+        pm, pc, ps, pe, pa = h["p"]
+        hive_b200.host_pick_actions_ptr(h["n"], pm, pc, ps, pe, h["seed"], args.max_turn, pa)
+        # H2D 4 B/game -> kernels -> D2H (200 + 4 + 4) B/game, all queued; the other parts are handled meanwhile
+        h["b"].step_async_ptr(pa, pm, pc, ps)
 
     for h in halves:
         h["b"].legal_into(h["mask_h"].data_ptr(), h["count_h"].data_ptr())

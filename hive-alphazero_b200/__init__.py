@@ -7,7 +7,7 @@ The package name carries a hyphen; import it as ``import hive_b200`` (root-level
 from . import config
 from ._build import LIB_PATH, build
 from ._capi import ENV_SYMBOLS, MCTS_SYMBOLS, HiveError, lib
-from .env import GamePlay, HiveBatch, host_pick_actions
+from .env import GamePlay, HiveBatch, host_pick_actions, host_pick_actions_ptr
 from .mcts import HivePlayer, MctsBatch, WaveGraph
 
 
@@ -31,4 +31,4 @@ def __getattr__(name):
     raise AttributeError(name)
 
 __all__ = ["config", "build", "lib", "LIB_PATH", "ENV_SYMBOLS", "HiveError", "GamePlay", "HiveBatch",
-           "host_pick_actions", "HivePlayer", "MctsBatch", "WaveGraph", "MCTS_SYMBOLS"]
+           "host_pick_actions", "host_pick_actions_ptr", "HivePlayer", "MctsBatch", "WaveGraph", "MCTS_SYMBOLS"]

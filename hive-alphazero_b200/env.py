@@ -188,6 +188,13 @@ def host_pick_actions(mask, count, packed_status, episodes, seed, max_turn, acti
           "hive_host_pick_actions")
 
 
+def host_pick_actions_ptr(n, mask_ptr, count_ptr, status_ptr, episodes_ptr, seed, max_turn, actions_ptr):
+    """hive_host_pick_actions on raw host addresses (a tight host loop computes them once: ndarray.ctypes.data costs
+    microseconds per access)."""
+    check(lib().hive_host_pick_actions(n, mask_ptr, count_ptr, status_ptr, episodes_ptr, seed, max_turn, actions_ptr),
+          "hive_host_pick_actions")
+
+
 class _State:
     """The slice of Game_State (game_state.py:10-119) the hot-path callers read."""
 

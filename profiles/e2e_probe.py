@@ -1,24 +1,37 @@
-"""Where does the host-driven (e2e) environment step spend its time?  Prints per-call means (us)."""
+"""Where does the host-driven (e2e) loop of bench.py spend its time?  Same loop (`parts` pipelined parts of a 16,384-game
+batch, graph-replayed hive_step_host_async, hive_wait_results), with the three calls of an iteration timed separately.
+usage: python profiles/e2e_probe.py [parts] [iterations]"""
 import sys, time
 sys.path.insert(0, '.')
 import numpy as np, torch
 import hive_b200
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
-b = hive_b200.HiveBatch(n)
-mask_h = torch.empty((n, 25), dtype=torch.int64).pin_memory(); count_h = torch.empty(n, dtype=torch.int32).pin_memory()
-status_h = torch.empty(n, dtype=torch.int32).pin_memory(); actions_h = torch.empty(n, dtype=torch.int32).pin_memory()
-mask_np, count_np = mask_h.numpy().view(np.uint64), count_h.numpy()
-status_np, actions_np = status_h.numpy().view(np.uint32), actions_h.numpy()
-episodes = np.zeros(n, dtype=np.uint32)
-T = dict(legal=0.0, status=0.0, pick=0.0, step=0.0, sync=0.0)
-K = 300
-for it in range(K + 20):
-    if it == 20:
+parts = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+K = int(sys.argv[2]) if len(sys.argv) > 2 else 1500
+n = 16384
+P = []
+for i in range(parts):
+    cnt = n // parts + (1 if i < n % parts else 0)
+    st = torch.cuda.Stream()
+    b = hive_b200.HiveBatch(cnt, stream=st.cuda_stream)
+    mask_h = torch.empty((cnt, 25), dtype=torch.int64).pin_memory(); count_h = torch.empty(cnt, dtype=torch.int32).pin_memory()
+    status_h = torch.empty(cnt, dtype=torch.int32).pin_memory(); actions_h = torch.empty(cnt, dtype=torch.int32).pin_memory()
+    ep = np.zeros(cnt, dtype=np.uint32)
+    b.legal_into(mask_h.data_ptr(), count_h.data_ptr()); b.status_packed_into(status_h.data_ptr())
+    P.append(dict(b=b, st=st, keep=(mask_h, count_h, status_h, actions_h, ep), n=cnt,
+                  p=(mask_h.data_ptr(), count_h.data_ptr(), status_h.data_ptr(), ep.ctypes.data, actions_h.data_ptr())))
+T = dict(wait=0.0, pick=0.0, launch=0.0)
+for it in range(K + 30):
+    if it == 30:
         for k in T: T[k] = 0.0
-    t0 = time.perf_counter(); b.legal_into(mask_h.data_ptr(), count_h.data_ptr())
-    t1 = time.perf_counter(); b.status_packed_into(status_h.data_ptr())
-    t2 = time.perf_counter(); hive_b200.host_pick_actions(mask_np, count_np, status_np, episodes, 7, 55, actions_np)
-    t3 = time.perf_counter(); b.step_ptr(actions_h.data_ptr())
-    t4 = time.perf_counter(); b.sync(); t5 = time.perf_counter()
-    T['legal'] += t1 - t0; T['status'] += t2 - t1; T['pick'] += t3 - t2; T['step'] += t4 - t3; T['sync'] += t5 - t4
-print({k: round(v / K * 1e6, 1) for k, v in T.items()}, 'us per step; n =', n)
+        torch.cuda.synchronize(); t_start = time.perf_counter()
+    for h in P:
+        pm, pc, ps, pe, pa = h["p"]
+        t0 = time.perf_counter(); h["b"].wait_results()
+        t1 = time.perf_counter(); hive_b200.host_pick_actions_ptr(h["n"], pm, pc, ps, pe, 7, 55, pa)
+        t2 = time.perf_counter(); h["b"].step_async_ptr(pa, pm, pc, ps)
+        t3 = time.perf_counter()
+        T["wait"] += t1 - t0; T["pick"] += t2 - t1; T["launch"] += t3 - t2
+for h in P: h["b"].sync()
+total = time.perf_counter() - t_start
+print({k: round(v / (K * parts) * 1e6, 1) for k, v in T.items()}, "us per part-iteration;", parts, "parts; full step",
+      round(total / K * 1e6, 1), "us ->", round(n / (total / K) / 1e6, 1), "M env-steps/s (upper bound: live games only)")
