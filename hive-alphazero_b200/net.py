@@ -163,6 +163,13 @@ class FoldedNet:
             ob = net.outblock
             self.vconv = put(*_fold(ob.conv.weight, ob.conv.bias, ob.bn))
             self.pconv = put(*_fold(ob.conv1.weight, ob.conv1.bias, ob.bn1))
+            # The heads on the NHWC activations the trunk produces: a 1x1 convolution is a plain GEMM over (board*cell,
+            # channel) rows, and the policy fc takes the cell-major flatten if its columns are permuted once from the
+            # reference's channel-major order (c*144 + cell, alpha_net.py:81) to cell*128 + c -- no layout copies per wave.
+            self.vlin = (self.vconv[0].reshape(1, CH).contiguous(), self.vconv[1])
+            self.plin = (self.pconv[0].reshape(POLICY_CH, CH).contiguous(), self.pconv[1])
+            self.fc_nhwc = ob.fc.weight.detach().view(C.ACTION_SPACE, POLICY_CH, CELLS).permute(0, 2, 1).reshape(
+                C.ACTION_SPACE, CELLS * POLICY_CH).to(self.device, dtype).contiguous()
             self.fc1 = (ob.fc1.weight.to(self.device, torch.float32), ob.fc1.bias.to(self.device, torch.float32))
             self.fc2 = (ob.fc2.weight.to(self.device, torch.float32), ob.fc2.bias.to(self.device, torch.float32))
             self.fc = (ob.fc.weight.to(self.device, dtype), ob.fc.bias.to(self.device, torch.float32))
@@ -211,11 +218,11 @@ class FoldedNet:
             x = self._trunk_tc(planes.to(self.dtype).contiguous())
         else:
             x = self._trunk_torch(planes)
-        v = F.relu(F.conv2d(x, self.vconv[0], self.vconv[1])).float().reshape(-1, CELLS)
+        rows = x.permute(0, 2, 3, 1).reshape(-1, CH)         # (B*144, 256): a view when x is NHWC in memory (both trunks)
+        v = F.relu(F.linear(rows, *self.vlin)).float().reshape(-1, CELLS)
         v = torch.tanh(F.linear(F.relu(F.linear(v, *self.fc1)), *self.fc2))
-        p = F.relu(F.conv2d(x, self.pconv[0], self.pconv[1]))
-        p = p.contiguous(memory_format=torch.contiguous_format).reshape(-1, CELLS * POLICY_CH)      # NCHW flatten
-        logits = F.linear(p, self.fc[0]).float() + self.fc[1]
+        p = F.relu(F.linear(rows, *self.plin)).reshape(-1, CELLS * POLICY_CH)     # cell-major flatten
+        logits = F.linear(p, self.fc_nhwc).float() + self.fc[1]
         return torch.softmax(logits, dim=1), v
 
     __call__ = forward
