@@ -13,7 +13,7 @@ using namespace hive;
 
 int main(int argc, char** argv) {
     const int B = argc > 1 ? atoi(argv[1]) : 5, C = argc > 2 ? atoi(argv[2]) : 256, check = argc > 3 ? atoi(argv[3]) : 1;
-    const int nC = C / 64;
+    const int nC = C / CONV_CHUNK_CH;
     srand(3);
     std::vector<float> x((size_t)B * 144 * C), w((size_t)256 * C * 9), bias(256), res((size_t)B * 144 * 256);
     auto q = [](float v) { return __bfloat162float(__float2bfloat16(v)); };
@@ -25,7 +25,7 @@ int main(int argc, char** argv) {
     for (size_t i = 0; i < x.size(); i++) hx[i] = __float2bfloat16(x[i]);
     for (size_t i = 0; i < res.size(); i++) hres[i] = __float2bfloat16(res[i]);
     std::vector<uint8_t> packed;
-    pack_conv_weights(w.data(), C, packed);                       // w is [oc][ic][3][3] fp32
+    pack_conv_weights(w.data(), C, CONV_KG, packed);                       // w is [oc][ic][3][3] fp32
     __nv_bfloat16 *dx, *dres, *dout; uint8_t* dw; float* dbias;
     cudaMalloc(&dx, hx.size() * 2); cudaMalloc(&dres, hres.size() * 2); cudaMalloc(&dout, (size_t)B * 144 * 256 * 2);
     cudaMalloc(&dw, packed.size()); cudaMalloc(&dbias, 256 * 4);
@@ -35,7 +35,7 @@ int main(int argc, char** argv) {
     cudaMemcpy(dbias, bias.data(), 256 * 4, cudaMemcpyHostToDevice);
     cudaMemset(dout, 0xFF, (size_t)B * 144 * 256 * 2);
     CUtensorMap map;
-    if (make_board_tensor_map(&map, dx, B, C)) { printf("tensor map encode failed\n"); return 2; }
+    if (make_board_tensor_map(&map, dx, B, C, CONV_PADW, CONV_PADH, CONV_KG)) { printf("tensor map encode failed\n"); return 2; }
     ConvArgs a; a.weights = dw; a.bias = dbias; a.residual = dres; a.out = dout; a.n_boards = B; a.n_chunks = nC; a.relu = 1;
     cudaFuncSetAttribute(hive_conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM_BYTES);
     int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);

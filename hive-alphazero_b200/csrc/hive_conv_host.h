@@ -10,19 +10,19 @@
 
 namespace hive {
 
-// w: [256 oc][C ic][3][3] fp32 (BatchNorm already folded) -> [2 halves][9 taps][C/64 chunks][8 k-groups][128 rows][8 ch] bf16
-inline void pack_conv_weights(const float* w, int C, std::vector<uint8_t>& out) {
-    const int nC = C / 64;
-    out.assign((size_t)2 * 9 * nC * 8 * 128 * 16, 0);
+// w: [256 oc][C ic][3][3] fp32 (BatchNorm already folded) -> [2 halves][9 taps][C/(8 KG) chunks][KG k-groups][128 rows][8 ch] bf16
+inline void pack_conv_weights(const float* w, int C, int KG, std::vector<uint8_t>& out) {
+    const int nC = C / (8 * KG);
+    out.assign((size_t)2 * 9 * nC * KG * 128 * 16, 0);
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out.data());
     for (int half = 0; half < 2; half++)
         for (int t = 0; t < 9; t++)
             for (int c = 0; c < nC; c++)
-                for (int kg = 0; kg < 8; kg++)
+                for (int kg = 0; kg < KG; kg++)
                     for (int r = 0; r < 128; r++)
                         for (int e = 0; e < 8; e++) {
-                            const int oc = half * 128 + r, ic = c * 64 + kg * 8 + e;
-                            const size_t dst = ((((size_t)(half * 9 + t) * nC + c) * 8 + kg) * 128 + r) * 8 + e;
+                            const int oc = half * 128 + r, ic = (c * KG + kg) * 8 + e;
+                            const size_t dst = ((((size_t)(half * 9 + t) * nC + c) * KG + kg) * 128 + r) * 8 + e;
                             o[dst] = __float2bfloat16(w[((size_t)oc * C + ic) * 9 + t]);
                         }
 }
@@ -31,8 +31,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// NHWC bf16 tensor [B][12][12][C] seen as 5-D {8 ch, W, H, C/8 ch-groups, B}; box = one zero-padded board (13 slots x 15 rows from pixel (-1,-1)) of 64 channels
-inline int make_board_tensor_map(CUtensorMap* map, const void* base, int B, int C) {
+// NHWC bf16 tensor [B][12][12][C] seen as 5-D {8 ch, W, H, C/8 ch-groups, B}; box = one zero-padded board (box_w slots x box_h rows,
+// out-of-range pixels zero-filled) of box_groups x 8 channels
+inline int make_board_tensor_map(CUtensorMap* map, const void* base, int B, int C, int box_w, int box_h, int box_groups) {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
         void* p = nullptr;
@@ -42,7 +43,7 @@ inline int make_board_tensor_map(CUtensorMap* map, const void* base, int B, int 
     }
     const cuuint64_t dims[5] = {8, 12, 12, (cuuint64_t)(C / 8), (cuuint64_t)B};
     const cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)12 * C * 2, 16, (cuuint64_t)144 * C * 2};   // bytes, dims 1..4
-    const cuuint32_t box[5] = {8, 13, 15, 8, 1};
+    const cuuint32_t box[5] = {8, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_groups, 1};
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,

@@ -25,34 +25,54 @@
 namespace hive {
 
 constexpr int CONV_OC_TILE = 128;                 // UMMA M
+#ifdef HIVE_CONV_N144
+// Variant without padding columns: N = 144 = the 12 x 12 pixels, row pitch 12.  A horizontal shift can then no longer
+// be an address offset (it would wrap into the neighbouring row), so the three column shifts dx = -1, 0, +1 are three
+// separate zero-filled tiles (three TMA boxes starting at x = dx); the vertical shift stays an offset of 12 slots.
+// Three times the operand bytes per board: 32-channel chunks keep two stages of two boards in shared memory.
+// Measured SLOWER than the padded form (941 vs 1,245 TFLOP/s at 2,048 boards: the tripled operand writes compete with the
+// MMA operand reads for shared-memory bandwidth); kept as a checked variant, not the default.
+constexpr int CONV_N = 144;
+constexpr int CONV_PADW = 12;
+constexpr int CONV_PADH = 14;
+constexpr int CONV_KG = 4;                        // 8-channel groups per chunk (32 input channels)
+constexpr int CONV_SHIFTS = 3;
+#else
 constexpr int CONV_N = 160;                       // UMMA N (12 rows x 13 slots = 156, rounded to 16)
 constexpr int CONV_PADW = 13;
 constexpr int CONV_PADH = 15;
-constexpr int CONV_PLANE_BYTES = CONV_PADH * CONV_PADW * 16;    // one 8-channel group of a padded board = 3,120 B
-constexpr int CONV_BOARD_BYTES = 8 * CONV_PLANE_BYTES;          // 64 channels = 24,960 B (195 x 128)
-constexpr int CONV_A_BYTES = 8 * CONV_OC_TILE * 16;             // 16,384 B
+constexpr int CONV_KG = 8;                        // 8-channel groups per chunk (64 input channels)
+constexpr int CONV_SHIFTS = 1;
+#endif
+constexpr int CONV_CHUNK_CH = CONV_KG * 8;        // input channels per chunk
+constexpr int CONV_SLOT_COLS = 160;               // TMEM columns between accumulator slots
+constexpr int CONV_PLANE_BYTES = CONV_PADH * CONV_PADW * 16;    // one 8-channel group of a padded board
+constexpr int CONV_TILE_BYTES = CONV_KG * CONV_PLANE_BYTES;     // one column shift of one chunk of a board
+constexpr int CONV_BOARD_BYTES = CONV_SHIFTS * CONV_TILE_BYTES; // 24,960 B (N = 160) / 32,256 B (N = 144)
+constexpr int CONV_A_BYTES = CONV_KG * CONV_OC_TILE * 16;       // 16,384 B / 8,192 B
 #ifndef CONV_BOARDS_PER_PASS
 #define CONV_BOARDS_PER_PASS 2
 #endif
 constexpr int CONV_BOARDS = CONV_BOARDS_PER_PASS;  // boards per weight pass (accumulators in TMEM)
-constexpr int CONV_A_STAGES = CONV_BOARDS == 1 ? 3 : 4;
+constexpr int CONV_A_STAGES = (CONV_BOARDS == 1 ? 3 : 4) * (8 / CONV_KG);
 constexpr int CONV_B_STAGES = 2;
 constexpr int CONV_CTAS_PER_SM = CONV_BOARDS == 1 ? 2 : 1;   // 1-board CTAs run two per SM: one's epilogue hides under the other's MMAs
 constexpr int CONV_TMEM_COLS = CONV_BOARDS == 1 ? 256 : 512;
 constexpr int CONV_SLOTS = CONV_BOARDS == 1 ? 1 : 3;          // accumulator slots of CONV_N columns, used round-robin
 constexpr int CONV_EPI_WARPS = CONV_BOARDS == 1 ? 4 : 8;      // epilogue warps (multiple of 4: one per TMEM lane quarter)
 constexpr int CONV_THREADS = 64 + 32 * CONV_EPI_WARPS;
-constexpr int CONV_TAIL_PAD = 0;                  // slot 159 + shift 28 = row 187 < 195: views never leave the tile
+constexpr int CONV_TAIL_PAD = 0;                  // last slot + largest shift stays inside the tile (187 < 195 / 167 < 168)
 constexpr int CONV_STAGE_STRIDE = 36;             // floats per staging row (32 + 4: keeps 16-byte alignment, spreads banks)
 constexpr int CONV_SMEM_BYTES = CONV_A_STAGES * CONV_A_BYTES + CONV_B_STAGES * CONV_BOARDS * CONV_BOARD_BYTES + CONV_TAIL_PAD +
                                 CONV_EPI_WARPS * 16 * CONV_STAGE_STRIDE * 4 + 1024;
+static_assert(CONV_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 struct ConvArgs {
     const uint8_t* weights;        // [2 halves][9 taps][n_chunks][16 KB] packed operand tiles of this layer
     const float* bias;             // [256]
     const __nv_bfloat16* __restrict__ residual; // [B][144][256] or null (never aliases `out`)
     __nv_bfloat16* __restrict__ out;            // [B][144][256]
-    int n_boards, n_chunks, relu;  // n_chunks = input channels / 64
+    int n_boards, n_chunks, relu;  // n_chunks = input channels / CONV_CHUNK_CH
 };
 
 __device__ __forceinline__ void bulk_load(void* smem, const void* gmem, uint32_t bytes, uint64_t* bar) {
@@ -102,7 +122,10 @@ __global__ void __launch_bounds__(CONV_THREADS, CONV_CTAS_PER_SM) hive_conv3x3_k
                     for (int j = 0; j < CONV_BOARDS; j++) {
                         int b = pair * CONV_BOARDS + j;
                         if (b >= a.n_boards) b = a.n_boards - 1;          // odd tail: reload the last board (result discarded)
-                        tma_load_5d(sB + (bs * CONV_BOARDS + j) * CONV_BOARD_BYTES, &in_map, &b_full[bs], 0, -1, -1, c * 8, b);
+#pragma unroll
+                        for (int sh = 0; sh < CONV_SHIFTS; sh++)      // one box per column shift (a single box from x = -1 when the pad column is kept)
+                            tma_load_5d(sB + (bs * CONV_BOARDS + j) * CONV_BOARD_BYTES + sh * CONV_TILE_BYTES, &in_map, &b_full[bs], 0,
+                                        CONV_SHIFTS == 1 ? -1 : sh - 1, -1, c * CONV_KG, b);
                     }
                     if (++bs == CONV_B_STAGES) { bs = 0; bph ^= 1; }
                     for (int t = 0; t < 9; t++) {
@@ -139,14 +162,15 @@ __global__ void __launch_bounds__(CONV_THREADS, CONV_CTAS_PER_SM) hive_conv3x3_k
                         mbar_wait(&a_full[as], aph);
                         tc_fence_after();
                         // descriptors differ only in their 14-bit start-address field: add to the low word
-                        const uint32_t kShift = (uint32_t)((t / 3) * CONV_PADW + (t % 3));              // 16-byte units (constant after unrolling)
+                        const uint32_t kShift = CONV_SHIFTS == 1 ? (uint32_t)((t / 3) * CONV_PADW + (t % 3))   // 16-byte units (constant after unrolling)
+                                                                 : (uint32_t)((t / 3) * CONV_PADW + (t % 3) * (CONV_TILE_BYTES >> 4));
                         const uint64_t a_lo = a_desc0 + (uint64_t)((uint32_t)(as * CONV_A_BYTES) >> 4);
 #pragma unroll
                         for (int j = 0; j < CONV_BOARDS; j++) {
                             const uint64_t b_lo = b_desc0 + (uint64_t)(((uint32_t)((bs * CONV_BOARDS + j) * CONV_BOARD_BYTES) >> 4) + kShift);
 #pragma unroll
-                            for (int ks = 0; ks < 4; ks++)
-                                mma_bf16(tmem + slot[j] * CONV_N, a_lo + (uint64_t)(ks * ((2 * CONV_OC_TILE * 16) >> 4)),
+                            for (int ks = 0; ks < CONV_KG / 2; ks++)
+                                mma_bf16(tmem + slot[j] * CONV_SLOT_COLS, a_lo + (uint64_t)(ks * ((2 * CONV_OC_TILE * 16) >> 4)),
                                          b_lo + (uint64_t)(ks * ((2 * CONV_PLANE_BYTES) >> 4)), idesc, (c | t | ks) != 0);
                         }
                         mma_commit(&a_empty[as]);                      // weight stage free when these MMAs retire
@@ -169,7 +193,8 @@ __global__ void __launch_bounds__(CONV_THREADS, CONV_CTAS_PER_SM) hive_conv3x3_k
         const int set = ew >> 2;
         float* stage = sStage + ew * 16 * CONV_STAGE_STRIDE;
         const int sl = lane >> 2, ch8 = (lane & 3) * 8;            // phase-2 role: slots sl and sl+8, channels ch8..ch8+7
-        constexpr int G = CONV_N / 16 / SETS;                      // column groups per warp
+        constexpr int NG = CONV_N / 16;                            // column groups of an accumulator (10 / 9)
+        constexpr int G = (NG + SETS - 1) / SETS;                  // column groups per warp (the last set may own a dummy one)
         constexpr int CH = 5;                                      // column groups held in registers at a time
         static_assert(G % CH == 0, "column groups per warp must be a multiple of the register chunk");
         uint32_t full_ph = 0;
@@ -187,7 +212,7 @@ __global__ void __launch_bounds__(CONV_THREADS, CONV_CTAS_PER_SM) hive_conv3x3_k
                 // element offset of (group g, k-th slot of this lane) or -1 for a padding slot
                 auto slot_off = [&](int g, int k) -> long long {      // g counts from this warp's first group
                     const int n = (g0 + g) * 16 + sl + 8 * k, y = n / CONV_PADW, x = n - y * CONV_PADW;
-                    return (valid && x < 12 && y < 12) ? (long long)(bbase + (size_t)(y * 12 + x) * 256) : -1;
+                    return (valid && g0 + g < NG && x < 12 && y < 12) ? (long long)(bbase + (size_t)(y * 12 + x) * 256) : -1;
                 };
 #pragma unroll
                 for (int c0 = 0; c0 < G; c0 += CH) {
@@ -212,7 +237,7 @@ __global__ void __launch_bounds__(CONV_THREADS, CONV_CTAS_PER_SM) hive_conv3x3_k
                     uint32_t v[CH][16];
 #pragma unroll
                     for (int g = 0; g < CH; g++)
-                        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + slot * CONV_N + (g0 + c0 + g) * 16, v[g]);
+                        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + slot * CONV_SLOT_COLS + (g0 + c0 + g) * 16, v[g]);
                     tmem_ld_wait();
                     if (c0 + CH >= G) {
                         // the accumulator now lives in registers: hand the TMEM slot back to the MMA issuer

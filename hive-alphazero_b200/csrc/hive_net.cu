@@ -79,9 +79,9 @@ int net_create(int device, void* stream, int max_boards, hive_net_t** out) {
     const size_t B = (size_t)max_boards;
     CUDA_TRY(cudaMalloc(&n->x0, B * 144 * 64 * 2));
     for (int i = 0; i < 3; i++) CUDA_TRY(cudaMalloc(&n->act[i], B * 144 * 256 * 2));
-    if (make_board_tensor_map(&n->map_x0, n->x0, max_boards, 64)) return fail(HIVE_E_CUDA, "net_create: cuTensorMapEncodeTiled failed (stem input)");
+    if (make_board_tensor_map(&n->map_x0, n->x0, max_boards, 64, CONV_PADW, CONV_PADH, CONV_KG)) return fail(HIVE_E_CUDA, "net_create: cuTensorMapEncodeTiled failed (stem input)");
     for (int i = 0; i < 3; i++)
-        if (make_board_tensor_map(&n->map_act[i], n->act[i], max_boards, 256)) return fail(HIVE_E_CUDA, "net_create: cuTensorMapEncodeTiled failed");
+        if (make_board_tensor_map(&n->map_act[i], n->act[i], max_boards, 256, CONV_PADW, CONV_PADH, CONV_KG)) return fail(HIVE_E_CUDA, "net_create: cuTensorMapEncodeTiled failed");
     CUDA_TRY(cudaFuncSetAttribute(hive_conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM_BYTES));
     *out = n;
     return 0;
@@ -111,14 +111,14 @@ int net_load_conv_host(hive_net_t* n, int layer, const float* w, const float* bi
         for (int ic = 0; ic < cin; ic++)
             memcpy(&wp[((size_t)oc * cpad + ic) * 9], &w[((size_t)oc * cin + ic) * 9], 9 * sizeof(float));
     std::vector<uint8_t> packed;
-    pack_conv_weights(wp.data(), cpad, packed);
+    pack_conv_weights(wp.data(), cpad, CONV_KG, packed);
     CUDA_TRY(cudaStreamSynchronize(n->stream));
     cudaFree(n->weights[layer]); cudaFree(n->bias[layer]);
     CUDA_TRY(cudaMalloc(&n->weights[layer], packed.size()));
     CUDA_TRY(cudaMalloc(&n->bias[layer], 256 * 4));
     CUDA_TRY(cudaMemcpy(n->weights[layer], packed.data(), packed.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(n->bias[layer], bias, 256 * 4, cudaMemcpyHostToDevice));
-    n->n_chunks[layer] = cpad / 64;
+    n->n_chunks[layer] = cpad / CONV_CHUNK_CH;
     n->loaded |= 0;   // counted below
     int cnt = 0;
     for (int i = 0; i < NET_LAYERS; i++) cnt += n->weights[i] != nullptr;

@@ -17,11 +17,8 @@ for spec in sys.argv[1:]:
     for src in B.sources():
         base = os.path.basename(src)
         obj = os.path.join(B.HERE, "build", "%s_%s.o" % (name, base[:-3]))
-        if base == "hive_env.cu" or not os.path.exists(os.path.join(B.HERE, "build", base[:-3] + ".o")):
-            flags = [f for f in B.NVCC_FLAGS if f != "-shared"] + B.EXTRA_FLAGS.get(base, []) + defs
-            subprocess.check_call(["nvcc"] + flags + ["-c", "-o", obj, src])
-        else:
-            obj = os.path.join(B.HERE, "build", base[:-3] + ".o")
+        flags = [f for f in B.NVCC_FLAGS if f != "-shared"] + B.EXTRA_FLAGS.get(base, []) + defs
+        subprocess.check_call(["nvcc"] + flags + ["-c", "-o", obj, src])
         objs.append(obj)
     lib = os.path.join(out_dir, "lib_%s.so" % name)
     subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib] + objs)
