@@ -6,9 +6,9 @@ The package name carries a hyphen; import it as ``import hive_b200`` (root-level
 """
 from . import config
 from ._build import LIB_PATH, build
-from ._capi import ENV_SYMBOLS, MCTS_SYMBOLS, HiveError, lib
+from ._capi import ENV_SYMBOLS, MCTS_SYMBOLS, HiveError, SearchError, lib
 from .env import GamePlay, HiveBatch, host_pick_actions, host_pick_actions_ptr
-from .mcts import HivePlayer, MctsBatch, WaveGraph
+from .mcts import HashEvaluator, HivePlayer, MctsBatch, WaveGraph
 
 
 def __getattr__(name):
@@ -31,4 +31,4 @@ def __getattr__(name):
     raise AttributeError(name)
 
 __all__ = ["config", "build", "lib", "LIB_PATH", "ENV_SYMBOLS", "HiveError", "GamePlay", "HiveBatch",
-           "host_pick_actions", "host_pick_actions_ptr", "HivePlayer", "MctsBatch", "WaveGraph", "MCTS_SYMBOLS"]
+           "host_pick_actions", "host_pick_actions_ptr", "HivePlayer", "MctsBatch", "WaveGraph", "HashEvaluator", "SearchError", "MCTS_SYMBOLS"]

@@ -19,11 +19,17 @@ MCTS_SYMBOLS = [
     "mcts_create", "mcts_destroy", "mcts_set_params", "mcts_set_root_noise_host", "mcts_begin", "mcts_descend",
     "mcts_expand", "mcts_pending_host", "mcts_dev_leaf_planes", "mcts_dev_leaf_policy", "mcts_dev_leaf_value", "mcts_dev_pending_mask",
     "mcts_leaf_planes_host", "mcts_set_leaf_eval_host", "mcts_policy_host", "mcts_root_stats_host", "mcts_launch_count",
+    "mcts_error_host", "mcts_hash_eval_dev", "mcts_stream",
 ]
 
 
 class HiveError(RuntimeError):
     pass
+
+
+class SearchError(HiveError):
+    """A search tree ran out of its node / edge arena or path depth (HIVE_E_SEARCH): the move would come from
+    fewer simulations than asked for, so the call fails instead."""
 
 
 def lib():
@@ -86,6 +92,10 @@ def lib():
     L.mcts_root_stats_host.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp]
     L.mcts_launch_count.argtypes = [vp]
     L.mcts_launch_count.restype = ctypes.c_longlong
+    L.mcts_error_host.argtypes = [vp, vp]
+    L.mcts_hash_eval_dev.argtypes = [vp, vp, vp, vp, i32, u64, vp]
+    L.mcts_stream.argtypes = [vp]
+    L.mcts_stream.restype = vp
     L.net_create.argtypes = [i32, vp, i32, ctypes.POINTER(vp)]
     L.net_destroy.argtypes = [vp]
     L.net_load_conv_host.argtypes = [vp, i32, vp, vp, i32]
@@ -97,6 +107,8 @@ def lib():
 
 
 def check(rc, what=""):
+    if rc == -4:
+        raise SearchError("%s failed (%d): %s" % (what, rc, lib().hive_last_error().decode()))
     if rc < 0:
         raise HiveError("%s failed (%d): %s" % (what, rc, lib().hive_last_error().decode()))
     return rc

@@ -241,6 +241,7 @@ int hive::create_env(int n_games, int device, void* stream, int slices, hive_env
         CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
     CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&h->copy_done, cudaEventDisableTiming));
+    for (int b = 0; b < 2; b++) CUDA_TRY(cudaEventCreateWithFlags(&h->act_read_ev[b], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreate(&h->t0));
     CUDA_TRY(cudaEventCreate(&h->t1));
     const size_t n = (size_t)n_games;
@@ -343,6 +344,7 @@ int hive_destroy(hive_env_t* h) {
     if (h->results_ev) cudaEventDestroy(h->results_ev);
     cudaFree(h->d_actions[0]); cudaFree(h->d_actions[1]); cudaFree(h->d_mask); cudaFree(h->hop_lines);
     if (h->copy_done) cudaEventDestroy(h->copy_done);
+    for (int b = 0; b < 2; b++) if (h->act_read_ev[b]) cudaEventDestroy(h->act_read_ev[b]);
     if (h->t0) cudaEventDestroy(h->t0);
     if (h->t1) cudaEventDestroy(h->t1);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -382,14 +384,19 @@ int hive_step_host(hive_env_t* h, const int32_t* actions) {
     if (check(h)) return HIVE_E_HANDLE;
     if (!actions) return fail(HIVE_E_ARG, "hive_step_host: null actions");
     CUDA_TRY(cudaSetDevice(h->device));
-    // double-buffered device copy of the actions on a side stream: the caller's buffer is free
-    // again when this returns, and the previous step may still be reading the other buffer.
-    int32_t* d = h->d_actions[h->act_flip];
+    // double-buffered device copy of the actions on a side stream: the caller's buffer is free again when this
+    // returns, and the previous step may still be reading the other buffer.  The buffer used now was read by the step
+    // of two calls ago: the copy waits for that step's event before it overwrites it.
+    const int flip = h->act_flip;
+    int32_t* d = h->d_actions[flip];
     h->act_flip ^= 1;
+    if (h->act_used[flip]) CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->act_read_ev[flip], 0));
     CUDA_TRY(cudaMemcpyAsync(d, actions, (size_t)h->n * 4, cudaMemcpyHostToDevice, h->copy_stream));
     CUDA_TRY(cudaEventRecord(h->copy_done, h->copy_stream));
     CUDA_TRY(cudaStreamWaitEvent(h->stream, h->copy_done, 0));
     int rc = launch_env(h, OP_STEP, d, nullptr, 0, 0, 0, nullptr);
+    CUDA_TRY(cudaEventRecord(h->act_read_ev[flip], h->stream));
+    h->act_used[flip] = true;
     CUDA_TRY(cudaEventSynchronize(h->copy_done));
     return rc;
 }

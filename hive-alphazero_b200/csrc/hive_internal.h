@@ -46,6 +46,8 @@ struct hive_env {
     int use_graph = 1;
     int32_t* d_actions[2] = {nullptr, nullptr};
     int act_flip = 0;
+    cudaEvent_t act_read_ev[2] = {nullptr, nullptr};   // behind the step that read d_actions[b] (hive_step_host)
+    bool act_used[2] = {false, false};
     uint8_t* d_mask = nullptr;
     uint32_t* hop_lines = nullptr;
     cudaEvent_t copy_done = nullptr, t0 = nullptr, t1 = nullptr;

@@ -28,6 +28,7 @@ struct hive_mcts {
     int32_t* pending = nullptr;
     double* noise = nullptr;
     double* pi = nullptr; int32_t* out_action = nullptr; int32_t* out_sum_n = nullptr;
+    uint32_t* search_no = nullptr; uint32_t* error_any = nullptr;
     long long launches = 0;
 };
 
@@ -44,29 +45,24 @@ MctsArgs make_args(hive_mcts* m) {
     a.trees = m->trees; a.nodes = m->nodes; a.htab = m->htab;
     a.e_action = m->e_action; a.e_n = m->e_n; a.e_w = m->e_w; a.e_q = m->e_q; a.e_p = m->e_p;
     a.noise = m->noise; a.pi = m->pi; a.out_action = m->out_action; a.out_sum_n = m->out_sum_n;
+    a.search_no = m->search_no; a.error_any = m->error_any;
     return a;
 }
 int check(const hive_mcts* m) { return m && m->n > 0 ? 0 : fail(HIVE_E_HANDLE, "bad mcts handle"); }
 int blocks_for(int n) { return (n + MCTS_WARPS - 1) / MCTS_WARPS; }
+int search_failed(uint32_t flags) {
+    return fail(HIVE_E_SEARCH, std::string("search gave up on at least one tree:") + ((flags & 2u) ? " node arena full;" : "") +
+                                   ((flags & 4u) ? " edge arena full (raise edges_per_sim in mcts_create);" : "") +
+                                   ((flags & 8u) ? " simulation deeper than MCTS_MAX_DEPTH;" : "") +
+                                   " the statistics of the flagged trees hold fewer simulations than asked for");
+}
 
 }  // namespace
 
 extern "C" {
 
-int mcts_create(hive_env_t* env, int sims, int edges_per_sim, hive_mcts_t** out) {
-    if (!env || env->n <= 0 || sims < 1 || !out) return fail(HIVE_E_ARG, "mcts_create: bad arguments");
-    *out = nullptr;
-    CUDA_TRY(cudaSetDevice(env->device));
-    hive_mcts* m = new hive_mcts();
-    m->env = env; m->n = env->n; m->sims = sims;
-    int rc = create_env(env->n, env->device, env->stream, 1, &m->sim);   // same stream: strict ordering; one slice
-    if (rc) { delete m; return rc; }
-    m->node_cap = sims + 1;
-    if (edges_per_sim <= 0) edges_per_sim = 96;
-    m->edge_cap = sims * edges_per_sim + 256;
-    int ht = 64;
-    while (ht < 2 * m->node_cap) ht <<= 1;
-    m->ht_size = ht;
+static int mcts_alloc(hive_mcts* m) {
+    hive_env* env = m->env;
     const size_t n = (size_t)m->n;
     CUDA_TRY(cudaMalloc(&m->trees, n * sizeof(MctsTree)));
     CUDA_TRY(cudaMalloc(&m->nodes, n * m->node_cap * sizeof(MctsNode)));
@@ -86,9 +82,37 @@ int mcts_create(hive_env_t* env, int sims, int edges_per_sim, hive_mcts_t** out)
     CUDA_TRY(cudaMalloc(&m->pi, n * 1584 * 8));
     CUDA_TRY(cudaMalloc(&m->out_action, n * 4));
     CUDA_TRY(cudaMalloc(&m->out_sum_n, n * 4));
+    CUDA_TRY(cudaMalloc(&m->search_no, n * 4));
+    CUDA_TRY(cudaMalloc(&m->error_any, 4));
+    CUDA_TRY(cudaMemsetAsync(m->search_no, 0, n * 4, env->stream));
+    CUDA_TRY(cudaMemsetAsync(m->error_any, 0, 4, env->stream));
     CUDA_TRY(cudaMemsetAsync(m->trees, 0, n * sizeof(MctsTree), env->stream));
     CUDA_TRY(cudaMemsetAsync(m->need_eval, 0, n, env->stream));
+    CUDA_TRY(cudaMemsetAsync(m->leaf_p, 0, n * 1584 * 4, env->stream));
+    CUDA_TRY(cudaMemsetAsync(m->leaf_v, 0, n * 8, env->stream));
     CUDA_TRY(cudaStreamSynchronize(env->stream));
+    return 0;
+}
+
+int mcts_create(hive_env_t* env, int sims, int edges_per_sim, hive_mcts_t** out) {
+    if (!env || env->n <= 0 || sims < 1 || !out) return fail(HIVE_E_ARG, "mcts_create: bad arguments");
+    *out = nullptr;
+    CUDA_TRY(cudaSetDevice(env->device));
+    hive_mcts* m = new hive_mcts();
+    m->env = env; m->n = env->n; m->sims = sims;
+    int rc = create_env(env->n, env->device, env->stream, 1, &m->sim);   // same stream: strict ordering; one slice
+    if (rc) { delete m; return rc; }
+    m->node_cap = sims + 1;
+    // Edge arena: a node stores one edge per legal action.  The reference's own 1,000-game run peaks at 130 legal
+    // actions and averages ~51; 160 per simulation keeps a tree whose EVERY node sits at that peak inside
+    // the arena.  A tree that still runs out stops, is flagged, and mcts_policy_host fails loudly (HIVE_E_SEARCH).
+    if (edges_per_sim <= 0) edges_per_sim = 160;
+    m->edge_cap = sims * edges_per_sim + 256;
+    int ht = 64;
+    while (ht < 2 * m->node_cap) ht <<= 1;
+    m->ht_size = ht;
+    rc = mcts_alloc(m);
+    if (rc) { const std::string why = hive_last_error(); mcts_destroy(m); return fail(rc, why); }
     *out = m;
     return 0;
 }
@@ -97,11 +121,11 @@ int mcts_destroy(hive_mcts_t* m) {
     if (!m) return 0;
     cudaSetDevice(m->env->device);
     cudaStreamSynchronize(m->env->stream);
-    hive_destroy(m->sim);
+    if (m->sim) hive_destroy(m->sim);
     cudaFree(m->trees); cudaFree(m->nodes); cudaFree(m->htab); cudaFree(m->e_action); cudaFree(m->e_n);
     cudaFree(m->e_w); cudaFree(m->e_q); cudaFree(m->e_p); cudaFree(m->leaf_p); cudaFree(m->leaf_v);
     cudaFree(m->need_eval); cudaFree(m->env_mask); cudaFree(m->tree_mask); cudaFree(m->pending); cudaFree(m->noise); cudaFree(m->pi);
-    cudaFree(m->out_action); cudaFree(m->out_sum_n);
+    cudaFree(m->out_action); cudaFree(m->out_sum_n); cudaFree(m->search_no); cudaFree(m->error_any);
     delete m;
     return 0;
 }
@@ -137,6 +161,7 @@ int mcts_begin(hive_mcts_t* m, const uint8_t* tree_mask) {
         CUDA_TRY(cudaMemcpyAsync(m->tree_mask, tree_mask, m->n, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaStreamSynchronize(st));
     }
+    CUDA_TRY(cudaMemsetAsync(m->error_any, 0, 4, st));
     MctsArgs a = make_args(m);
     mcts_reset_kernel<<<m->n, MCTS_WARPS * 32, 0, st>>>(a);
     CUDA_TRY(cudaGetLastError());
@@ -220,9 +245,57 @@ int mcts_policy_host(hive_mcts_t* m, double* pi, int32_t* action, int32_t* sum_n
     if (pi) CUDA_TRY(cudaMemcpyAsync(pi, m->pi, (size_t)m->n * 1584 * 8, cudaMemcpyDeviceToHost, st));
     if (action) CUDA_TRY(cudaMemcpyAsync(action, m->out_action, (size_t)m->n * 4, cudaMemcpyDeviceToHost, st));
     if (sum_n) CUDA_TRY(cudaMemcpyAsync(sum_n, m->out_sum_n, (size_t)m->n * 4, cudaMemcpyDeviceToHost, st));
+    uint32_t flags = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flags, m->error_any, 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (flags) return search_failed(flags);
     return 0;
 }
+
+int mcts_error_host(hive_mcts_t* m, uint32_t* flags) {
+    if (check(m)) return HIVE_E_HANDLE;
+    if (!flags) return fail(HIVE_E_ARG, "mcts_error_host: null output");
+    CUDA_TRY(cudaSetDevice(m->env->device));
+    CUDA_TRY(cudaMemcpyAsync(flags, m->error_any, 4, cudaMemcpyDeviceToHost, m->env->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->env->stream));
+    return 0;
+}
+
+// ---- deterministic stand-in network on the device (parity tests of the device leaf-evaluation path): a pure function
+// of the leaf's bf16 planes and a salt.  The NumPy twin is oracle/mcts_oracle.py::device_hash_net.
+//   key  = splitmix64(salt ^ sum_j splitmix64(j<<16 | planes[j]))          (sum mod 2^64, order-free)
+//   p[a] = x^6, x = (splitmix64(key ^ (a+1)*0x9E3779B97F4A7C15) >> 40) * 2^-24   (float32 products x2 = x*x, x4 = x2*x2, x4*x2)
+//   v    = (splitmix64(key ^ 0x5bf03635) >> 11) * 2^-52 - 1                    (double)
+__global__ void __launch_bounds__(128) mcts_hash_eval_kernel(const uint16_t* __restrict__ planes, float* __restrict__ policy,
+                                                             double* __restrict__ value, const uint8_t* __restrict__ mask, uint64_t salt) {
+    const int b = blockIdx.x;
+    if (mask && !mask[b]) return;
+    __shared__ uint64_t part[4];
+    const uint16_t* src = planes + (size_t)b * HIVE_PLANES_ELEMS;
+    uint64_t h = 0;
+    for (int j = threadIdx.x; j < HIVE_PLANES_ELEMS; j += 128) h += splitmix64(((uint64_t)j << 16) | (uint64_t)src[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(FULL, h, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = h;
+    __syncthreads();
+    const uint64_t key = splitmix64(salt ^ (part[0] + part[1] + part[2] + part[3]));
+    for (int a = threadIdx.x; a < 1584; a += 128) {
+        const float x = (float)(uint32_t)(splitmix64(key ^ ((uint64_t)(a + 1) * 0x9E3779B97F4A7C15ULL)) >> 40) * (1.0f / 16777216.0f);
+        const float x2 = __fmul_rn(x, x), x4 = __fmul_rn(x2, x2);
+        policy[(size_t)b * 1584 + a] = __fmul_rn(x4, x2);
+    }
+    if (threadIdx.x == 0) value[b] = __dsub_rn((double)(splitmix64(key ^ 0x5bf03635ULL) >> 11) * (1.0 / 4503599627370496.0), 1.0);
+}
+
+int mcts_hash_eval_dev(const uint16_t* planes_dev, float* policy_dev, double* value_dev, const uint8_t* mask_dev, int n,
+                       uint64_t salt, void* stream) {
+    if (!planes_dev || !policy_dev || !value_dev || n < 1) return fail(HIVE_E_ARG, "mcts_hash_eval_dev: bad arguments");
+    mcts_hash_eval_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(planes_dev, policy_dev, value_dev, mask_dev, salt);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+void* mcts_stream(hive_mcts_t* m) { return m ? (void*)m->env->stream : nullptr; }
 
 int mcts_root_stats_host(hive_mcts_t* m, int tree, int max_edges, int32_t* action, int32_t* N, double* W, double* Q,
                          float* P, int32_t* info /*[6]: n_edges, sum_n, n_nodes, sims_done, error, root_selects*/) {

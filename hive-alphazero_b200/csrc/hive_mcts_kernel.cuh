@@ -67,6 +67,8 @@ struct MctsArgs {
     const double* noise;                                    // [n][noise_rows][noise_cols]
     double* pi;                                             // [n][1584] output policy
     int32_t* out_action; int32_t* out_sum_n;                // [n]
+    uint32_t* search_no;                                    // [n] searches begun in this slot (device noise stream position)
+    uint32_t* error_any;                                    // [1] OR of 1 << T.error over all trees since mcts_begin
 };
 
 __device__ __forceinline__ uint32_t key_hash(int lane, int cell, int level, int player) {
@@ -138,13 +140,38 @@ __device__ __forceinline__ void backup_path(const MctsArgs& a, int t, MctsTree& 
     }
 }
 
+// A simulation that cannot go on (arena full, path too deep): take its virtual losses back (solo_play.py:205-208
+// reversed: N-1, W+1) so that the statistics hold only finished simulations, flag the tree and the batch.
+// The search of this tree stops (mcts_descend_kernel marks it TREE_DONE); the host raises on the flag.
+__device__ __forceinline__ void abort_simulation(const MctsArgs& a, int t, MctsTree& T, int depth, int code, int lane) {
+    if (lane != 0) return;
+    MctsNode* nodes = a.nodes + (size_t)t * a.node_cap;
+    const size_t eb = (size_t)t * a.edge_cap;
+    for (int d = depth - 1; d >= 0; d--) {
+        MctsNode& nd = nodes[T.path_node[d]];
+        const size_t e = eb + nd.edge_off + T.path_edge[d];
+        nd.sum_n -= 1;
+        a.e_n[e] -= 1;
+        a.e_w[e] = a.e_w[e] + 1.0;
+        a.e_q[e] = a.e_n[e] > 0 ? a.e_w[e] / (double)a.e_n[e] : 0.0;
+    }
+    T.error = code;
+    atomicOr(a.error_any, 1u << code);
+}
+
+// seed of the device Dirichlet row of root visit `visit` of search number `search` of tree t
+__device__ __forceinline__ uint64_t noise_row_seed(uint64_t seed, int t, uint32_t search, int visit) {
+    uint64_t s = splitmix64(seed ^ ((uint64_t)(uint32_t)t * 0xD1342543DE82EF95ULL));
+    return splitmix64(s ^ ((uint64_t)search << 32) ^ (uint64_t)(uint32_t)visit);
+}
+
 __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_reset_kernel(MctsArgs a) {
     const int t = blockIdx.x;
     if (a.tree_mask && !a.tree_mask[t]) return;
     int32_t* ht = a.htab + (size_t)t * a.ht_size;
     for (int i = threadIdx.x; i < a.ht_size; i += blockDim.x) ht[i] = -1;
     for (int i = threadIdx.x; i < (int)(sizeof(MctsTree) / 4); i += blockDim.x) reinterpret_cast<int32_t*>(a.trees + t)[i] = 0;
-    if (threadIdx.x == 0) { a.need_eval[t] = 0; a.env_mask[t] = 0; }
+    if (threadIdx.x == 0) { a.need_eval[t] = 0; a.env_mask[t] = 0; a.search_no[t] += 1u; }
 }
 
 __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_descend_kernel(MctsArgs a) {
@@ -197,7 +224,6 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_descend_kernel(MctsArgs 
             const int id = tree_lookup(a, t, lane, cell, level, side);
             if (id < 0) {
                 // ---- not in the tree: hand the position to the evaluator (solo_play.py:188-197)
-                if (depth >= MCTS_MAX_DEPTH) { if (lane == 0) T.error = 3; break; }
                 if (lane < N_PIECE) { sim->cell[lane] = (uint8_t)cell; sim->level[lane] = (uint8_t)level; }
                 if (depth == 0) {
                     // the root itself: its legal set and planes were produced by the step that created the
@@ -216,6 +242,12 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_descend_kernel(MctsArgs 
                     a.env_mask[t] = depth > 0 ? 1 : 0;
                     atomicAdd(a.pending, 1);
                 }
+                return;
+            }
+            if (depth >= MCTS_MAX_DEPTH) {                         // the path arrays are full: give the simulation up
+                abort_simulation(a, t, T, depth, 3, lane);
+                __syncwarp();
+                if (lane == 0) T.state = TREE_DONE;
                 return;
             }
             // ---- the move that led here pushes (own-any, opp-any) of this position (env_hive.py:436-445)
@@ -251,26 +283,30 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_descend_kernel(MctsArgs 
                 }
                 double best = -999.0;
                 int bi = 0x7fffffff;
-                double gam[6];                                      // device noise: up to 192 edges per node
+                // device noise: a fresh Dirichlet(0.3) row per root visit (solo_play.py:323) = normalised Gamma(0.3) draws
+                // from a counter-based stream keyed by (seed, tree, search number of this slot, root visit, edge).  The
+                // draws of the row are parked in this tree's output-policy row (unused until mcts_finalize_kernel
+                // rewrites it); every lane reads back only what it wrote itself.
+                double* gam = a.pi + (size_t)t * 1584;
                 if (is_root && !a.noise) {
+                    const uint64_t row_seed = noise_row_seed(a.noise_seed, t, a.search_no[t], T.root_selects);
                     double s = 0.0;
-#pragma unroll
-                    for (int j = 0; j < 6; j++) {
-                        const int i = lane + 32 * j;
-                        gam[j] = (i < ne) ? gamma_sample(0.3, a.noise_seed ^ ((uint64_t)t << 40) ^ ((uint64_t)T.root_selects << 16) ^ (uint64_t)i) : 0.0;
-                        s += gam[j];
+                    for (int i = lane; i < ne; i += 32) {
+                        const double g = gamma_sample(0.3, row_seed ^ ((uint64_t)i * 0x9E3779B97F4A7C15ULL));
+                        gam[i] = g;
+                        s += g;
                     }
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
                     gsum = s;
                 }
-                for (int i = lane, j = 0; i < ne; i += 32, j++) {
+                for (int i = lane; i < ne; i += 32) {
                     const float p = a.e_p[e0 + i];
                     const double q = a.e_q[e0 + i];
                     const int n = a.e_n[e0 + i];
                     double u;
                     if (is_root) {
-                        const double nz = noise ? noise[i] : (j < 6 ? gam[j] / gsum : 0.0);
+                        const double nz = noise ? noise[i] : gam[i] / gsum;
                         const double pp = (double)(0.75f * p) + 0.25 * nz;        // (1-e)*p_ + e*noise[i]
                         u = 0.7 * pp * xx / (double)(1 + n);
                     } else {
@@ -330,7 +366,9 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_expand_kernel(MctsArgs a
     const int ne = count > 0 ? count : 1;
     const int id = T.n_nodes, off = T.edges_used;
     if (id >= a.node_cap || off + ne > a.edge_cap) {
-        if (lane == 0) { T.error = (id >= a.node_cap) ? 1 : 2; T.state = TREE_IDLE; a.need_eval[t] = 0; }
+        // arena full: the simulation is given up (virtual losses taken back), the tree stops and the batch is flagged
+        abort_simulation(a, t, T, T.depth, (id >= a.node_cap) ? 1 : 2, lane);
+        if (lane == 0) { T.state = TREE_IDLE; a.need_eval[t] = 0; a.env_mask[t] = 0; }
         return;
     }
     int cell = HAND, level = 0;

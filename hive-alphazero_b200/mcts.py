@@ -96,6 +96,14 @@ class MctsBatch:
     def dev_pending_mask(self): return lib().mcts_dev_pending_mask(self._h)
     @property
     def launches(self): return lib().mcts_launch_count(self._h)
+    @property
+    def stream_ptr(self): return lib().mcts_stream(self._h)
+
+    def errors(self):
+        """OR of (1 << code) over the trees of the running search: 2 node arena, 4 edge arena, 8 depth."""
+        flags = ctypes.c_uint32(0)
+        check(lib().mcts_error_host(self._h, ctypes.byref(flags)), "mcts_error_host")
+        return flags.value
 
     def search_host(self, evaluate, tree_mask=None):
         """Full search with a host evaluator ``evaluate(leaf_env) -> (p float32[1584], v float)`` called
@@ -144,13 +152,15 @@ class MctsBatch:
         return waves
 
     def actions(self):
-        """Only the chosen moves (int32[n]) -- skips the 12.7 KB/tree policy read-back."""
+        """Only the chosen moves (int32[n]) -- skips the 12.7 KB/tree policy read-back.
+        Raises SearchError if any tree of the search was cut short (arena / depth)."""
         action = np.empty(self.n, dtype=np.int32)
         check(lib().mcts_policy_host(self._h, None, action.ctypes.data, None), "mcts_policy_host")
         return action
 
     def policy(self):
-        """(pi float64[n,1584], action int32[n], sum_n int32[n]) -- calc_policy + apply_temperature."""
+        """(pi float64[n,1584], action int32[n], sum_n int32[n]) -- calc_policy + apply_temperature.
+        Raises SearchError if any tree of the search was cut short (arena / depth)."""
         pi = np.empty((self.n, C.ACTION_SPACE), dtype=np.float64)
         action = np.empty(self.n, dtype=np.int32)
         sum_n = np.empty(self.n, dtype=np.int32)
@@ -166,6 +176,19 @@ class MctsBatch:
         k = int(info[0])
         return dict(action=a[:k], n=n[:k], w=w[:k], q=q[:k], p=p[:k], sum_n=int(info[1]), n_nodes=int(info[2]),
                     sims_done=int(info[3]), error=int(info[4]), root_selects=int(info[5]))
+
+
+class HashEvaluator:
+    """evaluate_device callback backed by the library's deterministic stand-in network (mcts_hash_eval_dev):
+    policy / value are a pure hash of the leaf's planes and `salt`.  For parity tests of the device leaf path."""
+
+    def __init__(self, salt, stream_ptr):
+        self.salt, self.stream_ptr, self.calls = int(salt), stream_ptr, 0
+
+    def __call__(self, planes_ptr, policy_ptr, value_ptr, mask_ptr, n):
+        check(lib().mcts_hash_eval_dev(planes_ptr, policy_ptr, value_ptr, mask_ptr, int(n), self.salt, self.stream_ptr),
+              "mcts_hash_eval_dev")
+        self.calls += 1
 
 
 class WaveGraph:

@@ -40,6 +40,7 @@ extern "C" {
 #define HIVE_E_ARG (-1)
 #define HIVE_E_CUDA (-2)
 #define HIVE_E_HANDLE (-3)
+#define HIVE_E_SEARCH (-4)          /* a search tree ran out of its arena / depth budget (mcts_policy_host) */
 
 typedef struct hive_env hive_env_t;
 
@@ -143,7 +144,10 @@ float hive_last_kernel_ms(hive_env_t* h);
  */
 typedef struct hive_mcts hive_mcts_t;
 /* capacity for `sims` simulations per move (simulation_num_per_move, solo_play.py:23,98);
- * edges_per_sim <= 0 picks the default edge arena (96 edges per simulation and tree). */
+ * edges_per_sim <= 0 picks the default edge arena (160 edges per simulation and tree; the reference's games peak
+ * at 130 legal actions).  A tree that runs out of nodes / edges / path depth gives the running simulation up
+ * (virtual losses taken back), stops, and makes mcts_policy_host fail with HIVE_E_SEARCH -- never a silent
+ * short search. */
 int mcts_create(hive_env_t* env, int sims, int edges_per_sim, hive_mcts_t** out);
 int mcts_destroy(hive_mcts_t* m);
 int mcts_set_params(hive_mcts_t* m, int sims, int max_turn /*MAX_GAME_LENGTH*/, uint64_t noise_seed);
@@ -164,8 +168,19 @@ void* mcts_dev_pending_mask(hive_mcts_t* m);
 /* the same through host buffers (expand_and_evaluate, solo_play.py:260-291) */
 int mcts_leaf_planes_host(hive_mcts_t* m, uint16_t* planes_bf16, uint8_t* pending_mask);
 int mcts_set_leaf_eval_host(hive_mcts_t* m, const float* policy, const double* value);
-/* HivePlayer.action's return: pi[n][1584] (float64 like the reference), move, sum N */
+/* HivePlayer.action's return: pi[n][1584] (float64 like the reference), move, sum N.  Returns HIVE_E_SEARCH (outputs
+ * still written) if any tree of this search was flagged (see mcts_create). */
 int mcts_policy_host(hive_mcts_t* m, double* pi, int32_t* action, int32_t* sum_n);
+/* OR of (1 << error code) over the trees of the running search: 2 node arena, 4 edge arena, 8 depth (synchronises) */
+int mcts_error_host(hive_mcts_t* m, uint32_t* flags);
+/* Deterministic stand-in for the network ON THE DEVICE, for parity tests of the device leaf-evaluation path
+ * (expand_and_evaluate, solo_play.py:260-291, with a reproducible evaluator): policy / value are a pure hash of the
+ * row's bf16 planes and `salt` (formula at the kernel in csrc/hive_mcts.cu).  Rows with mask_dev[row] == 0 are left
+ * untouched (mask_dev may be NULL).  All pointers are device pointers; `stream` is a cudaStream_t. */
+int mcts_hash_eval_dev(const uint16_t* planes_dev, float* policy_dev, double* value_dev, const uint8_t* mask_dev, int n,
+                       uint64_t salt, void* stream);
+/* the cudaStream_t the search (and its environment handle) queues its work on */
+void* mcts_stream(hive_mcts_t* m);
 /* root edges of one tree in ascending action order; info[6] = n_edges, sum_n, n_nodes, sims_done,
  * error (1 node arena, 2 edge arena, 3 depth), root_selects */
 int mcts_root_stats_host(hive_mcts_t* m, int tree, int max_edges, int32_t* action, int32_t* N, double* W, double* Q,

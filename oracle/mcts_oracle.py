@@ -38,6 +38,36 @@ def hash_net(planes_hwc):
     return p, v
 
 
+def _splitmix64_np(x):
+    """splitmix64 over uint64 arrays (wrap-around arithmetic)."""
+    with np.errstate(over="ignore"):
+        x = x + np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return x ^ (x >> np.uint64(31))
+
+
+def device_hash_net(planes_hwc, salt=0):
+    """NumPy twin of the library's on-device stand-in network (mcts_hash_eval_dev, csrc/hive_mcts.cu): a pure
+    function of the bf16 CHW planes the device holds and a salt.  (12,12,56) planes -> (p float32[1584], v float)."""
+    chw = np.ascontiguousarray(np.asarray(planes_hwc, dtype=np.float32).transpose(2, 0, 1)).reshape(-1)
+    bf16 = (chw.view(np.uint32) >> 16).astype(np.uint64)                 # exact: the planes hold small integers
+    j = np.arange(bf16.size, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        h = _splitmix64_np((j << np.uint64(16)) | bf16).sum(dtype=np.uint64)
+        key = _splitmix64_np(np.uint64(salt) ^ h)
+        a = np.arange(1, ACTION_SPACE + 1, dtype=np.uint64)
+        u = _splitmix64_np(key ^ (a * np.uint64(0x9E3779B97F4A7C15))) >> np.uint64(40)
+    x = u.astype(np.float32) * np.float32(1.0 / 16777216.0)
+    x2 = x * x
+    x4 = x2 * x2
+    p = (x4 * x2).astype(np.float32)
+    with np.errstate(over="ignore"):
+        k = _splitmix64_np(key ^ np.uint64(0x5bf03635)) >> np.uint64(11)
+    v = float(np.float64(k) * (1.0 / 4503599627370496.0) - 1.0)
+    return p, v
+
+
 class _Edge:
     __slots__ = ("n", "w", "q", "p")
 

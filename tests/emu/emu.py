@@ -49,6 +49,8 @@ def lib():
         L.emu_mcts_expand.argtypes = [vp]
         L.emu_mcts_finalize.argtypes = [vp, vp, vp, vp]
         L.emu_mcts_root.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp]
+        L.emu_mcts_error.argtypes = [vp]
+        L.emu_mcts_error.restype = ctypes.c_uint
         _lib = L
     return _lib
 
@@ -164,6 +166,10 @@ class EmuMcts:
             self._chk(lib().emu_mcts_expand(self._h))
             waves += 1
         return waves
+
+    def errors(self):
+        """OR of 1 << error code over the trees of the last search (2 node arena, 4 edge arena, 8 depth)."""
+        return int(lib().emu_mcts_error(self._h))
 
     def policy(self):
         pi = np.zeros((self.n, 1584), dtype=np.float64)

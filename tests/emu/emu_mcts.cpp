@@ -23,6 +23,8 @@ struct EmuMcts {
     std::vector<double> e_w, e_q, leaf_v, noise, pi;
     std::vector<float> e_p, leaf_p;
     std::vector<uint8_t> need_eval, env_mask;
+    std::vector<uint32_t> search_no;
+    uint32_t error_any = 0;
     const uint32_t* root_legal = nullptr; const int32_t* root_count = nullptr; const uint16_t* root_planes = nullptr;
     int32_t pending;
     int noise_rows = 0, noise_cols = 0;
@@ -41,6 +43,7 @@ static MctsArgs args_of(EmuMcts* m) {
     a.e_action = m->e_action.data(); a.e_n = m->e_n.data(); a.e_w = m->e_w.data(); a.e_q = m->e_q.data(); a.e_p = m->e_p.data();
     a.noise = m->noise_rows ? m->noise.data() : nullptr; a.pi = m->pi.data();
     a.out_action = m->out_action.data(); a.out_sum_n = m->out_sum_n.data();
+    a.search_no = m->search_no.data(); a.error_any = &m->error_any;
     return a;
 }
 static void k_reset(void* p) { mcts_reset_kernel(*(MctsArgs*)p); }
@@ -59,7 +62,7 @@ void* emu_mcts_create(int n, int sims, int edges_per_sim) {
     m->htab.resize((size_t)n * ht); m->e_n.resize((size_t)n * m->edge_cap); m->e_action.resize((size_t)n * m->edge_cap);
     m->e_w.resize((size_t)n * m->edge_cap); m->e_q.resize((size_t)n * m->edge_cap); m->e_p.resize((size_t)n * m->edge_cap);
     m->leaf_p.resize((size_t)n * 1584); m->leaf_v.resize(n); m->need_eval.resize(n); m->env_mask.resize(n); m->pi.resize((size_t)n * 1584);
-    m->out_action.resize(n); m->out_sum_n.resize(n);
+    m->out_action.resize(n); m->out_sum_n.resize(n); m->search_no.assign(n, 0);
     memset(m->sim_recs.data(), 0, n * sizeof(GameRec));
     return m;
 }
@@ -71,6 +74,7 @@ void emu_mcts_set_noise(void* h, const double* noise, int rows, int cols) {
 int emu_mcts_begin(void* h, const void* root_recs, const uint32_t* root_legal, const int32_t* root_count, const uint16_t* root_planes) {
     EmuMcts* m = (EmuMcts*)h;
     m->root = (const GameRec*)root_recs; m->root_legal = root_legal; m->root_count = root_count; m->root_planes = root_planes;
+    m->error_any = 0;
     MctsArgs a = args_of(m);
     for (int b = 0; b < m->n; b++) { int rc = emu::run_block(k_reset, &a, b, MCTS_WARPS * 32, m->sched++); if (rc) return rc; }
     return 0;
@@ -108,6 +112,7 @@ int emu_mcts_finalize(void* h, double* pi, int32_t* action, int32_t* sum_n) {
     memcpy(pi, m->pi.data(), (size_t)m->n * 1584 * 8); memcpy(action, m->out_action.data(), m->n * 4); memcpy(sum_n, m->out_sum_n.data(), m->n * 4);
     return 0;
 }
+unsigned emu_mcts_error(void* h) { return ((EmuMcts*)h)->error_any; }
 int emu_mcts_root(void* h, int t, int max_edges, int32_t* action, int32_t* N, double* W, double* Q, float* P, int32_t* info) {
     EmuMcts* m = (EmuMcts*)h;
     const MctsTree& T = m->trees[t];

@@ -138,3 +138,90 @@ def test_kernels_on_injected_roots(j):
     pi, action, sum_n = m.policy()
     assert st["error"] == 0
     _check_injected(j, st, pi[0], action[0], sum_n[0])
+
+
+# ---- robustness: a tree that outgrows its arena must stop cleanly and be flagged (never a silent short search)
+def test_edge_arena_overflow_is_flagged_and_leaves_clean_statistics():
+    b = EmuBatch(2, sched_seed=5)
+    rng = np.random.RandomState(4)
+    env = OracleEnv()
+    for _ in range(14):
+        la = env.actions()
+        a = int(la[rng.randint(len(la))])
+        env.move(a)
+        b.step(np.array([a, a], dtype=np.int32))
+    sims = 24
+    m = EmuMcts(b, sims, edges_per_sim=1)              # 24 + 256 edges: the arena fills after a few expansions
+    m.set_noise(np.full((2, sims, 256), 1.0 / 64))
+    m.search(hash_net)
+    assert m.errors() & 4                               # edge arena flagged for the batch
+    for t in range(2):
+        st = m.root_stats(t)
+        assert st["error"] == 2 and st["sims_done"] < sims
+        # the aborted simulation took its virtual losses back: counts are those of the finished simulations only
+        assert st["n"].sum() == st["sum_n"] == st["sims_done"] - 1 and (st["n"] >= 0).all()
+        assert np.isfinite(st["w"]).all() and (np.abs(st["w"]) <= st["n"] + 1e-9).all()
+        live = st["n"] > 0
+        assert (st["q"][live] == st["w"][live] / st["n"][live]).all() and (st["q"][~live] == 0).all()
+
+
+def test_device_noise_differs_between_searches_of_one_slot():
+    """Root Dirichlet noise generated in the kernel: a fresh stream per search of the same slot (the reference draws
+    fresh np.random.dirichlet rows every time), identical for identical (seed, slot, search number)."""
+    b = EmuBatch(1, sched_seed=9)
+    rng = np.random.RandomState(8)
+    env = OracleEnv()
+    for _ in range(9):
+        la = env.actions()
+        a = int(la[rng.randint(len(la))])
+        env.move(a)
+        b.step(np.array([a], dtype=np.int32))
+    flat = lambda planes: (np.full(1584, 1.0 / 1584, dtype=np.float32), 0.0)      # flat net: the noise decides
+    m = EmuMcts(b, 40)
+    m.search(flat)
+    n1 = m.root_stats(0)["n"].copy()
+    m.search(flat)
+    n2 = m.root_stats(0)["n"].copy()
+    assert n1.sum() == n2.sum() == 39 and (n1 != n2).any()
+    m2 = EmuMcts(b, 40)                                 # a new handle restarts the slot's stream
+    m2.search(flat)
+    assert (m2.root_stats(0)["n"] == n1).all()
+
+
+# ---- 250 / 500 simulations (BASELINE configs[3] / [4] depths) run by the real reference player: mcts_deep.npz
+GD = np.load(os.path.join(ROOT, "tests", "golden", "mcts_deep.npz"))
+
+
+def _check_deep(i, st, pi, action, sum_n):
+    k = int(GD["n_edges"][i])
+    assert st["action"].tolist() == GD["e_action"][i][:k].tolist() and st["n"].tolist() == GD["e_n"][i][:k].tolist()
+    assert (st["w"] == GD["e_w"][i][:k]).all() and (st["q"] == GD["e_q"][i][:k]).all() and (st["p"] == GD["e_p"][i][:k]).all()
+    assert st["sum_n"] == GD["sum_n"][i] and st["n_nodes"] == GD["n_nodes"][i]
+    assert action == GD["action"][i] and (pi == GD["policy"][i]).all() and sum_n == GD["sum_n"][i]
+
+
+@pytest.mark.parametrize("i", range(len(GD["seed"])))
+def test_oracle_matches_reference_player_deep(i):
+    assert int(GD["sims"][i]) in (250, 500)
+    env = OracleEnv()
+    for a in GD["prefix"][i][:GD["n_prefix"][i]]:
+        env.move(int(a))
+    m = MctsOracle(hash_net, int(GD["sims"][i]))
+    np.random.seed(int(GD["seed"][i]))
+    action, policy, sum_all = m.action(env)
+    acts, n, w, q, p, sum_n, n_nodes = m.root_stats(env)
+    _check_deep(i, dict(action=acts, n=n, w=w, q=q, p=p, sum_n=sum_n, n_nodes=n_nodes), policy, action, sum_n)
+
+
+@pytest.mark.parametrize("i", [1, 3])
+def test_kernels_match_reference_player_deep(i):
+    b = EmuBatch(1, sched_seed=200 + i)
+    for a in GD["prefix"][i][:GD["n_prefix"][i]]:
+        b.step(np.array([a], dtype=np.int32))
+    sims, k = int(GD["sims"][i]), int(GD["n_edges"][i])
+    m = EmuMcts(b, sims, edges_per_sim=160)
+    m.set_noise(_recorded_noise(int(GD["seed"][i]), sims, k))
+    m.search(hash_net)
+    pi, action, sum_n = m.policy()
+    assert m.errors() == 0
+    _check_deep(i, m.root_stats(0), pi[0], action[0], sum_n[0])

@@ -120,3 +120,28 @@ def test_facade_on_injected_roots_incl_pass_edge(hb, j):
     assert st["error"] == 0 and st["action"].tolist() == GI["e_action"][j][:k].tolist()
     assert st["n"].tolist() == GI["e_n"][j][:k].tolist() and (st["w"] == GI["e_w"][j][:k]).all() and (st["p"] == GI["e_p"][j][:k]).all()
     assert st["n_nodes"] == GI["n_nodes"][j] and action == GI["action"][j] and (np.array(policy) == GI["policy"][j]).all()
+
+
+GD = np.load(os.path.join(ROOT, "tests", "golden", "mcts_deep.npz"))
+
+
+@pytest.mark.parametrize("i", range(len(GD["seed"])))
+def test_hiveplayer_facade_reproduces_reference_at_250_and_500_sims(hb, i):
+    """BASELINE configs[3] / [4] depths: searches of 250 and 500 simulations by the real reference player."""
+    from oracle.mcts_oracle import hash_net
+    env = hb.GamePlay()
+    for a in GD["prefix"][i][:GD["n_prefix"][i]]:
+        env.move(int(a))
+    pl = hb.HivePlayer()
+    pl.none_queue = False
+    pl.simulation_num_per_move = int(GD["sims"][i])
+    pl.expand_and_evaluate_with_net = lambda e: hash_net(e.encode_board())
+    np.random.seed(int(GD["seed"][i]))
+    action, (policy, sum_all) = pl.action(env)
+    st = pl._mcts.root_stats(0)
+    k = GD["n_edges"][i]
+    assert st["error"] == 0 and st["sims_done"] == GD["sims"][i]
+    assert st["action"].tolist() == GD["e_action"][i][:k].tolist() and st["n"].tolist() == GD["e_n"][i][:k].tolist()
+    assert (st["w"] == GD["e_w"][i][:k]).all() and (st["q"] == GD["e_q"][i][:k]).all() and (st["p"] == GD["e_p"][i][:k]).all()
+    assert st["sum_n"] == GD["sum_n"][i] and st["n_nodes"] == GD["n_nodes"][i]
+    assert action == GD["action"][i] and (np.array(policy) == GD["policy"][i]).all() and sum_all == GD["sum_all"][i]
