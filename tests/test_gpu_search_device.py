@@ -18,18 +18,28 @@ def hb():
 
 
 def _positions(hb, n, seed, stream=None, max_ply=40):
-    """n games at different depths (2..40 plies of random play), on the device and in the oracle."""
+    """n games at different depths (2..40 plies of random play), on the device and in the oracle.  A search from a
+    finished game has no root node (in the reference too: HivePlayer.action raises), so a draw of games in which one
+    ended is thrown away and the next seed is tried -- deterministic, the oracle decides."""
     from oracle.hive_oracle import OracleEnv
+    for attempt in range(50):
+        envs = [OracleEnv() for _ in range(n)]
+        rng = np.random.RandomState(seed + 1000 * attempt)
+        plies = []
+        for ply in range(max_ply):
+            acts = np.full(n, -2, dtype=np.int32)
+            for t, e in enumerate(envs):
+                la = e.actions()
+                if ply < 2 + (t * 37) % (max_ply - 1) and not e.game_is_over():
+                    acts[t] = la[rng.randint(len(la))] if len(la) else -1
+                    e.move(int(acts[t]))
+            plies.append(acts)
+        if not any(e.game_is_over() for e in envs):
+            break
+    else:
+        raise AssertionError("no draw without a finished game")
     b = hb.HiveBatch(n, stream=stream)
-    envs = [OracleEnv() for _ in range(n)]
-    rng = np.random.RandomState(seed)
-    for ply in range(max_ply):
-        acts = np.full(n, -2, dtype=np.int32)
-        for t, e in enumerate(envs):
-            la = e.actions()
-            if ply < 2 + (t * 37) % (max_ply - 1) and not e.game_is_over():
-                acts[t] = la[rng.randint(len(la))] if len(la) else -1
-                e.move(int(acts[t]))
+    for acts in plies:
         b.step(acts)
     return b, envs
 
