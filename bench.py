@@ -317,7 +317,7 @@ def main():
     env_steps_all = allsum(float(env_steps))
     value = env_steps_all / (ms_max * 1e-3)
 
-    # roofline, this rank.  One "launch" of the hot path = one step = analyse -> flood -> moves -> encode over
+    # roofline, this rank.  One "launch" of the hot path = one step = step kernel + plane store over
     # the whole batch (cut into slices inside one CUDA graph); algorithmic bytes as in SURVEY 8d / DESIGN.md.
     peak, peak_src = measured_peak()
     n_steps = max(args.steps, 1)
@@ -325,7 +325,7 @@ def main():
     launch_s = ms * 1e-3 / n_steps
     achieved = per_launch_bytes / launch_s / 1e9
     # the dominant kernel alone (hive_planes_kernel: reads 1,120 B of bit planes, writes 16,128 B of bf16 planes per
-    # game through the TMA): timed live with events between the five kernels of un-sliced steps
+    # game through the TMA): timed live with events around the two kernels of un-sliced steps
     prof = [batch.profile_step(seed, args.max_turn) for _ in range(12)][2:]
     kms = {k: sum(p[k] for p in prof) / len(prof) for k in prof[0]}
     PLANES_BYTES = 16128 + 1120
@@ -341,7 +341,7 @@ def main():
     batch.sync()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "write_only_stream_gbs": write_only, "frac_of_write_only_stream": achieved / write_only,
-                "traffic": ncu_traffic(), "kernel": "env step = hive_analyse + hive_flood + hive_moves + hive_encode + hive_planes kernels",
+                "traffic": ncu_traffic(), "kernel": "env step = hive_step_kernel + hive_planes_kernel",
                 "peak_source": peak_src, "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP,
                 "env_steps_per_launch": env_steps / n_steps, "launch_us": launch_s * 1e6,
                 "kernels_per_step": launches / n_steps, "dominant_kernel": dominant}

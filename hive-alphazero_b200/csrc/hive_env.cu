@@ -1,10 +1,10 @@
 // hive_env.cu -- environment kernels + C ABI (include/hive_b200.h) for sm_100a.
 //
-// One kernel, `hive_env_kernel`, is the whole GamePlay.move() of the reference
-// (hive_engine/env_hive.py:99-171) for a batch of games: apply the action, regenerate the legal
-// set of the new side to move, encode its 56 planes, push history, test for the end of the game.
-// Four kernels per step (hive_env_kernel.cuh): analyse (warp per game) -> flood -> moves (thread per
-// queued piece from batch-wide queues, move searches grouped by piece type) -> encode (warp per game).
+// One step of a batch of games is the whole GamePlay.move() of the reference (hive_engine/env_hive.py:99-171): apply
+// the action, regenerate the legal set of the new side to move, encode its 56 planes, push history, test for the end
+// of the game.  Two kernels per step (hive_env_kernel.cuh): hive_step_kernel (32 games per CTA: analyse -> one-hive
+// floods -> move searches -> legal mask + bit planes) and hive_planes_kernel (bit planes -> bf16 planes through the
+// TMA, persistent, on its own stream beside the next step).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -26,7 +26,7 @@
 #include "hive_tables.h"
 
 #ifndef HIVE_DEFAULT_SLICES
-#define HIVE_DEFAULT_SLICES 8
+#define HIVE_DEFAULT_SLICES 2
 #endif
 
 using namespace hive;
@@ -74,7 +74,7 @@ int launch_env(hive_env* h, int op, const int32_t* actions, const uint8_t* mask,
         }
         CUDA_TRY(cudaGraphLaunch(g.exec, h->stream));
         const int S = h->n_sub;
-        h->launches += 5 * S;
+        h->launches += 2 * S;
     }
     if (h->timing) CUDA_TRY(cudaEventRecord(h->t1, h->stream));
     return 0;
@@ -91,23 +91,7 @@ static EnvArgs slice_args(hive_env* h, int s, int per, int op, const int32_t* ac
     a.chosen = chosen ? chosen + off : nullptr; a.hop_lines = h->hop_lines;
     a.seed = seed; a.n = cnt > 0 ? cnt : 0; a.op = op; a.max_turn = max_turn; a.auto_reset = auto_reset;
     a.g_offset = off; a.n_total = h->n;
-    a.scratch = h->scratch + off; a.bq = h->bq[s];
     return a;
-}
-// Launch of one kernel of a slice's chain.  `pdl`: programmatic stream serialization -- the grid may be made resident
-// while its predecessor in the stream still runs (its CTAs wait in chain_wait_then_release), which takes the launch
-// latency (7 us per dependent kernel in the v8 trace, 4 per step) off the chain's critical path.
-static cudaError_t launch_chain_kernel(void (*kernel)(EnvArgs), int blocks, int threads, cudaStream_t st, bool pdl, const EnvArgs& a) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kernel, a);
-}
-static cudaError_t launch_encode_part(const EnvArgs& a, cudaStream_t st, bool pdl = false) {
-    return launch_chain_kernel(hive_encode_kernel, (a.n + HIVE_ENCODE_WARPS - 1) / HIVE_ENCODE_WARPS, HIVE_ENCODE_WARPS * 32, st, pdl, a);
 }
 // The plane-store kernel is persistent: the store launches that run at the same time (`concurrent` slices) share
 // store_ctas_per_sm CTAs per SM, so each grid is resident at once and never queues in front of other kernels.
@@ -121,9 +105,9 @@ static void launch_planes_part(hive_env* h, const EnvArgs& a, cudaStream_t st, i
     hive_planes_kernel<<<blocks, HIVE_STORE_WARPS * 32, STORE_STAGE_BYTES, st>>>(a);
 }
 
-// `repeat` steps of one slice: analyse -> flood -> moves -> encode on stream `st`, and the plane store of every step on
-// stream `ss`, so that it runs beside the next step's kernels (the bit planes it reads are double-buffered; step k+2's
-// encode waits for step k's store).  With st != ss the chain ends joined on `st`.
+// `repeat` steps of one slice: the step kernel on stream `st`, and the plane store of every step on stream `ss`, so
+// that it runs beside the next step's kernel (the bit planes it reads are double-buffered; step k+2's kernel waits
+// for step k's store).  With st != ss the chain ends joined on `st`.
 // `defer_store_join` (single steps only): `st` is NOT joined with the plane store; the caller joins
 // stored_ev[s][0] itself, after whatever it wants to run beside the store (the result downloads of the host-driven step).
 static int launch_slice_chain(hive_env* h, int s, EnvArgs a, cudaStream_t st, cudaStream_t ss, int concurrent, int repeat,
@@ -131,15 +115,9 @@ static int launch_slice_chain(hive_env* h, int s, EnvArgs a, cudaStream_t st, cu
     const bool side = st != ss;
     for (int rep = 0; rep < repeat; rep++) {
         a.bits = h->bits[rep & 1] + (size_t)a.g_offset * BITS_WORDS;
-        const int pdl = h->pdl_mask;                            // bit 0 analyse, 1 flood, 2 moves, 3 encode
-        CUDA_TRY(launch_chain_kernel(hive_analyse_kernel, (a.n + GROUP - 1) / GROUP, GROUP * 32, st, (pdl & 1) && rep > 0, a));
-        int sblocks = (int)(((long long)a.n * N_PIECE + SEARCH_THREADS - 1) / SEARCH_THREADS);
-        if (sblocks > h->search_blocks) sblocks = h->search_blocks;
-        CUDA_TRY(launch_chain_kernel(hive_flood_kernel, sblocks, SEARCH_THREADS, st, pdl & 2, a));
-        CUDA_TRY(launch_chain_kernel(hive_moves_kernel, sblocks, SEARCH_THREADS, st, pdl & 4, a));
         const bool waits_store = side && rep >= 2;
         if (waits_store) CUDA_TRY(cudaStreamWaitEvent(st, h->stored_ev[s][rep & 1], 0));    // this bit-plane buffer is free again
-        CUDA_TRY(launch_encode_part(a, st, (pdl & 8) && (!waits_store || (pdl & 16))));
+        hive_step_kernel<<<(a.n + SG - 1) / SG, STEP_THREADS, 0, st>>>(a);
         if (side) {
             CUDA_TRY(cudaEventRecord(h->encoded_ev[s], st));
             CUDA_TRY(cudaStreamWaitEvent(ss, h->encoded_ev[s], 0));
@@ -152,7 +130,7 @@ static int launch_slice_chain(hive_env* h, int s, EnvArgs a, cudaStream_t st, cu
         if (repeat > 1) CUDA_TRY(cudaStreamWaitEvent(st, h->stored_ev[s][repeat & 1], 0));
     }
     CUDA_TRY(cudaGetLastError());
-    h->launches += 5 * repeat;
+    h->launches += 2 * repeat;
     return 0;
 }
 
@@ -166,8 +144,8 @@ static int launch_env_kernels(hive_env* h, int op, const int32_t* actions, const
     CUDA_TRY(cudaStreamIsCapturing(h->stream, &cap_state));
     int S = (cap_state == cudaStreamCaptureStatusActive || h->n_sub < h->host_slices) ? h->n_sub : h->host_slices;
     if (force_slices > 0) S = force_slices < h->n_sub ? force_slices : h->n_sub;
-    // slices are multiples of GROUP games so that CTAs never straddle two slices
-    const int per = ((h->n + S - 1) / S + GROUP - 1) / GROUP * GROUP;
+    // slices are multiples of SG games so that CTAs never straddle two slices
+    const int per = ((h->n + S - 1) / S + SG - 1) / SG * SG;
     const bool side = S > 1 || repeat > 1;                 // side streams in use (else everything goes down h->stream)
     const bool defer = deferred_stores && side && repeat == 1 && !h->skip_planes;
     if (deferred_stores) *deferred_stores = 0;
@@ -216,6 +194,16 @@ int hive_trace_read(void* host, int cap) {
 }
 #endif
 
+#ifdef HIVE_PHASE_CLOCKS
+// experiment builds only: summed SM clocks per phase of the step kernel ([7] = CTAs), optionally zeroed after the read
+int hive_phase_clocks(unsigned long long* out, int reset) {
+    cudaDeviceSynchronize();
+    if (out) cudaMemcpyFromSymbol(out, g_phase_clk, 64);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_phase_clk, z, 64); }
+    return 0;
+}
+#endif
+
 const char* hive_last_error(void) { return g_err.c_str(); }
 int hive_abi_version(void) { return 1; }
 
@@ -247,6 +235,12 @@ int hive::create_env(int n_games, int device, void* stream, int slices, hive_env
     const size_t n = (size_t)n_games;
     // static + dynamic shared memory of the plane-store kernel exceeds the 48 KB default
     CUDA_TRY(cudaFuncSetAttribute(hive_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STORE_STAGE_BYTES));
+    // the step kernels and the persistent plane stores share the SMs: both ask for the largest shared-memory carve-out, so
+    // that an SM never has to drain to be re-partitioned before a CTA of the other kernel fits
+    if (!getenv("HIVE_B200_NO_CARVEOUT")) {
+        CUDA_TRY(cudaFuncSetAttribute(hive_planes_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CUDA_TRY(cudaFuncSetAttribute(hive_step_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
     for (int b = 0; b < 2; b++) {
         CUDA_TRY(cudaMalloc(&h->bits[b], n * BITS_WORDS * 4));
         CUDA_TRY(cudaMemsetAsync(h->bits[b], 0, n * BITS_WORDS * 4, h->stream));
@@ -256,13 +250,12 @@ int hive::create_env(int n_games, int device, void* stream, int slices, hive_env
     CUDA_TRY(cudaMalloc(&h->count, n * 4));
     CUDA_TRY(cudaMalloc(&h->status, n * 4));
     CUDA_TRY(cudaMalloc(&h->planes, n * HIVE_PLANES_ELEMS * 2));
-    CUDA_TRY(cudaMalloc(&h->scratch, n * sizeof(GameScratch)));
     {
         const char* e = getenv("HIVE_B200_SLICES");
         int S = slices > 0 ? slices : (e ? atoi(e) : HIVE_DEFAULT_SLICES);
         if (S < 1) S = 1;
         if (S > hive_env::MAX_SUB) S = hive_env::MAX_SUB;
-        while (S > 1 && n_games < S * GROUP * 8) S--;         // small batches are not worth slicing
+        while (S > 1 && n_games < S * SG * 2) S--;            // small batches are not worth slicing
         h->n_sub = S;
         const char* ec = getenv("HIVE_B200_STORE_CTAS");
         h->store_ctas_per_sm = ec && atoi(ec) > 0 ? atoi(ec) : 2;
@@ -272,8 +265,6 @@ int hive::create_env(int n_games, int device, void* stream, int slices, hive_env
         h->async_slices = as && atoi(as) > 0 ? atoi(as) : 4;
         if (h->async_slices > h->n_sub) h->async_slices = h->n_sub;
         h->skip_planes = getenv("HIVE_B200_EXPERIMENT_SKIP_PLANES") != nullptr;   // measurement aid: the step without its plane store
-        const char* pm = getenv("HIVE_B200_PDL");
-        h->pdl_mask = pm ? atoi(pm) : 0;
         const char* sg = getenv("HIVE_B200_SPLIT_GRAPHS");
         h->split_graphs = sg ? atoi(sg) : 1;
         const char* ug = getenv("HIVE_B200_GRAPH");
@@ -281,28 +272,23 @@ int hive::create_env(int n_games, int device, void* stream, int slices, hive_env
     }
     CUDA_TRY(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&h->results_ev, cudaEventDisableTiming));
-    // a slice's work queues hold the largest slice any launch mode cuts (host-issued steps use fewer, larger slices)
-    int min_slices = h->n_sub < h->host_slices ? h->n_sub : h->host_slices;
-    if (h->async_slices < min_slices) min_slices = h->async_slices;
-    const size_t qgames = (n + min_slices - 1) / min_slices + 2 * GROUP;
     for (int s = 0; s < h->n_sub; s++) {
-        CUDA_TRY(cudaStreamCreateWithFlags(&h->sub_stream[s], cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&h->store_stream[s], cudaStreamNonBlocking));
+        {   // HIVE_B200_PRIO (experiment): 1 = step kernels above the plane stores, 2 = the other way round
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            const char* pe = getenv("HIVE_B200_PRIO");
+            const int mode = pe ? atoi(pe) : 0;
+            CUDA_TRY(cudaStreamCreateWithPriority(&h->sub_stream[s], cudaStreamNonBlocking, mode == 1 ? hi : mode == 2 ? lo : 0));
+            CUDA_TRY(cudaStreamCreateWithPriority(&h->store_stream[s], cudaStreamNonBlocking, mode == 1 ? lo : mode == 2 ? hi : 0));
+        }
         CUDA_TRY(cudaEventCreateWithFlags(&h->join_ev[s], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&h->encoded_ev[s], cudaEventDisableTiming));
         for (int b = 0; b < 2; b++) CUDA_TRY(cudaEventCreateWithFlags(&h->stored_ev[s][b], cudaEventDisableTiming));
-        CUDA_TRY(cudaMalloc(&h->bq[s].counters, 8 * 4));
-        CUDA_TRY(cudaMemsetAsync(h->bq[s].counters, 0, 8 * 4, h->stream));
-        CUDA_TRY(cudaMalloc(&h->bq[s].flood, qgames * N_PIECE * 4));
-        for (int c = 0; c < 4; c++) CUDA_TRY(cudaMalloc(&h->bq[s].mv[c], qgames * 6 * 4));
     }
     {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
         h->sm_count = sms;
-        const long long want = ((long long)n * N_PIECE + SEARCH_THREADS - 1) / SEARCH_THREADS;
-        const long long cap = (long long)sms * 16;                 // 16 x 128-thread CTAs fill an SM
-        h->search_blocks = (int)(want < cap ? want : cap);
     }
     CUDA_TRY(cudaMalloc(&h->d_actions[0], n * 4));
     CUDA_TRY(cudaMalloc(&h->d_actions[1], n * 4));
@@ -330,10 +316,8 @@ int hive_destroy(hive_env_t* h) {
     if (h->multi_graph.exec && h->multi_graph.exec != h->slice_exec[0]) cudaGraphExecDestroy(h->multi_graph.exec);
     for (int s = 0; s < hive_env::MAX_SUB; s++) if (h->slice_exec[s]) cudaGraphExecDestroy(h->slice_exec[s]);
     if (h->host_graph.exec) cudaGraphExecDestroy(h->host_graph.exec);
-    cudaFree(h->recs); cudaFree(h->legal); cudaFree(h->count); cudaFree(h->status); cudaFree(h->planes); cudaFree(h->scratch); cudaFree(h->bits[0]); cudaFree(h->bits[1]);
+    cudaFree(h->recs); cudaFree(h->legal); cudaFree(h->count); cudaFree(h->status); cudaFree(h->planes); cudaFree(h->bits[0]); cudaFree(h->bits[1]);
     for (int s = 0; s < h->n_sub; s++) {
-        cudaFree(h->bq[s].counters); cudaFree(h->bq[s].flood);
-        for (int c = 0; c < 4; c++) cudaFree(h->bq[s].mv[c]);
         if (h->sub_stream[s]) cudaStreamDestroy(h->sub_stream[s]);
         if (h->store_stream[s]) cudaStreamDestroy(h->store_stream[s]);
         if (h->encoded_ev[s]) cudaEventDestroy(h->encoded_ev[s]);
@@ -519,7 +503,7 @@ int hive_step_random_multi(hive_env_t* h, uint64_t seed, int max_turn, int auto_
             // slices are issued level by level (all analyse kernels, then all floods, ...: profiles/README.md,
             // v8 trace), which lines the slices' phases up and leaves the SMs to one kernel type at a time;
             // separate graphs are separate launch queues, so the chains drift apart and their phases mix.
-            const int per = ((h->n + S - 1) / S + GROUP - 1) / GROUP * GROUP;
+            const int per = ((h->n + S - 1) / S + SG - 1) / SG * SG;
             for (int s = 0; s < S; s++) {
                 const EnvArgs a = slice_args(h, s, per, OP_RANDOM, nullptr, nullptr, seed, max_turn, auto_reset, nullptr);
                 if (a.n <= 0) break;
@@ -549,50 +533,31 @@ int hive_step_random_multi(hive_env_t* h, uint64_t seed, int max_turn, int auto_
             CUDA_TRY(cudaStreamWaitEvent(h->stream, h->join_ev[s], 0));
         }
     }
-    h->launches += 5LL * h->n_sub * n_steps;
+    h->launches += 2LL * h->n_sub * n_steps;
     if (h->timing) CUDA_TRY(cudaEventRecord(h->t1, h->stream));
     return 0;
 }
 
-// One rollout step with CUDA events between the four kernels (whole batch as one slice, no graph):
-// ms[0..4] = analyse, flood, moves, encode, planes.  For bench.py's per-kernel roofline; it advances the games.
+// One rollout step with CUDA events around its two kernels (whole batch as one slice, no graph):
+// ms[0] = step kernel, ms[1] = plane store.  For bench.py's per-kernel roofline; it advances the games.
 int hive_profile_step(hive_env_t* h, uint64_t seed, int max_turn, float* ms) {
     if (check(h)) return HIVE_E_HANDLE;
     if (!ms || max_turn < 1 || max_turn > 250) return fail(HIVE_E_ARG, "hive_profile_step: bad arguments");
     CUDA_TRY(cudaSetDevice(h->device));
-    cudaEvent_t ev[6];
-    for (int i = 0; i < 6; i++) CUDA_TRY(cudaEventCreate(&ev[i]));
-    EnvArgs a;
-    a.recs = h->recs; a.legal = h->legal; a.count = h->count; a.status = h->status; a.planes = h->planes;
-    a.actions = nullptr; a.mask = nullptr; a.chosen = nullptr; a.hop_lines = h->hop_lines;
-    a.seed = seed; a.n = h->n; a.op = OP_RANDOM; a.max_turn = max_turn; a.auto_reset = 1; a.g_offset = 0; a.n_total = h->n;
-    a.scratch = h->scratch; a.bits = h->bits[0];
-    // slice 0's queues are sized for a slice: use a whole-batch set allocated on the fly
-    BatchQueues q;
-    const size_t n = (size_t)h->n;
-    CUDA_TRY(cudaMalloc(&q.counters, 32)); CUDA_TRY(cudaMemsetAsync(q.counters, 0, 32, h->stream));
-    CUDA_TRY(cudaMalloc(&q.flood, n * N_PIECE * 4));
-    for (int c = 0; c < 4; c++) CUDA_TRY(cudaMalloc(&q.mv[c], n * 6 * 4));
-    a.bq = q;
-    const int groups = (h->n + GROUP - 1) / GROUP;
+    cudaEvent_t ev[3];
+    for (int i = 0; i < 3; i++) CUDA_TRY(cudaEventCreate(&ev[i]));
+    EnvArgs a = slice_args(h, 0, h->n, OP_RANDOM, nullptr, nullptr, seed, max_turn, 1, nullptr);
+    a.bits = h->bits[0];
     CUDA_TRY(cudaEventRecord(ev[0], h->stream));
-    hive_analyse_kernel<<<groups, GROUP * 32, 0, h->stream>>>(a);
+    hive_step_kernel<<<(h->n + SG - 1) / SG, STEP_THREADS, 0, h->stream>>>(a);
     CUDA_TRY(cudaEventRecord(ev[1], h->stream));
-    hive_flood_kernel<<<h->search_blocks, SEARCH_THREADS, 0, h->stream>>>(a);
+    if (!h->skip_planes) launch_planes_part(h, a, h->stream, 0);   // alone on the GPU: uncapped
     CUDA_TRY(cudaEventRecord(ev[2], h->stream));
-    hive_moves_kernel<<<h->search_blocks, SEARCH_THREADS, 0, h->stream>>>(a);
-    CUDA_TRY(cudaEventRecord(ev[3], h->stream));
-    CUDA_TRY(launch_encode_part(a, h->stream));
-    CUDA_TRY(cudaEventRecord(ev[4], h->stream));
-    launch_planes_part(h, a, h->stream, 0);                    // alone on the GPU: uncapped
-    CUDA_TRY(cudaEventRecord(ev[5], h->stream));
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    for (int i = 0; i < 5; i++) CUDA_TRY(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
-    for (int i = 0; i < 6; i++) cudaEventDestroy(ev[i]);
-    cudaFree(q.counters); cudaFree(q.flood);
-    for (int c = 0; c < 4; c++) cudaFree(q.mv[c]);
-    h->launches += 5;
+    for (int i = 0; i < 2; i++) CUDA_TRY(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+    for (int i = 0; i < 3; i++) cudaEventDestroy(ev[i]);
+    h->launches += 2;
     return 0;
 }
 

@@ -15,9 +15,6 @@
 
 namespace hive {
 
-#ifndef HIVE_ENCODE_WARPS
-#define HIVE_ENCODE_WARPS 8                        // games per CTA of the encode kernel
-#endif
 enum Op { OP_RESET = 0, OP_STEP = 1, OP_EVAL = 2, OP_RANDOM = 3, OP_INIT = 4 };   // INIT = first reset, zeroes the counters
 
 struct EnvArgs {
@@ -26,13 +23,11 @@ struct EnvArgs {
     int32_t* count;        // [n]
     uint32_t* status;      // [n] turn | winner<<8 | done<<16
     uint16_t* planes;      // [n][56*144] bf16
-    GameScratch* scratch;  // [n] kernel-to-kernel intermediates (L2 resident)
-    uint32_t* bits;        // [n][BITS_WORDS] bit planes, encode kernel -> plane-store kernel (this step's buffer of two)
-    BatchQueues bq;        // batch-wide work queues
+    uint32_t* bits;        // [n][BITS_WORDS] bit planes, step kernel -> plane-store kernel (this step's buffer of two)
     const int32_t* actions;
     const uint8_t* mask;
     int32_t* chosen;
-    const uint32_t* hop_lines;   // GEO_* tables (hive_core.cuh): hop lines, neighbour ranks, neighbour cells
+    const uint32_t* hop_lines;   // GEO_* tables (hive_core.cuh): hop lines, neighbour ranks, neighbour cells, neighbourhood boards
     uint64_t seed;
     int n, op, max_turn, auto_reset;
     int g_offset, n_total;   // this launch covers games [g_offset, g_offset+n) of a batch of n_total (pointers are pre-offset)
@@ -63,43 +58,105 @@ struct TraceScope {
 #define HIVE_TRACE_SCOPE(k, a)
 #endif
 
-// Programmatic dependent launch (hive_env.cu launches the kernels of a slice's chain with
-// cudaLaunchAttributeProgrammaticStreamSerialization): a kernel's CTAs may become resident while the kernel before it in
-// the stream is still running; they wait here until that grid has completed and its writes are visible, and only then
-// let their own dependent start launching (so at most one kernel of a chain is pre-launched).  Without the launch
-// attribute both instructions return at once.
-__device__ __forceinline__ void chain_wait_then_release() {
-#ifndef HIVE_EMU
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+// ---- optional per-phase clocks of the step kernel (builds with -DHIVE_PHASE_CLOCKS only; profiles/phase_probe.py):
+// thread 0 of every CTA adds the SM clocks it spent between the phase barriers to g_phase_clk[phase], CTAs to [7]
+#ifdef HIVE_PHASE_CLOCKS
+__device__ unsigned long long g_phase_clk[8];
+#define HIVE_PHASE_MARK(i) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&g_phase_clk[i], (unsigned long long)(t_ - phase_t_)); phase_t_ = t_; } } while (0)
+#define HIVE_PHASE_BEGIN() long long phase_t_ = clock64(); if (threadIdx.x == 0) atomicAdd(&g_phase_clk[7], 1ull)
+#else
+#define HIVE_PHASE_MARK(i)
+#define HIVE_PHASE_BEGIN()
 #endif
+
+// ==========================================================================================================
+// The step kernel: GamePlay.move() of 32 games per CTA (env_hive.py:99-171), in five phases separated by block
+// barriers.  In the analyse and encode phases LANE <-> GAME (a warp's 32 lanes work on 32 different games, so board
+// algebra, hashing, the legal-mask scatter ... are plain per-thread code without a single shuffle), and the warps of
+// the CTA split the work by PIECE (analyse) or by OUTPUT (encode: legal mask halves, plane groups, history,
+// mobility planes).  In the search phases THREAD <-> QUEUED PIECE: the pieces that need a one-hive flood or a move
+// search are collected in CTA-local queues, the move queues one per piece class, so that a warp runs 32 Ant floods,
+// or 32 Spider walks ... of different games side by side.  Per-game fields live in shared memory as [field][lane]
+// (bank = lane: conflict-free for any per-lane index).
+//   1a (warp 0)   decode the operation, pick / apply the action, boards, placements
+//   1b (all)      per piece: stack height, top, ring occupancy, turn gates; queue floods and move searches
+//   2  (all)      one-hive floods; survivors join the move queues
+//   3  (all)      move searches by class; move sets -> shared rows
+//   4  (all)      legal mask (shared), 56 bit planes -> a.bits, history push
+//   5  (warps 0,1) legal mask, count, status, record header out
+#ifndef HIVE_STEP_WARPS
+#define HIVE_STEP_WARPS 8
+#endif
+constexpr int SG = 32;                                   // games per CTA
+constexpr int SW = HIVE_STEP_WARPS, STEP_THREADS = SW * 32;
+static_assert(SW >= 2 && SW <= 16, "warps per CTA of the step kernel");
+#ifndef HIVE_STEP_MIN_CTAS
+#define HIVE_STEP_MIN_CTAS (768 / (HIVE_STEP_WARPS * 32))
+#endif
+
+struct __align__(16) StepShared {
+    union {
+        uint32_t legal[LEGAL_WORDS][SG];     // phases 3..5 (zeroed at the start of phase 3)
+        struct {                             // phases 1b..2: the hive as a graph of occupied cells, node = top piece of a cell
+            uint32_t cmap[36][SG];           // byte c: the top piece standing on cell c
+            uint32_t adj[N_PIECE][SG];       // per top piece: the top pieces of its occupied neighbour cells
+        } graph;
+    };
+    uint32_t rows[N_PIECE][5][SG];   // move set of every searched piece (own: its action list; opponent: its mobility set)
+    uint32_t info[N_PIECE][SG];      // cell | height<<8 | top<<12 | level<<13 | ring<<16
+    uint32_t pc[11][SG];             // record bytes 0..43 after the action: cell[22], level[22]
+    uint32_t occ[5][SG], own[5][SG], opp[5][SG], place[5][SG];
+    uint32_t head[SG];               // turn | cq_w<<8 | cq_b<<16
+    uint32_t flags[SG];              // live | push_history<<1 | prev_winner<<8
+    uint32_t pin[SG];                // pinned pieces (lifting them breaks the hive)
+    uint32_t placeable[SG];          // in-hand pieces of the side to move that may be placed on `place`
+    uint32_t nonempty[SG];           // searched pieces with a non-empty move set
+    uint32_t nlegal[SG], episode[SG], steps[SG];
+    uint32_t n_flood, n_mv[4];       // queue fill: floods; move classes 0 Ant, 1 Grasshopper, 2 Spider, 3 Queen/Beetle
+    uint32_t any_live, next_task, pad_[1];
+    uint16_t q_flood[SG * N_PIECE];  // item = slot | piece<<5 | wants_moves<<10
+    uint16_t q_mv[4][SG * 6];
+};
+
+__device__ __forceinline__ BB bb_onehot(int c) { return bb_bit(c); }   // HAND (255) selects no word: empty board
+
+// append `item` to a CTA queue for every lane with `cond` (one shared-memory atomic per warp)
+__device__ __forceinline__ void queue_push(uint32_t* counter, uint16_t* q, bool cond, uint32_t item, int lane) {
+    const unsigned m = __ballot_sync(FULL, cond);
+    if (m) {
+        const int leader = __ffs(m) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+        base = __shfl_sync(FULL, base, leader);
+        if (cond) q[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)item;
+    }
 }
 
-// ---- kernel 1: decode the operation, apply the action, analyse the new position (warp <-> game)
-__global__ void __launch_bounds__(GROUP * 32, 64 / GROUP) hive_analyse_kernel(EnvArgs a) {
-    __shared__ GroupQueues q;
-    __shared__ uint32_t occ_s[GROUP][8];
-    chain_wait_then_release();
-    HIVE_TRACE_SCOPE(0, a);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = blockIdx.x * GROUP + warp;
-    if (tid < 5) (&q.n_flood)[tid] = 0;
-    __syncthreads();
-
+// ---- phase 1a (one warp, lane <-> game)
+__device__ __forceinline__ void step_prologue(StepShared& s, const EnvArgs& a, int lane, int g) {
     bool live = g < a.n;
+    uint32_t pc[11];
+#pragma unroll
+    for (int i = 0; i < 11; i++) pc[i] = 0;
+    int turn = 1, winner = 0;
+    uint32_t episode = 0, steps = 0;
+    bool push = false;
     if (live) {
         GameRec* rec = a.recs + g;
-        int cell = HAND, level = 0;
-        if (lane < N_PIECE) { cell = rec->cell[lane]; level = rec->level[lane]; }
+        const uint4* r4 = reinterpret_cast<const uint4*>(rec);
+        const uint4 v0 = r4[0], v1 = r4[1], v2 = r4[2], v3 = r4[3];
+        LegalRow lrow;                                          // the random policy picks from the current legal mask: fetched with the record
+        if (a.op == OP_RANDOM) lrow = load_legal_row(a.legal + (size_t)g * LEGAL_WORDS);
+        pc[0] = v0.x; pc[1] = v0.y; pc[2] = v0.z; pc[3] = v0.w; pc[4] = v1.x; pc[5] = v1.y; pc[6] = v1.z; pc[7] = v1.w;
+        pc[8] = v2.x; pc[9] = v2.y; pc[10] = v2.z;
         // header words: [11] = turn|winner|done|flags, [12] episode, [13] steps, [14] n_legal
-        uint32_t* hw = reinterpret_cast<uint32_t*>(rec);
-        const uint32_t h11 = hw[11];
-        int turn = h11 & 0xFF, winner = (h11 >> 8) & 0xFF;
+        const uint32_t h11 = v2.w;
+        turn = h11 & 0xFF; winner = (h11 >> 8) & 0xFF;
         const int done = (h11 >> 16) & 0xFF;
-        uint32_t episode = hw[12], steps = hw[13];
-        const uint32_t n_legal_prev = hw[14];
+        episode = v3.x; steps = v3.y;
+        const uint32_t n_legal_prev = v3.z;
 
-        bool do_reset = false, push = false;
+        bool do_reset = false;
         int action = HIVE_NOOP;
         if (a.op == OP_RESET) {
             if (a.mask && !a.mask[g]) live = false; else do_reset = true;
@@ -120,154 +177,539 @@ __global__ void __launch_bounds__(GROUP * 32, 64 / GROUP) hive_analyse_kernel(En
             } else {
                 const uint64_t gid = (uint64_t)(g + a.g_offset) + (uint64_t)a.n_total * episode;
                 const uint64_t x = splitmix64(a.seed ^ (gid << 32) ^ (uint64_t)turn);
-                action = select_kth_action(a.legal + (size_t)g * LEGAL_WORDS, lane, (int)(x % n_legal_prev));
+                action = kth_legal_action(lrow, (int)(x % n_legal_prev));
             }
-            if (a.chosen && lane == 0) a.chosen[g] = (do_reset || !live) ? HIVE_NOOP : action;
+            if (a.chosen) a.chosen[g] = (do_reset || !live) ? HIVE_NOOP : action;
         }
-        __syncwarp();
         if (live) {
             if (do_reset) {                                     // GamePlay.new_game, env_hive.py:61-97
-                cell = HAND; level = 0; turn = 1; winner = 0; episode++;
-                if (lane < 20) reinterpret_cast<uint4*>(rec->hist)[lane] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                for (int i = 0; i < 11; i++) pc[i] = i < 5 ? 0xFFFFFFFFu : i == 5 ? 0x0000FFFFu : 0u;   // 22 x HAND, levels 0
+                turn = 1; winner = 0; episode++;
+                uint4* h4 = reinterpret_cast<uint4*>(rec->hist);
+#pragma unroll
+                for (int i = 0; i < 20; i++) h4[i] = make_uint4(0u, 0u, 0u, 0u);
                 push = true;                                    // add_history starts True (env_hive.py:51)
             } else if (action >= 0) {                           // env_hive.py:105-148
                 const int side = (turn & 1) ? 0 : 1;
                 const int k = action % 11, end = action / 11, p = side * 11 + k;
-                const int h_end = __popc(__ballot_sync(FULL, cell == end));
-                if (lane == p) { cell = end; level = h_end; }   // level = len(end_tile.pieces) before the move
+                int h_end = 0;                                  // level = len(end_tile.pieces) before the move
+#pragma unroll
+                for (int q = 0; q < N_PIECE; q++) h_end += (int)(((pc[q >> 2] >> (8 * (q & 3))) & 0xFFu) == (uint32_t)end);
+                const int wc = p >> 2, shc = 8 * (p & 3), wl = (22 + p) >> 2, shl = 8 * ((22 + p) & 3);
+                const uint32_t mc = 0xFFu << shc, vc = (uint32_t)end << shc, ml = 0xFFu << shl, vl = (uint32_t)h_end << shl;
+#pragma unroll
+                for (int i = 0; i < 11; i++) {
+                    uint32_t w = pc[i];
+                    w = wc == i ? (w & ~mc) | vc : w;
+                    w = wl == i ? (w & ~ml) | vl : w;
+                    pc[i] = w;
+                }
                 turn++; steps++; push = true;
             } else if (action == -1) {                          // pass, env_hive.py:100-103
                 turn++; steps++;
             }
-            __syncwarp();
-            if (lane < N_PIECE) { rec->cell[lane] = (uint8_t)cell; rec->level[lane] = (uint8_t)level; }
-            if (lane == 0) { hw[12] = episode; hw[13] = steps; }
-            eval_analyse(a.scratch[g], q, occ_s[warp], warp, lane, cell, level, turn, push, winner, a.hop_lines);
-        } else if (lane == 0) {
-            a.scratch[g].head[2] = 0;                           // not evaluated in this launch
+        } else {
+            a.bits[(size_t)g * BITS_WORDS + BITS_LIVE] = 0u;    // not evaluated in this launch: the plane store leaves this game's planes alone
         }
     }
-    __syncthreads();
-    // publish this group's work: reserve a slice of every batch-wide queue (one atomic per class and CTA)
-    if (tid < 5) { const uint32_t c = (&q.n_flood)[tid]; q.base[tid] = c ? atomicAdd(a.bq.counters + tid, c) : 0u; }
-    __syncthreads();
+
+    // boards; hand masks (colour-relative)
+    const int side = (turn & 1) ? 0 : 1;                        // game_state.py:58-62
+    BB white = bb_zero(), black = bb_zero();
+    uint32_t hand_w = 0, hand_b = 0;
+#pragma unroll
+    for (int p = 0; p < N_PIECE; p++) {
+        const int c = (pc[p >> 2] >> (8 * (p & 3))) & 0xFF;
+        const BB b = bb_onehot(c);
+        if (p < 11) { white = white | b; hand_w |= (uint32_t)(c == HAND) << p; }
+        else { black = black | b; hand_b |= (uint32_t)(c == HAND) << (p - 11); }
+    }
+    // stacks: only beetles climb (pieces 1, 2, 12, 13), so the cells with more than one piece are the cells of the
+    // beetles above level 0, and the top piece there is the beetle no other beetle stands on
+    BB stackc = bb_zero(), top_w = bb_zero(), top_b = bb_zero();
     {
-        const uint32_t g0 = (uint32_t)blockIdx.x * GROUP;
-        const int nf = (int)q.n_flood;
-        for (int i = tid; i < nf; i += GROUP * 32) {
-            const uint32_t it = q.flood[i];
-            a.bq.flood[q.base[0] + i] = ((g0 + (it & 15u)) << 6) | (((it >> 4) & 31u) << 1) | ((it >> 9) & 1u);
+        int bcell[4], blev[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int p = j < 2 ? 1 + j : 10 + j;
+            bcell[j] = (pc[p >> 2] >> (8 * (p & 3))) & 0xFF;
+            blev[j] = (pc[(22 + p) >> 2] >> (8 * ((22 + p) & 3))) & 0xFF;
+            if (bcell[j] == HAND) blev[j] = 0;
         }
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-            const int nm = (int)q.n_mv[c];
-            for (int i = tid; i < nm; i += GROUP * 32) {
-                const uint32_t it = q.mv[c][i];
-                a.bq.mv[c][q.base[1 + c] + i] = ((g0 + (it & 15u)) << 6) | (((it >> 4) & 31u) << 1) | 1u;
+        for (int j = 0; j < 4; j++) {
+            bool covered = false;
+#pragma unroll
+            for (int j2 = 0; j2 < 4; j2++) if (j2 != j) covered = covered || (bcell[j2] == bcell[j] && blev[j2] == blev[j] + 1);
+            const BB b = blev[j] >= 1 ? bb_onehot(bcell[j]) : bb_zero();
+            stackc = stackc | b;
+            if (!covered) { if (j < 2) top_w = top_w | b; else top_b = top_b | b; }
+        }
+    }
+    const BB occ = white | black;
+    const BB top_opp = side ? (bb_andn(white, stackc) | top_w) : (bb_andn(black, stackc) | top_b);
+    const int cq_w = pc[0] & 0xFF, cq_b = (pc[2] >> 24) & 0xFF;
+    const bool wq_on = cq_w != HAND, bq_on = cq_b != HAND;
+
+    // placements (env_hive.py:217-225; move_checker.py:168-179): the first in-hand piece of each type of the side to move
+    const uint32_t in_hand = side ? hand_b : hand_w;
+    uint32_t first = 0;
+    { uint32_t t;
+      t = in_hand & 0x001u; first |= t & (0u - t);
+      t = in_hand & 0x006u; first |= t & (0u - t);
+      t = in_hand & 0x018u; first |= t & (0u - t);
+      t = in_hand & 0x0E0u; first |= t & (0u - t);
+      t = in_hand & 0x700u; first |= t & (0u - t); }
+    BB place;
+    if (turn == 1) place = bb_bit(START_CELL);
+    else {
+        const BB frontier = bb_andn(bb_nbrs(occ), occ);
+        if (turn == 2) place = frontier & bb_bit(TURN2_CELL);
+        else {
+            place = bb_andn(frontier, bb_nbrs(top_opp));
+            if (turn == 7 || turn == 8) {
+                const bool ok_q = obeys_queen_by_4(turn, wq_on, bq_on, true, side), ok_n = obeys_queen_by_4(turn, wq_on, bq_on, false, side);
+                first = (ok_q ? first & 1u : 0u) | (ok_n ? first & ~1u : 0u);
             }
         }
     }
+#pragma unroll
+    for (int i = 0; i < 11; i++) s.pc[i][lane] = pc[i];
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        s.occ[i][lane] = occ.w[i];
+        s.own[i][lane] = side ? black.w[i] : white.w[i];
+        s.opp[i][lane] = side ? white.w[i] : black.w[i];
+        s.place[i][lane] = place.w[i];
+    }
+    s.head[lane] = (uint32_t)turn | ((uint32_t)cq_w << 8) | ((uint32_t)cq_b << 16);
+    s.flags[lane] = (live ? 1u : 0u) | ((uint32_t)push << 1) | ((uint32_t)winner << 8);
+    s.pin[lane] = 0; s.nonempty[lane] = 0; s.nlegal[lane] = 0;
+    s.placeable[lane] = first << (11 * side);
+    s.episode[lane] = episode; s.steps[lane] = steps;
+    const unsigned lv = __ballot_sync(FULL, live);
+    if (lane == 0) s.any_live = lv;
 }
 
-// ---- kernel 2: one-hive floods over the batch-wide flood queue (thread <-> queued piece)
-constexpr int SEARCH_THREADS = 128;
-__global__ void __launch_bounds__(SEARCH_THREADS) hive_flood_kernel(EnvArgs a) {
-    chain_wait_then_release();
-    HIVE_TRACE_SCOPE(1, a);
-    const int lane = threadIdx.x & 31;
-    const int nf = (int)a.bq.counters[0];
-    const int stride = gridDim.x * SEARCH_THREADS;
-    for (int t0 = (blockIdx.x * SEARCH_THREADS + threadIdx.x) - lane; t0 < nf; t0 += stride) {   // warp-uniform loop
-        const int t = t0 + lane;
-        bool push = false;
-        uint32_t item = 0;
-        int cls = 0;
-        if (t < nf) {
-            item = a.bq.flood[t];
-            const int p = (item >> 1) & 31;
-            GameScratch& gs = a.scratch[item >> 6];
-            const bool pinned = eval_flood(gs, p);
-            if (pinned) atomicOr(&gs.head[1], 1u << p);
-            else if (item & 1u) { push = true; cls = move_class(piece_type_of(p >= 11 ? p - 11 : p)); }
-        }
-        // survivors that want a move search join the move queues (one atomic per class and warp)
+// ---- phase 1b (all warps; lane <-> game, the warps take the pieces in turn): stacks; which piece tops which cell
+__device__ __forceinline__ void step_stacks(StepShared& s, int warp, int lane) {
+    const bool live = s.flags[lane] & 1u;
+    int bc[4];                                              // cells of the beetles above level 0 (else: no cell)
+    {
+        const uint32_t w0 = s.pc[0][lane], w3 = s.pc[3][lane], w5 = s.pc[5][lane], w6 = s.pc[6][lane], w8 = s.pc[8][lane];
+        const int c1 = (w0 >> 8) & 0xFF, c2 = (w0 >> 16) & 0xFF, c12 = w3 & 0xFF, c13 = (w3 >> 8) & 0xFF;
+        const int l1 = (w5 >> 24) & 0xFF, l2 = w6 & 0xFF, l12 = (w8 >> 16) & 0xFF, l13 = (w8 >> 24) & 0xFF;
+        bc[0] = (l1 >= 1 && c1 != HAND) ? c1 : 0x100; bc[1] = (l2 >= 1 && c2 != HAND) ? c2 : 0x101;
+        bc[2] = (l12 >= 1 && c12 != HAND) ? c12 : 0x102; bc[3] = (l13 >= 1 && c13 != HAND) ? c13 : 0x103;
+    }
+    for (int p = warp; p < N_PIECE; p += SW) {              // warp-uniform
+        const int c = (s.pc[p >> 2][lane] >> (8 * (p & 3))) & 0xFF;
+        const int lv = (s.pc[(22 + p) >> 2][lane] >> (8 * ((22 + p) & 3))) & 0xFF;
+        const bool on = live && c != HAND;
+        // pieces sharing a cell (tile.pieces); top piece <=> level+1 == len (env_hive.py:213)
+        const int height = 1 + (int)(bc[0] == c) + (int)(bc[1] == c) + (int)(bc[2] == c) + (int)(bc[3] == c);
+        const bool top = on && lv == height - 1;
+        s.info[p][lane] = (uint32_t)c | ((uint32_t)height << 8) | ((uint32_t)top << 12) | ((uint32_t)lv << 13);
+        if (top) reinterpret_cast<uint8_t*>(&s.graph.cmap[c >> 2][lane])[c & 3] = (uint8_t)p;
+    }
+}
+
+// ---- phase 1c (all warps; lane <-> game): ring occupancy, hive graph, turn gates; queue floods and move searches
+__device__ __forceinline__ void step_pieces(StepShared& s, int warp, int lane, const uint32_t* __restrict__ geo) {
+    const uint32_t hd = s.head[lane];
+    const int turn = hd & 0xFF, cq_w = (hd >> 8) & 0xFF, cq_b = (hd >> 16) & 0xFF;
+    const int side = (turn & 1) ? 0 : 1;
+    const bool wq_on = cq_w != HAND, bq_on = cq_b != HAND, ownq_on = (side == 0 ? cq_w : cq_b) != HAND;
+    uint32_t pin_bits = 0;
+    for (int p = warp; p < N_PIECE; p += SW) {              // warp-uniform
+        const int color = p >= 11 ? 1 : 0, k = p - 11 * color, type = piece_type_of(k);
+        const uint32_t info = s.info[p][lane];
+        const int c = info & 0xFF, height = (info >> 8) & 0xF;
+        const bool top = (info >> 12) & 1u;
+        const bool on = (s.flags[lane] & 1u) && c != HAND;
+        const bool own = color == side;
+        uint32_t ring = 0, adj = 0;                         // occupancy of the six neighbours (cells from the GEO_NBR table)
+        if (on && (top || type == T_QUEEN)) {
+            const uint32_t n03 = __ldg(geo + GEO_NBR + 2 * c), n45 = __ldg(geo + GEO_NBR + 2 * c + 1);
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-            const unsigned m = __ballot_sync(FULL, push && cls == c);
-            if (m) {
-                uint32_t base = 0;
-                const int leader = __ffs(m) - 1;
-                if (lane == leader) base = atomicAdd(a.bq.counters + 1 + c, (uint32_t)__popc(m));
-                base = __shfl_sync(FULL, base, leader);
-                if (push && cls == c) a.bq.mv[c][base + __popc(m & ((1u << lane) - 1u))] = item;
+            for (int i = 0; i < 6; i++) {
+                const uint32_t nb = ((i < 4 ? n03 : n45) >> (8 * (i & 3))) & 0xFFu;
+                if ((s.occ[nb >> 5][lane] >> (nb & 31)) & 1u) {
+                    ring |= 1u << i;
+                    adj |= 1u << reinterpret_cast<const uint8_t*>(&s.graph.cmap[nb >> 2][lane])[nb & 3];
+                }
+            }
+            s.graph.adj[p][lane] = adj;
+            s.info[p][lane] = info | (ring << 16);
+        }
+        // turn gates shared by every candidate of a piece (move_checker.py:38-55)
+        bool gate = true;
+        if (turn <= 2) gate = false;                                             // no on-board mover can exist / matter
+        else if (turn <= 6) gate = ownq_on;                                      // queen_is_on_board: colour by turn parity
+        else if (turn <= 8) gate = obeys_queen_by_4(turn, wq_on, bq_on, type == T_QUEEN, color);
+        // opponent mobility is only consumed through the own queen's neighbourhood (env_hive.py:459-478)
+        const bool wants = top && gate && (own || ownq_on);
+        bool pinned_now = false, need_flood = false;
+        if (top && height == 1) {
+            if (ring == 0) pinned_now = true;                                    // nothing left on the board -> `return False`
+            else need_flood = __popc(ring & ~rot6l(ring)) > 1;                   // >1 arc of neighbours: may be an articulation point
+        }
+        if (pinned_now) pin_bits |= 1u << p;
+        const uint32_t item = (uint32_t)lane | ((uint32_t)p << 5) | ((uint32_t)wants << 10);
+        queue_push(&s.n_flood, s.q_flood, need_flood, item, lane);
+        const int cls = move_class(type);
+        queue_push(&s.n_mv[cls], s.q_mv[cls], on && !need_flood && wants && !pinned_now, item, lane);
+    }
+    if (pin_bits) atomicOr(&s.pin[lane], pin_bits);
+}
+
+// one thread, one one-hive test (move_checker.py:58-83 / env_hive.py:509-530) on the graph of occupied cells: lift the
+// top piece `p` (alone on its cell) and test that its neighbour cells stay connected.  Returns true if pinned.
+__device__ __forceinline__ bool flood_graph(const StepShared& s, int slot, int p) {
+    const uint32_t goal = s.graph.adj[p][slot], removed = 1u << p;
+    uint32_t reach = goal & (0u - goal), todo = reach;       // reached cells; reached cells whose neighbours are still to be added
+    while (todo) {                                           // one flat loop (a node per trip): the lanes of a warp stay together
+        if ((reach & goal) == goal) return false;
+        const int i = __ffs(todo) - 1; todo &= todo - 1;
+        const uint32_t nw = s.graph.adj[i][slot] & ~(reach | removed);
+        reach |= nw; todo |= nw;
+    }
+    return (reach & goal) != goal;
+}
+
+// ---- phase 4 helpers (lane <-> game)
+struct EncodeCtx {
+    int lane, side, turn, cq_w, cq_b;
+    bool live, push;         // every lane runs every task (warp-uniform loops); the lanes without a live game store nothing
+    uint32_t has_row, placeable, pin;   // has_row: searched, unpinned pieces with a non-empty move set
+    uint32_t* bits;
+    GameRec* rec;
+};
+__device__ __forceinline__ BB piece_row(const StepShared& s, const EncodeCtx& e, int p) {
+    BB r = bb_zero();
+    if ((e.has_row >> p) & 1u) {
+#pragma unroll
+        for (int i = 0; i < 5; i++) r.w[i] = s.rows[p][i][e.lane];
+    } else if ((e.placeable >> p) & 1u) {
+#pragma unroll
+        for (int i = 0; i < 5; i++) r.w[i] = s.place[i][e.lane];
+    }
+    return r;
+}
+// four consecutive planes (20 words) -> bits[first_plane*5 ...] as five 16-byte stores (first_plane % 4 == 0)
+__device__ __forceinline__ void store_plane_quad(const EncodeCtx& e, int first_plane, const uint32_t (&r)[20]) {
+    if (!e.live) return;
+    uint4* dst = reinterpret_cast<uint4*>(e.bits + first_plane * 5);
+#pragma unroll
+    for (int i = 0; i < 5; i++) dst[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+}
+
+// dense legal mask a = cell*11 + k of the own pieces k0..k1-1 (env_hive.py:287-304) into shared memory
+__device__ __forceinline__ void encode_legal(StepShared& s, const EncodeCtx& e, int k0, int k1) {
+    int cnt = 0;
+    for (int kk = k0; kk < k1; kk++) {
+        const BB m = piece_row(s, e, e.side * 11 + kk);
+#pragma unroll
+        for (int w = 0; w < 5; w++) {
+            uint32_t mm = m.w[w];
+            cnt += __popc(mm);
+            while (__ballot_sync(FULL, mm != 0u)) {          // warp-uniform trip count: the lanes stay together
+                if (mm) {
+                    const int b = __ffs(mm) - 1; mm &= mm - 1;
+                    const int act = (w * 32 + b) * 11 + kk;
+                    atomicOr(&s.legal[act >> 5][e.lane], 1u << (act & 31));
+                }
             }
         }
     }
+    if (cnt) atomicAdd(&s.nlegal[e.lane], (uint32_t)cnt);
 }
 
-// ---- kernel 3: move searches, warps homogeneous in piece type (thread <-> queued piece)
-__global__ void __launch_bounds__(SEARCH_THREADS) hive_moves_kernel(EnvArgs a) {
-    chain_wait_then_release();
-    HIVE_TRACE_SCOPE(2, a);
-    // move classes start at warp boundaries so that warps stay homogeneous
-    const int n0 = (int)a.bq.counters[1], n1 = (int)a.bq.counters[2], n2 = (int)a.bq.counters[3], n3 = (int)a.bq.counters[4];
-    const int s1 = (n0 + 31) & ~31, s2 = s1 + ((n1 + 31) & ~31), s3 = s2 + ((n2 + 31) & ~31), total = s3 + n3;
-    const int stride = gridDim.x * SEARCH_THREADS;
-    for (int t = blockIdx.x * SEARCH_THREADS + threadIdx.x; t < total; t += stride) {
-        int cls, idx, cnt;
-        if (t < s1) { cls = 0; idx = t; cnt = n0; }
-        else if (t < s2) { cls = 1; idx = t - s1; cnt = n1; }
-        else if (t < s3) { cls = 2; idx = t - s2; cnt = n2; }
-        else { cls = 3; idx = t - s3; cnt = n3; }
-        if (idx < cnt) {
-            const uint32_t item = a.bq.mv[cls][idx];
-            eval_moves(a.scratch[item >> 6], (item >> 1) & 31, a.hop_lines);
+// planes 0-11 (which = 0: pieces of the side to move + their union) or 12-23 (which = 1: the opponent's)
+__device__ __forceinline__ void encode_piece_planes(const StepShared& s, const EncodeCtx& e, int which) {
+    const int base = (which ? 1 - e.side : e.side) * 11;
+#pragma unroll
+    for (int grp = 0; grp < 3; grp++) {
+        uint32_t r[20];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int kk = grp * 4 + j;
+            if (kk < 11) {
+                const BB b = bb_onehot((int)(s.info[base + kk][e.lane] & 0xFFu));
+#pragma unroll
+                for (int i = 0; i < 5; i++) r[j * 5 + i] = b.w[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < 5; i++) r[j * 5 + i] = which ? s.opp[i][e.lane] : s.own[i][e.lane];
+            }
         }
+        store_plane_quad(e, (which ? 12 : 0) + grp * 4, r);
     }
 }
 
-// ---- kernel 4: legal mask, bit planes, history, terminal test, small outputs (warp <-> game).  Everything the
-// next step needs is written here; the 16 KB of bf16 planes per game are left to kernel 5, which runs on its own
-// stream beside the next step's kernels.
-__global__ void __launch_bounds__(HIVE_ENCODE_WARPS * 32, 6) hive_encode_kernel(EnvArgs a) {
-    __shared__ WarpScratch scratch[HIVE_ENCODE_WARPS];
-    chain_wait_then_release();
-    HIVE_TRACE_SCOPE(3, a);
+// planes 24-35: beetle levels, occupancy, the turn slot, occupied queen neighbours, stuck pieces
+__device__ __forceinline__ void encode_misc_planes(const StepShared& s, const EncodeCtx& e, const uint32_t* __restrict__ geo) {
+    const int own0 = e.side * 11, opp0 = (1 - e.side) * 11;
+    uint32_t r[20];
+    BB lvl[6];                                               // 24-26 own beetles at level 2,3,4; 27-29 the opponent's
+#pragma unroll
+    for (int i = 0; i < 6; i++) lvl[i] = bb_zero();
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t info = s.info[(j < 2 ? own0 : opp0) + 1 + (j & 1)][e.lane];
+        const int c = info & 0xFF, lv = (info >> 13) & 7;
+        if (c != HAND && lv >= 2) {
+            const BB b = bb_onehot(c);
+#pragma unroll
+            for (int t = 0; t < 3; t++) if (lv == t + 2) lvl[(j < 2 ? 0 : 3) + t] = lvl[(j < 2 ? 0 : 3) + t] | b;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int i = 0; i < 5; i++) r[j * 5 + i] = lvl[j].w[i];
+    store_plane_quad(e, 24, r);
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        r[i] = lvl[4].w[i]; r[5 + i] = lvl[5].w[i];
+        r[10 + i] = s.occ[i][e.lane];                        // 30
+        r[15 + i] = i == 0 ? (uint32_t)e.turn : i == 1 ? 1u : 0u;   // slot of plane 31: turn, "evaluated in this launch"
+    }
+    store_plane_quad(e, 28, r);
+    // 32 / 33: occupied neighbours of the own / the opponent's queen
+    const int q_own = e.side ? e.cq_b : e.cq_w, q_opp = e.side ? e.cq_w : e.cq_b;
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        r[i] = q_own != HAND ? (__ldg(geo + GEO_NBRMASK + q_own * 5 + i) & s.occ[i][e.lane]) : 0u;
+        r[5 + i] = q_opp != HAND ? (__ldg(geo + GEO_NBRMASK + q_opp * 5 + i) & s.occ[i][e.lane]) : 0u;
+    }
+    // 34: own pieces without a legal action; 35: opponent pieces covered or pinned
+    BB stuck_own = bb_zero(), stuck_opp = bb_zero();
+    for (int kk = 0; kk < 11; kk++) {
+        const uint32_t io = s.info[own0 + kk][e.lane], ip = s.info[opp0 + kk][e.lane];
+        const int co = io & 0xFF, cp = ip & 0xFF;
+        if (co != HAND) {
+            if (!((io >> 12) & 1u) || !((e.has_row >> (own0 + kk)) & 1u)) stuck_own = stuck_own | bb_onehot(co);
+        }
+        if (cp != HAND && (!((ip >> 12) & 1u) || ((e.pin >> (opp0 + kk)) & 1u))) stuck_opp = stuck_opp | bb_onehot(cp);
+    }
+#pragma unroll
+    for (int i = 0; i < 5; i++) { r[10 + i] = stuck_own.w[i]; r[15 + i] = stuck_opp.w[i]; }
+    store_plane_quad(e, 32, r);
+}
+
+// planes 36-43: the 4-step history of the side to move (env_hive.py:431-445), then the push of this position
+__device__ __forceinline__ void encode_history(const StepShared& s, const EncodeCtx& e) {
+    if (!e.live) return;
+    uint4* h4 = reinterpret_cast<uint4*>(&e.rec->hist[e.side][0][0][0]);     // 40 words = 10 x 16 B
+    uint32_t h[40];
+#pragma unroll
+    for (int i = 0; i < 10; i++) { const uint4 v = h4[i]; h[4 * i] = v.x; h[4 * i + 1] = v.y; h[4 * i + 2] = v.z; h[4 * i + 3] = v.w; }
+    uint4* dst = reinterpret_cast<uint4*>(e.bits + 36 * 5);
+#pragma unroll
+    for (int i = 0; i < 10; i++) dst[i] = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+    if (e.push) {                                            // only after a real move / at reset: ages 0..2 -> 1..3
+        uint32_t nh[40];
+#pragma unroll
+        for (int i = 0; i < 5; i++) { nh[i] = s.own[i][e.lane]; nh[5 + i] = s.opp[i][e.lane]; }
+#pragma unroll
+        for (int i = 0; i < 30; i++) nh[10 + i] = h[i];
+#pragma unroll
+        for (int i = 0; i < 10; i++) h4[i] = make_uint4(nh[4 * i], nh[4 * i + 1], nh[4 * i + 2], nh[4 * i + 3]);
+    }
+}
+
+// N words f[0..N) -> bits[OFF ...) with the widest stores the alignment of OFF allows (compile-time peeling)
+template <int OFF, int N>
+__device__ __forceinline__ void store_words(uint32_t* bits, const uint32_t (&f)[N]) {
+    int i = 0;
+    if ((OFF + i) % 2 && i < N) { bits[OFF + i] = f[i]; i += 1; }
+    if ((OFF + i) % 4 && i + 1 < N) { *reinterpret_cast<uint2*>(bits + OFF + i) = make_uint2(f[i], f[i + 1]); i += 2; }
+#pragma unroll
+    for (int j = 0; j < N / 4; j++)
+        if (i + 3 < N) { *reinterpret_cast<uint4*>(bits + OFF + i) = make_uint4(f[i], f[i + 1], f[i + 2], f[i + 3]); i += 4; }
+    if (i + 1 < N) { *reinterpret_cast<uint2*>(bits + OFF + i) = make_uint2(f[i], f[i + 1]); i += 2; }
+    if (i < N) { bits[OFF + i] = f[i]; i += 1; }
+}
+
+// three of the planes 44-49 (WHICH = 1: opponent pieces able to reach the j-th empty neighbour of the own queen) or 50-55
+// (WHICH = 0: own on-board pieces whose action list holds the j-th empty neighbour of the opponent's queen); j = rank of
+// the neighbour in tile.adjacent_tiles order (env_hive.py:448-478; GEO_RANK); HALF = 0: ranks 0-2, 1: ranks 3-5
+template <int WHICH, int HALF>
+__device__ __forceinline__ void encode_mobility(const StepShared& s, const EncodeCtx& e, const uint32_t* __restrict__ geo) {
+    const int col = WHICH ? 1 - e.side : e.side, base = col * 11;
+    const int qc = col ? e.cq_w : e.cq_b;                    // the queen of the other colour than the pieces
+    uint32_t nbr_by_rank[3];
+    bool any_empty = false;
+#pragma unroll
+    for (int r = 0; r < 3; r++) nbr_by_rank[r] = 0xFFFFu;    // no empty neighbour of that rank
+    if (qc != HAND) {
+        const uint32_t n03 = __ldg(geo + GEO_NBR + 2 * qc), n45 = __ldg(geo + GEO_NBR + 2 * qc + 1), ranks = __ldg(geo + GEO_RANK + qc);
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            const uint32_t nb = ((i < 4 ? n03 : n45) >> (8 * (i & 3))) & 0xFFu, rank = (ranks >> (3 * i)) & 7u;
+            const bool empty = !((s.occ[nb >> 5][e.lane] >> (nb & 31)) & 1u);
+#pragma unroll
+            for (int r = 0; r < 3; r++) if (empty && rank == (uint32_t)(r + 3 * HALF)) { nbr_by_rank[r] = nb; any_empty = true; }
+        }
+    }
+    BB pl[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) pl[r] = bb_zero();
+    uint32_t todo = any_empty ? (e.has_row >> base) & 0x7FFu : 0u;   // the searched pieces of that colour with a non-empty move set
+    while (__ballot_sync(FULL, todo != 0u)) {                // warp-uniform trip count: the lanes stay together
+        if (todo) {
+            const int kk = __ffs(todo) - 1; todo &= todo - 1;
+            const int p = base + kk;
+            const BB m = piece_row(s, e, p);
+            const BB b = bb_onehot((int)(s.info[p][e.lane] & 0xFFu));
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                const uint32_t nb = nbr_by_rank[r];
+                if (nb != 0xFFFFu && bb_test(m, (int)nb)) pl[r] = pl[r] | b;
+            }
+        }
+    }
+    uint32_t f[15];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int i = 0; i < 5; i++) f[r * 5 + i] = pl[r].w[i];
+    if (e.live) store_words<(WHICH ? 44 : 50) * 5 + 15 * HALF, 15>(e.bits, f);
+}
+
+__global__ void __launch_bounds__(STEP_THREADS, HIVE_STEP_MIN_CTAS) hive_step_kernel(EnvArgs a) {
+    __shared__ StepShared s;
+    HIVE_TRACE_SCOPE(0, a);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = blockIdx.x * HIVE_ENCODE_WARPS + warp;
-    if (blockIdx.x == 0 && tid < 8) a.bq.counters[tid] = 0;     // the queues are consumed: reset for the next step
-    if (g >= a.n) return;
-    // every global read of this game is issued before the first use (also for games this launch skips)
-    GameRec* rec = a.recs + g;
-    const EncodeIn in = encode_fetch(a.scratch[g], lane);
-    const uint4 h4 = reinterpret_cast<const uint4*>(rec->hist)[lane < 20 ? lane : 0];
-    WarpScratch& sm = scratch[warp];
-    uint32_t* bits = a.bits + (size_t)g * BITS_WORDS;
-    if (lane < 20) reinterpret_cast<uint4*>(&sm.hist[0][0][0][0])[lane] = h4;    // consumed before the exit test: keeps the load up here
-    if (!(in.head.z & 1u)) {
-        if (lane == 0) bits[BITS_LIVE] = 0u;                    // the plane store leaves this game's planes alone
-        return;
-    }
-    __syncwarp();
-    const EvalResult r = eval_encode(sm, in, lane, a.hop_lines);
-    const int turn = in.head.x & 0xFF;
-    if (lane == 0) {
-        uint32_t* w = reinterpret_cast<uint32_t*>(rec);
-        const uint32_t st = (uint32_t)turn | ((uint32_t)r.winner << 8) | ((uint32_t)r.done << 16);
-        w[11] = st; w[14] = (uint32_t)r.n_legal;
-        a.count[g] = r.n_legal;
-        a.status[g] = st;
-        sm.planes[31][0] = (uint32_t)turn; sm.planes[31][1] = 1u;
-    }
-    if (lane < 20) reinterpret_cast<uint4*>(rec->hist)[lane] = reinterpret_cast<const uint4*>(&sm.hist[0][0][0][0])[lane];
-    if (lane < 25) reinterpret_cast<uint2*>(a.legal + (size_t)g * LEGAL_WORDS)[lane] = reinterpret_cast<const uint2*>(sm.legal)[lane];
-    __syncwarp();
-    {   // 1120 B of bit planes -> L2 (70 x 16 B)
-        const uint4* src = reinterpret_cast<const uint4*>(&sm.planes[0][0]);
-        uint4* dst = reinterpret_cast<uint4*>(bits);
+    const int g = blockIdx.x * SG + lane;
+    const uint32_t* geo = a.hop_lines;
+    HIVE_PHASE_BEGIN();
+    if (warp == 0) step_prologue(s, a, lane, g);
+    else if (warp == SW - 1 && lane < 6) (&s.n_flood)[lane == 5 ? 6 : lane] = 0u;      // queue fills, next_task (never in the prologue's warp: it must stay converged)
+    __syncthreads();
+    HIVE_PHASE_MARK(0);
+    if (!s.any_live) return;
+
+    step_stacks(s, warp, lane);
+    __syncthreads();
+    step_pieces(s, warp, lane, geo);
+    __syncthreads();
+    HIVE_PHASE_MARK(1);
+
+    {   // ---- phase 2: one-hive tests (thread <-> queued piece)
+        const int nf = (int)s.n_flood;
+        for (int t0 = tid - lane; t0 < nf; t0 += STEP_THREADS) {               // warp-uniform loop
+            const int t = t0 + lane;
+            bool pushm = false;
+            uint32_t item = 0;
+            int cls = 0;
+            if (t < nf) {
+                item = s.q_flood[t];
+                const int slot = item & 31, p = (item >> 5) & 31;
+                if (flood_graph(s, slot, p)) atomicOr(&s.pin[slot], 1u << p);
+                else if ((item >> 10) & 1u) { pushm = true; cls = move_class(piece_type_of(p >= 11 ? p - 11 : p)); }
+            }
+            // survivors that want a move search join the move queues
 #pragma unroll
-        for (int i = 0; i < 3; i++) { const int t = lane + 32 * i; if (t < BITS_WORDS / 4) dst[t] = src[t]; }
+            for (int c = 0; c < 4; c++) queue_push(&s.n_mv[c], s.q_mv[c], pushm && cls == c, item, lane);
+        }
     }
+    __syncthreads();
+    HIVE_PHASE_MARK(2);
+    for (int i = tid; i < LEGAL_WORDS * SG; i += STEP_THREADS) (&s.legal[0][0])[i] = 0u;    // the hive graph is dead: its space becomes the legal mask
+
+    {   // ---- phase 3: move searches, warps homogeneous in piece class (thread <-> queued piece)
+        const int n0 = (int)s.n_mv[0], n1 = (int)s.n_mv[1], n2 = (int)s.n_mv[2], n3 = (int)s.n_mv[3];
+        const int s1 = (n0 + 31) & ~31, s2 = s1 + ((n1 + 31) & ~31), s3 = s2 + ((n2 + 31) & ~31), total = s3 + n3;
+        for (int t = tid; t < total; t += STEP_THREADS) {
+            int cls, idx, cnt;
+            if (t < s1) { cls = 0; idx = t; cnt = n0; }
+            else if (t < s2) { cls = 1; idx = t - s1; cnt = n1; }
+            else if (t < s3) { cls = 2; idx = t - s2; cnt = n2; }
+            else { cls = 3; idx = t - s3; cnt = n3; }
+            if (idx < cnt) {
+                const uint32_t item = s.q_mv[cls][idx];
+                const int slot = item & 31, p = (item >> 5) & 31;
+                BB occ;
+#pragma unroll
+                for (int i = 0; i < 5; i++) occ.w[i] = s.occ[i][slot];
+                const BB mv = eval_moves(s.info[p][slot], occ, p, geo);
+                if (bb_any(mv)) {
+#pragma unroll
+                    for (int i = 0; i < 5; i++) s.rows[p][i][slot] = mv.w[i];
+                    atomicOr(&s.nonempty[slot], 1u << p);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    HIVE_PHASE_MARK(3);
+
+    const uint32_t flags = s.flags[lane];
+    const bool live = flags & 1u;
+    const uint32_t hd = s.head[lane];
+    EncodeCtx e;
+    {   // ---- phase 4: outputs (lane <-> game; the warps split the outputs)
+        e.lane = lane; e.turn = hd & 0xFF; e.cq_w = (hd >> 8) & 0xFF; e.cq_b = (hd >> 16) & 0xFF;
+        e.side = (e.turn & 1) ? 0 : 1;
+        e.live = live; e.push = (flags >> 1) & 1u;
+        e.pin = s.pin[lane];
+        e.has_row = live ? s.nonempty[lane] : 0u;
+        e.placeable = live ? s.placeable[lane] : 0u;
+        e.bits = a.bits + (size_t)g * BITS_WORDS; e.rec = a.recs + g;
+    }
+    // the outputs are cut into 19 tasks of very different length (longest first); a warp takes the next one when it is free
+    for (;;) {
+        uint32_t task = 0;
+        if (lane == 0) task = atomicAdd(&s.next_task, 1u);
+        task = __shfl_sync(FULL, task, 0);
+        if (task >= 19u) break;
+        {
+            switch (task) {
+                case 0: encode_misc_planes(s, e, geo); break;
+                case 1: case 2: case 3: encode_legal(s, e, 7 + (int)task, 8 + (int)task); break;          // Ants
+                case 4: encode_mobility<1, 0>(s, e, geo); break;
+                case 5: encode_mobility<1, 1>(s, e, geo); break;
+                case 6: encode_mobility<0, 0>(s, e, geo); break;
+                case 7: encode_mobility<0, 1>(s, e, geo); break;
+                case 8: case 9: case 10: encode_legal(s, e, (int)task - 3, (int)task - 2); break;         // Grasshoppers
+                case 11: case 12: encode_legal(s, e, (int)task - 8, (int)task - 7); break;                // Spiders
+                case 13: case 14: encode_legal(s, e, (int)task - 12, (int)task - 11); break;              // Beetles
+                case 15: encode_legal(s, e, 0, 1); break;                                                 // Queen
+                case 16: encode_piece_planes(s, e, 0); break;
+                case 17: encode_piece_planes(s, e, 1); break;
+                default: encode_history(s, e); break;
+            }
+        }
+    }
+    __syncthreads();
+    HIVE_PHASE_MARK(4);
+
+    if (live && warp < 2) {   // ---- phase 5: legal mask, count, status, record header
+        uint2* out = reinterpret_cast<uint2*>(a.legal + (size_t)g * LEGAL_WORDS);
+        const int i0 = warp ? 13 : 0, i1 = warp ? 25 : 13;
+        for (int i = i0; i < i1; i++) out[i] = make_uint2(s.legal[2 * i][lane], s.legal[2 * i + 1][lane]);
+        if (warp == 0) {
+            const int turn = hd & 0xFF, prev_winner = (flags >> 8) & 0xFF;
+            const uint32_t iw = s.info[0][lane], ib = s.info[11][lane];
+            // terminal test (move_checker.py:140-165): a queen on the board with six occupied neighbours
+            const bool ws = (iw & 0xFFu) != HAND && ((iw >> 16) & 63u) == 63u, bs = (ib & 0xFFu) != HAND && ((ib >> 16) & 63u) == 63u;
+            const int done = ws || bs;
+            const int winner = (ws && bs) ? prev_winner : ws ? 2 : bs ? 1 : prev_winner;
+            const uint32_t n_legal = s.nlegal[lane];
+            const uint32_t st = (uint32_t)turn | ((uint32_t)winner << 8) | ((uint32_t)done << 16);
+            uint4* r4 = reinterpret_cast<uint4*>(a.recs + g);
+            r4[0] = make_uint4(s.pc[0][lane], s.pc[1][lane], s.pc[2][lane], s.pc[3][lane]);
+            r4[1] = make_uint4(s.pc[4][lane], s.pc[5][lane], s.pc[6][lane], s.pc[7][lane]);
+            r4[2] = make_uint4(s.pc[8][lane], s.pc[9][lane], s.pc[10][lane], st);
+            r4[3] = make_uint4(s.episode[lane], s.steps[lane], n_legal, 0u);
+            a.count[g] = (int32_t)n_legal;
+            a.status[g] = st;
+        }
+    }
+    HIVE_PHASE_MARK(5);
 }
 
 // ---- kernel 5: bit planes -> bf16 CHW planes [56][144] per game, through the TMA (persistent: the grid is capped in

@@ -18,10 +18,8 @@ struct hive_env {
     int32_t* count = nullptr;
     uint32_t* status = nullptr;
     uint16_t* planes = nullptr;
-    hive::GameScratch* scratch = nullptr;
     uint32_t* bits[2] = {nullptr, nullptr};   // bit planes, encode kernel -> plane-store kernel (double-buffered over steps)
     static constexpr int MAX_SUB = 16;
-    hive::BatchQueues bq[MAX_SUB] = {};
     int n_sub = 1;                  // the batch is cut into n_sub slices whose kernel chains overlap on side streams
     int sm_count = 148, store_ctas_per_sm = 2;   // the persistent plane-store kernels together keep this many CTAs per SM
     int host_slices = 2;            // slices of a step the host launches kernel by kernel (graph replays use n_sub)
@@ -29,7 +27,6 @@ struct hive_env {
     cudaEvent_t encoded_ev[MAX_SUB] = {}, stored_ev[MAX_SUB][2] = {};
     cudaEvent_t fork_ev = nullptr, join_ev[MAX_SUB] = {};
     cudaEvent_t results_ev = nullptr;   // behind the result downloads of the last hive_step_host_async (hive_wait_results)
-    int search_blocks = 0;
     // the step of the resident rollout loop is replayed from a CUDA graph (same arguments every step)
     struct StepGraph { int op = -1; const void* actions = nullptr; const void* mask = nullptr; void* chosen = nullptr;
                        uint64_t seed = 0; int max_turn = 0, auto_reset = 0; cudaGraphExec_t exec = nullptr; } graph, multi_graph;
@@ -42,7 +39,6 @@ struct hive_env {
     cudaGraphExec_t slice_exec[MAX_SUB] = {};   // multi-step rollout: one graph per slice, each on its own stream
     bool skip_planes = false;       // measurement aid (HIVE_B200_EXPERIMENT_SKIP_PLANES): results are then incomplete
     int split_graphs = 1;
-    int pdl_mask = 0;               // HIVE_B200_PDL: programmatic dependent launch per chain kernel, off by default (measured: no gain) (bit 0 analyse .. 3 encode; 16: also when encode waits on a store event)
     int use_graph = 1;
     int32_t* d_actions[2] = {nullptr, nullptr};
     int act_flip = 0;

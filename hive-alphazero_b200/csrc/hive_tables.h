@@ -4,6 +4,7 @@
 //   [GEO_RANK, +144)  per cell: rank of each of its six neighbours in tile.adjacent_tiles order, 3 bits per direction
 //                     (board_tiles order: q descending, then r ascending; tile.py:111-123, :156-203)
 //   [GEO_NBR , +288)  per cell two words: the six neighbour cells as bytes (d0..d3 | d4, d5), torus of tile.py:114-121
+//   [GEO_NBRMASK, +720) 144 x 5 words: the six neighbours of every cell as a board
 // (offsets GEO_* are defined next to the device code that uses them, in hive_core.cuh; include that first)
 #pragma once
 #include <stdint.h>
@@ -40,6 +41,7 @@ inline void build_geometry_tables(std::vector<uint32_t>& t) {
         t[GEO_RANK + c] = ranks;
         t[GEO_NBR + 2 * c] = (uint32_t)nb[0] | ((uint32_t)nb[1] << 8) | ((uint32_t)nb[2] << 16) | ((uint32_t)nb[3] << 24);
         t[GEO_NBR + 2 * c + 1] = (uint32_t)nb[4] | ((uint32_t)nb[5] << 8);
+        for (int i = 0; i < 6; i++) t[GEO_NBRMASK + c * 5 + (nb[i] >> 5)] |= 1u << (nb[i] & 31);
     }
 }
 

@@ -165,10 +165,10 @@ class HiveBatch:
     def launches(self): return lib().hive_launch_count(self._h)
 
     def profile_step(self, seed, max_turn=C.MAX_GAME_LENGTH):
-        """One rollout step timed kernel by kernel: dict(analyse, flood, moves, encode, planes) in ms."""
-        ms = (ctypes.c_float * 5)()
+        """One rollout step timed kernel by kernel: dict(step, planes) in ms."""
+        ms = (ctypes.c_float * 2)()
         check(lib().hive_profile_step(self._h, seed, max_turn, ms), "hive_profile_step")
-        return dict(zip(("analyse", "flood", "moves", "encode", "planes"), [float(x) for x in ms]))
+        return dict(zip(("step", "planes"), [float(x) for x in ms]))
 
     def probe_write_stream(self, reps=20):
         """GB/s of a write-only stream over this batch's planes arena (roofline aid; clobbers the planes)."""

@@ -123,7 +123,7 @@ void* hive_dev_planes(hive_env_t* h);    /* [n][56][144] bf16                   
 long long hive_launch_count(const hive_env_t* h);
 /* last kernel's device time in ms measured with events on the handle's stream (0 if timing is
  * off); hive_set_timing(h,1) enables per-launch events. */
-/* one rollout step with events between its five kernels: ms[5] = analyse, flood, moves, encode, planes */
+/* one rollout step with events around its two kernels: ms[2] = step kernel, plane store */
 int hive_profile_step(hive_env_t* h, uint64_t seed, int max_turn, float* ms);
 int hive_set_timing(hive_env_t* h, int on);
 /* Roofline aid: GB/s of a write-only stream (16-byte stores, nothing read) over this batch's planes arena,

@@ -1,7 +1,7 @@
 """Un-sliced environment step for the ncu --set full capture (whole 16,384-game batch per kernel, so the 264 MB of
 planes do not fit the 126 MB L2 and dram__bytes_* are the step's real HBM traffic).  The games are advanced
 `warm` random steps first (positions of every game age), then the CUDA profiler range covers `reps` steps issued
-by hive_profile_step (analyse -> flood -> moves -> encode -> planes, one launch each, on one stream):
+by hive_profile_step (step kernel -> plane store, one launch each, on one stream):
 
     ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:hive_ \
         -o gpurun_out/step python profiles/step_probe.py

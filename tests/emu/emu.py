@@ -21,7 +21,8 @@ def build(force=False):
     newest = max(os.path.getmtime(s) for s in srcs)
     if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < newest:
         cpps = [s for s in srcs if s.startswith(_HERE) and s.endswith(".cpp")]
-        subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", _LIB] + cpps)
+        defs = os.environ.get("HIVE_EMU_DEFS", "").split()          # e.g. -DHIVE_STEP_WARPS=6: emulate a variant build
+        subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", _LIB] + defs + cpps)
     return _LIB
 
 

@@ -13,10 +13,7 @@ static void build_lines() {
     if (g_lines.empty()) build_geometry_tables(g_lines);
 }
 
-static void k_analyse(void* p) { hive_analyse_kernel(*(EnvArgs*)p); }
-static void k_flood(void* p) { hive_flood_kernel(*(EnvArgs*)p); }
-static void k_moves(void* p) { hive_moves_kernel(*(EnvArgs*)p); }
-static void k_encode(void* p) { hive_encode_kernel(*(EnvArgs*)p); }
+static void k_step(void* p) { hive_step_kernel(*(EnvArgs*)p); }
 static void k_planes(void* p) { hive_planes_kernel(*(EnvArgs*)p); }
 
 extern "C" {
@@ -31,35 +28,13 @@ int emu_env_run(void* recs, uint32_t* legal, int32_t* count, uint32_t* status, u
     a.actions = actions; a.mask = mask; a.chosen = chosen; a.hop_lines = g_lines.data();
     a.seed = seed; a.n = n; a.op = op; a.max_turn = max_turn; a.auto_reset = auto_reset;
     a.g_offset = 0; a.n_total = n;
-    static std::vector<GameScratch> scratch;
-    static std::vector<uint32_t> counters(8, 0), qflood, qmv[4];
-    const int groups = (n + GROUP - 1) / GROUP;
-    if ((int)scratch.size() < n) scratch.resize(n);
-    if ((int)qflood.size() < n * N_PIECE) qflood.resize(n * N_PIECE);
-    for (int c = 0; c < 4; c++) if ((int)qmv[c].size() < n * 6) qmv[c].resize(n * 6);
     static std::vector<uint32_t> bits;
     if ((int)bits.size() < n * BITS_WORDS) bits.resize((size_t)n * BITS_WORDS);
-    a.scratch = scratch.data(); a.bits = bits.data();
-    a.bq.counters = counters.data(); a.bq.flood = qflood.data();
-    for (int c = 0; c < 4; c++) a.bq.mv[c] = qmv[c].data();
-    for (int b = 0; b < groups; b++) {
-        int rc = emu::run_block(k_analyse, &a, b, GROUP * 32, sched_seed + (uint64_t)b);
-        if (rc) return rc;
-    }
-    const int search_blocks = 3;        // fewer blocks than work: exercises the grid-stride loops
-    emu::g_gridDim.x = search_blocks;
-    for (int b = 0; b < search_blocks; b++) {
-        int rc = emu::run_block(k_flood, &a, b, SEARCH_THREADS, sched_seed + 1000 + (uint64_t)b);
-        if (rc) return rc;
-    }
-    for (int b = 0; b < search_blocks; b++) {
-        int rc = emu::run_block(k_moves, &a, b, SEARCH_THREADS, sched_seed + 1500 + (uint64_t)b);
-        if (rc) return rc;
-    }
-    const int enc_blocks = (n + HIVE_ENCODE_WARPS - 1) / HIVE_ENCODE_WARPS;
-    emu::g_gridDim.x = enc_blocks;
-    for (int b = 0; b < enc_blocks; b++) {
-        int rc = emu::run_block(k_encode, &a, b, HIVE_ENCODE_WARPS * 32, sched_seed + 2000 + (uint64_t)b);
+    a.bits = bits.data();
+    const int blocks = (n + SG - 1) / SG;
+    emu::g_gridDim.x = blocks;
+    for (int b = 0; b < blocks; b++) {
+        int rc = emu::run_block(k_step, &a, b, STEP_THREADS, sched_seed + (uint64_t)b);
         if (rc) return rc;
     }
     int store_blocks = (n + HIVE_STORE_WARPS - 1) / HIVE_STORE_WARPS;

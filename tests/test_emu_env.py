@@ -88,20 +88,24 @@ def test_noop_and_masked_reset():
     _compare(e, 1, o)
 
 
-def test_batch_of_nine_games_two_ctas():
-    """9 games = one full 8-game CTA + a partial one: exercises the CTA-wide work queues."""
-    n = 9
+def test_batch_of_forty_games_two_ctas():
+    """40 games = one full 32-game CTA + a partial one, the games of different ages (lane <-> game in the analyse and
+    encode phases: every lane of a warp sits at another position; CTA-wide flood / move queues shared by 32 games)."""
+    n = 40
     e = EmuBatch(n, sched_seed=11)
     oracles = [OracleEnv() for _ in range(n)]
     rngs = [np.random.RandomState(500 + g) for g in range(n)]
-    for _ in range(56):
+    for ply in range(62):
         actions = np.full(n, -2, dtype=np.int32)
         for g, o in enumerate(oracles):
-            _compare(e, g, o)
-            if o.game_is_over() or o.turn >= 55:
+            if ply % 3 == 0 or g < 3:
+                _compare(e, g, o)
+            if ply < g % 7 or o.game_is_over() or o.turn >= 55:     # late starters; finished games idle (NOOP)
                 continue
             acts = o.actions()
             a = int(acts[rngs[g].randint(len(acts))]) if len(acts) else -1
             o.move(a)
             actions[g] = a
         e.step(actions)
+    for g, o in enumerate(oracles):
+        _compare(e, g, o)
