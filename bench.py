@@ -45,12 +45,13 @@ def parse():
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--max-turn", type=int, default=55)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--min-window-ms", type=float, default=50.0, help="the K-step block is repeated until the timed region is this long")
     ap.add_argument("--chunk", type=int, default=50, help="rollout steps per CUDA-graph launch (1 = one launch per step)")
     ap.add_argument("--no-selfplay", action="store_true", help="skip the self-play (configs[2]) side measurement")
     ap.add_argument("--selfplay-games", type=int, default=2048)
     ap.add_argument("--selfplay-sims", type=int, default=50)
     ap.add_argument("--selfplay-moves", type=int, default=2)
-    ap.add_argument("--e2e-parts", type=int, default=3, help="host-driven path: pipelined parts of the batch (each on its own stream)")
+    ap.add_argument("--e2e-parts", type=int, default=0, help="host-driven path: parts of the batch, each its own handle and streams (0: two per driver thread)")
     return ap.parse_args()
 
 
@@ -271,13 +272,10 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    if world > 1:
-        # the ranks of one box share its host cores: give the host policy pool of every rank its share
-        try:
-            cores = len(os.sched_getaffinity(0))
-        except AttributeError:
-            cores = os.cpu_count() or 1
-        os.environ.setdefault("HIVE_B200_HOST_THREADS", str(max(1, min(16, cores // world))))
+    try:
+        host_cores = len(os.sched_getaffinity(0))       # the ranks of one box share its host cores
+    except AttributeError:
+        host_cores = os.cpu_count() or 1
     hive_b200.build()
     n = args.games
     stream = torch.cuda.Stream()
@@ -285,32 +283,48 @@ def main():
     seed = args.seed + 1000003 * rank            # independent games per rank (sharded, no data-path collective)
 
     # ------------------------------------------------------------------ resident (device-timed)
+    # The timed region is at least --min-window-ms long whatever --steps says: the K-step block (one CUDA-graph launch of
+    # min(chunk, K) steps, then single steps up to K) is repeated R times between the two events, and everything is
+    # reported per env step (ms_per_step = window / (K * R); config.timed_steps = K * R).  A 20-step window is 1.5 ms:
+    # one graph-launch latency and a max over ranks of eight such windows would be most of what it measures.
     for _ in range(max(args.warmup, 3)):
         batch.step_random(seed, args.max_turn, True)
-    if args.chunk > 1:
-        batch.step_random_multi(seed, min(args.chunk, args.steps), args.max_turn, True)      # graph capture + one replay, untimed
+    full = min(args.chunk, args.steps)                  # the multi-step graph captured during warm-up
+    if full > 1:
+        batch.step_random_multi(seed, full, args.max_turn, True)      # graph capture + one replay, untimed
+
+    def k_steps():                                      # EXACTLY args.steps steps: graph launches of `full` steps, then single steps
+        done_steps = 0
+        while done_steps < args.steps:
+            if full > 1 and args.steps - done_steps >= full:
+                batch.step_random_multi(seed, full, args.max_turn, True)
+                done_steps += full
+            else:                                       # (a shorter multi-step graph would be captured inside the timed region)
+                batch.step_random(seed, args.max_turn, True)
+                done_steps += 1
+
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     batch.sync()
+    ev0.record(stream)
+    k_steps()                                           # pilot block (untimed for the result): sizes R
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    pilot_ms = max(allmax(ev0.elapsed_time(ev1)), 1e-3)
+    repeats = max(1, int(np.ceil(args.min_window_ms / pilot_ms)))
     steps0 = int(batch.counters()[0].astype(np.int64).sum())
     launches0 = batch.launches
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     torch.cuda.synchronize()
     ev0.record(stream)
-    done_steps = 0
-    full = min(args.chunk, args.steps)                  # the multi-step graph captured during warm-up
-    while done_steps < args.steps:                      # EXACTLY args.steps steps: graph launches of `full` steps, then single steps
-        if full > 1 and args.steps - done_steps >= full:
-            batch.step_random_multi(seed, full, args.max_turn, True)
-            done_steps += full
-        else:                                           # (a shorter multi-step graph would be captured inside the timed region)
-            batch.step_random(seed, args.max_turn, True)
-            done_steps += 1
+    for _ in range(repeats):
+        k_steps()
     ev1.record(stream)
     torch.cuda.synchronize()
     barrier()
     ms = ev0.elapsed_time(ev1)
+    timed_steps = args.steps * repeats
     launches = batch.launches - launches0
     env_steps = int(batch.counters()[0].astype(np.int64).sum()) - steps0
     ms_max = allmax(ms)
@@ -320,7 +334,7 @@ def main():
     # roofline, this rank.  One "launch" of the hot path = one step = step kernel + plane store over
     # the whole batch (cut into slices inside one CUDA graph); algorithmic bytes as in SURVEY 8d / DESIGN.md.
     peak, peak_src = measured_peak()
-    n_steps = max(args.steps, 1)
+    n_steps = max(timed_steps, 1)
     per_launch_bytes = BYTES_PER_ENV_STEP * env_steps / n_steps
     launch_s = ms * 1e-3 / n_steps
     achieved = per_launch_bytes / launch_s / 1e9
@@ -347,62 +361,39 @@ def main():
                 "kernels_per_step": launches / n_steps, "dominant_kernel": dominant}
 
     # ------------------------------------------------------------------ e2e (host buffers)
-    # The same 16,384 games driven from the host through the C ABI: every step reads legal masks,
-    # counts and status D2H into pinned memory, picks the actions on the host (hive_host_pick_actions,
-    # the twin of the device policy) and sends them H2D.  The batch is cut in two halves on two
-    # streams so that the host works on one half while the GPU steps the other.
-    k_e2e = min(args.steps, 1500)
-    halves = []
-    parts = max(1, args.e2e_parts)
-    for hi, cnt in enumerate([n // parts + (1 if i < n % parts else 0) for i in range(parts)]):
-        st = torch.cuda.Stream()
-        hb = hive_b200.HiveBatch(cnt, device=local_rank, stream=st.cuda_stream)
-        mask_h = torch.empty((cnt, 25), dtype=torch.int64).pin_memory()
-        count_h = torch.empty(cnt, dtype=torch.int32).pin_memory()
-        status_h = torch.empty(cnt, dtype=torch.int32).pin_memory()
-        actions_h = torch.empty(cnt, dtype=torch.int32).pin_memory()
-        halves.append(dict(b=hb, st=st, mask_h=mask_h, count_h=count_h, status_h=status_h, actions_h=actions_h,
-                           mask=mask_h.numpy().view(np.uint64), count=count_h.numpy(), status=status_h.numpy().view(np.uint32),
-                           actions=actions_h.numpy(), episodes=np.zeros(cnt, dtype=np.uint32), seed=seed + 77 * (hi + 1), n=cnt))
-        h = halves[-1]                                  # raw addresses once: the loop below runs every ~40 us
-        h["p"] = (mask_h.data_ptr(), count_h.data_ptr(), status_h.data_ptr(), h["episodes"].ctypes.data, actions_h.data_ptr())
-
-    def e2e_half(h):
-        h["b"].wait_results()                                                        # this part's last downloads have landed (its planes may still be in flight)
-        pm, pc, ps, pe, pa = h["p"]
-        hive_b200.host_pick_actions_ptr(h["n"], pm, pc, ps, pe, h["seed"], args.max_turn, pa)
-        # H2D 4 B/game -> kernels -> D2H (200 + 4 + 4) B/game, all queued; the other parts are handled meanwhile
-        h["b"].step_async_ptr(pa, pm, pc, ps)
-
-    for h in halves:
-        h["b"].legal_into(h["mask_h"].data_ptr(), h["count_h"].data_ptr())
-        h["b"].status_packed_into(h["status_h"].data_ptr())
-    for _ in range(5):
-        for h in halves:
-            e2e_half(h)
-    for h in halves:
-        h["b"].sync()
-    s0 = sum(int(h["b"].counters()[0].astype(np.int64).sum()) for h in halves)
+    # The same 16,384 games driven from the host through the C ABI (hive_host_loop_*): every step of a part copies its
+    # actions H2D from pinned memory, runs the kernels and reads legal masks, counts and status back D2H; the policy
+    # (the host twin of the device policy) runs on native driver threads, each walking over its own parts while the GPU
+    # steps the others.  No Python inside the timed loop.
+    # host threads of this rank: one driver thread per part, the rest is the policy pool the drivers share
+    e2e_budget = int(os.environ.get("HIVE_B200_E2E_THREADS", str(max(2, min(16, host_cores // max(world, 1))))))
+    e2e_parts = args.e2e_parts if args.e2e_parts > 0 else max(2, min(4, e2e_budget // 4))
+    os.environ["HIVE_B200_HOST_THREADS"] = str(max(1, e2e_budget - e2e_parts) + 1)      # pool workers + the calling driver
+    loop = hive_b200.HostLoop(n, device=local_rank, parts=e2e_parts, threads=e2e_parts)
+    loop.run(8, seed=seed, max_turn=args.max_turn)                                   # builds the per-part graphs
+    pilot = loop.run(20, seed=seed, max_turn=args.max_turn)
+    k_e2e = max(args.steps, int(np.ceil(20 * args.min_window_ms * 1e-3 / max(pilot["seconds"], 1e-6))))
+    s0 = loop.env_steps()
     barrier()
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(k_e2e):
-        for h in halves:
-            e2e_half(h)
-    for h in halves:
-        h["b"].sync()                                                                # the last step's results have landed
+    r_e2e = loop.run(k_e2e, seed=seed, max_turn=args.max_turn)
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
     barrier()
-    e2e_steps = sum(int(h["b"].counters()[0].astype(np.int64).sum()) for h in halves) - s0
+    e2e_steps = loop.env_steps() - s0
+    dt = r_e2e["seconds"]
     e2e_value = allsum(float(e2e_steps)) / allmax(dt)
+    busy = r_e2e["policy_seconds"] / max(dt, 1e-9)
+    pcie_gbs = (200 + 4 + 4 + 4) * e2e_steps / max(dt, 1e-9) / 1e9
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": (200 + 4 + 4) * n,
-           "steps": k_e2e, "parts": parts, "host_threads_per_rank": int(os.environ.get("HIVE_B200_HOST_THREADS", min(16, os.cpu_count() or 1))),
-           "note": "per-GPU bytes per step of all %d games; %d pipelined parts of the batch on their own streams, host "
-           "picks actions (C-ABI twin of the device policy, host worker pool) for one part while the GPU steps the others; "
-           "planes stay in HBM for the net" % (n, parts)}
-    for h in halves:
-        h["b"].close()
+           "steps": k_e2e, "parts": loop.parts, "host_threads_per_rank": e2e_budget, "driver_threads": loop.threads, "host_cores": host_cores,
+           "policy_share_of_thread_time": busy, "wait_share_of_thread_time": r_e2e["wait_seconds"] / max(dt, 1e-9),
+           "pcie_gbs_this_rank": pcie_gbs,
+           "bound": "host threads" if busy > 0.6 else ("PCIe" if pcie_gbs > 40.0 else "GPU step latency of a part"),
+           "note": "per-GPU bytes per step of all %d games; %d parts of the batch, each its own environment handle, streams and pinned "
+           "buffers (one CUDA-graph launch per part and step: H2D actions, kernels, D2H masks/counts/status); %d native driver "
+           "threads run the policy (C-ABI twin of the device policy) for their parts while the GPU steps the others; planes stay in "
+           "HBM for the net" % (n, loop.parts, loop.threads)}
+    loop.close()
     clocks = sampler.stop()                       # sampled over both timed regions (resident rollout + host-driven e2e)
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N=1)
@@ -422,11 +413,12 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_max / max(args.steps, 1), "higher_is_better": True,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_max / max(timed_steps, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic (random-legal-move games from reset, "
             "counter-based splitmix64 policy; planes emitted as bf16)",
             "config": {"workload": WORKLOAD, "games_per_gpu": n, "max_turn": args.max_turn, "auto_reset": True,
-                       "steps_per_graph_launch": args.chunk,
+                       "steps_per_graph_launch": full, "timed_steps": timed_steps, "repeats_of_steps_block": repeats,
+                       "timed_window_ms": ms_max,
                        "parallelism": "games sharded %d-way, no data-path collective" % world,
                        "cache": "per-GPU working set %.0f MB (state+legal+planes) > 126 MB L2: inputs larger than L2"
                                 % (n * (384 + 200 + 8 + 16128) / 1e6)},

@@ -7,7 +7,7 @@ The package name carries a hyphen; import it as ``import hive_b200`` (root-level
 from . import config
 from ._build import LIB_PATH, build
 from ._capi import ENV_SYMBOLS, MCTS_SYMBOLS, HiveError, SearchError, lib
-from .env import GamePlay, HiveBatch, host_pick_actions, host_pick_actions_ptr
+from .env import GamePlay, HiveBatch, HostLoop, host_pick_actions, host_pick_actions_ptr
 from .mcts import HashEvaluator, HivePlayer, MctsBatch, WaveGraph
 
 
@@ -30,5 +30,5 @@ def __getattr__(name):
         return EvaluatorMatch
     raise AttributeError(name)
 
-__all__ = ["config", "build", "lib", "LIB_PATH", "ENV_SYMBOLS", "HiveError", "GamePlay", "HiveBatch",
+__all__ = ["config", "build", "lib", "LIB_PATH", "ENV_SYMBOLS", "HiveError", "GamePlay", "HiveBatch", "HostLoop",
            "host_pick_actions", "host_pick_actions_ptr", "HivePlayer", "MctsBatch", "WaveGraph", "HashEvaluator", "SearchError", "MCTS_SYMBOLS"]

@@ -13,7 +13,12 @@ ENV_SYMBOLS = [
     "hive_status_host", "hive_status_packed_host", "hive_host_pick_actions", "hive_counters_host", "hive_state_key", "hive_load_state", "hive_dump_state",
     "hive_copy_state", "hive_dev_state", "hive_dev_legal", "hive_dev_count", "hive_dev_status", "hive_dev_planes",
     "hive_launch_count", "hive_profile_step", "hive_probe_write_stream", "hive_set_timing", "hive_last_kernel_ms",
+    "hive_host_loop_create", "hive_host_loop_destroy", "hive_host_loop_parts", "hive_host_loop_threads", "hive_host_loop_part",
+    "hive_host_loop_run", "hive_host_loop_env_steps",
 ]
+# void policy(void* user, int part, int first_game, int n, const u64* mask, const i32* count, const u32* status, i32* actions)
+POLICY_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                             ctypes.c_void_p, ctypes.c_void_p)
 NET_SYMBOLS = ["net_create", "net_destroy", "net_load_conv_host", "net_trunk_forward", "net_launch_count"]
 MCTS_SYMBOLS = [
     "mcts_create", "mcts_destroy", "mcts_set_params", "mcts_set_root_noise_host", "mcts_begin", "mcts_descend",
@@ -74,6 +79,15 @@ def lib():
     L.hive_probe_write_stream.argtypes = [vp, i32, vp]
     L.hive_last_kernel_ms.argtypes = [vp]
     L.hive_last_kernel_ms.restype = ctypes.c_float
+    L.hive_host_loop_create.argtypes = [i32, i32, i32, i32, ctypes.POINTER(vp)]
+    L.hive_host_loop_destroy.argtypes = [vp]
+    L.hive_host_loop_parts.argtypes = [vp]
+    L.hive_host_loop_threads.argtypes = [vp]
+    L.hive_host_loop_part.argtypes = [vp, i32, vp]
+    L.hive_host_loop_part.restype = vp
+    L.hive_host_loop_run.argtypes = [vp, i32, u64, i32, vp, vp, vp, vp, vp]
+    L.hive_host_loop_env_steps.argtypes = [vp]
+    L.hive_host_loop_env_steps.restype = ctypes.c_longlong
     f64p, dbl = vp, ctypes.c_double
     L.mcts_create.argtypes = [vp, i32, i32, ctypes.POINTER(vp)]
     L.mcts_destroy.argtypes = [vp]

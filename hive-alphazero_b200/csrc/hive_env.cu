@@ -246,9 +246,11 @@ int hive::create_env(int n_games, int device, void* stream, int slices, hive_env
         CUDA_TRY(cudaMemsetAsync(h->bits[b], 0, n * BITS_WORDS * 4, h->stream));
     }
     CUDA_TRY(cudaMalloc(&h->recs, n * sizeof(GameRec)));
-    CUDA_TRY(cudaMalloc(&h->legal, n * LEGAL_WORDS * 4));
-    CUDA_TRY(cudaMalloc(&h->count, n * 4));
-    CUDA_TRY(cudaMalloc(&h->status, n * 4));
+    // legal masks, counts and status words sit in ONE arena (208 B per game) so that the host-driven step brings them
+    // down with a single copy
+    CUDA_TRY(cudaMalloc(&h->legal, n * (LEGAL_WORDS * 4 + 8)));
+    h->count = reinterpret_cast<int32_t*>(h->legal + n * LEGAL_WORDS);
+    h->status = reinterpret_cast<uint32_t*>(h->count + n);
     CUDA_TRY(cudaMalloc(&h->planes, n * HIVE_PLANES_ELEMS * 2));
     {
         const char* e = getenv("HIVE_B200_SLICES");
@@ -316,7 +318,7 @@ int hive_destroy(hive_env_t* h) {
     if (h->multi_graph.exec && h->multi_graph.exec != h->slice_exec[0]) cudaGraphExecDestroy(h->multi_graph.exec);
     for (int s = 0; s < hive_env::MAX_SUB; s++) if (h->slice_exec[s]) cudaGraphExecDestroy(h->slice_exec[s]);
     if (h->host_graph.exec) cudaGraphExecDestroy(h->host_graph.exec);
-    cudaFree(h->recs); cudaFree(h->legal); cudaFree(h->count); cudaFree(h->status); cudaFree(h->planes); cudaFree(h->bits[0]); cudaFree(h->bits[1]);
+    cudaFree(h->recs); cudaFree(h->legal); cudaFree(h->planes); cudaFree(h->bits[0]); cudaFree(h->bits[1]);
     for (int s = 0; s < h->n_sub; s++) {
         if (h->sub_stream[s]) cudaStreamDestroy(h->sub_stream[s]);
         if (h->store_stream[s]) cudaStreamDestroy(h->store_stream[s]);
@@ -398,13 +400,26 @@ static bool is_pinned_host(const void* p) {
 // hive_wait_results returns while the 16 KB/game of planes are still being written (hive_sync waits for those too).
 static int queue_host_step(hive_env* h, int32_t* d, const int32_t* actions, uint64_t* mask, int32_t* count, uint32_t* packed_status,
                            int slices) {
-    CUDA_TRY(cudaMemcpyAsync(d, actions, (size_t)h->n * 4, cudaMemcpyHostToDevice, h->stream));
+    // page-locked actions are read by the step kernel straight from host memory (4 B per game, coalesced: one PCIe read
+    // per warp) instead of through a copy node of their own; pageable ones are staged
+    const int32_t* act = actions;
+    if (!is_pinned_host(actions)) {
+        CUDA_TRY(cudaMemcpyAsync(d, actions, (size_t)h->n * 4, cudaMemcpyHostToDevice, h->stream));
+        act = d;
+    }
     int deferred = 0;
-    int rc = launch_env_kernels(h, OP_STEP, d, nullptr, 0, 0, 0, nullptr, 1, slices > 0 ? slices : h->host_slices, &deferred);
+    int rc = launch_env_kernels(h, OP_STEP, act, nullptr, 0, 0, 0, nullptr, 1, slices > 0 ? slices : h->host_slices, &deferred);
     if (rc) return rc;
-    if (mask) CUDA_TRY(cudaMemcpyAsync(mask, h->legal, (size_t)h->n * LEGAL_WORDS * 4, cudaMemcpyDeviceToHost, h->stream));
-    if (count) CUDA_TRY(cudaMemcpyAsync(count, h->count, (size_t)h->n * 4, cudaMemcpyDeviceToHost, h->stream));
-    if (packed_status) CUDA_TRY(cudaMemcpyAsync(packed_status, h->status, (size_t)h->n * 4, cudaMemcpyDeviceToHost, h->stream));
+    const size_t n = (size_t)h->n;
+    if (mask && count && packed_status && reinterpret_cast<uint8_t*>(count) == reinterpret_cast<uint8_t*>(mask) + n * LEGAL_WORDS * 4 &&
+        reinterpret_cast<uint8_t*>(packed_status) == reinterpret_cast<uint8_t*>(count) + n * 4) {
+        // the caller's buffers are laid out like the device arena: one download
+        CUDA_TRY(cudaMemcpyAsync(mask, h->legal, n * (LEGAL_WORDS * 4 + 8), cudaMemcpyDeviceToHost, h->stream));
+    } else {
+        if (mask) CUDA_TRY(cudaMemcpyAsync(mask, h->legal, n * LEGAL_WORDS * 4, cudaMemcpyDeviceToHost, h->stream));
+        if (count) CUDA_TRY(cudaMemcpyAsync(count, h->count, n * 4, cudaMemcpyDeviceToHost, h->stream));
+        if (packed_status) CUDA_TRY(cudaMemcpyAsync(packed_status, h->status, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    }
     cudaStreamCaptureStatus cap_state = cudaStreamCaptureStatusNone;
     CUDA_TRY(cudaStreamIsCapturing(h->stream, &cap_state));
     CUDA_TRY(cudaEventRecordWithFlags(h->results_ev, h->stream,
@@ -643,8 +658,9 @@ static inline uint64_t host_splitmix64(uint64_t x) {
     return x ^ (x >> 31);
 }
 
-static void pick_range(int g0, int g1, int n, const uint64_t* mask, const int32_t* count, const uint32_t* packed_status,
-                       uint32_t* episodes, uint64_t seed, int max_turn, int32_t* actions) {
+}  // extern "C"
+void hive::pick_range(int g0, int g1, int n, const uint64_t* mask, const int32_t* count, const uint32_t* packed_status,
+                      uint32_t* episodes, uint64_t seed, int max_turn, int32_t* actions) {
     for (int g = g0; g < g1; g++) {
         const uint32_t st = packed_status[g];
         const int turn = st & 0xFF, done = (st >> 16) & 0xFF;
@@ -667,6 +683,7 @@ static void pick_range(int g0, int g1, int n, const uint64_t* mask, const int32_
         actions[g] = a;
     }
 }
+extern "C" {
 
 // A small persistent worker pool for the host-side policy twin (the caller's thread takes a share too).
 // The host-driven loop calls it every few tens of microseconds, far below the wake-up latency of a sleeping

@@ -55,6 +55,9 @@ struct hive_env {
 namespace hive {
 // hive_create with an explicit slice count (<= 0: default)
 int create_env(int n_games, int device, void* stream, int slices, hive_env** out);
+// the random policy's host twin for games [g0, g1) of a batch of n (hive_host_pick_actions), on the calling thread
+void pick_range(int g0, int g1, int n, const uint64_t* mask, const int32_t* count, const uint32_t* packed_status,
+                uint32_t* episodes, uint64_t seed, int max_turn, int32_t* actions);
 // sets the thread-local error text and returns `code`
 int fail(int code, const std::string& msg);
 // one environment step / evaluation over the whole batch (see hive_env_kernel.cuh for `op`)

@@ -30,9 +30,20 @@ class HiveBatch:
         check(lib().hive_create(self.n, self.device, stream, ctypes.byref(h)), "hive_create")
         self._h = h
 
+    @classmethod
+    def borrowed(cls, handle, device=0):
+        """View of a hive_env_t* owned by someone else (a part of a HostLoop): never destroyed from here."""
+        b = cls.__new__(cls)
+        b._h = ctypes.c_void_p(handle)
+        b._owned = False
+        b.n = lib().hive_num_games(b._h)
+        b.device = int(device)
+        return b
+
     def close(self):
         if getattr(self, "_h", None):
-            lib().hive_destroy(self._h)
+            if getattr(self, "_owned", True):
+                lib().hive_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -193,6 +204,64 @@ def host_pick_actions_ptr(n, mask_ptr, count_ptr, status_ptr, episodes_ptr, seed
     microseconds per access)."""
     check(lib().hive_host_pick_actions(n, mask_ptr, count_ptr, status_ptr, episodes_ptr, seed, max_turn, actions_ptr),
           "hive_host_pick_actions")
+
+
+class HostLoop:
+    """The host-driven game loop of a whole batch inside the library (hive_host_loop_*, include/hive_b200.h): the batch is
+    cut into parts, native driver threads wait for a part's legal masks / counts / status, run the policy and launch the
+    part's next step while the GPU steps the other parts (woker/self_play.py:54-56,116-193 is the loop this replaces).
+    policy=None: the host twin of the on-device random policy; else a callable
+    policy(part, first_game, mask u64[n,25], count i32[n], status u32[n], actions i32[n]) writing `actions` in place
+    (called from the driver threads; Python callables serialise on the interpreter lock)."""
+
+    def __init__(self, n_games, device=0, parts=8, threads=4):
+        from ._capi import POLICY_FN
+        self._fn_type = POLICY_FN
+        self.n = int(n_games)
+        self.device = int(device)
+        h = ctypes.c_void_p()
+        check(lib().hive_host_loop_create(self.n, int(device), int(parts), int(threads), ctypes.byref(h)), "hive_host_loop_create")
+        self._h = h
+        self.parts = lib().hive_host_loop_parts(h)
+        self.threads = lib().hive_host_loop_threads(h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().hive_host_loop_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def env_steps(self):
+        return int(lib().hive_host_loop_env_steps(self._h))
+
+    def part(self, i):
+        """(borrowed HiveBatch view of part i, index of its first game in the batch)"""
+        first = ctypes.c_int()
+        eh = lib().hive_host_loop_part(self._h, int(i), ctypes.byref(first))
+        if not eh:
+            raise IndexError(i)
+        return HiveBatch.borrowed(eh, self.device), first.value
+
+    def run(self, n_steps, seed=0, max_turn=C.MAX_GAME_LENGTH, policy=None):
+        """n_steps steps of every part.  Returns dict(seconds, policy_seconds, wait_seconds)."""
+        cb = None
+        if policy is not None:
+            def tramp(user, part, first, n, mask, count, status, actions):
+                m = np.ctypeslib.as_array(ctypes.cast(mask, ctypes.POINTER(ctypes.c_uint64)), shape=(n, 25))
+                c = np.ctypeslib.as_array(ctypes.cast(count, ctypes.POINTER(ctypes.c_int32)), shape=(n,))
+                st = np.ctypeslib.as_array(ctypes.cast(status, ctypes.POINTER(ctypes.c_uint32)), shape=(n,))
+                a = np.ctypeslib.as_array(ctypes.cast(actions, ctypes.POINTER(ctypes.c_int32)), shape=(n,))
+                policy(part, first, m, c, st, a)
+            cb = self._fn_type(tramp)
+        sec, pol, wait = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+        check(lib().hive_host_loop_run(self._h, int(n_steps), int(seed), int(max_turn), cb, None,
+                                       ctypes.byref(sec), ctypes.byref(pol), ctypes.byref(wait)), "hive_host_loop_run")
+        return {"seconds": sec.value, "policy_seconds": pol.value, "wait_seconds": wait.value}
 
 
 class _State:

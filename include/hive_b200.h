@@ -98,6 +98,32 @@ int hive_status_packed_host(hive_env_t* h, uint32_t* packed);
  * x = splitmix64(seed ^ (g + n*episodes[g])<<32 ^ turn).  Pure host code, no GPU work. */
 int hive_host_pick_actions(int n, const uint64_t* mask, const int32_t* count, const uint32_t* packed_status,
                            uint32_t* episodes, uint64_t seed, int max_turn, int32_t* actions);
+/* ---- the host-driven game loop inside the library ----------------------------------------------------------------
+ * The reference's self-play worker is a host loop around GamePlay: actions() -> policy -> move()
+ * (woker/self_play.py:54-56,116-193).  hive_host_loop_* runs that loop natively for a whole batch: the batch is cut
+ * into n_parts parts (each a hive_env of its own with page-locked staging buffers; every step of a part is ONE CUDA
+ * graph launch: H2D actions -> step -> D2H legal masks / counts / status), and n_threads driver threads walk over
+ * their parts: wait for the part's downloads, call the policy, launch the part's next step -- while the GPU steps the
+ * other parts.  policy == NULL: the host twin of the on-device random policy (hive_host_pick_actions, per-part seed
+ * seed + 77*(part+1)).  A policy gets the part's host buffers (mask [n][25] u64, count [n], status [n] packed
+ * turn | winner<<8 | done<<16) and writes actions[n] (an action id, -1 pass, HIVE_RESET, HIVE_NOOP); it is called
+ * concurrently for different parts from different threads. */
+typedef struct hive_host_loop hive_host_loop_t;
+typedef void (*hive_policy_fn)(void* user, int part, int first_game, int n, const uint64_t* mask, const int32_t* count,
+                               const uint32_t* packed_status, int32_t* actions);
+int hive_host_loop_create(int n_games, int device, int n_parts, int n_threads, hive_host_loop_t** out);
+int hive_host_loop_destroy(hive_host_loop_t* l);
+int hive_host_loop_parts(const hive_host_loop_t* l);
+int hive_host_loop_threads(const hive_host_loop_t* l);
+/* the environment of one part (its games are [first_game, first_game + hive_num_games) of the batch) */
+hive_env_t* hive_host_loop_part(hive_host_loop_t* l, int part, int* first_game);
+/* n_steps steps of every part; returns when all results and planes have landed.  seconds: wall time of the loop;
+ * policy_seconds / wait_seconds: mean time a driver thread spent inside the policy / waiting for downloads. */
+int hive_host_loop_run(hive_host_loop_t* l, int n_steps, uint64_t seed, int max_turn, hive_policy_fn policy, void* user,
+                       double* seconds, double* policy_seconds, double* wait_seconds);
+/* sum of the env-step counters of all parts (difference across a run = the steps it made) */
+long long hive_host_loop_env_steps(hive_host_loop_t* l);
+
 /* counters: env steps and episodes per slot */
 int hive_counters_host(hive_env_t* h, uint32_t* steps, uint32_t* episodes);
 
