@@ -51,6 +51,11 @@ def parse():
     ap.add_argument("--selfplay-games", type=int, default=2048)
     ap.add_argument("--selfplay-sims", type=int, default=50)
     ap.add_argument("--selfplay-moves", type=int, default=2)
+    ap.add_argument("--no-selfplay-deep", action="store_true", help="skip configs[3] (250 sims, sharded) and configs[4] (evaluator match)")
+    ap.add_argument("--sharded-games", type=int, default=8192, help="configs[3]: games sharded over the ranks")
+    ap.add_argument("--sharded-sims", type=int, default=250)
+    ap.add_argument("--evaluator-games", type=int, default=1024, help="configs[4]: games per GPU")
+    ap.add_argument("--evaluator-sims", type=int, default=500)
     ap.add_argument("--e2e-parts", type=int, default=0, help="host-driven path: parts of the batch, each its own handle and streams (0: two per driver thread)")
     return ap.parse_args()
 
@@ -181,56 +186,163 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def run_selfplay(args, hive_b200, torch, dist, rank, world, local_rank, allsum, allmax, barrier):
-    """BASELINE configs[2]: AlphaZero self-play, 50 sims/move, random-init net, 2,048 concurrent games
-    per GPU.  Reports moves/s and sims/s (whole job) and the tensor-pipe utilisation they imply."""
+def _cpu_mcts_worker(job):
+    """One process of the CPU search baseline: sequential 50-simulation searches of the oracle's HivePlayer restatement
+    (hash-net stand-in for the network) from random positions; returns (moves, seconds)."""
+    seed, budget_s, sims = job
     import numpy as np
+    from oracle.hive_oracle import OracleEnv
+    from oracle.mcts_oracle import MctsOracle, hash_net
+    rng = np.random.RandomState(seed)
+    env = OracleEnv()
+    for _ in range(6 + seed % 12):
+        la = env.actions()
+        env.move(int(la[rng.randint(len(la))]) if len(la) else -1)
+    np.random.seed(seed)
+    moves, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < budget_s:
+        if env.game_is_over() or env.turn >= 55:
+            env.reset()
+        a = MctsOracle(hash_net, sims).action(env)[0]
+        env.move(int(a))
+        moves += 1
+    return moves, time.perf_counter() - t0
+
+
+def cpu_mcts_rate(budget_s, procs, sims=50):
+    """moves/s of the sequential CPU search (oracle/mcts_oracle.py) on `procs` host processes, ~budget_s of wall time."""
+    from concurrent.futures import ProcessPoolExecutor
+    import multiprocessing as mp
+    t0 = time.perf_counter()
+    with ProcessPoolExecutor(procs, mp_context=mp.get_context("spawn")) as ex:
+        res = list(ex.map(_cpu_mcts_worker, [(100 + i, budget_s, sims) for i in range(procs)]))
+    moves = sum(r[0] for r in res)
+    dt = max(r[1] for r in res)
+    return moves / dt, moves, dt, time.perf_counter() - t0
+
+
+def run_selfplay(args, hive_b200, torch, dist, rank, world, local_rank, allsum, allmax, barrier):
+    """BASELINE configs[2], [3], [4] -- AlphaZero self-play (50 sims, 2,048 games per GPU), sharded self-play (250 sims,
+    8,192 games over the ranks) and the evaluator match (500 sims, two nets, 1,024 games per GPU).  Whole-job moves/s,
+    sims/s and the tensor-pipe utilisation they imply; the NCCL weight broadcast (bf16 on the wire, weights reloaded in
+    place) and the all-gather of the packed samples of the timed moves sit INSIDE the timed regions."""
+    import numpy as np
+    from importlib import import_module
+    par = import_module("hive-alphazero_b200.parallel")
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         tf_peak, tf_src = float(peaks["bf16_tflops_sustained"]), "measured sustained (MEASURED_PEAKS.json)"
     except Exception:
         tf_peak, tf_src = 1400.0, "fallback (B200_PROFILING.md ~1.4 PFLOP/s sustained)"
+    hbm_peak, _ = measured_peak()
+    stream = torch.cuda.Stream()
+    n2 = args.selfplay_games
+    _, n3 = par.shard_games(args.sharded_games, world, rank)
+    n4 = args.evaluator_games
     torch.manual_seed(0)
     net = hive_b200.HiveNet().eval().cuda()
-    bcast = 0
-    if dist is not None:
-        from importlib import import_module
-        par = import_module("hive-alphazero_b200.parallel")
-        bcast = par.broadcast_weights(net, src=0)              # NCCL: weights from rank 0
-    folded = hive_b200.FoldedNet(net, device="cuda")
-    stream = torch.cuda.Stream()
-    n, sims = args.selfplay_games, args.selfplay_sims
-    folded.attach_trunk(stream_ptr=stream.cuda_stream, max_boards=n)     # tcgen05 implicit-GEMM trunk (csrc/hive_conv_kernel.cuh)
-    with torch.cuda.stream(stream):
-        sp = hive_b200.SelfPlayBatch(n, sims, hive_b200.LeafEvaluator(folded), device=local_rank,
-                                     stream=stream.cuda_stream, seed=args.seed + rank,
-                                     wave_graph=hive_b200.WaveGraph(stream))     # one search wave = one CUDA graph replay
-        sp.play_moves(1)                                       # warm-up move (autotune, allocations): turn 1 -> 2
-        barrier()
+    torch.manual_seed(1)
+    net_best = hive_b200.HiveNet().eval().cuda()
+    for m in (net, net_best):
+        par.broadcast_weights(m, src=0, wire_dtype=torch.bfloat16)
+    folded = hive_b200.FoldedNet(net, device="cuda").attach_trunk(stream_ptr=stream.cuda_stream, max_boards=max(n2, n3, n4))
+    folded_best = hive_b200.FoldedNet(net_best, device="cuda").attach_trunk(stream_ptr=stream.cuda_stream, max_boards=n4)
+
+    def timed_collectives_before(model, fold):
+        """weight broadcast from rank 0 (bf16 on the wire) + in-place reload of the folded network; seconds, bytes"""
+        t0 = time.perf_counter()
+        nbytes = par.broadcast_weights(model, src=0, wire_dtype=torch.bfloat16) if dist is not None else 0
+        if dist is not None:
+            fold.reload(model)
         torch.cuda.synchronize()
-        r_open = sp.play_moves(5)                              # turns 2..6: the reference's opening schedule (policy read-back + noise mix)
-        r = sp.play_moves(args.selfplay_moves)                 # turns 7..: the search's own move, nothing but the action comes back
-        torch.cuda.synchronize()
-    barrier()
-    gathered = None
-    if dist is not None:
-        par_rows = torch.from_numpy(np.packbits((sp.env.planes_bf16() != 0).reshape(n, -1), axis=1)[:, :991].copy())
-        gathered = int(par.allgather_samples(par_rows, device="cuda").shape[0])     # NCCL: sample all-gather
-    secs = allmax(r["seconds"])
-    moves = allsum(float(r["moves"]))
-    sims_per_s = moves * sims / secs
-    open_moves, open_secs = allsum(float(r_open["moves"])), allmax(r_open["seconds"])
-    return {"workload": "configs[2]: AlphaZero self-play, %d sims/move, model_hive net random-init, %d concurrent games per GPU"
-                        % (sims, n),
-            "moves_per_s": moves / secs, "sims_per_s": sims_per_s, "moves": int(moves), "seconds": secs,
-            "opening_moves_per_s": open_moves / open_secs, "opening_moves": int(open_moves),
-            "full_game_moves_per_s_estimate": 54.0 / (5.0 / (open_moves / open_secs) + 49.0 / (moves / secs)),
-            "waves": int(r["waves"]), "tensor_util": sims_per_s * 6.56e9 / (tf_peak * 1e12 * world),
-            "tensor_peak_tflops": tf_peak, "tensor_peak_source": tf_src,
-            "net": "BN-folded bf16; 39 trunk 3x3 convs = hand-written tcgen05 implicit GEMM (TMA halo tile, TMEM "
-                   "accumulators, fused bias/residual/ReLU); heads = library GEMMs",
-            "trunk_kernel_launches": int(folded.trunk.launches),
-            "weights_broadcast_bytes": int(bcast), "samples_allgathered": gathered}
+        return time.perf_counter() - t0, nbytes
+
+    def selfplay_config(tag, n, sims, skip_plies, open_moves, timed_moves):
+        with torch.cuda.stream(stream):
+            sp = hive_b200.SelfPlayBatch(n, sims, hive_b200.LeafEvaluator(folded), device=local_rank, stream=stream.cuda_stream,
+                                         seed=args.seed + rank, collect=True, wave_graph=hive_b200.WaveGraph(stream))
+            for _ in range(skip_plies):                         # random plies from reset (synthetic random-opening positions)
+                sp.env.step_random(args.seed + 5 + rank, args.max_turn, False)
+            sp.play_moves(1)                                    # warm-up move: graph capture, allocations
+            r_open = None
+            if open_moves:
+                barrier(); torch.cuda.synchronize()
+                r_open = sp.play_moves(open_moves)              # the reference's opening schedule (noise mix, policy read-back)
+            barrier(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            t_bcast, nbytes = timed_collectives_before(net, folded)
+            r = sp.play_moves(timed_moves)                      # search + policy read-back + sample assembly (collect=True)
+            torch.cuda.synchronize()
+            t_pack0 = time.perf_counter()
+            rows = sp.packed_rows(timed_moves)
+            gathered = par.allgather_samples(torch.from_numpy(rows), device="cuda") if dist is not None else torch.from_numpy(rows)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            stats = sp.mcts.tree_stats(256)
+        secs = allmax(t1 - t0)
+        moves = allsum(float(r["moves"]))
+        sims_per_s = moves * sims / secs
+        e_bar, d_bar = stats["edges_per_node"], stats["select_depth"]
+        bytes_per_sim = d_bar * (16 * e_bar + 16) + (16 * e_bar + 384) + 2 * 16128 + 3168
+        out = {"workload": tag, "games_this_rank": n, "sims_per_move": sims,
+               "moves_per_s": moves / secs, "sims_per_s": sims_per_s, "moves": int(moves), "seconds": secs,
+               "seconds_search_and_samples": allmax(r["seconds"]), "seconds_weight_broadcast": allmax(t_bcast),
+               "seconds_pack_and_allgather": allmax(t1 - t_pack0), "weights_broadcast_bytes": int(nbytes),
+               "samples_allgathered": int(gathered.shape[0]), "sample_row_bytes": int(rows.shape[1]) if rows.ndim == 2 else 0,
+               "waves": int(r["waves"]), "tensor_util": sims_per_s * 6.56e9 / (tf_peak * 1e12 * world),
+               "search_hbm": {"edges_per_node": e_bar, "select_depth": d_bar, "bytes_per_sim": bytes_per_sim,
+                              "achieved_gbs_per_gpu": sims_per_s / world * bytes_per_sim / 1e9,
+                              "frac_of_hbm_peak": sims_per_s / world * bytes_per_sim / 1e9 / hbm_peak}}
+        if r_open is not None:
+            om, osec = allsum(float(r_open["moves"])), allmax(r_open["seconds"])
+            out["opening_moves_per_s"] = om / osec
+            out["full_game_moves_per_s_estimate"] = 54.0 / (5.0 / (om / osec) + 49.0 / (moves / secs))
+        del sp
+        return out
+
+    res = {"tensor_peak_tflops": tf_peak, "tensor_peak_source": tf_src,
+           "net": "BN-folded bf16; 39 trunk 3x3 convs = hand-written tcgen05 implicit GEMM (TMA halo tile, TMEM "
+                  "accumulators, fused bias/residual/ReLU); heads = library GEMMs"}
+    c2 = selfplay_config("configs[2]: AlphaZero self-play, %d sims/move, model_hive net random-init, %d concurrent games per GPU"
+                         % (args.selfplay_sims, n2), n2, args.selfplay_sims, 0, 5, args.selfplay_moves)
+    res.update(c2)                                              # configs[2] stays at the top level of the block (as in round 1)
+    res["trunk_kernel_launches"] = int(folded.trunk.launches)
+    if not args.no_selfplay_deep:
+        res["config3"] = selfplay_config("configs[3]: self-play %d sims/move, %d games sharded over %d B200, NCCL weight broadcast + "
+                                         "sample all-gather" % (args.sharded_sims, args.sharded_games, world),
+                                         n3, args.sharded_sims, 7, 0, 1)
+        # configs[4]: evaluator match, new vs best net
+        with torch.cuda.stream(stream):
+            ev = hive_b200.EvaluatorMatch(n4, args.evaluator_sims, hive_b200.LeafEvaluator(folded), hive_b200.LeafEvaluator(folded_best),
+                                          device=local_rank, stream=stream.cuda_stream, seed=7 + rank, torch_stream=stream)
+            ev.play(max_plies=5)                                # 4 random plies + one searched ply (warm-up, graph capture)
+            barrier(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            t_bcast, nbytes = timed_collectives_before(net, folded)       # the candidate's weights arrive
+            w0 = ev.waves
+            r = ev.play(max_plies=2)                            # two searched plies (one by each colour)
+            torch.cuda.synchronize()
+            tally = torch.tensor([r["new_wins"], r["best_wins"], r["draws"]], dtype=torch.int64, device="cuda")
+            if dist is not None:
+                dist.all_reduce(tally)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+        secs, moves = allmax(t1 - t0), allsum(2.0 * n4)
+        res["config4"] = {"workload": "configs[4]: evaluator match, %d sims/move, new vs best net, %d games per GPU on %d B200"
+                                      % (args.evaluator_sims, n4, world),
+                          "moves_per_s": moves / secs, "sims_per_s": moves * args.evaluator_sims / secs, "searched_moves": int(moves),
+                          "seconds": secs, "seconds_weight_broadcast": allmax(t_bcast), "weights_broadcast_bytes": int(nbytes),
+                          "waves": int(ev.waves - w0), "tensor_util": moves * args.evaluator_sims / secs * 6.56e9 / (tf_peak * 1e12 * world),
+                          "tally_after_two_plies": [int(x) for x in tally.tolist()]}
+    # the reference's sequential CPU search next to it (rank 0, N = 1 only; bounded sample)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        procs = max(1, min(os.cpu_count() or 1, 16))
+        rate, moves, dt, wall = cpu_mcts_rate(8.0, procs, args.selfplay_sims)
+        res["cpu_baseline"] = {"value": rate, "unit": "moves/s", "cores": procs, "kind": "port", "sims_per_move": args.selfplay_sims,
+                               "sample": "%d sequential %d-simulation searches (oracle/mcts_oracle.py, the restatement of "
+                                         "HivePlayer.action, hash-net stand-in for the network, no GPU) on %d processes in %.1f s"
+                                         % (moves, args.selfplay_sims, procs, dt)}
+    return res
 
 
 def main():

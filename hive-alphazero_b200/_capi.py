@@ -24,7 +24,7 @@ MCTS_SYMBOLS = [
     "mcts_create", "mcts_destroy", "mcts_set_params", "mcts_set_root_noise_host", "mcts_begin", "mcts_descend",
     "mcts_expand", "mcts_pending_host", "mcts_dev_leaf_planes", "mcts_dev_leaf_policy", "mcts_dev_leaf_value", "mcts_dev_pending_mask",
     "mcts_leaf_planes_host", "mcts_set_leaf_eval_host", "mcts_policy_host", "mcts_root_stats_host", "mcts_launch_count",
-    "mcts_error_host", "mcts_hash_eval_dev", "mcts_stream",
+    "mcts_error_host", "mcts_hash_eval_dev", "mcts_stream", "mcts_tree_stats_host",
 ]
 
 
@@ -108,6 +108,7 @@ def lib():
     L.mcts_launch_count.restype = ctypes.c_longlong
     L.mcts_error_host.argtypes = [vp, vp]
     L.mcts_hash_eval_dev.argtypes = [vp, vp, vp, vp, i32, u64, vp]
+    L.mcts_tree_stats_host.argtypes = [vp, i32, vp]
     L.mcts_stream.argtypes = [vp]
     L.mcts_stream.restype = vp
     L.net_create.argtypes = [i32, vp, i32, ctypes.POINTER(vp)]

@@ -295,6 +295,35 @@ int mcts_hash_eval_dev(const uint16_t* planes_dev, float* policy_dev, double* va
     return 0;
 }
 
+// Shape of the trees of the last search, averaged over the first `max_trees` trees that hold nodes (read back and
+// reduced on the host; a measurement call, not on any hot path): out[0] = mean edges per node (E), out[1] = mean
+// select depth per simulation (D: every select bumps the sum_n of the node it leaves, so sum over nodes of sum_n = all
+// selects), out[2] = mean nodes per tree, out[3] = mean simulations per tree.
+int mcts_tree_stats_host(hive_mcts_t* m, int max_trees, double* out) {
+    if (!m || !out || max_trees < 1) return fail(HIVE_E_ARG, "mcts_tree_stats_host: bad arguments");
+    CUDA_TRY(cudaSetDevice(m->env->device));
+    CUDA_TRY(cudaStreamSynchronize(m->env->stream));
+    const int nt = max_trees < m->n ? max_trees : m->n;
+    std::vector<MctsTree> trees(nt);
+    std::vector<MctsNode> nodes((size_t)nt * m->node_cap);
+    CUDA_TRY(cudaMemcpy(trees.data(), m->trees, (size_t)nt * sizeof(MctsTree), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(nodes.data(), m->nodes, nodes.size() * sizeof(MctsNode), cudaMemcpyDeviceToHost));
+    double n_nodes = 0, n_edges = 0, selects = 0, sims = 0, used = 0;
+    for (int t = 0; t < nt; t++) {
+        if (trees[t].n_nodes <= 0) continue;
+        used += 1; n_nodes += trees[t].n_nodes; sims += trees[t].sims_done;
+        for (int i = 0; i < trees[t].n_nodes && i < m->node_cap; i++) {
+            const MctsNode& nd = nodes[(size_t)t * m->node_cap + i];
+            n_edges += nd.n_edges; selects += nd.sum_n;
+        }
+    }
+    out[0] = n_nodes > 0 ? n_edges / n_nodes : 0.0;
+    out[1] = sims > 0 ? selects / sims : 0.0;
+    out[2] = used > 0 ? n_nodes / used : 0.0;
+    out[3] = used > 0 ? sims / used : 0.0;
+    return 0;
+}
+
 void* mcts_stream(hive_mcts_t* m) { return m ? (void*)m->env->stream : nullptr; }
 
 int mcts_root_stats_host(hive_mcts_t* m, int tree, int max_edges, int32_t* action, int32_t* N, double* W, double* Q,

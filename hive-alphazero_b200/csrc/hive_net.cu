@@ -113,9 +113,10 @@ int net_load_conv_host(hive_net_t* n, int layer, const float* w, const float* bi
     std::vector<uint8_t> packed;
     pack_conv_weights(wp.data(), cpad, CONV_KG, packed);
     CUDA_TRY(cudaStreamSynchronize(n->stream));
-    cudaFree(n->weights[layer]); cudaFree(n->bias[layer]);
-    CUDA_TRY(cudaMalloc(&n->weights[layer], packed.size()));
-    CUDA_TRY(cudaMalloc(&n->bias[layer], 256 * 4));
+    // a reload (new weights after a broadcast) goes into the SAME device buffers: a layer's packed size depends on
+    // its shape only, and CUDA graphs captured over this trunk keep pointing at valid, current weights
+    if (!n->weights[layer]) CUDA_TRY(cudaMalloc(&n->weights[layer], packed.size()));
+    if (!n->bias[layer]) CUDA_TRY(cudaMalloc(&n->bias[layer], 256 * 4));
     CUDA_TRY(cudaMemcpy(n->weights[layer], packed.data(), packed.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(n->bias[layer], bias, 256 * 4, cudaMemcpyHostToDevice));
     n->n_chunks[layer] = cpad / CONV_CHUNK_CH;

@@ -105,6 +105,12 @@ class MctsBatch:
         check(lib().mcts_error_host(self._h, ctypes.byref(flags)), "mcts_error_host")
         return flags.value
 
+    def tree_stats(self, max_trees=256):
+        """dict(edges_per_node, select_depth, nodes_per_tree, sims_per_tree) of the last search (first max_trees trees)."""
+        out = (ctypes.c_double * 4)()
+        check(lib().mcts_tree_stats_host(self._h, int(max_trees), out), "mcts_tree_stats_host")
+        return dict(edges_per_node=out[0], select_depth=out[1], nodes_per_tree=out[2], sims_per_tree=out[3])
+
     def search_host(self, evaluate, tree_mask=None):
         """Full search with a host evaluator ``evaluate(leaf_env) -> (p float32[1584], v float)`` called
         once per new position (expand_and_evaluate, solo_play.py:260-278). Returns the number of waves."""

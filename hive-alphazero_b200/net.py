@@ -111,10 +111,14 @@ class TensorCoreTrunk:
         h = ctypes.c_void_p()
         check(self._lib.net_create(int(device_index), stream_ptr, int(max_boards), ctypes.byref(h)), "net_create")
         self._h, self.max_boards = h, int(max_boards)
+        self.load(folded_fp32)
+
+    def load(self, folded_fp32):
+        """(Re)load the 39 folded convolutions; the packed operands keep their device addresses."""
         for layer, (w, b) in enumerate(folded_fp32):
             w = np.ascontiguousarray(w.detach().float().cpu().numpy())
             b = np.ascontiguousarray(b.detach().float().cpu().numpy())
-            check(self._lib.net_load_conv_host(h, layer, w.ctypes.data, b.ctypes.data, w.shape[1]), "net_load_conv_host")
+            self._check(self._lib.net_load_conv_host(self._h, layer, w.ctypes.data, b.ctypes.data, w.shape[1]), "net_load_conv_host")
 
     def close(self):
         if getattr(self, "_h", None):
@@ -173,6 +177,26 @@ class FoldedNet:
             self.fc1 = (ob.fc1.weight.to(self.device, torch.float32), ob.fc1.bias.to(self.device, torch.float32))
             self.fc2 = (ob.fc2.weight.to(self.device, torch.float32), ob.fc2.bias.to(self.device, torch.float32))
             self.fc = (ob.fc.weight.to(self.device, dtype), ob.fc.bias.to(self.device, torch.float32))
+
+    @torch.no_grad()
+    def reload(self, net):
+        """Take over the weights of `net` IN PLACE (after a weight broadcast): every device tensor and the tensor-core
+        trunk's packed operands keep their addresses, so CUDA graphs captured over this network stay valid."""
+        fresh = FoldedNet(net, device=self.device, dtype=self.dtype)
+
+        def take(dst, src):
+            for d, s_ in zip(dst, src):
+                d.copy_(s_)
+        take(self.stem, fresh.stem)
+        for (a1, a2), (b1, b2) in zip(self.blocks, fresh.blocks):
+            take(a1, b1); take(a2, b2)
+        for name in ("vconv", "pconv", "vlin", "plin", "fc1", "fc2", "fc"):
+            take(getattr(self, name), getattr(fresh, name))
+        self.fc_nhwc.copy_(fresh.fc_nhwc)
+        self._folded_fp32 = fresh._folded_fp32
+        if self.trunk is not None:
+            self.trunk.load(self._folded_fp32)
+        return self
 
     def trunk_weights(self):
         """[(w (256,Cin,3,3), b (256,)) ...] of the 39 folded 3x3 convolutions, in execution order."""

@@ -16,9 +16,11 @@ def shard_games(total_games, world_size, rank):
     return start, base + (1 if rank < extra else 0)
 
 
-def broadcast_weights(module, src=0):
-    """Every rank ends up with rank `src`'s parameters and buffers (one flat bf16-safe broadcast per
-    tensor dtype group). Returns the number of bytes broadcast."""
+def broadcast_weights(module, src=0, wire_dtype=None):
+    """Every rank ends up with rank `src`'s parameters and buffers (one flat broadcast per tensor dtype group).
+    wire_dtype=torch.bfloat16 sends the floating-point tensors as bf16 (51.8 M parameters -> 103.6 MB instead of 207 MB,
+    SURVEY.md 8e); every rank, the source included, then holds the bf16-rounded values, so all replicas stay identical.
+    Returns the number of bytes broadcast."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return 0
     tensors = [p.data for p in module.parameters()] + [b.data for b in module.buffers()]
@@ -28,6 +30,8 @@ def broadcast_weights(module, src=0):
         groups.setdefault(t.dtype, []).append(t)
     for dtype, ts in groups.items():
         flat = torch.cat([t.reshape(-1) for t in ts])
+        if wire_dtype is not None and dtype.is_floating_point and dtype != wire_dtype:
+            flat = flat.to(wire_dtype)
         dist.broadcast(flat, src=src)
         nbytes += flat.numel() * flat.element_size()
         off = 0

@@ -122,6 +122,29 @@ class SelfPlayBatch:
         self.env.sync()
         return dict(moves=self.moves - moves0, seconds=time.perf_counter() - t0, waves=self.waves - waves0)
 
+    def packed_rows(self, last_moves):
+        """The samples of the last `last_moves` plies of every game as fixed 1,960-byte records (parallel.pack_samples:
+        55 binary planes + turn byte, sparse policy, value byte) -- what the ranks all-gather.  The value of a game
+        still running is not known yet: its records carry 0 (the finished ones are rewritten by `_finish`)."""
+        from .parallel import pack_samples
+        rows = [smp for per_game in self.samples for smp in per_game[-last_moves:]] if last_moves > 0 else []
+        if not rows:
+            return np.zeros((0, 1960), dtype=np.uint8)
+        planes = np.stack([r[0] for r in rows]).reshape(len(rows), C.STATE_FEATURES, 144)
+        pi = np.stack([r[1] for r in rows])
+        bits = np.packbits(planes != 0, axis=2, bitorder="little")                       # (N, 56, 18)
+        turn = ((planes[:, 31, 0].astype(np.uint32) << 16).view(np.float32)).astype(np.uint8)
+        planes_bits = np.concatenate([np.delete(bits, 31, axis=1).reshape(len(rows), 55 * 18), turn[:, None]], axis=1)
+        r, c = np.nonzero(pi > 0)                                                        # sparse policy: row-major, ascending actions
+        starts = np.searchsorted(r, np.arange(len(rows)))
+        pos = np.arange(len(r)) - starts[r]
+        keep = pos < 160
+        idx = np.full((len(rows), 160), -1, dtype=np.int32)
+        val = np.zeros((len(rows), 160), dtype=np.float32)
+        idx[r[keep], pos[keep]] = c[keep]
+        val[r[keep], pos[keep]] = pi[r[keep], c[keep]]
+        return pack_samples(planes_bits, idx, val, np.zeros(len(rows), dtype=np.int8))
+
     def _finish(self, g, winner, turn):
         value_white = 1 if winner == 1 else (-1 if winner == 2 else 0)
         self.finished.append((value_white, turn))

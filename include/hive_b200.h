@@ -199,6 +199,10 @@ int mcts_set_leaf_eval_host(hive_mcts_t* m, const float* policy, const double* v
 int mcts_policy_host(hive_mcts_t* m, double* pi, int32_t* action, int32_t* sum_n);
 /* OR of (1 << error code) over the trees of the running search: 2 node arena, 4 edge arena, 8 depth (synchronises) */
 int mcts_error_host(hive_mcts_t* m, uint32_t* flags);
+/* Shape of the trees of the last search over the first max_trees trees (measurement call: reads the trees back):
+ * out[0] mean edges per node, out[1] mean select depth per simulation, out[2] mean nodes per tree, out[3] mean
+ * simulations per tree -- the E and D of the per-simulation byte budget. */
+int mcts_tree_stats_host(hive_mcts_t* m, int max_trees, double* out);
 /* Deterministic stand-in for the network ON THE DEVICE, for parity tests of the device leaf-evaluation path
  * (expand_and_evaluate, solo_play.py:260-291, with a reproducible evaluator): policy / value are a pure hash of the
  * row's bf16 planes and `salt` (formula at the kernel in csrc/hive_mcts.cu).  Rows with mask_dev[row] == 0 are left
