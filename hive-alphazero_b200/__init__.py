@@ -16,7 +16,7 @@ def __getattr__(name):
     if name in ("HiveNet", "FoldedNet", "LeafEvaluator", "SplitEvaluator", "host_net_callable", "device_view"):
         from . import net
         return getattr(net, name)
-    if name in ("SelfPlayBatch", "write_play_file", "sample_to_reference_row"):
+    if name in ("SelfPlayBatch", "write_play_file", "sample_to_reference_row", "self_play_buffer", "evaluation_report", "accept_new_network"):
         from . import selfplay
         return getattr(selfplay, name)
     if name in ("Trainer", "alpha_loss", "samples_to_tensors", "discounted_value", "load_play_file", "load_play_files", "rows_to_tensors"):

@@ -11,7 +11,7 @@ ENV_SYMBOLS = [
     "hive_last_error", "hive_abi_version", "hive_create", "hive_destroy", "hive_num_games", "hive_sync",
     "hive_reset", "hive_step_host", "hive_step", "hive_step_host_async", "hive_wait_results", "hive_step_random", "hive_step_random_multi", "hive_legal_host", "hive_encode_host",
     "hive_status_host", "hive_status_packed_host", "hive_host_pick_actions", "hive_counters_host", "hive_state_key", "hive_load_state", "hive_dump_state",
-    "hive_copy_state", "hive_dev_state", "hive_dev_legal", "hive_dev_count", "hive_dev_status", "hive_dev_planes",
+    "hive_copy_state", "hive_record_host", "hive_dev_state", "hive_dev_legal", "hive_dev_count", "hive_dev_status", "hive_dev_planes",
     "hive_launch_count", "hive_profile_step", "hive_probe_write_stream", "hive_set_timing", "hive_last_kernel_ms",
     "hive_host_loop_create", "hive_host_loop_destroy", "hive_host_loop_parts", "hive_host_loop_threads", "hive_host_loop_part",
     "hive_host_loop_run", "hive_host_loop_env_steps",
@@ -69,6 +69,7 @@ def lib():
     L.hive_load_state.argtypes = [vp, i32, i32, vp, vp]
     L.hive_dump_state.argtypes = [vp, i32, vp, vp, vp]
     L.hive_copy_state.argtypes = [vp, i32, vp, i32]
+    L.hive_record_host.argtypes = [vp, i32, vp]
     for name in ("hive_dev_state", "hive_dev_legal", "hive_dev_count", "hive_dev_status", "hive_dev_planes"):
         getattr(L, name).argtypes = [vp]
         getattr(L, name).restype = vp

@@ -855,6 +855,16 @@ int hive_load_state(hive_env_t* h, int game, int turn, const uint8_t* cells, con
     return launch_env(h, OP_EVAL, nullptr, h->d_mask, 0, 0, 0, nullptr);
 }
 
+int hive_record_host(hive_env_t* h, int game, void* rec384) {
+    if (check(h)) return HIVE_E_HANDLE;
+    if (game < 0 || game >= h->n || !rec384) return fail(HIVE_E_ARG, "hive_record_host: bad arguments");
+    std::vector<GameRec> r;
+    int rc = fetch_recs(h, r, game, 1);
+    if (rc) return rc;
+    memcpy(rec384, &r[0], sizeof(GameRec));
+    return 0;
+}
+
 int hive_copy_state(hive_env_t* dst, int dst_game, hive_env_t* src, int src_game) {
     if (check(dst) || check(src)) return HIVE_E_HANDLE;
     if (dst_game < 0 || dst_game >= dst->n || src_game < 0 || src_game >= src->n)

@@ -150,6 +150,12 @@ class HiveBatch:
             raise ValueError("cells/levels must have 22 entries")
         check(lib().hive_load_state(self._h, int(g), int(turn), c.ctypes.data, l.ctypes.data), "hive_load_state")
 
+    def record(self, g):
+        """The raw 384-byte record of game g (uint8[384]): cells, levels, header, counters, plane history."""
+        rec = np.zeros(384, dtype=np.uint8)
+        check(lib().hive_record_host(self._h, int(g), rec.ctypes.data), "hive_record_host")
+        return rec
+
     def dump_state(self, g):
         turn = ctypes.c_int32()
         c = np.empty(22, dtype=np.uint8)
@@ -265,18 +271,32 @@ class HostLoop:
 
 
 class _State:
-    """The slice of Game_State (game_state.py:10-119) the hot-path callers read."""
+    """The slice of Game_State (game_state.py:10-119) the hot-path callers read.  `turn` is cached by the facade after
+    every step (one status read per move, not one per access)."""
 
     def __init__(self, env):
         self._env = env
         self.winner = None
-
-    @property
-    def turn(self):
-        return int(self._env._batch.status()[0][0])
+        self.turn = 1
 
     def player(self):          # game_state.py:58-62
         return 0 if self.turn % 2 == 1 else 1
+
+
+class _TileView:
+    """What callers read of a reference Tile (tile.py:10-30): board coordinates and the printable label."""
+
+    def __init__(self, q, r):
+        self.index_xy = [q, r]
+        self.core_index = (C.index_char[q], C.index_number[r])
+        self.axial_coords = (q, r)
+
+    def __repr__(self):
+        return "Tile%s" % (self.core_index,)
+
+
+_HAND_TILE = type("_HandTile", (), {"index_xy": [99, 99], "core_index": ("-", "-"), "axial_coords": (99, 99),
+                                    "__repr__": lambda self: "Tile(hand)"})()
 
 
 class GamePlay:
@@ -294,11 +314,72 @@ class GamePlay:
         self._batch = HiveBatch(1, device=device)
         self.state = _State(self)
         self._stale_key_player = None
+        # board_matrix[q, r] (env_hive.py:33,90): one view object per cell, read by solo_play.py:127-134 for printing
+        self.board_matrix = np.empty((C.MAX_MAP_FULL, C.MAX_MAP_FULL), dtype=object)
+        for q in range(C.MAX_MAP_FULL):
+            for r in range(C.MAX_MAP_FULL):
+                self.board_matrix[q, r] = _TileView(q, r)
         self._refresh()
 
     # -- internal
     def _refresh(self):
+        """One read of the new position per step: legal list, turn, winner, done; the key is rebuilt on first use."""
         self.encoded_action = self._batch.actions(0).tolist()
+        turn, winner, done = self._batch.status()
+        self.state.turn = int(turn[0])
+        self._winner_code, self._done = int(winner[0]), bool(done[0])
+        self._key = None
+        self._pos = None
+
+    def _position(self):
+        if self._pos is None:
+            self._pos = self._batch.dump_state(0)
+        return self._pos
+
+    def _pieces_set(self, color):
+        """{key: [tile, level, piece type name]} in the reference's order (env_hive.py:71-87; keys "<class 'pieces.Queen'>0" ...)."""
+        _, cells, levels = self._position()
+        out = {}
+        for k in range(11):
+            c = int(cells[color * 11 + k])
+            tile = _HAND_TILE if c == 255 else self.board_matrix[c // 12, c % 12]
+            out["<class 'pieces.%s'>%d" % (C.PIECE_CLASS[k], C.PIECE_NUM[k])] = [tile, int(levels[color * 11 + k]), C.PIECE_CLASS[k]]
+        return out
+
+    @property
+    def white_pieces_set(self):
+        return self._pieces_set(0)
+
+    @property
+    def black_pieces_set(self):
+        return self._pieces_set(1)
+
+    def _history(self, side):
+        """history_white / history_black (env_hive.py:38-39,436-445): newest first, each entry (12,12,2) = the mover's own
+        pieces and the opponent's, as pushed when that side was to move; ages without a push yet are absent."""
+        rec = self._batch.record(0)
+        words = rec[64:64 + 320].view(np.uint32).reshape(2, 4, 2, 5)[side]
+        out = []
+        for age in range(4):
+            bits = np.unpackbits(words[age].view(np.uint8).reshape(2, 20), axis=1, bitorder="little")[:, :144]
+            if not bits.any() and age > 0:
+                break
+            out.append(bits.reshape(2, 12, 12).transpose(1, 2, 0).astype(np.float64))
+        return out
+
+    @property
+    def history_white(self):
+        return self._history(0)
+
+    @property
+    def history_black(self):
+        return self._history(1)
+
+    def human_play(self):                                 # env_hive.py:185-194
+        """The reference re-derives the frontier, the legal list and the planes after a piece was dragged by hand in the
+        GUI.  Here a position only changes through move(), whose kernel has already done all of that: the call re-reads
+        the device's view."""
+        self._refresh()
 
     def new_game(self):                                   # env_hive.py:61-97
         self._batch.reset()
@@ -329,12 +410,11 @@ class GamePlay:
         return np.ascontiguousarray(p.transpose(1, 2, 0)).astype(np.float64)
 
     def game_is_over(self):                               # move_checker.py:140-165
-        _, winner, done = self._batch.status()
-        if winner[0] == 1:
+        if self._winner_code == 1:
             self.state.winner = C.PIECE_WHITE
-        elif winner[0] == 2:
+        elif self._winner_code == 2:
             self.state.winner = C.PIECE_BLACK
-        return bool(done[0])
+        return self._done
 
     def turn(self):
         return self.state.turn
@@ -344,7 +424,9 @@ class GamePlay:
 
     @property
     def state_key(self):                                  # env_hive.py:150-168
-        key = self._batch.state_key(0)
+        if self._key is None:
+            self._key = self._batch.state_key(0)
+        key = self._key
         if self._stale_key_player is not None:            # skip_turn leaves the key untouched (:493-496)
             key = key[:-1] + self._stale_key_player
         return key
@@ -363,7 +445,7 @@ class GamePlay:
 
     def position(self):
         """(turn, cells[22], levels[22]) -- see hive_dump_state."""
-        return self._batch.dump_state(0)
+        return self._position()
 
     def load_position(self, turn, cells, levels):
         self._batch.load_state(0, turn, cells, levels)
@@ -378,7 +460,9 @@ class GamePlay:
         other._batch.copy_state_from(0, self._batch, 0)
         other._batch.sync()
         other.state = _State(other)
-        other.state.winner = self.state.winner
+        other.state.winner, other.state.turn = self.state.winner, self.state.turn
         other._stale_key_player = self._stale_key_player
         other.encoded_action = list(self.encoded_action)
+        other.board_matrix = self.board_matrix
+        other._winner_code, other._done, other._key, other._pos = self._winner_code, self._done, self._key, self._pos
         return other

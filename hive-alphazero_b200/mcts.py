@@ -270,11 +270,12 @@ class HivePlayer:
             self._mcts_key = key
         return self._mcts
 
-    def action(self, env, non_queue=True):                 # solo_play.py:110-151
+    def search_moves(self, env):                           # solo_play.py:153-165
+        """simulation_num_per_move simulations from env's position (sequential semantics, none_queue=False).  Returns
+        (max leaf value, first leaf value) like the reference -- here (root Q max, root Q of the first edge), the values
+        its callers only print; the tree stays on the device for calc_policy."""
         if not isinstance(env, GamePlay):
-            raise TypeError("HivePlayer.action needs a hive_b200.GamePlay")
-        self.max_depth = env.state.turn
-        self.main_key_state = env.state_key
+            raise TypeError("HivePlayer needs a hive_b200.GamePlay")
         m = self._tree_for(env)
         sims = self.simulation_num_per_move
         n_edges = max(len(env.actions()), 1)
@@ -285,8 +286,22 @@ class HivePlayer:
                 noise[0, r] = np.random.dirichlet([C.dirichlet_alpha] * n_edges)
         m.set_root_noise(noise)
         m.search_host(self.expand_and_evaluate)
-        pi, action, sum_n = m.policy()
-        policy, sum_all = pi[0], float(sum_n[0])
+        st = m.root_stats(0)
+        q = st["q"]
+        return (float(q.max()) if len(q) else 0.0), (float(q[0]) if len(q) else 0.0)
+
+    def calc_policy(self, env):                            # solo_play.py:351-374
+        """(policy float64[1584], sum of visit counts) of the last search_moves(env)."""
+        pi, _, sum_n = self._tree_for(env).policy()
+        return pi[0], float(sum_n[0])
+
+    def action(self, env, non_queue=True):                 # solo_play.py:110-151
+        if not isinstance(env, GamePlay):
+            raise TypeError("HivePlayer.action needs a hive_b200.GamePlay")
+        self.max_depth = env.state.turn
+        self.main_key_state = env.state_key
+        self.search_moves(env)
+        policy, sum_all = self.calc_policy(env)
         p = self.apply_temperature(policy, int(env.state.turn + 1) / 2)
         my_action = int(np.random.choice(range(C.ACTION_SPACE), p=p))
         return my_action, [list(policy), sum_all]

@@ -165,6 +165,88 @@ class SelfPlayBatch:
             self.finished_samples.extend(data)
 
 
+def self_play_buffer(cur=None, make_player=None, device=0):
+    """Drop-in for the reference's one-game worker (woker/self_play_with_train.py:146-219, the runnable statement of
+    woker/self_play.py:116-193), RNG-stream exact: one GamePlay, two HivePlayers, the opening schedule
+    (random move on turns 1-2; while error = 0.7 - int(turn+1)/2*0.15 >= 0.1 sample from (1-error)*pi[legal] +
+    error*Dir(0.5)), rows [planes (12,12,56) nested list, pi[1584], value, [game_len_for_side, move_idx_for_side]],
+    value = +-1 from the winner's side and -1 for BOTH sides of a drawn / cut game.  Returns (data, [value_white]).
+    `cur`: the reference's list of pipe bundles (popped / pushed back, handed to the players; may be None);
+    `make_player(pipes)`: builds a configured hive_b200.HivePlayer (default: HivePlayer(pipes=pipes))."""
+    from .env import GamePlay
+    from .mcts import HivePlayer
+    board = GamePlay(HEIGHT_MAP=C.HEIGHT - 100, WIDTH_MAP=C.WIDTH - 500, device=device)
+    pipes = cur.pop() if cur else None
+    make_player = make_player or (lambda p: HivePlayer(pipes=p))
+    white, black = make_player(pipes), make_player(pipes)
+    state_policy_player = []
+    black_count = white_count = 0
+    e = 0.7
+    while not board.game_is_over():
+        if board.state.player() == 0:
+            action, policy = white.action(board)
+            player = 'W'
+            white_count += 1
+            counter = white_count
+        else:
+            action, policy = black.action(board)
+            player = 'B'
+            black_count += 1
+            counter = black_count
+        if board.state.turn <= 2:
+            action = np.random.choice(board.actions())
+        policy = policy[0]
+        error = e - int(board.state.turn + 1) / 2 * 0.15
+        actions = board.actions()
+        if error >= 0.1 and len(actions) != 0:
+            p = np.array(policy)[actions]
+            noise = np.random.dirichlet([0.5] * len(actions))
+            p = (1 - error) * np.array(p) + error * noise
+            p /= p.sum()
+            action = np.random.choice(board.actions(), p=p)
+        state = board.encode_board(player)
+        state_policy_player.append([state.tolist(), policy, player, counter])
+        board.move(action)
+        if board.state.turn >= C.MAX_GAME_LENGTH:
+            break
+    value_white = 0
+    if board.game_is_over():
+        if board.state.winner == C.PIECE_WHITE:
+            value_white = 1
+        elif board.state.winner == C.PIECE_BLACK:
+            value_white = -1
+    white.finish_game(value_white)
+    black.finish_game(-value_white)
+    data = []
+    for state, policy, player, counter in state_policy_player:
+        value, game_lens = (value_white, white_count) if player == "W" else (-value_white, black_count)
+        if value_white == 0:
+            value = -1
+        data.append([state, policy, value, [game_lens, counter]])
+    if cur is not None:
+        cur.append(pipes)
+    return data, [value_white]
+
+
+def evaluation_report(win_lose, game_lens, state_keys):
+    """What the reference's evaluation worker prints every ten games (woker/evaluation.py:66-88): white win rate =
+    share of +1 in win_lose, mean game length, and the share of distinct final positions (de-dup by final state_key)."""
+    wl = np.asarray(win_lose)
+    values, counts = np.unique(wl, return_counts=True)
+    return dict(total_games=int(len(wl)), white_win_rate=float((wl == 1).sum() / max(len(wl), 1)),
+                mean_game_len=float(np.round(np.mean(game_lens), 2)) if len(game_lens) else 0.0,
+                distinct_final_positions=float(len(np.unique(list(state_keys))) / max(len(wl), 1)),
+                counter={int(v): int(c) for v, c in zip(values, counts)})
+
+
+def accept_new_network(new_wins, best_wins, threshold=0.55):
+    """The new-vs-best gate of the evaluator (AlphaZero's rule, hive-report.pdf p.6): the candidate replaces the best
+    network when it wins at least `threshold` of the decided games (draws do not count).  (accepted, win_share)"""
+    decided = new_wins + best_wins
+    share = new_wins / decided if decided else 0.0
+    return bool(decided > 0 and share >= threshold), float(share)
+
+
 def sample_to_reference_row(planes_bf16, pi, value, lens):
     """One finished sample in the reference's on-disk form (self_play.py:160,190):
     [planes 12x12x56 nested list, pi[1584], value, [game_len_for_side, move_idx_for_side]]."""

@@ -135,6 +135,9 @@ int hive_state_key(hive_env_t* h, int game, char* buf, int buflen);
  * (env_hive.py:71-87).  History is cleared by load. */
 int hive_load_state(hive_env_t* h, int game, int turn, const uint8_t* cells, const uint8_t* levels);
 int hive_dump_state(hive_env_t* h, int game, int32_t* turn, uint8_t* cells, uint8_t* levels);
+/* the raw HIVE_STATE_BYTES record of one game (cells, levels, turn / winner / done, counters, the 4-step plane
+ * history of both sides: history_white / history_black of env_hive.py:38-39,436-445) */
+int hive_record_host(hive_env_t* h, int game, void* rec384);
 /* whole-record snapshot (HIVE_STATE_BYTES each) -- the deepcopy(env) of solo_play.py:158 */
 int hive_copy_state(hive_env_t* dst, int dst_game, hive_env_t* src, int src_game);
 

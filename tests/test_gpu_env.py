@@ -247,3 +247,49 @@ def test_async_host_step_graph_replay_matches_device_policy(hb):
         assert (dev.planes_bf16() == b.planes_bf16()).all()
         assert [a.tolist() for a in dev.status()] == [a.tolist() for a in b.status()]
         assert [x.tolist() for x in dev.counters()] == [x.tolist() for x in b.counters()]
+
+
+def test_facade_attributes_callers_read():
+    """human_play, white_pieces_set / black_pieces_set, board_matrix, history_white / history_black and the cached
+    turn / state_key (env_hive.py:33-39,185-194; solo_play.py:127-134 reads the piece keys and board_matrix[..].core_index)."""
+    import hive_b200 as hb
+    from oracle.hive_oracle import OracleEnv
+    env, o = hb.GamePlay(), OracleEnv()
+    rng = np.random.RandomState(5)
+    pushed = {0: [], 1: []}
+    for ply in range(14):
+        side = env.state.player()
+        pushed[side].insert(0, env.encode_board()[:, :, [11, 23]].copy())       # what this evaluation pushed (env_hive.py:436-445)
+        assert env.state.turn == o.turn and env.turn() == o.turn
+        hist = env.history_white if side == 0 else env.history_black
+        assert len(hist) == min(len(pushed[side]), 4)
+        for a, b in zip(hist, pushed[side]):
+            assert (a == b).all()
+        la = env.actions()
+        a = int(la[rng.randint(len(la))])
+        env.move(a); o.move(a)
+    keys = list(env.white_pieces_set.keys())
+    assert keys[0] == "<class 'pieces.Queen'>0" and keys[10] == "<class 'pieces.Ant'>2" and len(keys) == 11
+    _, cells, levels = env.position()
+    for color, pset in enumerate((env.white_pieces_set, env.black_pieces_set)):
+        for k, (key, (tile, level, name)) in enumerate(pset.items()):
+            c = int(cells[color * 11 + k])
+            assert level == int(levels[color * 11 + k])
+            if c == 255:
+                assert tile.axial_coords == (99, 99)
+            else:
+                assert tile is env.board_matrix[c // 12, c % 12] and tile.core_index == (hb.config.index_char[c // 12], hb.config.index_number[c % 12])
+    key = env.state_key
+    env.human_play()                                            # nothing moved by hand: same position, same outputs
+    assert env.state_key == key and env.actions() == o.actions().tolist()
+    # public search entry points of the player (solo_play.py:153-165,351-374)
+    from oracle.mcts_oracle import hash_net
+    pl = hb.HivePlayer()
+    pl.simulation_num_per_move = 12
+    pl.expand_and_evaluate_with_net = lambda e: hash_net(e.encode_board())
+    np.random.seed(3)
+    pl.search_moves(env)
+    policy, sum_all = pl.calc_policy(env)
+    np.random.seed(3)
+    _, (policy2, sum_all2) = pl.action(env)
+    assert (policy == np.asarray(policy2)).all() and sum_all == sum_all2 == 11.0
