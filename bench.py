@@ -301,8 +301,9 @@ def run_selfplay(args, hive_b200, torch, dist, rank, world, local_rank, allsum, 
         return out
 
     res = {"tensor_peak_tflops": tf_peak, "tensor_peak_source": tf_src,
-           "net": "BN-folded bf16; 39 trunk 3x3 convs = hand-written tcgen05 implicit GEMM (TMA halo tile, TMEM "
-                  "accumulators, fused bias/residual/ReLU); heads = library GEMMs"}
+           "net": "BN-folded bf16, every kernel of a wave hand-written sm_100a: 39 trunk 3x3 convs = tcgen05 implicit GEMM (TMA halo "
+                  "tile, TMEM accumulators, fused bias/residual/ReLU); heads = two tcgen05 GEMMs (both 1x1 convs as one, policy fc) "
+                  "+ softmax / value-MLP kernel writing into the search's leaf arenas (net_forward)"}
     c2 = selfplay_config("configs[2]: AlphaZero self-play, %d sims/move, model_hive net random-init, %d concurrent games per GPU"
                          % (args.selfplay_sims, n2), n2, args.selfplay_sims, 0, 5, args.selfplay_moves)
     res.update(c2)                                              # configs[2] stays at the top level of the block (as in round 1)

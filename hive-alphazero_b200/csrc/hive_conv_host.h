@@ -51,4 +51,25 @@ inline int make_board_tensor_map(CUtensorMap* map, const void* base, int B, int 
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
+// Row-major bf16 matrix [rows][K] (K multiple of 8) seen as 3-D {8 elements, rows, K/8 k-groups}; box = {8, box_rows,
+// box_groups}: lands in shared memory as [k-group][row][8 elements], the K-major no-swizzle UMMA operand layout.
+// Rows past the end are zero-filled.
+inline int make_rows_tensor_map(CUtensorMap* map, const void* base, uint64_t rows, int K, int box_rows, int box_groups) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || !p) return -1;
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    const cuuint64_t dims[3] = {8, (cuuint64_t)rows, (cuuint64_t)(K / 8)};
+    const cuuint64_t strides[2] = {(cuuint64_t)K * 2, 16};       // bytes, dims 1..2
+    const cuuint32_t box[3] = {8, (cuuint32_t)box_rows, (cuuint32_t)box_groups};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
 }  // namespace hive

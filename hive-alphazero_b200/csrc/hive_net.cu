@@ -1,4 +1,4 @@
-// hive_net.cu -- C ABI of the network trunk on the tensor cores (include/hive_b200.h, net_*).
+// hive_net.cu -- C ABI of the network on the tensor cores (include/hive_b200.h, net_*): trunk and heads.
 // Stem + 19 residual blocks of alpha_zero/alpha_net.py (ConvBlock :25-34, ResBlock :36-54) = 39 3x3
 // convolutions with folded BatchNorm, each one launch of hive_conv3x3_kernel (hive_conv_kernel.cuh).
 #include <cuda.h>
@@ -12,6 +12,7 @@
 
 #include "hive_conv_host.h"
 #include "hive_conv_kernel.cuh"
+#include "hive_heads_kernel.cuh"
 #include "hive_internal.h"
 
 using namespace hive;
@@ -29,6 +30,17 @@ struct hive_net {
     int n_chunks[NET_LAYERS] = {};
     int loaded = 0;
     long long launches = 0;
+    // heads (alpha_net.py:56-80; kernels in hive_heads_kernel.cuh)
+    CUtensorMap map_rows;                 // act[2] (the trunk's output after 19 blocks) as [boards*144][256] rows
+    uint8_t* head_w1 = nullptr;           // both 1x1 convolutions packed as one 144-row operand
+    float* head_b1 = nullptr;             // [144]
+    uint8_t* head_wfc = nullptr;          // policy fc, nine 176-row column tiles x 288 chunks
+    float* head_bfc = nullptr;            // [1584]
+    float* head_fc1_w = nullptr; float* head_fc1_b = nullptr; float* head_fc2_w = nullptr; float* head_fc2_b = nullptr;
+    __nv_bfloat16* fc_a = nullptr;        // policy activations in the fc's A-operand layout
+    float* value_cells = nullptr;         // [max][144]
+    float* logits = nullptr;              // [max][1584]
+    bool heads_loaded = false;
 };
 
 namespace {
@@ -83,6 +95,21 @@ int net_create(int device, void* stream, int max_boards, hive_net_t** out) {
     for (int i = 0; i < 3; i++)
         if (make_board_tensor_map(&n->map_act[i], n->act[i], max_boards, 256, CONV_PADW, CONV_PADH, CONV_KG)) return fail(HIVE_E_CUDA, "net_create: cuTensorMapEncodeTiled failed");
     CUDA_TRY(cudaFuncSetAttribute(hive_conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM_BYTES));
+    // heads
+    if (make_rows_tensor_map(&n->map_rows, n->act[2], (uint64_t)B * 144, 256, HEAD_M, 8)) return fail(HIVE_E_CUDA, "net_create: cuTensorMapEncodeTiled failed (head rows)");
+    const size_t mt = (B + HEAD_M - 1) / HEAD_M;
+    CUDA_TRY(cudaMalloc(&n->head_w1, HC_W_BYTES));
+    CUDA_TRY(cudaMalloc(&n->head_b1, HC_N * 4));
+    CUDA_TRY(cudaMalloc(&n->head_wfc, (size_t)FC_NT * FC_CHUNKS * FC_B_BYTES));
+    CUDA_TRY(cudaMalloc(&n->head_bfc, 1584 * 4));
+    CUDA_TRY(cudaMalloc(&n->head_fc1_w, 64 * 144 * 4)); CUDA_TRY(cudaMalloc(&n->head_fc1_b, 64 * 4));
+    CUDA_TRY(cudaMalloc(&n->head_fc2_w, 64 * 4)); CUDA_TRY(cudaMalloc(&n->head_fc2_b, 4));
+    CUDA_TRY(cudaMalloc(&n->fc_a, mt * FC_CHUNKS * HEAD_A_BYTES));
+    CUDA_TRY(cudaMemset(n->fc_a, 0, mt * FC_CHUNKS * HEAD_A_BYTES));      // rows of boards past the batch stay finite
+    CUDA_TRY(cudaMalloc(&n->value_cells, B * 144 * 4));
+    CUDA_TRY(cudaMalloc(&n->logits, B * 1584 * 4));
+    CUDA_TRY(cudaFuncSetAttribute(hive_head_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HC_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(hive_head_fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM_BYTES));
     *out = n;
     return 0;
 }
@@ -94,6 +121,9 @@ int net_destroy(hive_net_t* n) {
     cudaFree(n->x0);
     for (int i = 0; i < 3; i++) cudaFree(n->act[i]);
     for (int i = 0; i < NET_LAYERS; i++) { cudaFree(n->weights[i]); cudaFree(n->bias[i]); }
+    cudaFree(n->head_w1); cudaFree(n->head_b1); cudaFree(n->head_wfc); cudaFree(n->head_bfc);
+    cudaFree(n->head_fc1_w); cudaFree(n->head_fc1_b); cudaFree(n->head_fc2_w); cudaFree(n->head_fc2_b);
+    cudaFree(n->fc_a); cudaFree(n->value_cells); cudaFree(n->logits);
     delete n;
     return 0;
 }
@@ -150,6 +180,78 @@ int net_trunk_forward(hive_net_t* n, const uint16_t* planes_chw_dev, int n_board
         cur = nxt;
     }
     *out_nhwc = reinterpret_cast<uint16_t*>(n->act[cur]);
+    return 0;
+}
+
+// The heads (alpha_net.py:56-80), BatchNorm folded into the two 1x1 convolutions by the caller:
+//   pconv_w [128][256], pconv_b [128]   policy conv;   vconv_w [256], vconv_b [1]   value conv
+//   fc_w [1584][18432] with CELL-MAJOR columns (k = cell*128 + channel: the reference's channel-major flatten
+//   c*144 + cell of alpha_net.py:77 permuted once), fc_b [1584];  fc1 [64][144] + [64], fc2 [64] + [1]   value MLP.
+// A reload writes into the same device buffers (captured graphs stay valid).
+int net_load_heads_host(hive_net_t* n, const float* pconv_w, const float* pconv_b, const float* vconv_w, const float* vconv_b,
+                        const float* fc_w, const float* fc_b, const float* fc1_w, const float* fc1_b, const float* fc2_w, const float* fc2_b) {
+    if (check(n)) return HIVE_E_HANDLE;
+    if (!pconv_w || !pconv_b || !vconv_w || !vconv_b || !fc_w || !fc_b || !fc1_w || !fc1_b || !fc2_w || !fc2_b)
+        return fail(HIVE_E_ARG, "net_load_heads_host: null argument");
+    CUDA_TRY(cudaSetDevice(n->device));
+    CUDA_TRY(cudaStreamSynchronize(n->stream));
+    {   // [4 chunks][8 k-groups][144 rows][8]: rows 0..127 policy conv, row 128 value conv, the rest zero
+        std::vector<__nv_bfloat16> w1((size_t)HC_W_BYTES / 2, __float2bfloat16(0.f));
+        std::vector<float> b1(HC_N, 0.f);
+        for (int r = 0; r <= 128; r++)
+            for (int k = 0; k < 256; k++) {
+                const float v = r < 128 ? pconv_w[(size_t)r * 256 + k] : vconv_w[k];
+                w1[((((size_t)(k >> 6) * 8 + ((k >> 3) & 7)) * HC_N + r) * 8) + (k & 7)] = __float2bfloat16(v);
+            }
+        for (int r = 0; r < 128; r++) b1[r] = pconv_b[r];
+        b1[128] = vconv_b[0];
+        CUDA_TRY(cudaMemcpy(n->head_w1, w1.data(), HC_W_BYTES, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(n->head_b1, b1.data(), HC_N * 4, cudaMemcpyHostToDevice));
+    }
+    {   // [9 column tiles][288 chunks][8 k-groups][176 rows][8]
+        std::vector<__nv_bfloat16> wf((size_t)FC_NT * FC_CHUNKS * FC_B_BYTES / 2);
+        for (int o = 0; o < 1584; o++) {
+            const int nt = o / FC_N, rr = o - nt * FC_N;
+            const float* src = fc_w + (size_t)o * FC_K;
+            for (int k = 0; k < FC_K; k++)
+                wf[(((((size_t)nt * FC_CHUNKS + (k >> 6)) * 8 + ((k >> 3) & 7)) * FC_N + rr) * 8) + (k & 7)] = __float2bfloat16(src[k]);
+        }
+        CUDA_TRY(cudaMemcpy(n->head_wfc, wf.data(), wf.size() * 2, cudaMemcpyHostToDevice));
+    }
+    CUDA_TRY(cudaMemcpy(n->head_bfc, fc_b, 1584 * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(n->head_fc1_w, fc1_w, 64 * 144 * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(n->head_fc1_b, fc1_b, 64 * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(n->head_fc2_w, fc2_w, 64 * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(n->head_fc2_b, fc2_b, 4, cudaMemcpyHostToDevice));
+    n->heads_loaded = true;
+    return 0;
+}
+
+// ChessNet.forward (alpha_net.py:82-95) for n_boards positions: planes (device bf16 [n][56][144]) -> policy_dev (device
+// float32 [n][1584], softmax) and value_dev (device float64 [n], tanh) -- e.g. mcts_dev_leaf_planes / _policy / _value, so a
+// search wave runs without a single copy or library kernel.  Queued on the handle's stream.
+int net_forward(hive_net_t* n, const uint16_t* planes_chw_dev, int n_boards, float* policy_dev, double* value_dev) {
+    if (check(n)) return HIVE_E_HANDLE;
+    if (!policy_dev || !value_dev) return fail(HIVE_E_ARG, "net_forward: null output");
+    if (!n->heads_loaded) return fail(HIVE_E_ARG, "net_forward: the heads are not loaded (net_load_heads_host)");
+    uint16_t* nhwc = nullptr;
+    int rc = net_trunk_forward(n, planes_chw_dev, n_boards, &nhwc);
+    if (rc) return rc;
+    if (reinterpret_cast<__nv_bfloat16*>(nhwc) != n->act[2]) return fail(HIVE_E_CUDA, "net_forward: unexpected trunk output buffer");
+    HeadConvArgs hc;
+    hc.w = n->head_w1; hc.bias = n->head_b1; hc.fc_a = n->fc_a; hc.value_cells = n->value_cells; hc.n_rows = n_boards * 144;
+    const int tiles = (hc.n_rows + HEAD_M - 1) / HEAD_M;
+    hive_head_conv_kernel<<<tiles < n->sms ? tiles : n->sms, HEAD_THREADS, HC_SMEM_BYTES, n->stream>>>(n->map_rows, hc);
+    HeadFcArgs hf;
+    hf.fc_a = n->fc_a; hf.w = n->head_wfc; hf.bias = n->head_bfc; hf.logits = n->logits; hf.n_boards = n_boards;
+    hive_head_fc_kernel<<<dim3(FC_NT, (n_boards + HEAD_M - 1) / HEAD_M), HEAD_THREADS, FC_SMEM_BYTES, n->stream>>>(hf);
+    HeadFinishArgs fin;
+    fin.logits = n->logits; fin.value_cells = n->value_cells; fin.fc1_w = n->head_fc1_w; fin.fc1_b = n->head_fc1_b;
+    fin.fc2_w = n->head_fc2_w; fin.fc2_b = n->head_fc2_b; fin.policy = policy_dev; fin.value = value_dev; fin.mask = nullptr;
+    fin.n_boards = n_boards;
+    hive_head_finish_kernel<<<(n_boards + FIN_WARPS - 1) / FIN_WARPS, FIN_WARPS * 32, 0, n->stream>>>(fin);
+    CUDA_TRY(cudaGetLastError());
+    n->launches += 3;
     return 0;
 }
 

@@ -319,6 +319,7 @@ class GamePlay:
         for q in range(C.MAX_MAP_FULL):
             for r in range(C.MAX_MAP_FULL):
                 self.board_matrix[q, r] = _TileView(q, r)
+        self._pushes = [1, 0]                             # history entries pushed per side (reset pushes white's first)
         self._refresh()
 
     # -- internal
@@ -360,10 +361,8 @@ class GamePlay:
         rec = self._batch.record(0)
         words = rec[64:64 + 320].view(np.uint32).reshape(2, 4, 2, 5)[side]
         out = []
-        for age in range(4):
+        for age in range(min(self._pushes[side], 4)):      # the device keeps the four newest; older ones never reach the planes
             bits = np.unpackbits(words[age].view(np.uint8).reshape(2, 20), axis=1, bitorder="little")[:, :144]
-            if not bits.any() and age > 0:
-                break
             out.append(bits.reshape(2, 12, 12).transpose(1, 2, 0).astype(np.float64))
         return out
 
@@ -385,6 +384,7 @@ class GamePlay:
         self._batch.reset()
         self.state.winner = None
         self._stale_key_player = None
+        self._pushes = [1, 0]
         self._refresh()
 
     def move(self, move, with_skip=False):                # env_hive.py:99-171
@@ -396,6 +396,8 @@ class GamePlay:
         self._batch.step(np.array([move], dtype=np.int32))
         self._stale_key_player = None
         self._refresh()
+        if move >= 0:                                     # a real move pushes the new mover's boards; a pass does not (env_hive.py:100-103)
+            self._pushes[self.state.player()] += 1
 
     def actions(self):                                    # env_hive.py:182
         return self.encoded_action
@@ -450,6 +452,7 @@ class GamePlay:
     def load_position(self, turn, cells, levels):
         self._batch.load_state(0, turn, cells, levels)
         self._stale_key_player = None
+        self._pushes = [0, 0]                             # history is cleared by a load
         self._refresh()
 
     def __deepcopy__(self, memo):                         # solo_play.py:158 deep-copies the env
@@ -465,4 +468,5 @@ class GamePlay:
         other.encoded_action = list(self.encoded_action)
         other.board_matrix = self.board_matrix
         other._winner_code, other._done, other._key, other._pos = self._winner_code, self._done, self._key, self._pos
+        other._pushes = list(self._pushes)
         return other

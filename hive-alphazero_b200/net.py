@@ -105,13 +105,26 @@ class TensorCoreTrunk:
     """The 39 folded 3x3 convolutions on the tensor cores (net_create / net_load_conv_host /
     net_trunk_forward)."""
 
-    def __init__(self, folded_fp32, device_index, stream_ptr, max_boards):
+    def __init__(self, folded_fp32, device_index, stream_ptr, max_boards, heads_fp32=None):
         from ._capi import check, lib
         self._lib, self._check = lib(), check
         h = ctypes.c_void_p()
         check(self._lib.net_create(int(device_index), stream_ptr, int(max_boards), ctypes.byref(h)), "net_create")
         self._h, self.max_boards = h, int(max_boards)
+        self.has_heads = False
         self.load(folded_fp32)
+        if heads_fp32 is not None:
+            self.load_heads(heads_fp32)
+
+    def load_heads(self, heads_fp32):
+        """The ten head tensors (fp32, CPU) in net_load_heads_host's order; reloads keep the device addresses."""
+        arrs = [np.ascontiguousarray(t.detach().float().cpu().numpy()) for t in heads_fp32]
+        self._check(self._lib.net_load_heads_host(self._h, *[a.ctypes.data for a in arrs]), "net_load_heads_host")
+        self.has_heads = True
+
+    def forward_into(self, planes_ptr, n_boards, policy_ptr, value_ptr):
+        """Whole network: planes (device bf16 [n][56][144]) -> policy (device f32 [n][1584]), value (device f64 [n])."""
+        self._check(self._lib.net_forward(self._h, planes_ptr, int(n_boards), policy_ptr, value_ptr), "net_forward")
 
     def load(self, folded_fp32):
         """(Re)load the 39 folded convolutions; the packed operands keep their device addresses."""
@@ -177,6 +190,13 @@ class FoldedNet:
             self.fc1 = (ob.fc1.weight.to(self.device, torch.float32), ob.fc1.bias.to(self.device, torch.float32))
             self.fc2 = (ob.fc2.weight.to(self.device, torch.float32), ob.fc2.bias.to(self.device, torch.float32))
             self.fc = (ob.fc.weight.to(self.device, dtype), ob.fc.bias.to(self.device, torch.float32))
+            # the same heads for the hand-written kernels (net_load_heads_host): fp32 on the host, fc columns cell-major
+            pw, pb = _fold(ob.conv1.weight, ob.conv1.bias, ob.bn1)
+            vw, vb = _fold(ob.conv.weight, ob.conv.bias, ob.bn)
+            self._heads_fp32 = [t.detach().float().cpu().contiguous() for t in (
+                pw.reshape(POLICY_CH, CH), pb, vw.reshape(CH), vb.reshape(1),
+                ob.fc.weight.detach().view(C.ACTION_SPACE, POLICY_CH, CELLS).permute(0, 2, 1).reshape(C.ACTION_SPACE, CELLS * POLICY_CH),
+                ob.fc.bias, ob.fc1.weight, ob.fc1.bias, ob.fc2.weight.reshape(-1), ob.fc2.bias.reshape(1))]
 
     @torch.no_grad()
     def reload(self, net):
@@ -193,9 +213,10 @@ class FoldedNet:
         for name in ("vconv", "pconv", "vlin", "plin", "fc1", "fc2", "fc"):
             take(getattr(self, name), getattr(fresh, name))
         self.fc_nhwc.copy_(fresh.fc_nhwc)
-        self._folded_fp32 = fresh._folded_fp32
+        self._folded_fp32, self._heads_fp32 = fresh._folded_fp32, fresh._heads_fp32
         if self.trunk is not None:
             self.trunk.load(self._folded_fp32)
+            self.trunk.load_heads(self._heads_fp32)
         return self
 
     def trunk_weights(self):
@@ -211,7 +232,7 @@ class FoldedNet:
         if self.device.type != "cuda":
             raise RuntimeError("the tensor-core trunk needs a CUDA device (there is no CPU fallback)")
         idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
-        self.trunk = TensorCoreTrunk(self._folded_fp32, idx, stream_ptr, max_boards)
+        self.trunk = TensorCoreTrunk(self._folded_fp32, idx, stream_ptr, max_boards, heads_fp32=self._heads_fp32)
         return self
 
     def _trunk_torch(self, planes):
@@ -237,7 +258,18 @@ class FoldedNet:
     @torch.no_grad()
     def forward(self, planes, trunk=None):
         """planes (B,56,12,12) bf16/fp32 on the device -> (p (B,1584) fp32, v (B,1) fp32).
-        trunk: None = the tensor-core kernel if attached else torch; "torch" forces the library path."""
+        trunk: None = the hand-written network (trunk + heads) if attached, else torch; "tc" = tensor-core trunk + library
+        heads; "torch" forces the library path."""
+        if self.trunk is not None and trunk is None and self.trunk.has_heads:
+            # the whole network as hand-written sm_100a kernels (net_forward): trunk + heads, no library kernel
+            pl = planes.to(self.dtype).contiguous()
+            n = pl.shape[0]
+            p = torch.empty((n, C.ACTION_SPACE), dtype=torch.float32, device=self.device)
+            v = torch.empty((n,), dtype=torch.float64, device=self.device)
+            for s in range(0, n, self.trunk.max_boards):
+                e = min(n, s + self.trunk.max_boards)
+                self.trunk.forward_into(pl[s:e].data_ptr(), e - s, p[s:e].data_ptr(), v[s:e].data_ptr())
+            return p, v.float().reshape(-1, 1)
         if self.trunk is not None and trunk != "torch":
             x = self._trunk_tc(planes.to(self.dtype).contiguous())
         else:
@@ -272,6 +304,15 @@ class LeafEvaluator:
         self.calls = 0
 
     def __call__(self, planes_ptr, policy_ptr, value_ptr, mask_ptr, n):
+        trunk = self.net.trunk
+        if trunk is not None and trunk.has_heads:
+            # planes arena -> policy / value arenas by the library's own kernels: no copy, no torch kernel in the wave
+            step = min(self.max_batch, trunk.max_boards)
+            for s in range(0, n, step):
+                e = min(n, s + step)
+                trunk.forward_into(planes_ptr + s * C.STATE_FEATURES * CELLS * 2, e - s, policy_ptr + s * C.ACTION_SPACE * 4, value_ptr + s * 8)
+            self.calls += 1
+            return
         dev = self.net.device
         planes = device_view(planes_ptr, (n, C.STATE_FEATURES, BOARD, BOARD), "<u2", dev).view(torch.bfloat16)
         policy = device_view(policy_ptr, (n, C.ACTION_SPACE), "<f4", dev)

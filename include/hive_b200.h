@@ -235,6 +235,16 @@ int net_load_conv_host(hive_net_t* n, int layer, const float* w, const float* bi
 /* planes: device bf16 [n_boards][56][144]; *out_nhwc: device bf16 [n_boards][144][256], valid until the
  * next call.  Stream-ordered on the handle's stream. */
 int net_trunk_forward(hive_net_t* n, const uint16_t* planes_chw_dev, int n_boards, uint16_t** out_nhwc);
+/* The heads (alpha_net.py:56-80), BatchNorm folded into the two 1x1 convolutions by the caller: pconv_w [128][256],
+ * pconv_b [128]; vconv_w [256], vconv_b [1]; fc_w [1584][18432] with CELL-MAJOR columns (k = cell*128 + channel: the
+ * reference's flatten c*144 + cell permuted once), fc_b [1584]; fc1_w [64][144], fc1_b [64]; fc2_w [64], fc2_b [1]. */
+int net_load_heads_host(hive_net_t* n, const float* pconv_w, const float* pconv_b, const float* vconv_w, const float* vconv_b,
+                        const float* fc_w, const float* fc_b, const float* fc1_w, const float* fc1_b, const float* fc2_w, const float* fc2_b);
+/* ChessNet.forward (alpha_net.py:82-95; api_hive.py:60-74 is the server loop it replaces) for n_boards positions:
+ * planes_chw_dev device bf16 [n][56][144] -> policy_dev device float32 [n][1584] (softmax), value_dev device float64 [n]
+ * (tanh).  Trunk (39 tcgen05 convolutions) + heads (two tcgen05 GEMMs + one finishing kernel), all hand-written
+ * sm_100a kernels queued on the handle's stream; the outputs may be the search's leaf arenas. */
+int net_forward(hive_net_t* n, const uint16_t* planes_chw_dev, int n_boards, float* policy_dev, double* value_dev);
 long long net_launch_count(const hive_net_t* n);
 
 #ifdef __cplusplus

@@ -128,3 +128,41 @@ def test_selfplay_samples_and_evaluator_match(tmp_path):
         r = ev.play()
     assert r["games"] == 16 and r["new_wins"] + r["best_wins"] + r["draws"] == 16 and r["moves"] > 16 * 20
     assert 0 < r["distinct_final_positions"] <= 1 and 20 < r["mean_game_len"] <= 55 and 0 <= r["white_win_rate"] <= 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_boards", [67, 300])
+def test_heads_kernels_match_references(n_boards):
+    """The whole network as hand-written kernels (net_forward: tcgen05 trunk + tcgen05 heads + finishing kernel) against
+    the fp32 reference architecture (<= 1e-2, BASELINE.json) and against the library heads on the SAME trunk output
+    (isolates the three head kernels: 1x1 convs, policy fc, softmax / value MLP); partial row tiles (67, 300 boards)."""
+    import hive_b200
+    torch.manual_seed(0)
+    net = hive_b200.HiveNet().eval()
+    _randomize_bn(net, 5)
+    with torch.no_grad():                                                  # lively heads: non-trivial biases everywhere
+        for p in net.outblock.parameters():
+            p.add_(0.004 * torch.randn_like(p))
+    b = hive_b200.HiveBatch(n_boards)
+    for _ in range(30):
+        b.step_random(11, 55, True)
+    planes = torch.from_numpy(b.planes().copy()).cuda()
+    with torch.no_grad():
+        p_ref, v_ref = net.cuda()(planes)
+    folded = hive_b200.FoldedNet(net, device="cuda").attach_trunk(stream_ptr=torch.cuda.current_stream().cuda_stream, max_boards=384)
+    p_lib, v_lib = folded(planes, trunk="tc")                              # tensor-core trunk + library heads
+    launches0 = folded.trunk.launches
+    p, v = folded(planes)                                                  # trunk + heads kernels, nothing else
+    torch.cuda.synchronize()
+    assert folded.trunk.launches - launches0 == 40 + 3
+    # (the library path rounds the 1,584 logits to bf16 before the softmax; here they stay float32, so the fp32 reference is the closer one)
+    assert float((p - p_lib).abs().max()) <= 1e-2 and float((v - v_lib).abs().max()) <= 1e-2
+    assert float((p - p_ref).abs().max()) <= float((p_lib - p_ref).abs().max()) + 1e-3
+    assert float((p - p_ref).abs().max()) <= 1e-2 and float((v - v_ref).abs().max()) <= 1e-2
+    assert torch.allclose(p.sum(1), torch.ones(n_boards, device="cuda"), atol=1e-4)
+    # written straight into caller-owned arenas (what the search's wave does)
+    pol = torch.full((n_boards, 1584), -1.0, device="cuda")
+    val = torch.full((n_boards,), -7.0, dtype=torch.float64, device="cuda")
+    hive_b200.LeafEvaluator(folded)(planes.to(torch.bfloat16).contiguous().data_ptr(), pol.data_ptr(), val.data_ptr(), 0, n_boards)
+    torch.cuda.synchronize()
+    assert torch.equal(pol, p) and torch.equal(val.float().reshape(-1, 1), v)
