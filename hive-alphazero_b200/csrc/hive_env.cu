@@ -91,6 +91,7 @@ static EnvArgs slice_args(hive_env* h, int s, int per, int op, const int32_t* ac
     a.chosen = chosen ? chosen + off : nullptr; a.hop_lines = h->hop_lines;
     a.seed = seed; a.n = cnt > 0 ? cnt : 0; a.op = op; a.max_turn = max_turn; a.auto_reset = auto_reset;
     a.g_offset = off; a.n_total = h->n;
+    a.stagger_ns = h->stagger_ns; a.stagger_div = h->sm_count > 0 ? h->sm_count : 148;
     return a;
 }
 // The plane-store kernel is persistent: the store launches that run at the same time (`concurrent` slices) share
@@ -240,6 +241,7 @@ int hive::create_env(int n_games, int device, void* stream, int slices, hive_env
     if (!getenv("HIVE_B200_NO_CARVEOUT")) {
         CUDA_TRY(cudaFuncSetAttribute(hive_planes_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CUDA_TRY(cudaFuncSetAttribute(hive_step_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CUDA_TRY(cudaFuncSetAttribute(hive_rollout_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
     for (int b = 0; b < 2; b++) {
         CUDA_TRY(cudaMalloc(&h->bits[b], n * BITS_WORDS * 4));
@@ -269,6 +271,10 @@ int hive::create_env(int n_games, int device, void* stream, int slices, hive_env
         h->skip_planes = getenv("HIVE_B200_EXPERIMENT_SKIP_PLANES") != nullptr;   // measurement aid: the step without its plane store
         const char* sg = getenv("HIVE_B200_SPLIT_GRAPHS");
         h->split_graphs = sg ? atoi(sg) : 1;
+        const char* sg2 = getenv("HIVE_B200_STAGGER_US");
+        h->stagger_ns = (sg2 ? atoi(sg2) : 25) * 1000;
+        const char* rk = getenv("HIVE_B200_ROLLOUT_KERNEL");
+        h->use_rollout_kernel = rk ? atoi(rk) : 0;         // measured slower than the per-step kernels (profiles/README.md): off
         const char* ug = getenv("HIVE_B200_GRAPH");
         h->use_graph = ug ? atoi(ug) : 1;
     }
@@ -493,6 +499,16 @@ int hive_step_random_multi(hive_env_t* h, uint64_t seed, int max_turn, int auto_
     if (max_turn < 1 || max_turn > 250 || n_steps < 1 || n_steps > 4096) return fail(HIVE_E_ARG, "hive_step_random_multi: bad arguments");
     CUDA_TRY(cudaSetDevice(h->device));
     if (h->timing) CUDA_TRY(cudaEventRecord(h->t0, h->stream));
+    if (h->use_rollout_kernel) {
+        // one launch: every CTA walks through the n_steps steps of its 32 games and stores their planes itself
+        EnvArgs a = slice_args(h, 0, h->n, OP_RANDOM, nullptr, nullptr, seed, max_turn, auto_reset, nullptr);
+        a.bits = h->bits[0];
+        hive_rollout_kernel<<<(h->n + SG - 1) / SG, STEP_THREADS, 0, h->stream>>>(a, n_steps);
+        CUDA_TRY(cudaGetLastError());
+        h->launches += 1;
+        if (h->timing) CUDA_TRY(cudaEventRecord(h->t1, h->stream));
+        return 0;
+    }
     hive_env::StepGraph& g = h->multi_graph;
     const bool hit = g.exec && g.seed == seed && g.max_turn == max_turn && g.auto_reset == auto_reset && g.op == n_steps;
     const int S = h->n_sub;

@@ -31,6 +31,7 @@ struct EnvArgs {
     uint64_t seed;
     int n, op, max_turn, auto_reset;
     int g_offset, n_total;   // this launch covers games [g_offset, g_offset+n) of a batch of n_total (pointers are pre-offset)
+    int stagger_ns, stagger_div;   // rollout kernel: start offset between the CTAs of one SM, CTAs per wave (= #SMs)
 };
 
 // ---- optional per-CTA timeline (builds with -DHIVE_TRACE only; profiles/trace_probe.py reads it)
@@ -579,9 +580,9 @@ __device__ __forceinline__ void encode_mobility(const StepShared& s, const Encod
     if (e.live) store_words<(WHICH ? 44 : 50) * 5 + 15 * HALF, 15>(e.bits, f);
 }
 
-__global__ void __launch_bounds__(STEP_THREADS, HIVE_STEP_MIN_CTAS) hive_step_kernel(EnvArgs a) {
-    __shared__ StepShared s;
-    HIVE_TRACE_SCOPE(0, a);
+// phases 1..5 of one step of the CTA's 32 games (all threads; ends without a trailing barrier).  Returns the mask of the
+// games evaluated in this step (identical in every thread).
+__device__ __forceinline__ unsigned step_phases(StepShared& s, const EnvArgs& a) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.x * SG + lane;
     const uint32_t* geo = a.hop_lines;
@@ -590,7 +591,8 @@ __global__ void __launch_bounds__(STEP_THREADS, HIVE_STEP_MIN_CTAS) hive_step_ke
     else if (warp == SW - 1 && lane < 6) (&s.n_flood)[lane == 5 ? 6 : lane] = 0u;      // queue fills, next_task (never in the prologue's warp: it must stay converged)
     __syncthreads();
     HIVE_PHASE_MARK(0);
-    if (!s.any_live) return;
+    const unsigned live_mask = s.any_live;
+    if (!live_mask) return 0u;
 
     step_stacks(s, warp, lane);
     __syncthreads();
@@ -710,6 +712,94 @@ __global__ void __launch_bounds__(STEP_THREADS, HIVE_STEP_MIN_CTAS) hive_step_ke
         }
     }
     HIVE_PHASE_MARK(5);
+    return live_mask;
+}
+
+__global__ void __launch_bounds__(STEP_THREADS, HIVE_STEP_MIN_CTAS) hive_step_kernel(EnvArgs a) {
+    __shared__ StepShared s;
+    HIVE_TRACE_SCOPE(0, a);
+    step_phases(s, a);
+}
+
+// ---- the rollout kernel (experiment, HIVE_B200_ROLLOUT_KERNEL=1; measured SLOWER than the per-step kernels, 102 vs 66 us
+// per step: a CTA's own plane store -- 512 KB per step through a 4 KB staging ring per warp -- sits on its critical path):
+// n_steps consecutive OP_RANDOM steps of the CTA's 32 games in ONE launch.  Games are independent
+// and a CTA owns its games' records, legal masks and bit planes, so nothing orders the CTAs: each walks through its steps
+// at its own pace (no kernel boundary per step to wait at for the slowest CTA of a launch, no launch gap), and after
+// every step it stores its games' planes itself -- phase 6: the bit planes it has just written (L2) are expanded to
+// bf16 through the TMA, SG / SW games per warp, with the staging ring laid over the step's shared memory; the bulk
+// stores drain to HBM while the next step is computed.
+#ifndef HIVE_ROLL_STAGE_PLANES
+#define HIVE_ROLL_STAGE_PLANES 7
+#endif
+constexpr int RSP = HIVE_ROLL_STAGE_PLANES;
+struct __align__(128) RollStoreShared {
+    uint4 stage[SW][STAGE_BUFS * RSP * 18];
+    uint4 lut[256];
+    uint32_t planes[SW][BITS_WORDS];
+    uint32_t lut_addr;
+};
+union __align__(128) RollShared {
+    StepShared step;
+    RollStoreShared store;
+};
+
+#ifndef HIVE_ROLL_MIN_CTAS
+#define HIVE_ROLL_MIN_CTAS (1024 / (HIVE_STEP_WARPS * 32))     // every CTA of a 16,384-game batch resident at once (4 per SM)
+#endif
+__global__ void __launch_bounds__(STEP_THREADS, HIVE_ROLL_MIN_CTAS) hive_rollout_kernel(EnvArgs a, int n_steps) {
+    __shared__ RollShared sm;
+    HIVE_TRACE_SCOPE(5, a);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifndef HIVE_EMU
+    {   // The CTAs that share an SM (blocks i, i + #SMs, i + 2 #SMs ... of a launch) start a fraction of a step apart, so that
+        // one of them stores planes while the others compute: all CTAs do the same work per step and would otherwise
+        // stay in lock step, computing together and then queueing for HBM together.
+        const unsigned wave = blockIdx.x / a.stagger_div;
+        if (a.stagger_ns && wave) {
+            unsigned long long t0, t;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+            do { __nanosleep(1000); asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); } while (t - t0 < (unsigned long long)a.stagger_ns * (wave & 3u));
+        }
+    }
+#endif
+    for (int step = 0; step < n_steps; step++) {
+        const unsigned live_mask = step_phases(sm.step, a);
+        __syncthreads();                                        // the step's shared memory is dead; its global writes are visible to the CTA
+        if (live_mask) {   // ---- phase 6: bit planes -> bf16 CHW planes [56][144] per game (warp <-> game)
+            RollStoreShared& st = sm.store;
+            for (int t = tid; t < 256; t += STEP_THREADS) fill_bf16_lut(st.lut, t);
+#ifndef HIVE_EMU
+            if (tid == 0) st.lut_addr = (uint32_t)__cvta_generic_to_shared(st.lut);
+#endif
+            __syncthreads();
+            const uint32_t lut_s = *reinterpret_cast<volatile uint32_t*>(&st.lut_addr);
+            constexpr int NV = BITS_WORDS / 4;                  // 70 uint4 per game
+            uint32_t* mine = st.planes[warp];
+            uint4 v[3];
+            auto fetch = [&](int slot) {
+                const uint4* src = reinterpret_cast<const uint4*>(a.bits + (size_t)(blockIdx.x * SG + slot) * BITS_WORDS);
+#pragma unroll
+                for (int i = 0; i < 3; i++) { const int t = lane + 32 * i; v[i] = src[t < NV ? t : 0]; }
+            };
+            unsigned todo = 0;                                  // this warp's evaluated games: slots warp, warp + SW, ...
+            for (int slot = warp; slot < SG; slot += SW) if ((live_mask >> slot) & 1u) todo |= 1u << slot;
+            if (todo) fetch(__ffs(todo) - 1);
+            while (todo) {
+                const int slot = __ffs(todo) - 1; todo &= todo - 1;
+                __syncwarp();                                   // the previous game's planes have been expanded
+#pragma unroll
+                for (int i = 0; i < 3; i++) { const int t = lane + 32 * i; if (t < NV) reinterpret_cast<uint4*>(mine)[t] = v[i]; }
+                __syncwarp();
+                const uint32_t turn = mine[BITS_TURN];
+                if (todo) fetch(__ffs(todo) - 1);               // the next game's bit planes arrive during the expansion
+                store_planes_bulk_t<RSP>(reinterpret_cast<const uint8_t*>(mine), st.lut, lut_s, st.stage[warp], lane, (int)turn,
+                                         a.planes + (size_t)(blockIdx.x * SG + slot) * HIVE_PLANES_ELEMS);
+            }
+            if (lane == 0) bulk_wait_read<0>();                 // the copy engine has read the staging ring (the writes to HBM go on)
+            __syncthreads();                                    // before the next step reuses the shared memory
+        }
+    }
 }
 
 // ---- kernel 5: bit planes -> bf16 CHW planes [56][144] per game, through the TMA (persistent: the grid is capped in

@@ -40,6 +40,8 @@ struct hive_env {
     bool skip_planes = false;       // measurement aid (HIVE_B200_EXPERIMENT_SKIP_PLANES): results are then incomplete
     int split_graphs = 1;
     int use_graph = 1;
+    int stagger_ns = 25000;         // rollout kernel: start offset between the CTAs sharing an SM (HIVE_B200_STAGGER_US)
+    int use_rollout_kernel = 0;     // HIVE_B200_ROLLOUT_KERNEL=1: hive_step_random_multi as ONE persistent launch (measured slower; default: per-step kernels in graphs)
     int32_t* d_actions[2] = {nullptr, nullptr};
     int act_flip = 0;
     cudaEvent_t act_read_ev[2] = {nullptr, nullptr};   // behind the step that read d_actions[b] (hive_step_host)

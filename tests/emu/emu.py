@@ -35,6 +35,8 @@ def lib():
         L.emu_env_run.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_uint64,
                                   ctypes.c_int, ctypes.c_int, vp, ctypes.c_uint64]
         L.emu_env_run.restype = ctypes.c_int
+        L.emu_env_rollout.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint64]
+        L.emu_env_rollout.restype = ctypes.c_int
         L.emu_last_error.restype = ctypes.c_char_p
         L.emu_mcts_create.restype = vp
         L.emu_mcts_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
@@ -89,6 +91,14 @@ class EmuBatch:
 
     def step_random(self, seed, max_turn=55, auto_reset=1):
         self._run(OP_RANDOM, seed=seed, max_turn=max_turn, auto_reset=auto_reset)
+
+    def step_random_multi(self, seed, n_steps, max_turn=55, auto_reset=1):
+        """n_steps random steps through the rollout kernel (one launch; every CTA loops and stores its own planes)."""
+        self.sched_seed += 7919
+        rc = lib().emu_env_rollout(self.recs.ctypes.data, self.legal.ctypes.data, self.count.ctypes.data, self.status.ctypes.data,
+                                   self.planes.ctypes.data, self.n, seed, max_turn, auto_reset, n_steps, self.sched_seed)
+        if rc:
+            raise RuntimeError("emulator: " + lib().emu_last_error().decode())
 
     def load(self, g, turn, cells, levels):
         self.recs[g, :] = 0

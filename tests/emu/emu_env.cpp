@@ -27,7 +27,7 @@ int emu_env_run(void* recs, uint32_t* legal, int32_t* count, uint32_t* status, u
     a.recs = (GameRec*)recs; a.legal = legal; a.count = count; a.status = status; a.planes = planes;
     a.actions = actions; a.mask = mask; a.chosen = chosen; a.hop_lines = g_lines.data();
     a.seed = seed; a.n = n; a.op = op; a.max_turn = max_turn; a.auto_reset = auto_reset;
-    a.g_offset = 0; a.n_total = n;
+    a.g_offset = 0; a.n_total = n; a.stagger_ns = 0; a.stagger_div = 148;
     static std::vector<uint32_t> bits;
     if ((int)bits.size() < n * BITS_WORDS) bits.resize((size_t)n * BITS_WORDS);
     a.bits = bits.data();
@@ -42,6 +42,27 @@ int emu_env_run(void* recs, uint32_t* legal, int32_t* count, uint32_t* status, u
     emu::g_gridDim.x = store_blocks;
     for (int b = 0; b < store_blocks; b++) {
         int rc = emu::run_block(k_planes, &a, b, HIVE_STORE_WARPS * 32, sched_seed + 3000 + (uint64_t)b);
+        if (rc) return rc;
+    }
+    return 0;
+}
+// n_steps OP_RANDOM steps through the rollout kernel (every CTA loops over its steps and stores its planes itself)
+int emu_env_rollout(void* recs, uint32_t* legal, int32_t* count, uint32_t* status, uint16_t* planes, int n, uint64_t seed,
+                    int max_turn, int auto_reset, int n_steps, uint64_t sched_seed) {
+    build_lines();
+    EnvArgs a;
+    a.recs = (GameRec*)recs; a.legal = legal; a.count = count; a.status = status; a.planes = planes;
+    a.actions = nullptr; a.mask = nullptr; a.chosen = nullptr; a.hop_lines = g_lines.data();
+    a.seed = seed; a.n = n; a.op = OP_RANDOM; a.max_turn = max_turn; a.auto_reset = auto_reset;
+    a.g_offset = 0; a.n_total = n; a.stagger_ns = 0; a.stagger_div = 148;
+    static std::vector<uint32_t> bits;
+    if ((int)bits.size() < n * BITS_WORDS) bits.resize((size_t)n * BITS_WORDS);
+    a.bits = bits.data();
+    struct Call { EnvArgs a; int n_steps; } call = {a, n_steps};
+    const int blocks = (n + SG - 1) / SG;
+    emu::g_gridDim.x = blocks;
+    for (int b = 0; b < blocks; b++) {
+        int rc = emu::run_block([](void* p) { Call* c = (Call*)p; hive_rollout_kernel(c->a, c->n_steps); }, &call, b, STEP_THREADS, sched_seed + (uint64_t)b);
         if (rc) return rc;
     }
     return 0;

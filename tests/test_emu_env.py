@@ -109,3 +109,21 @@ def test_batch_of_forty_games_two_ctas():
         e.step(actions)
     for g, o in enumerate(oracles):
         _compare(e, g, o)
+
+
+def test_rollout_kernel_equals_single_steps():
+    """hive_rollout_kernel (n steps in one launch, every CTA looping on its own and storing its planes itself) leaves the
+    batch exactly where n single random steps leave it -- records, legal masks, counts, status and planes."""
+    n, seed = 37, 0xBEEF
+    a, b = EmuBatch(n, sched_seed=21), EmuBatch(n, sched_seed=22)
+    for _ in range(3):
+        a.step_random(seed); b.step_random(seed)
+    for _ in range(9):
+        a.step_random(seed)
+    b.step_random_multi(seed, 9)
+    assert (a.recs == b.recs).all() and (a.legal == b.legal).all() and (a.count == b.count).all()
+    assert (a.status == b.status).all() and (a.planes == b.planes).all()
+    b.step_random_multi(seed, 60)                       # across the turn-55 cut: resets inside the loop
+    for _ in range(60):
+        a.step_random(seed)
+    assert (a.recs == b.recs).all() and (a.planes == b.planes).all() and (a.legal == b.legal).all()
