@@ -246,7 +246,8 @@ def run_selfplay(args, hive_b200, torch, dist, rank, world, local_rank, allsum, 
     for m in (net, net_best):
         par.broadcast_weights(m, src=0, wire_dtype=torch.bfloat16)
     folded = hive_b200.FoldedNet(net, device="cuda").attach_trunk(stream_ptr=stream.cuda_stream, max_boards=max(n2, n3, n4))
-    folded_best = hive_b200.FoldedNet(net_best, device="cuda").attach_trunk(stream_ptr=stream.cuda_stream, max_boards=n4)
+    side_stream = torch.cuda.Stream()                          # the second network of the evaluator match runs beside the first
+    folded_best = hive_b200.FoldedNet(net_best, device="cuda").attach_trunk(stream_ptr=side_stream.cuda_stream, max_boards=n4)
 
     def timed_collectives_before(model, fold):
         """weight broadcast from rank 0 (bf16 on the wire) + in-place reload of the folded network; seconds, bytes"""
@@ -314,7 +315,8 @@ def run_selfplay(args, hive_b200, torch, dist, rank, world, local_rank, allsum, 
                                          n3, args.sharded_sims, 7, 0, 1)
         # configs[4]: evaluator match, new vs best net
         with torch.cuda.stream(stream):
-            ev = hive_b200.EvaluatorMatch(n4, args.evaluator_sims, hive_b200.LeafEvaluator(folded), hive_b200.LeafEvaluator(folded_best),
+            ev = hive_b200.EvaluatorMatch(n4, args.evaluator_sims, hive_b200.LeafEvaluator(folded),
+                                          hive_b200.LeafEvaluator(folded_best, stream=side_stream),
                                           device=local_rank, stream=stream.cuda_stream, seed=7 + rank, torch_stream=stream)
             ev.play(max_plies=5)                                # 4 random plies + one searched ply (warm-up, graph capture)
             barrier(); torch.cuda.synchronize()

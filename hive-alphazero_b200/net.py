@@ -299,8 +299,11 @@ def device_view(ptr, shape, typestr, device="cuda"):
 class LeafEvaluator:
     """evaluate_device callback for MctsBatch.search_device: planes arena -> policy / value arenas."""
 
-    def __init__(self, folded, max_batch=4096):
+    def __init__(self, folded, max_batch=4096, stream=None):
+        """stream: the torch stream the network's kernels are queued on when it is NOT the caller's current stream (the
+        trunk was attached with that stream's pointer); SplitEvaluator then forks / joins around the call."""
         self.net, self.max_batch = folded, max_batch
+        self.stream = stream
         self.calls = 0
 
     def __call__(self, planes_ptr, policy_ptr, value_ptr, mask_ptr, n):
@@ -327,18 +330,41 @@ class LeafEvaluator:
 
 class SplitEvaluator:
     """Two networks in one search: rows [0, split) are evaluated by `first`, rows [split, n) by `second`
-    (the evaluator match keeps the games where the new net plays white in the first half)."""
+    (the evaluator match keeps the games where the new net plays white in the first half).
+    An evaluator with a `stream` of its own runs beside the other one: the call forks that stream off the caller's and
+    joins it again, so the persistent convolution CTAs of one network fill the SMs the other network's last partial wave
+    leaves idle (512 boards are 3.5 waves of 148 CTAs; two such launches side by side lose one tail instead of two)."""
 
     def __init__(self, first, second, split):
         self.first, self.second, self.split = first, second, int(split)
 
+    @staticmethod
+    def _run(ev, args):
+        side = getattr(ev, "stream", None)
+        if side is None:
+            ev(*args)
+            return None
+        main = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            ev(*args)
+            done = torch.cuda.Event()
+            done.record(side)
+        return done
+
     def __call__(self, planes_ptr, policy_ptr, value_ptr, mask_ptr, n):
         k = self.split
+        joins = []
         if k > 0:
-            self.first(planes_ptr, policy_ptr, value_ptr, mask_ptr, k)
+            joins.append(self._run(self.first, (planes_ptr, policy_ptr, value_ptr, mask_ptr, k)))
         if n > k:
-            self.second(planes_ptr + k * C.STATE_FEATURES * CELLS * 2, policy_ptr + k * C.ACTION_SPACE * 4,
-                        value_ptr + k * 8, mask_ptr + k, n - k)
+            joins.append(self._run(self.second, (planes_ptr + k * C.STATE_FEATURES * CELLS * 2, policy_ptr + k * C.ACTION_SPACE * 4,
+                                                 value_ptr + k * 8, mask_ptr + k if mask_ptr else mask_ptr, n - k)))
+        for done in joins:
+            if done is not None:
+                torch.cuda.current_stream().wait_event(done)
 
 
 def host_net_callable(folded):
