@@ -17,5 +17,5 @@ allt = sum(tot.values())
 print(sys.argv[2] if len(sys.argv) > 2 else sys.argv[1], "(%d launches)" % sum(cnt.values()))
 for k, v in tot.most_common():
     print("%-62s n=%5d  sum=%11.1f us  mean=%8.1f us  share=%.3f" % (k[:60], cnt[k], v, v / cnt[k], v / allt))
-lib = [k for k in tot if not k.startswith("hive::") and "chw_to_nhwc64" not in k and "hash_eval" not in k]
+lib = [k for k in tot if not (k.startswith(("hive::", "hive_", "mcts_")) or "chw_to_nhwc64" in k or "hash_eval" in k)]
 print("kernels that are not this repo's:", lib if lib else "none")
