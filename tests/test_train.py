@@ -74,3 +74,39 @@ def test_play_file_round_trip_matches_sample_tensors(tmp_path):
     x1, p1, v1 = hive_b200.rows_to_tensors(hive_b200.load_play_files(str(tmp_path)))
     x0, p0, v0 = hive_b200.samples_to_tensors(samples)
     assert torch.equal(x0, x1) and torch.allclose(p0, p1, atol=1e-7) and torch.allclose(v0, v1, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_closed_loop_on_the_device_selfplay_train_reload(tmp_path):
+    """Row f2 on the GPU: samples from a batched self-play -> Adam steps of the fp32 network on the device (loss falls) ->
+    the folded bf16 network and the tensor-core operands take the new weights over IN PLACE (the captured wave graph
+    stays valid) -> the next search sees the trained network; checkpoint in the reference's {'state_dict'} format."""
+    torch.manual_seed(0)
+    net = hive_b200.HiveNet().cuda()
+    stream = torch.cuda.Stream()
+    folded = hive_b200.FoldedNet(net, device="cuda").attach_trunk(stream_ptr=stream.cuda_stream, max_boards=32)
+    with torch.cuda.stream(stream):
+        sp = hive_b200.SelfPlayBatch(16, 6, hive_b200.LeafEvaluator(folded), stream=stream.cuda_stream, seed=4, collect=True,
+                                     wave_graph=hive_b200.WaveGraph(stream))
+        sp.play_moves(56)                                       # every game is cut at turn 55 (or ends) and flushed
+        assert len(sp.finished_samples) >= 16 * 50
+        x, p, v = hive_b200.samples_to_tensors(sp.finished_samples[:256])
+        planes = torch.from_numpy(sp.env.planes().copy()).cuda()
+        p_before, v_before = folded(planes)
+        tr = hive_b200.Trainer(net, lr=1e-3)
+        losses = [tr.step(x, p, v) for _ in range(6)]
+        assert losses[-1] < losses[0]
+        net.eval()
+        folded.reload(net)
+        p_after, v_after = folded(planes)
+        with torch.no_grad():
+            p_ref, v_ref = net(planes)
+        torch.cuda.synchronize()
+        assert float((p_after - p_before).abs().max()) > 1e-4               # the weights really changed ...
+        assert float((p_after - p_ref).abs().max()) <= 1e-2 and float((v_after - v_ref).abs().max()) <= 2e-2   # ... to the trained ones
+        r = sp.play_moves(2)                                    # the captured wave graph runs on with the reloaded network
+        assert r["moves"] == 32
+    path = str(tmp_path / "iter.pth.tar")
+    tr.save(path)
+    ck = torch.load(path)
+    assert set(ck) == {"state_dict"} and "outblock.fc.weight" in ck["state_dict"]
