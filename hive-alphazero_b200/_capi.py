@@ -19,7 +19,7 @@ ENV_SYMBOLS = [
 # void policy(void* user, int part, int first_game, int n, const u64* mask, const i32* count, const u32* status, i32* actions)
 POLICY_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                              ctypes.c_void_p, ctypes.c_void_p)
-NET_SYMBOLS = ["net_create", "net_destroy", "net_load_conv_host", "net_trunk_forward", "net_launch_count", "net_load_heads_host", "net_forward"]
+NET_SYMBOLS = ["net_create", "net_destroy", "net_load_conv_host", "net_trunk_forward", "net_launch_count", "net_load_heads_host", "net_forward", "net_load_conv_dev", "net_load_heads_dev"]
 MCTS_SYMBOLS = [
     "mcts_create", "mcts_destroy", "mcts_set_params", "mcts_set_root_noise_host", "mcts_begin", "mcts_descend",
     "mcts_expand", "mcts_pending_host", "mcts_dev_leaf_planes", "mcts_dev_leaf_policy", "mcts_dev_leaf_value", "mcts_dev_pending_mask",
@@ -117,6 +117,8 @@ def lib():
     L.net_load_conv_host.argtypes = [vp, i32, vp, vp, i32]
     L.net_trunk_forward.argtypes = [vp, vp, i32, ctypes.POINTER(vp)]
     L.net_load_heads_host.argtypes = [vp] * 11
+    L.net_load_heads_dev.argtypes = [vp] * 11
+    L.net_load_conv_dev.argtypes = [vp, i32, vp, vp, i32]
     L.net_forward.argtypes = [vp, vp, i32, vp, vp]
     L.net_launch_count.argtypes = [vp]
     L.net_launch_count.restype = ctypes.c_longlong

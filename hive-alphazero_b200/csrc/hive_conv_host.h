@@ -6,25 +6,40 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
+#include <thread>
 #include <vector>
 
 namespace hive {
+
+// fn(i) for i in [0, n) on a handful of host threads (weight packing after a broadcast sits in self-play's timed region)
+template <typename F>
+inline void parallel_for(int n, F fn) {
+    unsigned hc = std::thread::hardware_concurrency();
+    int nt = hc > 8 ? 8 : (hc > 1 ? (int)hc : 1);
+    if (nt > n) nt = n;
+    if (nt <= 1) { for (int i = 0; i < n; i++) fn(i); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++)
+        th.emplace_back([=] { for (int i = t; i < n; i += nt) fn(i); });
+    for (auto& x : th) x.join();
+}
 
 // w: [256 oc][C ic][3][3] fp32 (BatchNorm already folded) -> [2 halves][9 taps][C/(8 KG) chunks][KG k-groups][128 rows][8 ch] bf16
 inline void pack_conv_weights(const float* w, int C, int KG, std::vector<uint8_t>& out) {
     const int nC = C / (8 * KG);
     out.assign((size_t)2 * 9 * nC * KG * 128 * 16, 0);
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out.data());
-    for (int half = 0; half < 2; half++)
-        for (int t = 0; t < 9; t++)
-            for (int c = 0; c < nC; c++)
-                for (int kg = 0; kg < KG; kg++)
-                    for (int r = 0; r < 128; r++)
-                        for (int e = 0; e < 8; e++) {
-                            const int oc = half * 128 + r, ic = (c * KG + kg) * 8 + e;
-                            const size_t dst = ((((size_t)(half * 9 + t) * nC + c) * KG + kg) * 128 + r) * 8 + e;
-                            o[dst] = __float2bfloat16(w[((size_t)oc * C + ic) * 9 + t]);
-                        }
+    parallel_for(2 * 9, [=](int ht) {
+        const int half = ht / 9, t = ht % 9;
+        for (int c = 0; c < nC; c++)
+            for (int kg = 0; kg < KG; kg++)
+                for (int r = 0; r < 128; r++)
+                    for (int e = 0; e < 8; e++) {
+                        const int oc = half * 128 + r, ic = (c * KG + kg) * 8 + e;
+                        const size_t dst = ((((size_t)(half * 9 + t) * nC + c) * KG + kg) * 128 + r) * 8 + e;
+                        o[dst] = __float2bfloat16(w[((size_t)oc * C + ic) * 9 + t]);
+                    }
+    });
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

@@ -60,6 +60,51 @@ __global__ void __launch_bounds__(256) chw_to_nhwc64_kernel(const uint16_t* __re
     }
 }
 
+// ---- weight packing on the device (a reload after a weight broadcast sits in self-play's timed region)
+// w: [256][cin][3][3] fp32 -> [2 halves][9 taps][cpad/64 chunks][8 k-groups][128 rows][8 ch] bf16 (pack_conv_weights' layout)
+__global__ void pack_conv_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cin, int cpad) {
+    const int nC = cpad / (8 * CONV_KG);
+    const size_t total = (size_t)2 * 9 * nC * CONV_KG * 128 * 8;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        size_t r = i;
+        const int e = r % 8; r /= 8;
+        const int row = r % 128; r /= 128;
+        const int kg = r % CONV_KG; r /= CONV_KG;
+        const int c = r % nC; r /= nC;
+        const int t = r % 9; const int half = (int)(r / 9);
+        const int oc = half * 128 + row, ic = (c * CONV_KG + kg) * 8 + e;
+        out[i] = __float2bfloat16(ic < cin ? w[((size_t)oc * cin + ic) * 9 + t] : 0.f);
+    }
+}
+// both 1x1 convolutions -> [4 chunks][8 k-groups][144 rows][8] bf16; bias -> [144]
+__global__ void pack_head_conv_kernel(const float* __restrict__ pw, const float* __restrict__ pb, const float* __restrict__ vw,
+                                      const float* __restrict__ vb, __nv_bfloat16* __restrict__ out, float* __restrict__ bias) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < HC_W_BYTES / 2) {
+        int r = i;
+        const int e = r % 8; r /= 8;
+        const int row = r % HC_N; r /= HC_N;
+        const int kg = r % 8; const int c = r / 8;
+        const int k = (c * 8 + kg) * 8 + e;
+        out[i] = __float2bfloat16(row < 128 ? pw[(size_t)row * 256 + k] : row == 128 ? vw[k] : 0.f);
+    }
+    if (i < HC_N) bias[i] = i < 128 ? pb[i] : i == 128 ? vb[0] : 0.f;
+}
+// policy fc in the REFERENCE's layout [1584][128 channels * 144 cells] (alpha_net.py:77 flattens channel-major) ->
+// [9 column tiles][288 chunks][8 k-groups][176 rows][8] bf16 with cell-major K (k = cell*128 + channel)
+__global__ void pack_head_fc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
+    const size_t total = (size_t)1584 * FC_K;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        size_t r = i;
+        const int e = r % 8; r /= 8;
+        const int row = r % FC_N; r /= FC_N;
+        const int kg = r % 8; r /= 8;
+        const int kc = r % FC_CHUNKS; const int nt = (int)(r / FC_CHUNKS);
+        const int k = (kc * 8 + kg) * 8 + e, cell = k >> 7, ch = k & 127;
+        out[i] = __float2bfloat16(w[(size_t)(nt * FC_N + row) * FC_K + ch * 144 + cell]);
+    }
+}
+
 int check(const hive_net* n) { return n && n->max_boards > 0 ? 0 : fail(HIVE_E_HANDLE, "bad net handle"); }
 
 int launch_conv(hive_net* n, const CUtensorMap& in_map, int layer, const __nv_bfloat16* residual, __nv_bfloat16* out, int boards) {
@@ -183,6 +228,47 @@ int net_trunk_forward(hive_net_t* n, const uint16_t* planes_chw_dev, int n_board
     return 0;
 }
 
+// The same two loads from DEVICE tensors (fp32, e.g. the torch module's own parameters after folding): packing runs as
+// kernels on the handle's stream, nothing crosses PCIe -- the reload after a weight broadcast takes a few milliseconds.
+// net_load_heads_dev takes fc_w in the REFERENCE's layout ([1584][128*144], channel-major columns).
+int net_load_conv_dev(hive_net_t* n, int layer, const float* w_dev, const float* bias_dev, int cin) {
+    if (check(n)) return HIVE_E_HANDLE;
+    if (layer < 0 || layer >= NET_LAYERS || !w_dev || !bias_dev || (cin != 56 && cin != 256) || (layer == 0) != (cin == 56))
+        return fail(HIVE_E_ARG, "net_load_conv_dev: bad arguments");
+    CUDA_TRY(cudaSetDevice(n->device));
+    const int cpad = cin == 56 ? 64 : 256;
+    const size_t bytes = (size_t)2 * 9 * cpad * 128 * 2;
+    if (!n->weights[layer]) CUDA_TRY(cudaMalloc(&n->weights[layer], bytes));
+    if (!n->bias[layer]) CUDA_TRY(cudaMalloc(&n->bias[layer], 256 * 4));
+    pack_conv_kernel<<<256, 256, 0, n->stream>>>(w_dev, reinterpret_cast<__nv_bfloat16*>(n->weights[layer]), cin, cpad);
+    CUDA_TRY(cudaMemcpyAsync(n->bias[layer], bias_dev, 256 * 4, cudaMemcpyDeviceToDevice, n->stream));
+    CUDA_TRY(cudaGetLastError());
+    n->n_chunks[layer] = cpad / CONV_CHUNK_CH;
+    int cnt = 0;
+    for (int i = 0; i < NET_LAYERS; i++) cnt += n->weights[i] != nullptr;
+    n->loaded = cnt;
+    return 0;
+}
+
+int net_load_heads_dev(hive_net_t* n, const float* pconv_w, const float* pconv_b, const float* vconv_w, const float* vconv_b,
+                       const float* fc_w_ref, const float* fc_b, const float* fc1_w, const float* fc1_b, const float* fc2_w, const float* fc2_b) {
+    if (check(n)) return HIVE_E_HANDLE;
+    if (!pconv_w || !pconv_b || !vconv_w || !vconv_b || !fc_w_ref || !fc_b || !fc1_w || !fc1_b || !fc2_w || !fc2_b)
+        return fail(HIVE_E_ARG, "net_load_heads_dev: null argument");
+    CUDA_TRY(cudaSetDevice(n->device));
+    pack_head_conv_kernel<<<(HC_W_BYTES / 2 + 255) / 256, 256, 0, n->stream>>>(pconv_w, pconv_b, vconv_w, vconv_b,
+                                                                               reinterpret_cast<__nv_bfloat16*>(n->head_w1), n->head_b1);
+    pack_head_fc_kernel<<<1184, 256, 0, n->stream>>>(fc_w_ref, reinterpret_cast<__nv_bfloat16*>(n->head_wfc));
+    CUDA_TRY(cudaMemcpyAsync(n->head_bfc, fc_b, 1584 * 4, cudaMemcpyDeviceToDevice, n->stream));
+    CUDA_TRY(cudaMemcpyAsync(n->head_fc1_w, fc1_w, 64 * 144 * 4, cudaMemcpyDeviceToDevice, n->stream));
+    CUDA_TRY(cudaMemcpyAsync(n->head_fc1_b, fc1_b, 64 * 4, cudaMemcpyDeviceToDevice, n->stream));
+    CUDA_TRY(cudaMemcpyAsync(n->head_fc2_w, fc2_w, 64 * 4, cudaMemcpyDeviceToDevice, n->stream));
+    CUDA_TRY(cudaMemcpyAsync(n->head_fc2_b, fc2_b, 4, cudaMemcpyDeviceToDevice, n->stream));
+    CUDA_TRY(cudaGetLastError());
+    n->heads_loaded = true;
+    return 0;
+}
+
 // The heads (alpha_net.py:56-80), BatchNorm folded into the two 1x1 convolutions by the caller:
 //   pconv_w [128][256], pconv_b [128]   policy conv;   vconv_w [256], vconv_b [1]   value conv
 //   fc_w [1584][18432] with CELL-MAJOR columns (k = cell*128 + channel: the reference's channel-major flatten
@@ -210,12 +296,15 @@ int net_load_heads_host(hive_net_t* n, const float* pconv_w, const float* pconv_
     }
     {   // [9 column tiles][288 chunks][8 k-groups][176 rows][8]
         std::vector<__nv_bfloat16> wf((size_t)FC_NT * FC_CHUNKS * FC_B_BYTES / 2);
-        for (int o = 0; o < 1584; o++) {
+        __nv_bfloat16* wfp = wf.data();
+        parallel_for(1584, [=](int o) {
             const int nt = o / FC_N, rr = o - nt * FC_N;
             const float* src = fc_w + (size_t)o * FC_K;
-            for (int k = 0; k < FC_K; k++)
-                wf[(((((size_t)nt * FC_CHUNKS + (k >> 6)) * 8 + ((k >> 3) & 7)) * FC_N + rr) * 8) + (k & 7)] = __float2bfloat16(src[k]);
-        }
+            for (int k = 0; k < FC_K; k += 8) {                  // eight consecutive k share a 16-byte destination row
+                __nv_bfloat16* dst = wfp + ((((size_t)nt * FC_CHUNKS + (k >> 6)) * 8 + ((k >> 3) & 7)) * FC_N + rr) * 8;
+                for (int e = 0; e < 8; e++) dst[e] = __float2bfloat16(src[k + e]);
+            }
+        });
         CUDA_TRY(cudaMemcpy(n->head_wfc, wf.data(), wf.size() * 2, cudaMemcpyHostToDevice));
     }
     CUDA_TRY(cudaMemcpy(n->head_bfc, fc_b, 1584 * 4, cudaMemcpyHostToDevice));

@@ -117,9 +117,16 @@ class TensorCoreTrunk:
             self.load_heads(heads_fp32)
 
     def load_heads(self, heads_fp32):
-        """The ten head tensors (fp32, CPU) in net_load_heads_host's order; reloads keep the device addresses."""
-        arrs = [np.ascontiguousarray(t.detach().float().cpu().numpy()) for t in heads_fp32]
-        self._check(self._lib.net_load_heads_host(self._h, *[a.ctypes.data for a in arrs]), "net_load_heads_host")
+        """The ten head tensors (fp32) in net_load_heads_host's order; reloads keep the device addresses.  CUDA tensors
+        are packed by kernels on the device (net_load_heads_dev: the fc weight then comes in the REFERENCE's layout)."""
+        if heads_fp32[0].is_cuda:
+            ts = [t.detach().float().contiguous() for t in heads_fp32]
+            torch.cuda.synchronize()                                # the sources are ready, whatever stream made them
+            self._check(self._lib.net_load_heads_dev(self._h, *[t.data_ptr() for t in ts]), "net_load_heads_dev")
+            torch.cuda.synchronize()                                # ... and stay alive until the pack kernels have read them
+        else:
+            arrs = [np.ascontiguousarray(t.detach().float().cpu().numpy()) for t in heads_fp32]
+            self._check(self._lib.net_load_heads_host(self._h, *[a.ctypes.data for a in arrs]), "net_load_heads_host")
         self.has_heads = True
 
     def forward_into(self, planes_ptr, n_boards, policy_ptr, value_ptr):
@@ -128,6 +135,13 @@ class TensorCoreTrunk:
 
     def load(self, folded_fp32):
         """(Re)load the 39 folded convolutions; the packed operands keep their device addresses."""
+        if folded_fp32[0][0].is_cuda:                               # packed on the device (net_load_conv_dev)
+            ts = [(w.detach().float().contiguous(), b.detach().float().contiguous()) for w, b in folded_fp32]
+            torch.cuda.synchronize()
+            for layer, (w, b) in enumerate(ts):
+                self._check(self._lib.net_load_conv_dev(self._h, layer, w.data_ptr(), b.data_ptr(), w.shape[1]), "net_load_conv_dev")
+            torch.cuda.synchronize()
+            return
         for layer, (w, b) in enumerate(folded_fp32):
             w = np.ascontiguousarray(w.detach().float().cpu().numpy())
             b = np.ascontiguousarray(b.detach().float().cpu().numpy())
@@ -167,7 +181,8 @@ class FoldedNet:
             for i in range(N_RES):
                 r = getattr(net, "res_%i" % i)
                 folded += [_fold(r.conv1.weight, None, r.bn1), _fold(r.conv2.weight, None, r.bn2)]
-            self._folded_fp32 = [(w.detach().float().cpu(), b.detach().float().cpu()) for w, b in folded]
+            keep = (lambda t: t.detach().float().to(self.device).contiguous()) if self.device.type == "cuda" else (lambda t: t.detach().float().cpu())
+            self._folded_fp32 = [(keep(w), keep(b)) for w, b in folded]
         with torch.no_grad():
             def put(w, b):
                 w = w.to(self.device, dtype).contiguous(memory_format=torch.channels_last) if w.dim() == 4 else w.to(self.device, dtype)
@@ -193,9 +208,12 @@ class FoldedNet:
             # the same heads for the hand-written kernels (net_load_heads_host): fp32 on the host, fc columns cell-major
             pw, pb = _fold(ob.conv1.weight, ob.conv1.bias, ob.bn1)
             vw, vb = _fold(ob.conv.weight, ob.conv.bias, ob.bn)
-            self._heads_fp32 = [t.detach().float().cpu().contiguous() for t in (
-                pw.reshape(POLICY_CH, CH), pb, vw.reshape(CH), vb.reshape(1),
-                ob.fc.weight.detach().view(C.ACTION_SPACE, POLICY_CH, CELLS).permute(0, 2, 1).reshape(C.ACTION_SPACE, CELLS * POLICY_CH),
+            # (on a CUDA device they stay there and the fc weight keeps the reference's layout: net_load_heads_dev permutes)
+            on_dev = self.device.type == "cuda"
+            fc_w = ob.fc.weight.detach() if on_dev else ob.fc.weight.detach().view(C.ACTION_SPACE, POLICY_CH, CELLS).permute(0, 2, 1).reshape(
+                C.ACTION_SPACE, CELLS * POLICY_CH)
+            self._heads_fp32 = [t.detach().float().to(self.device if on_dev else "cpu").contiguous() for t in (
+                pw.reshape(POLICY_CH, CH), pb, vw.reshape(CH), vb.reshape(1), fc_w,
                 ob.fc.bias, ob.fc1.weight, ob.fc1.bias, ob.fc2.weight.reshape(-1), ob.fc2.bias.reshape(1))]
 
     @torch.no_grad()

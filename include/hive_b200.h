@@ -240,6 +240,12 @@ int net_trunk_forward(hive_net_t* n, const uint16_t* planes_chw_dev, int n_board
  * reference's flatten c*144 + cell permuted once), fc_b [1584]; fc1_w [64][144], fc1_b [64]; fc2_w [64], fc2_b [1]. */
 int net_load_heads_host(hive_net_t* n, const float* pconv_w, const float* pconv_b, const float* vconv_w, const float* vconv_b,
                         const float* fc_w, const float* fc_b, const float* fc1_w, const float* fc1_b, const float* fc2_w, const float* fc2_b);
+/* The same two loads from DEVICE fp32 tensors (the module's own parameters after BatchNorm folding): packed by kernels on
+ * the handle's stream, nothing crosses PCIe; reloads keep the device addresses of the packed operands (captured graphs
+ * stay valid).  net_load_heads_dev takes fc_w in the REFERENCE's layout [1584][128*144] (channel-major columns). */
+int net_load_conv_dev(hive_net_t* n, int layer, const float* w_dev, const float* bias_dev, int cin);
+int net_load_heads_dev(hive_net_t* n, const float* pconv_w, const float* pconv_b, const float* vconv_w, const float* vconv_b,
+                       const float* fc_w_ref, const float* fc_b, const float* fc1_w, const float* fc1_b, const float* fc2_w, const float* fc2_b);
 /* ChessNet.forward (alpha_net.py:82-95; api_hive.py:60-74 is the server loop it replaces) for n_boards positions:
  * planes_chw_dev device bf16 [n][56][144] -> policy_dev device float32 [n][1584] (softmax), value_dev device float64 [n]
  * (tanh).  Trunk (39 tcgen05 convolutions) + heads (two tcgen05 GEMMs + one finishing kernel), all hand-written
