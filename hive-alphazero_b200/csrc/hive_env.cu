@@ -91,12 +91,23 @@ static EnvArgs slice_args(hive_env* h, int s, int per, int op, const int32_t* ac
     a.chosen = chosen ? chosen + off : nullptr; a.hop_lines = h->hop_lines;
     a.seed = seed; a.n = cnt > 0 ? cnt : 0; a.op = op; a.max_turn = max_turn; a.auto_reset = auto_reset;
     a.g_offset = off; a.n_total = h->n;
+    a.shadow = h->shadow ? h->shadow + (size_t)off * BITS_WORDS : nullptr;
     a.stagger_ns = h->stagger_ns; a.stagger_div = h->sm_count > 0 ? h->sm_count : 148;
     return a;
 }
 // The plane-store kernel is persistent: the store launches that run at the same time (`concurrent` slices) share
 // store_ctas_per_sm CTAs per SM, so each grid is resident at once and never queues in front of other kernels.
 static void launch_planes_part(hive_env* h, const EnvArgs& a, cudaStream_t st, int concurrent) {
+    if (!h->full_store) {                                      // delta store: only the sectors that changed (hive_planes_delta_kernel)
+        int blocks = (a.n + HIVE_DELTA_WARPS - 1) / HIVE_DELTA_WARPS;
+        if (concurrent > 0) {
+            int cap = h->sm_count * h->delta_ctas_per_sm / concurrent;
+            if (cap < 1) cap = 1;
+            if (blocks > cap) blocks = cap;
+        }
+        hive_planes_delta_kernel<<<blocks, HIVE_DELTA_WARPS * 32, 0, st>>>(a);
+        return;
+    }
     int blocks = (a.n + HIVE_STORE_WARPS - 1) / HIVE_STORE_WARPS;
     if (concurrent > 0) {                                      // 0: alone on the GPU (profiling), one warp per game
         int cap = h->sm_count * h->store_ctas_per_sm / concurrent;
@@ -255,6 +266,19 @@ int hive::create_env(int n_games, int device, void* stream, int slices, hive_env
     h->status = reinterpret_cast<uint32_t*>(h->count + n);
     CUDA_TRY(cudaMalloc(&h->planes, n * HIVE_PLANES_ELEMS * 2));
     {
+        const char* rk0 = getenv("HIVE_B200_ROLLOUT_KERNEL");
+        const char* ds = getenv("HIVE_B200_DELTA_STORE");          // 1: hive_planes_delta_kernel (measured: same speed, 4x less HBM traffic)
+        h->full_store = !(ds && atoi(ds)) || (rk0 && atoi(rk0));   // (the rollout kernel stores full planes itself)
+        const char* dc = getenv("HIVE_B200_DELTA_CTAS");
+        h->delta_ctas_per_sm = dc && atoi(dc) > 0 ? atoi(dc) : 4;
+        if (!h->full_store) {   // planes arena and shadow start out equal: all zero
+            h->shadow_bytes = n * BITS_WORDS * 4;
+            CUDA_TRY(cudaMalloc(&h->shadow, h->shadow_bytes));
+            CUDA_TRY(cudaMemsetAsync(h->shadow, 0, h->shadow_bytes, h->stream));
+            CUDA_TRY(cudaMemsetAsync(h->planes, 0, n * HIVE_PLANES_ELEMS * 2, h->stream));
+        }
+    }
+    {
         const char* e = getenv("HIVE_B200_SLICES");
         int S = slices > 0 ? slices : (e ? atoi(e) : HIVE_DEFAULT_SLICES);
         if (S < 1) S = 1;
@@ -324,7 +348,7 @@ int hive_destroy(hive_env_t* h) {
     if (h->multi_graph.exec && h->multi_graph.exec != h->slice_exec[0]) cudaGraphExecDestroy(h->multi_graph.exec);
     for (int s = 0; s < hive_env::MAX_SUB; s++) if (h->slice_exec[s]) cudaGraphExecDestroy(h->slice_exec[s]);
     if (h->host_graph.exec) cudaGraphExecDestroy(h->host_graph.exec);
-    cudaFree(h->recs); cudaFree(h->legal); cudaFree(h->planes); cudaFree(h->bits[0]); cudaFree(h->bits[1]);
+    cudaFree(h->recs); cudaFree(h->legal); cudaFree(h->planes); cudaFree(h->bits[0]); cudaFree(h->bits[1]); cudaFree(h->shadow);
     for (int s = 0; s < h->n_sub; s++) {
         if (h->sub_stream[s]) cudaStreamDestroy(h->sub_stream[s]);
         if (h->store_stream[s]) cudaStreamDestroy(h->store_stream[s]);
@@ -569,7 +593,7 @@ int hive_step_random_multi(hive_env_t* h, uint64_t seed, int max_turn, int auto_
     return 0;
 }
 
-// One rollout step with CUDA events around its two kernels (whole batch as one slice, no graph):
+// One rollout step with CUDA events around its kernels (whole batch as one slice, no graph):
 // ms[0] = step kernel, ms[1] = plane store.  For bench.py's per-kernel roofline; it advances the games.
 int hive_profile_step(hive_env_t* h, uint64_t seed, int max_turn, float* ms) {
     if (check(h)) return HIVE_E_HANDLE;
@@ -616,7 +640,12 @@ int hive_probe_write_stream(hive_env_t* h, int reps, double* gbs) {
     CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     *gbs = (double)n_vec * 16.0 * reps / (ms * 1e-3) / 1e9;
-    return 0;    // the planes arena now holds the probe pattern: step or reset the batch before reading planes
+    if (h->shadow) {   // the arena holds the probe pattern: back to the all-zero state the delta store's shadow describes
+        CUDA_TRY(cudaMemsetAsync(h->shadow, 0, h->shadow_bytes, h->stream));
+        CUDA_TRY(cudaMemsetAsync(h->planes, 0, (size_t)h->n * HIVE_PLANES_ELEMS * 2, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    return 0;    // the planes arena no longer holds the games' planes: step or reset the batch before reading planes
 }
 
 int hive_legal_host(hive_env_t* h, uint64_t* mask, int32_t* count) {
@@ -895,6 +924,11 @@ int hive_copy_state(hive_env_t* dst, int dst_game, hive_env_t* src, int src_game
     CUDA_TRY(cudaMemcpyAsync(dst->status + dst_game, src->status + src_game, 4, cudaMemcpyDeviceToDevice, dst->stream));
     CUDA_TRY(cudaMemcpyAsync(dst->planes + (size_t)dst_game * HIVE_PLANES_ELEMS, src->planes + (size_t)src_game * HIVE_PLANES_ELEMS,
                              HIVE_PLANES_ELEMS * 2, cudaMemcpyDeviceToDevice, dst->stream));
+    if (dst->shadow) {   // the copied planes' bit image: the source's shadow row, or (full-store source) "unknown" = rewrite all
+        if (src->shadow) CUDA_TRY(cudaMemcpyAsync(dst->shadow + (size_t)dst_game * BITS_WORDS, src->shadow + (size_t)src_game * BITS_WORDS,
+                                                  BITS_WORDS * 4, cudaMemcpyDeviceToDevice, dst->stream));
+        else return fail(HIVE_E_ARG, "hive_copy_state: handles with different plane-store modes");
+    }
     return 0;
 }
 

@@ -24,6 +24,7 @@ struct EnvArgs {
     uint32_t* status;      // [n] turn | winner<<8 | done<<16
     uint16_t* planes;      // [n][56*144] bf16
     uint32_t* bits;        // [n][BITS_WORDS] bit planes, step kernel -> plane-store kernel (this step's buffer of two)
+    uint32_t* shadow;      // [n][BITS_WORDS] the bit planes the planes arena holds right now (delta plane store)
     const int32_t* actions;
     const uint8_t* mask;
     int32_t* chosen;
@@ -79,8 +80,9 @@ __device__ unsigned long long g_phase_clk[8];
 // search are collected in CTA-local queues, the move queues one per piece class, so that a warp runs 32 Ant floods,
 // or 32 Spider walks ... of different games side by side.  Per-game fields live in shared memory as [field][lane]
 // (bank = lane: conflict-free for any per-lane index).
-//   1a (warp 0)   decode the operation, pick / apply the action, boards, placements
-//   1b (all)      per piece: stack height, top, ring occupancy, turn gates; queue floods and move searches
+//   1a (warp 0)   decode the operation, pick / apply the action
+//   1b (all)      per piece: stack height, top, occupancy boards; then ring occupancy, hive graph, turn gates, queues
+//                 (the last warp also derives the placements)
 //   2  (all)      one-hive floods; survivors join the move queues
 //   3  (all)      move searches by class; move sets -> shared rows
 //   4  (all)      legal mask (shared), 56 bit planes -> a.bits, history push
@@ -215,79 +217,14 @@ __device__ __forceinline__ void step_prologue(StepShared& s, const EnvArgs& a, i
         }
     }
 
-    // boards; hand masks (colour-relative)
-    const int side = (turn & 1) ? 0 : 1;                        // game_state.py:58-62
-    BB white = bb_zero(), black = bb_zero();
-    uint32_t hand_w = 0, hand_b = 0;
-#pragma unroll
-    for (int p = 0; p < N_PIECE; p++) {
-        const int c = (pc[p >> 2] >> (8 * (p & 3))) & 0xFF;
-        const BB b = bb_onehot(c);
-        if (p < 11) { white = white | b; hand_w |= (uint32_t)(c == HAND) << p; }
-        else { black = black | b; hand_b |= (uint32_t)(c == HAND) << (p - 11); }
-    }
-    // stacks: only beetles climb (pieces 1, 2, 12, 13), so the cells with more than one piece are the cells of the
-    // beetles above level 0, and the top piece there is the beetle no other beetle stands on
-    BB stackc = bb_zero(), top_w = bb_zero(), top_b = bb_zero();
-    {
-        int bcell[4], blev[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int p = j < 2 ? 1 + j : 10 + j;
-            bcell[j] = (pc[p >> 2] >> (8 * (p & 3))) & 0xFF;
-            blev[j] = (pc[(22 + p) >> 2] >> (8 * ((22 + p) & 3))) & 0xFF;
-            if (bcell[j] == HAND) blev[j] = 0;
-        }
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            bool covered = false;
-#pragma unroll
-            for (int j2 = 0; j2 < 4; j2++) if (j2 != j) covered = covered || (bcell[j2] == bcell[j] && blev[j2] == blev[j] + 1);
-            const BB b = blev[j] >= 1 ? bb_onehot(bcell[j]) : bb_zero();
-            stackc = stackc | b;
-            if (!covered) { if (j < 2) top_w = top_w | b; else top_b = top_b | b; }
-        }
-    }
-    const BB occ = white | black;
-    const BB top_opp = side ? (bb_andn(white, stackc) | top_w) : (bb_andn(black, stackc) | top_b);
     const int cq_w = pc[0] & 0xFF, cq_b = (pc[2] >> 24) & 0xFF;
-    const bool wq_on = cq_w != HAND, bq_on = cq_b != HAND;
-
-    // placements (env_hive.py:217-225; move_checker.py:168-179): the first in-hand piece of each type of the side to move
-    const uint32_t in_hand = side ? hand_b : hand_w;
-    uint32_t first = 0;
-    { uint32_t t;
-      t = in_hand & 0x001u; first |= t & (0u - t);
-      t = in_hand & 0x006u; first |= t & (0u - t);
-      t = in_hand & 0x018u; first |= t & (0u - t);
-      t = in_hand & 0x0E0u; first |= t & (0u - t);
-      t = in_hand & 0x700u; first |= t & (0u - t); }
-    BB place;
-    if (turn == 1) place = bb_bit(START_CELL);
-    else {
-        const BB frontier = bb_andn(bb_nbrs(occ), occ);
-        if (turn == 2) place = frontier & bb_bit(TURN2_CELL);
-        else {
-            place = bb_andn(frontier, bb_nbrs(top_opp));
-            if (turn == 7 || turn == 8) {
-                const bool ok_q = obeys_queen_by_4(turn, wq_on, bq_on, true, side), ok_n = obeys_queen_by_4(turn, wq_on, bq_on, false, side);
-                first = (ok_q ? first & 1u : 0u) | (ok_n ? first & ~1u : 0u);
-            }
-        }
-    }
 #pragma unroll
     for (int i = 0; i < 11; i++) s.pc[i][lane] = pc[i];
 #pragma unroll
-    for (int i = 0; i < 5; i++) {
-        s.occ[i][lane] = occ.w[i];
-        s.own[i][lane] = side ? black.w[i] : white.w[i];
-        s.opp[i][lane] = side ? white.w[i] : black.w[i];
-        s.place[i][lane] = place.w[i];
-    }
+    for (int i = 0; i < 5; i++) { s.occ[i][lane] = 0u; s.own[i][lane] = 0u; s.opp[i][lane] = 0u; }     // filled by step_stacks
     s.head[lane] = (uint32_t)turn | ((uint32_t)cq_w << 8) | ((uint32_t)cq_b << 16);
     s.flags[lane] = (live ? 1u : 0u) | ((uint32_t)push << 1) | ((uint32_t)winner << 8);
     s.pin[lane] = 0; s.nonempty[lane] = 0; s.nlegal[lane] = 0;
-    s.placeable[lane] = first << (11 * side);
     s.episode[lane] = episode; s.steps[lane] = steps;
     const unsigned lv = __ballot_sync(FULL, live);
     if (lane == 0) s.any_live = lv;
@@ -296,6 +233,7 @@ __device__ __forceinline__ void step_prologue(StepShared& s, const EnvArgs& a, i
 // ---- phase 1b (all warps; lane <-> game, the warps take the pieces in turn): stacks; which piece tops which cell
 __device__ __forceinline__ void step_stacks(StepShared& s, int warp, int lane) {
     const bool live = s.flags[lane] & 1u;
+    const int side = (s.head[lane] & 1u) ? 0 : 1;           // turn odd: white to move (game_state.py:58-62)
     int bc[4];                                              // cells of the beetles above level 0 (else: no cell)
     {
         const uint32_t w0 = s.pc[0][lane], w3 = s.pc[3][lane], w5 = s.pc[5][lane], w6 = s.pc[6][lane], w8 = s.pc[8][lane];
@@ -313,7 +251,54 @@ __device__ __forceinline__ void step_stacks(StepShared& s, int warp, int lane) {
         const bool top = on && lv == height - 1;
         s.info[p][lane] = (uint32_t)c | ((uint32_t)height << 8) | ((uint32_t)top << 12) | ((uint32_t)lv << 13);
         if (top) reinterpret_cast<uint8_t*>(&s.graph.cmap[c >> 2][lane])[c & 3] = (uint8_t)p;
+        if (on) {                                           // occupancy boards (own / opponent by the side to move), one word each
+            const uint32_t bit = 1u << (c & 31);
+            atomicOr(&s.occ[c >> 5][lane], bit);
+            atomicOr(((p >= 11) == (side == 1)) ? &s.own[c >> 5][lane] : &s.opp[c >> 5][lane], bit);
+        }
     }
+}
+
+// ---- placements (env_hive.py:217-225; move_checker.py:168-179) -- one warp, lane <-> game, beside the pieces pass: the
+// board of cells where the side to move may place a piece and the first in-hand piece of each type that may go there
+__device__ __forceinline__ void step_placements(StepShared& s, int lane) {
+    const uint32_t hd = s.head[lane];
+    const int turn = hd & 0xFF, cq_w = (hd >> 8) & 0xFF, cq_b = (hd >> 16) & 0xFF;
+    const int side = (turn & 1) ? 0 : 1;
+    const bool wq_on = cq_w != HAND, bq_on = cq_b != HAND;
+    uint32_t in_hand = 0;                                   // colour-relative: bit k = own piece k still in hand
+    BB top_opp = bb_zero();
+    for (int k = 0; k < 11; k++) {
+        in_hand |= (uint32_t)((s.info[side * 11 + k][lane] & 0xFFu) == (uint32_t)HAND) << k;
+        const uint32_t io = s.info[(1 - side) * 11 + k][lane];
+        if ((io >> 12) & 1u) top_opp = top_opp | bb_onehot((int)(io & 0xFFu));
+    }
+    uint32_t first = 0;
+    { uint32_t t;
+      t = in_hand & 0x001u; first |= t & (0u - t);
+      t = in_hand & 0x006u; first |= t & (0u - t);
+      t = in_hand & 0x018u; first |= t & (0u - t);
+      t = in_hand & 0x0E0u; first |= t & (0u - t);
+      t = in_hand & 0x700u; first |= t & (0u - t); }
+    BB occ;
+#pragma unroll
+    for (int i = 0; i < 5; i++) occ.w[i] = s.occ[i][lane];
+    BB place;
+    if (turn == 1) place = bb_bit(START_CELL);
+    else {
+        const BB frontier = bb_andn(bb_nbrs(occ), occ);
+        if (turn == 2) place = frontier & bb_bit(TURN2_CELL);
+        else {
+            place = bb_andn(frontier, bb_nbrs(top_opp));
+            if (turn == 7 || turn == 8) {
+                const bool ok_q = obeys_queen_by_4(turn, wq_on, bq_on, true, side), ok_n = obeys_queen_by_4(turn, wq_on, bq_on, false, side);
+                first = (ok_q ? first & 1u : 0u) | (ok_n ? first & ~1u : 0u);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 5; i++) s.place[i][lane] = place.w[i];
+    s.placeable[lane] = first << (11 * side);
 }
 
 // ---- phase 1c (all warps; lane <-> game): ring occupancy, hive graph, turn gates; queue floods and move searches
@@ -597,6 +582,7 @@ __device__ __forceinline__ unsigned step_phases(StepShared& s, const EnvArgs& a)
     step_stacks(s, warp, lane);
     __syncthreads();
     step_pieces(s, warp, lane, geo);
+    if (warp == SW - 1) step_placements(s, lane);           // (the last warp has the fewest pieces)
     __syncthreads();
     HIVE_PHASE_MARK(1);
 
@@ -715,7 +701,11 @@ __device__ __forceinline__ unsigned step_phases(StepShared& s, const EnvArgs& a)
     return live_mask;
 }
 
+#ifdef HIVE_STEP_MAXNREG
+__global__ void __maxnreg__(HIVE_STEP_MAXNREG) hive_step_kernel(EnvArgs a) {
+#else
 __global__ void __launch_bounds__(STEP_THREADS, HIVE_STEP_MIN_CTAS) hive_step_kernel(EnvArgs a) {
+#endif
     __shared__ StepShared s;
     HIVE_TRACE_SCOPE(0, a);
     step_phases(s, a);
@@ -850,6 +840,101 @@ __global__ void __launch_bounds__(HIVE_STORE_WARPS * 32, HIVE_STORE_MIN_CTAS) hi
                               (int)turn, a.planes + (size_t)g * HIVE_PLANES_ELEMS);
     }
     if (lane == 0) bulk_wait_read<0>();                         // shared memory must outlive the copy engine's reads
+}
+
+// ---- kernel 5, delta form (HIVE_B200_DELTA_STORE=1; measured at the same speed as the full store, see profiles/README.md):
+// bit planes -> bf16 CHW planes, writing only the 32-byte sectors of a game's planes whose 16 cells differ from what the
+// planes arena already holds.  The arena is private to the handle and a game's planes are only ever written by the store
+// kernel, so a copy of the bit planes it stored last (a.shadow, 1,120 B per game) says exactly what is there: consecutive
+// positions of a game differ in about a fifth of their 504 sectors (every piece plane holds one bit, the history planes
+// shift by a ply, plane 31 is the turn number), so ~3.6 KB per game reach HBM instead of 16 KB -- but as scattered 32-byte
+// writes, which cost the HBM as much time as the 16 KB stream (30-35 us per 16,384 games either way).
+// Warp <-> game; the next game's rows arrive by cp.async while this game's sectors are written.
+#ifndef HIVE_DELTA_WARPS
+#define HIVE_DELTA_WARPS 2
+#endif
+__device__ __forceinline__ void store_sector(uint16_t* dst, uint4 lo, uint4 hi) {       // 16 cells = 32 bytes of bf16
+#ifdef HIVE_EMU
+    reinterpret_cast<uint4*>(dst)[0] = lo; reinterpret_cast<uint4*>(dst)[1] = hi;
+#else
+    asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x),
+                 "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");     // one 256-bit streaming store (an output, not the step's working set)
+#endif
+}
+// 16 bytes global -> shared without passing through registers (LDGSTS); groups are per thread
+__device__ __forceinline__ void async_copy16(void* dst_smem, const void* src) {
+#ifdef HIVE_EMU
+    memcpy(dst_smem, src, 16);
+#else
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+#endif
+}
+__device__ __forceinline__ void async_commit() {
+#ifndef HIVE_EMU
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int PENDING>
+__device__ __forceinline__ void async_wait() {
+#ifndef HIVE_EMU
+    asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
+#endif
+}
+__global__ void __launch_bounds__(HIVE_DELTA_WARPS * 32, 1024 / (HIVE_DELTA_WARPS * 32)) hive_planes_delta_kernel(EnvArgs a) {
+    __shared__ uint4 bf16_lut[256];
+    // per warp, double-buffered: the new bit planes and the shadow of the game in work and of the warp's next game (the
+    // next game's 2 x 1,120 B arrive while this game's sectors are written: a warp never waits for a load it has just issued)
+    __shared__ __align__(16) uint32_t rows[HIVE_DELTA_WARPS][2][2][BITS_WORDS];
+    HIVE_TRACE_SCOPE(4, a);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int t = tid; t < 256; t += HIVE_DELTA_WARPS * 32) fill_bf16_lut(bf16_lut, t);
+    __syncthreads();
+    constexpr int ROUNDS = (BITS_WORDS + 31) / 32;               // 9 words per lane
+    constexpr int NV = BITS_WORDS / 4;                           // 70 uint4 per row
+    const int g_stride = gridDim.x * HIVE_DELTA_WARPS;
+    auto fetch = [&](int g, int b) {
+        const uint4* nb = reinterpret_cast<const uint4*>(a.bits + (size_t)g * BITS_WORDS);
+        const uint4* sh = reinterpret_cast<const uint4*>(a.shadow + (size_t)g * BITS_WORDS);
+        for (int t = lane; t < 2 * NV; t += 32) {
+            const bool second = t >= NV;
+            async_copy16(reinterpret_cast<uint4*>(rows[warp][b][second ? 1 : 0]) + (second ? t - NV : t), second ? sh + (t - NV) : nb + t);
+        }
+        async_commit();
+    };
+    int g = blockIdx.x * HIVE_DELTA_WARPS + warp, b = 0;
+    if (g < a.n) fetch(g, 0);
+    for (; g < a.n; g += g_stride, b ^= 1) {
+        if (g + g_stride < a.n) { fetch(g + g_stride, b ^ 1); async_wait<1>(); } else async_wait<0>();
+        __syncwarp();                                            // every lane's copies of this game have landed
+        const uint32_t* nv = rows[warp][b][0];
+        const uint32_t* ov = rows[warp][b][1];
+        const uint32_t live = nv[BITS_LIVE], turn = nv[BITS_TURN], turn_old = ov[BITS_TURN];
+        if (live) {                                              // (else: not evaluated in this step, its planes stay as they are)
+            uint32_t* sh = a.shadow + (size_t)g * BITS_WORDS;
+            const uint32_t tb = __float_as_uint((float)turn) >> 16, tt = tb | (tb << 16);      // bf16(turn): turn <= 255 is exact
+            const uint4 turn4 = make_uint4(tt, tt, tt, tt);
+            uint16_t* out = a.planes + (size_t)g * HIVE_PLANES_ELEMS;
+            // lane <-> sector: a round covers 32 consecutive sectors = 1 KB of the game's planes, so the lanes that store
+            // touch at most 8 lines (scattered sectors per lane would cost the load/store unit a pass per lane)
+#pragma unroll 4
+            for (int j = 0; j < 16; j++) {
+                const int sct = lane + 32 * j;                   // 504 sectors: plane = sct / 9, 9 sectors (4.5 words) per plane
+                const int pl = (sct * 7282) >> 16, k = sct - 9 * pl, w = pl * 5 + (k >> 1), sft = (k & 1) * 16;
+                if (sct < 504) {
+                    const uint32_t hb = (nv[w] >> sft) & 0xFFFFu, ho = (ov[w] >> sft) & 0xFFFFu;
+                    // plane 31 = the turn number in every cell (its words hold the turn and the live flag, not bits)
+                    if (pl == 31 ? turn != turn_old : hb != ho)
+                        store_sector(out + sct * 16, pl == 31 ? turn4 : bf16_lut[hb & 0xFFu], pl == 31 ? turn4 : bf16_lut[hb >> 8]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < ROUNDS; i++) {                   // the shadow follows (lane <-> word, coalesced)
+                const int w = lane + 32 * i;
+                if (w < BITS_WORDS && nv[w] != ov[w]) sh[w] = nv[w];
+            }
+        }
+        __syncwarp();                                            // the rows of this buffer are free for the game after the next
+    }
 }
 
 }  // namespace hive

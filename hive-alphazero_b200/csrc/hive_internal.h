@@ -19,6 +19,10 @@ struct hive_env {
     uint32_t* status = nullptr;
     uint16_t* planes = nullptr;
     uint32_t* bits[2] = {nullptr, nullptr};   // bit planes, encode kernel -> plane-store kernel (double-buffered over steps)
+    uint32_t* shadow = nullptr;     // delta plane store: the bit planes whose expansion the planes arena holds right now, [game][word]
+    size_t shadow_bytes = 0;
+    bool full_store = true;         // every step rewrites all 16 KB of a game's planes (hive_planes_kernel, the TMA store); HIVE_B200_DELTA_STORE=1: only the changed sectors
+    int delta_ctas_per_sm = 4;      // HIVE_B200_DELTA_CTAS: cap of the delta store's grid (all concurrent store launches together)
     static constexpr int MAX_SUB = 16;
     int n_sub = 1;                  // the batch is cut into n_sub slices whose kernel chains overlap on side streams
     int sm_count = 148, store_ctas_per_sm = 2;   // the persistent plane-store kernels together keep this many CTAs per SM

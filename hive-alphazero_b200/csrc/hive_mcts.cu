@@ -40,6 +40,7 @@ MctsArgs make_args(hive_mcts* m) {
     a.ht_size = m->ht_size; a.noise_rows = m->noise_rows; a.noise_cols = m->noise_cols; a.noise_seed = m->noise_seed;
     a.root_recs = m->env->recs; a.sim_recs = m->sim->recs; a.sim_legal = m->sim->legal; a.sim_count = m->sim->count; a.sim_planes = m->sim->planes;
     a.root_legal = m->env->legal; a.root_count = m->env->count; a.root_planes = m->env->planes; a.env_mask = m->env_mask;
+    a.root_shadow = m->env->shadow; a.sim_shadow = m->env->shadow ? m->sim->shadow : nullptr;
     a.leaf_p = m->leaf_p; a.leaf_v = m->leaf_v; a.need_eval = m->need_eval;
     a.tree_mask = m->use_mask ? m->tree_mask : nullptr; a.pending = m->pending;
     a.trees = m->trees; a.nodes = m->nodes; a.htab = m->htab;

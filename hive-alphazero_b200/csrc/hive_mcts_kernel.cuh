@@ -54,6 +54,7 @@ struct MctsArgs {
     int32_t* sim_count;                                     // [n]
     uint16_t* sim_planes;                                   // [n][56*144] planes of the evaluated leaf
     const uint32_t* root_legal; const int32_t* root_count; const uint16_t* root_planes;   // the real games' outputs
+    const uint32_t* root_shadow; uint32_t* sim_shadow;      // delta plane store: bit images of root_planes / sim_planes (or null)
     uint8_t* env_mask;                                      // [n] leaf positions the environment kernels must evaluate
     const float* leaf_p;                                    // [n][1584] network policy of the leaf
     const double* leaf_v;                                   // [n] network value of the leaf
@@ -231,6 +232,8 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_descend_kernel(MctsArgs 
                     const uint4* ps = reinterpret_cast<const uint4*>(a.root_planes + (size_t)t * HIVE_PLANES_ELEMS);
                     uint4* pd = reinterpret_cast<uint4*>(a.sim_planes + (size_t)t * HIVE_PLANES_ELEMS);
                     for (int i = lane; i < HIVE_PLANES_ELEMS * 2 / 16; i += 32) pd[i] = ps[i];
+                    if (a.sim_shadow)                              // ... and the bit image the delta plane store keeps of them
+                        for (int i = lane; i < BITS_WORDS; i += 32) a.sim_shadow[(size_t)t * BITS_WORDS + i] = a.root_shadow[(size_t)t * BITS_WORDS + i];
                     for (int i = lane; i < LEGAL_WORDS; i += 32) a.sim_legal[(size_t)t * LEGAL_WORDS + i] = a.root_legal[(size_t)t * LEGAL_WORDS + i];
                     if (lane == 0) a.sim_count[t] = a.root_count[t];
                 }

@@ -33,7 +33,7 @@ def lib():
         L = ctypes.CDLL(_LIB)
         vp = ctypes.c_void_p
         L.emu_env_run.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_uint64,
-                                  ctypes.c_int, ctypes.c_int, vp, ctypes.c_uint64]
+                                  ctypes.c_int, ctypes.c_int, vp, ctypes.c_uint64, vp]
         L.emu_env_run.restype = ctypes.c_int
         L.emu_env_rollout.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint64]
         L.emu_env_rollout.restype = ctypes.c_int
@@ -42,7 +42,7 @@ def lib():
         L.emu_mcts_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.emu_mcts_destroy.argtypes = [vp]
         L.emu_mcts_set_noise.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int]
-        L.emu_mcts_begin.argtypes = [vp, vp, vp, vp, vp]
+        L.emu_mcts_begin.argtypes = [vp, vp, vp, vp, vp, vp]
         L.emu_mcts_descend.argtypes = [vp, vp]
         L.emu_mcts_planes.restype = vp
         L.emu_mcts_planes.argtypes = [vp]
@@ -61,8 +61,10 @@ def lib():
 class EmuBatch:
     """Host-memory twin of the device arenas of hive_env (same layouts)."""
 
-    def __init__(self, n, sched_seed=1):
+    def __init__(self, n, sched_seed=1, full_store=True):
         self.n = n
+        # delta plane store (HIVE_B200_DELTA_STORE=1): the bit image of `planes`, kept by the store kernel; None = full store (the default)
+        self.shadow = None if full_store else np.zeros((n, 280), dtype=np.uint32)
         self.recs = np.zeros((n, 384), dtype=np.uint8)
         self.legal = np.zeros((n, 50), dtype=np.uint32)
         self.count = np.zeros(n, dtype=np.int32)
@@ -79,7 +81,8 @@ class EmuBatch:
         rc = lib().emu_env_run(self.recs.ctypes.data, self.legal.ctypes.data, self.count.ctypes.data,
                                self.status.ctypes.data, self.planes.ctypes.data, self.n, op,
                                None if a is None else a.ctypes.data, None if m is None else m.ctypes.data,
-                               seed, max_turn, auto_reset, self.chosen.ctypes.data, self.sched_seed)
+                               seed, max_turn, auto_reset, self.chosen.ctypes.data, self.sched_seed,
+                               None if self.shadow is None else self.shadow.ctypes.data)
         if rc:
             raise RuntimeError("emulator: " + lib().emu_last_error().decode())
 
@@ -157,7 +160,8 @@ class EmuMcts:
     def search(self, net):
         """net(planes_hwc_f64) -> (p float32[1584], v float).  Runs all simulations."""
         self._chk(lib().emu_mcts_begin(self._h, self.batch.recs.ctypes.data, self.batch.legal.ctypes.data,
-                                       self.batch.count.ctypes.data, self.batch.planes.ctypes.data))
+                                       self.batch.count.ctypes.data, self.batch.planes.ctypes.data,
+                                       None if self.batch.shadow is None else self.batch.shadow.ctypes.data))
         pending = ctypes.c_int(0)
         p = np.zeros((self.n, 1584), dtype=np.float32)
         v = np.zeros(self.n, dtype=np.float64)

@@ -15,13 +15,15 @@ static void build_lines() {
 
 static void k_step(void* p) { hive_step_kernel(*(EnvArgs*)p); }
 static void k_planes(void* p) { hive_planes_kernel(*(EnvArgs*)p); }
+static void k_planes_delta(void* p) { hive_planes_delta_kernel(*(EnvArgs*)p); }
 
 extern "C" {
 
-// state: n x 384 B records; legal: n x 50 u32; count: n; planes: n x 8064 u16
+// state: n x 384 B records; legal: n x 50 u32; count: n; planes: n x 8064 u16; shadow: n x 280 u32 (the bit image
+// of `planes`, owned by the caller: the delta plane store, the product's default) or null (full plane store)
 int emu_env_run(void* recs, uint32_t* legal, int32_t* count, uint32_t* status, uint16_t* planes, int n, int op,
                 const int32_t* actions, const uint8_t* mask, uint64_t seed, int max_turn, int auto_reset,
-                int32_t* chosen, uint64_t sched_seed) {
+                int32_t* chosen, uint64_t sched_seed, uint32_t* shadow) {
     build_lines();
     EnvArgs a;
     a.recs = (GameRec*)recs; a.legal = legal; a.count = count; a.status = status; a.planes = planes;
@@ -30,12 +32,22 @@ int emu_env_run(void* recs, uint32_t* legal, int32_t* count, uint32_t* status, u
     a.g_offset = 0; a.n_total = n; a.stagger_ns = 0; a.stagger_div = 148;
     static std::vector<uint32_t> bits;
     if ((int)bits.size() < n * BITS_WORDS) bits.resize((size_t)n * BITS_WORDS);
-    a.bits = bits.data();
+    a.bits = bits.data(); a.shadow = shadow;
     const int blocks = (n + SG - 1) / SG;
     emu::g_gridDim.x = blocks;
     for (int b = 0; b < blocks; b++) {
         int rc = emu::run_block(k_step, &a, b, STEP_THREADS, sched_seed + (uint64_t)b);
         if (rc) return rc;
+    }
+    if (shadow) {
+        int delta_blocks = (n + HIVE_DELTA_WARPS - 1) / HIVE_DELTA_WARPS;
+        if (delta_blocks > 3) delta_blocks = 3;     // capped grid, as on the GPU
+        emu::g_gridDim.x = delta_blocks;
+        for (int b = 0; b < delta_blocks; b++) {
+            int rc = emu::run_block(k_planes_delta, &a, b, HIVE_DELTA_WARPS * 32, sched_seed + 3000 + (uint64_t)b);
+            if (rc) return rc;
+        }
+        return 0;
     }
     int store_blocks = (n + HIVE_STORE_WARPS - 1) / HIVE_STORE_WARPS;
     if (store_blocks > 2) store_blocks = 2;     // capped grid: warps walk over several games like the persistent launch on the GPU
@@ -57,7 +69,7 @@ int emu_env_rollout(void* recs, uint32_t* legal, int32_t* count, uint32_t* statu
     a.g_offset = 0; a.n_total = n; a.stagger_ns = 0; a.stagger_div = 148;
     static std::vector<uint32_t> bits;
     if ((int)bits.size() < n * BITS_WORDS) bits.resize((size_t)n * BITS_WORDS);
-    a.bits = bits.data();
+    a.bits = bits.data(); a.shadow = nullptr;
     struct Call { EnvArgs a; int n_steps; } call = {a, n_steps};
     const int blocks = (n + SG - 1) / SG;
     emu::g_gridDim.x = blocks;

@@ -8,7 +8,7 @@ using namespace hive;
 
 extern "C" int emu_env_run(void* recs, uint32_t* legal, int32_t* count, uint32_t* status, uint16_t* planes, int n, int op,
                            const int32_t* actions, const uint8_t* mask, uint64_t seed, int max_turn, int auto_reset,
-                           int32_t* chosen, uint64_t sched_seed);
+                           int32_t* chosen, uint64_t sched_seed, uint32_t* shadow);
 
 struct EmuMcts {
     int n, sims, node_cap, edge_cap, ht_size;
@@ -16,6 +16,8 @@ struct EmuMcts {
     std::vector<uint32_t> sim_legal, sim_status;
     std::vector<int32_t> sim_count;
     std::vector<uint16_t> sim_planes;
+    std::vector<uint32_t> sim_shadow;                       // delta plane store: bit image of sim_planes
+    const uint32_t* root_shadow = nullptr;
     std::vector<MctsTree> trees;
     std::vector<MctsNode> nodes;
     std::vector<int32_t> htab, e_n, out_action, out_sum_n;
@@ -38,6 +40,7 @@ static MctsArgs args_of(EmuMcts* m) {
     a.noise_rows = m->noise_rows; a.noise_cols = m->noise_cols; a.noise_seed = 7;
     a.root_recs = m->root; a.sim_recs = m->sim_recs.data(); a.sim_legal = m->sim_legal.data(); a.sim_count = m->sim_count.data(); a.sim_planes = m->sim_planes.data();
     a.root_legal = m->root_legal; a.root_count = m->root_count; a.root_planes = m->root_planes; a.env_mask = m->env_mask.data();
+    a.root_shadow = m->root_shadow; a.sim_shadow = m->root_shadow ? m->sim_shadow.data() : nullptr;
     a.leaf_p = m->leaf_p.data(); a.leaf_v = m->leaf_v.data(); a.need_eval = m->need_eval.data(); a.tree_mask = nullptr;
     a.pending = &m->pending; a.trees = m->trees.data(); a.nodes = m->nodes.data(); a.htab = m->htab.data();
     a.e_action = m->e_action.data(); a.e_n = m->e_n.data(); a.e_w = m->e_w.data(); a.e_q = m->e_q.data(); a.e_p = m->e_p.data();
@@ -58,7 +61,7 @@ void* emu_mcts_create(int n, int sims, int edges_per_sim) {
     m->n = n; m->sims = sims; m->node_cap = sims + 1; m->edge_cap = sims * edges_per_sim + 256;
     int ht = 64; while (ht < 2 * m->node_cap) ht <<= 1; m->ht_size = ht;
     m->sim_recs.resize(n); m->sim_legal.resize(n * 50); m->sim_status.resize(n); m->sim_count.resize(n);
-    m->sim_planes.resize((size_t)n * 56 * 144); m->trees.resize(n); m->nodes.resize((size_t)n * m->node_cap);
+    m->sim_planes.resize((size_t)n * 56 * 144); m->sim_shadow.resize((size_t)n * BITS_WORDS); m->trees.resize(n); m->nodes.resize((size_t)n * m->node_cap);
     m->htab.resize((size_t)n * ht); m->e_n.resize((size_t)n * m->edge_cap); m->e_action.resize((size_t)n * m->edge_cap);
     m->e_w.resize((size_t)n * m->edge_cap); m->e_q.resize((size_t)n * m->edge_cap); m->e_p.resize((size_t)n * m->edge_cap);
     m->leaf_p.resize((size_t)n * 1584); m->leaf_v.resize(n); m->need_eval.resize(n); m->env_mask.resize(n); m->pi.resize((size_t)n * 1584);
@@ -71,8 +74,10 @@ void emu_mcts_set_noise(void* h, const double* noise, int rows, int cols) {
     EmuMcts* m = (EmuMcts*)h;
     m->noise.assign(noise, noise + (size_t)m->n * rows * cols); m->noise_rows = rows; m->noise_cols = cols;
 }
-int emu_mcts_begin(void* h, const void* root_recs, const uint32_t* root_legal, const int32_t* root_count, const uint16_t* root_planes) {
+int emu_mcts_begin(void* h, const void* root_recs, const uint32_t* root_legal, const int32_t* root_count, const uint16_t* root_planes,
+                   const uint32_t* root_shadow) {
     EmuMcts* m = (EmuMcts*)h;
+    m->root_shadow = root_shadow;
     m->root = (const GameRec*)root_recs; m->root_legal = root_legal; m->root_count = root_count; m->root_planes = root_planes;
     m->error_any = 0;
     MctsArgs a = args_of(m);
@@ -86,7 +91,7 @@ int emu_mcts_descend(void* h, int* pending) {
     const int blocks = (m->n + MCTS_WARPS - 1) / MCTS_WARPS;
     for (int b = 0; b < blocks; b++) { int rc = emu::run_block(k_descend, &a, b, MCTS_WARPS * 32, m->sched++); if (rc) return rc; }
     int rc = emu_env_run(m->sim_recs.data(), m->sim_legal.data(), m->sim_count.data(), m->sim_status.data(), m->sim_planes.data(),
-                         m->n, /*OP_EVAL*/ 2, nullptr, m->env_mask.data(), 0, 55, 0, nullptr, m->sched++);
+                         m->n, /*OP_EVAL*/ 2, nullptr, m->env_mask.data(), 0, 55, 0, nullptr, m->sched++, m->root_shadow ? m->sim_shadow.data() : nullptr);
     if (rc) return rc;
     *pending = m->pending;
     return 0;

@@ -127,3 +127,34 @@ def test_rollout_kernel_equals_single_steps():
     for _ in range(60):
         a.step_random(seed)
     assert (a.recs == b.recs).all() and (a.planes == b.planes).all() and (a.legal == b.legal).all()
+
+
+def test_delta_plane_store_equals_full_store():
+    """hive_planes_delta_kernel (only the 32-byte sectors that differ from what the planes arena holds are rewritten;
+    HIVE_B200_DELTA_STORE=1) leaves the same planes as hive_planes_kernel (all 16 KB of every evaluated game rewritten) after every step:
+    random play across resets at the turn-55 cut, masked resets, and masked evaluations of loaded positions (games that
+    are not evaluated in a launch keep their planes and their shadow)."""
+    n, seed = 37, 0xD17A
+    a, b = EmuBatch(n, sched_seed=31, full_store=False), EmuBatch(n, sched_seed=32)
+    assert a.shadow is not None and b.shadow is None
+    for step in range(64):
+        a.step_random(seed); b.step_random(seed)
+        assert (a.planes == b.planes).all(), step
+        if step % 9 == 4:                                  # a few games start over
+            mask = (np.arange(n) % 5 == step % 5).astype(np.uint8)
+            a.reset(mask); b.reset(mask)
+            assert (a.planes == b.planes).all(), step
+        if step % 11 == 7:                                 # one game jumps to another game's position (OP_EVAL, masked)
+            src, dst = step % n, (3 * step + 1) % n
+            turn, cells, levels = a.turn(src), a.cells(src), a.levels(src)
+            a.load(dst, turn, cells, levels); b.load(dst, turn, cells, levels)
+            assert (a.planes == b.planes).all(), step
+    assert (a.recs == b.recs).all() and (a.legal == b.legal).all()
+    # the shadow is the bit image of the planes: expanding it reproduces them (plane 31 = turn in every cell)
+    sh = a.shadow
+    bits = np.unpackbits(sh.view(np.uint8).reshape(n, 56, 20)[:, :, :18], axis=2, bitorder="little")
+    vals = a.planes.astype(np.uint32) << 16
+    vals = vals.view(np.float32).reshape(n, 56, 144)
+    keep = np.arange(56) != 31
+    assert (vals[:, keep] == bits[:, keep]).all()
+    assert (vals[:, 31] == sh[:, 155].astype(np.float32)[:, None]).all()

@@ -56,10 +56,12 @@ def test_kernels_match_reference_player(i):
     assert action[0] == G["action"][i] and (pi[0] == G["policy"][i]).all() and sum_n[0] == G["sum_n"][i]
 
 
-def test_three_trees_in_one_batch():
-    """Independent trees in one launch (different positions, separate noise) vs the oracle."""
+@pytest.mark.parametrize("full_store", [True, False])
+def test_three_trees_in_one_batch(full_store):
+    """Independent trees in one launch (different positions, separate noise) vs the oracle.  full_store=False: the
+    delta plane store (the search copies a root's planes AND their shadow row into its working batch)."""
     n, sims = 3, 24
-    b = EmuBatch(n, sched_seed=77)
+    b = EmuBatch(n, sched_seed=77, full_store=full_store)
     envs = [OracleEnv() for _ in range(n)]
     rng = np.random.RandomState(3)
     for ply in range(9):

@@ -211,6 +211,39 @@ def test_multi_step_graph_equals_single_steps(hb):
     assert [x.tolist() for x in a.counters()] == [x.tolist() for x in b.counters()]
 
 
+def test_delta_plane_store_equals_full_store(hb, monkeypatch):
+    """HIVE_B200_DELTA_STORE=1 (hive_planes_delta_kernel: only the 32-byte sectors that differ from what the planes arena
+    holds are rewritten) leaves the same planes as the default full store after single steps, multi-step graphs across
+    resets, masked resets and hive_copy_state."""
+    n, seed = 2048, 777
+    a = hb.HiveBatch(n)
+    monkeypatch.setenv("HIVE_B200_DELTA_STORE", "1")
+    b = hb.HiveBatch(n)
+    c = hb.HiveBatch(n)
+    monkeypatch.delenv("HIVE_B200_DELTA_STORE")
+    for rnd in range(3):
+        for _ in range(5):
+            a.step_random(seed, 55, True); b.step_random(seed, 55, True)
+        assert (a.planes_bf16() == b.planes_bf16()).all()
+        a.step_random_multi(seed, 41); b.step_random_multi(seed, 41)
+        assert (a.planes_bf16() == b.planes_bf16()).all()
+        mask = (np.arange(n) % 7 == rnd).astype(np.uint8)
+        a.reset(mask); b.reset(mask)
+        assert (a.planes_bf16() == b.planes_bf16()).all()
+    # a copied game brings its planes and their bit image along: the next delta store of the copy starts from them
+    for g in (0, 5, n - 1):
+        c.copy_state_from(g, b, (g + 3) % n)
+    for _ in range(4):
+        c.step_random(seed, 55, False)
+    ref = hb.HiveBatch(n)
+    for g in (0, 5, n - 1):
+        ref.copy_state_from(g, a, (g + 3) % n)
+    for _ in range(4):
+        ref.step_random(seed, 55, False)
+    assert (c.planes_bf16() == ref.planes_bf16()).all()
+    assert (a.legal_mask()[0] == b.legal_mask()[0]).all()
+
+
 def test_async_host_step_graph_replay_matches_device_policy(hb):
     """hive_step_host_async from one fixed set of page-locked buffers (replayed as one CUDA graph from the second
     call on) == hive_step_random; the same loop from pageable buffers (plain path) gives the same games."""

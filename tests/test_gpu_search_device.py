@@ -94,6 +94,23 @@ def test_search_device_64_trees_50_sims_plain_and_graph(hb):
         _compare(m, expect, sims)
 
 
+def test_search_device_with_delta_plane_store(hb, monkeypatch):
+    """The same comparison with HIVE_B200_DELTA_STORE=1: the search copies a root's planes and their shadow row into its
+    working batch, and every leaf evaluation rewrites only the sectors that differ from the slot's previous leaf."""
+    from oracle.mcts_oracle import device_hash_net
+    monkeypatch.setenv("HIVE_B200_DELTA_STORE", "1")
+    n, sims, salt = 16, 50, 0x3C
+    b, envs = _positions(hb, n, 77)
+    noise, expect = _oracle_expectation(envs, sims, [lambda pl: device_hash_net(pl, salt)] * n, 900)
+    m = hb.MctsBatch(b, sims)
+    m.set_root_noise(noise)
+    m.search_device(hb.HashEvaluator(salt, m.stream_ptr))
+    assert m.errors() == 0
+    _compare(m, expect, sims)
+    m.search_device(hb.HashEvaluator(salt, m.stream_ptr))          # again from the same roots: same trees
+    _compare(m, expect, sims)
+
+
 @pytest.mark.parametrize("sims", [250, 500])
 def test_search_device_8_trees_deep(hb, sims):
     from oracle.mcts_oracle import device_hash_net
