@@ -253,6 +253,11 @@ int hive::create_env(int n_games, int device, void* stream, int slices, hive_env
         CUDA_TRY(cudaFuncSetAttribute(hive_planes_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CUDA_TRY(cudaFuncSetAttribute(hive_step_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CUDA_TRY(cudaFuncSetAttribute(hive_rollout_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        // (for the two persistent kernels of the queue-driven rollout this is a matter of progress, not of speed: an SM
+        // configured for one of them alone could never take a CTA of the other)
+        CUDA_TRY(cudaFuncSetAttribute(hive_rollout_q_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CUDA_TRY(cudaFuncSetAttribute(hive_planes_q_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CUDA_TRY(cudaFuncSetAttribute(hive_step_flow_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
     for (int b = 0; b < 2; b++) {
         CUDA_TRY(cudaMalloc(&h->bits[b], n * BITS_WORDS * 4));
@@ -299,6 +304,15 @@ int hive::create_env(int n_games, int device, void* stream, int slices, hive_env
         h->stagger_ns = (sg2 ? atoi(sg2) : 25) * 1000;
         const char* rk = getenv("HIVE_B200_ROLLOUT_KERNEL");
         h->use_rollout_kernel = rk ? atoi(rk) : 0;         // measured slower than the per-step kernels (profiles/README.md): off
+        const char* rq = getenv("HIVE_B200_ROLLOUT_QUEUE");
+        h->rollout_queue = rq ? atoi(rq) : 0;
+        const char* rc = getenv("HIVE_B200_ROLL_CTAS");
+        h->roll_ctas_per_sm = rc && atoi(rc) >= 1 && atoi(rc) <= 4 ? atoi(rc) : 2;    // default 2: two store CTAs fit beside them (a configuration without room for the store ends in the waits' time-out, not in a hang)
+        const char* qs = getenv("HIVE_B200_ROLL_STORE_CTAS");
+        h->roll_store_ctas_per_sm = qs && atoi(qs) >= 1 ? atoi(qs) : 2;
+        h->roll_sync_bytes = 128 + 2 * ((n + SG - 1) / SG) * 4;
+        CUDA_TRY(cudaMalloc(&h->roll_sync, h->roll_sync_bytes));
+        CUDA_TRY(cudaFuncSetAttribute(hive_planes_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STORE_STAGE_BYTES));
         const char* ug = getenv("HIVE_B200_GRAPH");
         h->use_graph = ug ? atoi(ug) : 1;
     }
@@ -348,7 +362,7 @@ int hive_destroy(hive_env_t* h) {
     if (h->multi_graph.exec && h->multi_graph.exec != h->slice_exec[0]) cudaGraphExecDestroy(h->multi_graph.exec);
     for (int s = 0; s < hive_env::MAX_SUB; s++) if (h->slice_exec[s]) cudaGraphExecDestroy(h->slice_exec[s]);
     if (h->host_graph.exec) cudaGraphExecDestroy(h->host_graph.exec);
-    cudaFree(h->recs); cudaFree(h->legal); cudaFree(h->planes); cudaFree(h->bits[0]); cudaFree(h->bits[1]); cudaFree(h->shadow);
+    cudaFree(h->recs); cudaFree(h->legal); cudaFree(h->planes); cudaFree(h->bits[0]); cudaFree(h->bits[1]); cudaFree(h->shadow); cudaFree(h->roll_sync);
     for (int s = 0; s < h->n_sub; s++) {
         if (h->sub_stream[s]) cudaStreamDestroy(h->sub_stream[s]);
         if (h->store_stream[s]) cudaStreamDestroy(h->store_stream[s]);
@@ -374,6 +388,17 @@ int hive_num_games(const hive_env_t* h) { return h ? h->n : HIVE_E_HANDLE; }
 int hive_sync(hive_env_t* h) {
     if (check(h)) return HIVE_E_HANDLE;
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (h->roll_pending) {   // a queue-driven rollout ran since the last sync: did one of its waits give up?
+        h->roll_pending = false;
+        unsigned err = 0;
+        CUDA_TRY(cudaMemcpy(&err, reinterpret_cast<const char*>(h->roll_sync) + 8, 4, cudaMemcpyDeviceToHost));
+        if (err) {
+            char msg[160];
+            snprintf(msg, sizeof msg, "queue-driven rollout: wait kind %u of ticket %u timed out (the batch is in an undefined state: reset it)",
+                     err >> 28, err & 0x0FFFFFFFu);
+            return fail(HIVE_E_CUDA, msg);
+        }
+    }
     return 0;
 }
 
@@ -530,6 +555,47 @@ int hive_step_random_multi(hive_env_t* h, uint64_t seed, int max_turn, int auto_
         hive_rollout_kernel<<<(h->n + SG - 1) / SG, STEP_THREADS, 0, h->stream>>>(a, n_steps);
         CUDA_TRY(cudaGetLastError());
         h->launches += 1;
+        if (h->timing) CUDA_TRY(cudaEventRecord(h->t1, h->stream));
+        return 0;
+    }
+    if (h->rollout_queue && n_steps >= 2 && h->full_store && !h->skip_planes) {
+        // the queue-driven rollout: two persistent kernels, CTAs take (group, step) tickets (hive_rollout_q_kernel)
+        const int G = (h->n + SG - 1) / SG;
+        EnvArgs a = slice_args(h, 0, h->n, OP_RANDOM, nullptr, nullptr, seed, max_turn, auto_reset, nullptr);
+        a.bits = h->bits[0];
+        cudaStream_t ss = h->store_stream[0];
+        if (h->roll_pending) { int rc = hive_sync(h); if (rc) return rc; }      // (reads the previous rollout's error word before it is zeroed)
+        CUDA_TRY(cudaMemsetAsync(h->roll_sync, 0, h->roll_sync_bytes, h->stream));
+        CUDA_TRY(cudaEventRecord(h->fork_ev, h->stream));
+        CUDA_TRY(cudaStreamWaitEvent(ss, h->fork_ev, 0));
+        int store_blocks = h->sm_count * h->roll_store_ctas_per_sm, step_blocks = h->sm_count * h->roll_ctas_per_sm;
+        if (store_blocks > G) store_blocks = G;
+        if (step_blocks > G) step_blocks = G;
+        // the store kernel first: its CTAs must find room (the step CTAs wait for it from their third step on; with at most
+        // two step CTAs per SM there is always room, whatever the placement)
+        hive_planes_q_kernel<<<store_blocks, HIVE_STORE_WARPS * 32, STORE_STAGE_BYTES, ss>>>(a, h->bits[1], n_steps, reinterpret_cast<RollSync*>(h->roll_sync));
+        if (h->rollout_queue == 2) {
+            // one launch per step, chained by programmatic stream serialization + per-group flags (hive_step_flow_kernel)
+            for (int k = 0; k < n_steps; k++) {
+                EnvArgs ak = a;
+                ak.bits = h->bits[k & 1];
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned)G); cfg.blockDim = dim3(STEP_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = h->stream;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = at; cfg.numAttrs = k > 0 ? 1 : 0;
+                CUDA_TRY(cudaLaunchKernelEx(&cfg, hive_step_flow_kernel, ak, k, reinterpret_cast<RollSync*>(h->roll_sync)));
+            }
+            h->launches += n_steps - 1;
+        } else {
+            hive_rollout_q_kernel<<<step_blocks, STEP_THREADS, 0, h->stream>>>(a, h->bits[1], n_steps, reinterpret_cast<RollSync*>(h->roll_sync));
+        }
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(h->stored_ev[0][0], ss));
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, h->stored_ev[0][0], 0));
+        h->launches += 2;
+        h->roll_pending = true;
         if (h->timing) CUDA_TRY(cudaEventRecord(h->t1, h->stream));
         return 0;
     }

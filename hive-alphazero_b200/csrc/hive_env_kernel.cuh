@@ -567,9 +567,9 @@ __device__ __forceinline__ void encode_mobility(const StepShared& s, const Encod
 
 // phases 1..5 of one step of the CTA's 32 games (all threads; ends without a trailing barrier).  Returns the mask of the
 // games evaluated in this step (identical in every thread).
-__device__ __forceinline__ unsigned step_phases(StepShared& s, const EnvArgs& a) {
+__device__ __forceinline__ unsigned step_phases(StepShared& s, const EnvArgs& a, int blk) {      // blk: which group of SG games
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = blockIdx.x * SG + lane;
+    const int g = blk * SG + lane;
     const uint32_t* geo = a.hop_lines;
     HIVE_PHASE_BEGIN();
     if (warp == 0) step_prologue(s, a, lane, g);
@@ -701,14 +701,10 @@ __device__ __forceinline__ unsigned step_phases(StepShared& s, const EnvArgs& a)
     return live_mask;
 }
 
-#ifdef HIVE_STEP_MAXNREG
-__global__ void __maxnreg__(HIVE_STEP_MAXNREG) hive_step_kernel(EnvArgs a) {
-#else
 __global__ void __launch_bounds__(STEP_THREADS, HIVE_STEP_MIN_CTAS) hive_step_kernel(EnvArgs a) {
-#endif
     __shared__ StepShared s;
     HIVE_TRACE_SCOPE(0, a);
-    step_phases(s, a);
+    step_phases(s, a, blockIdx.x);
 }
 
 // ---- the rollout kernel (experiment, HIVE_B200_ROLLOUT_KERNEL=1; measured SLOWER than the per-step kernels, 102 vs 66 us
@@ -754,7 +750,7 @@ __global__ void __launch_bounds__(STEP_THREADS, HIVE_ROLL_MIN_CTAS) hive_rollout
     }
 #endif
     for (int step = 0; step < n_steps; step++) {
-        const unsigned live_mask = step_phases(sm.step, a);
+        const unsigned live_mask = step_phases(sm.step, a, blockIdx.x);
         __syncthreads();                                        // the step's shared memory is dead; its global writes are visible to the CTA
         if (live_mask) {   // ---- phase 6: bit planes -> bf16 CHW planes [56][144] per game (warp <-> game)
             RollStoreShared& st = sm.store;
@@ -838,6 +834,195 @@ __global__ void __launch_bounds__(HIVE_STORE_WARPS * 32, HIVE_STORE_MIN_CTAS) hi
         if (live)
             store_planes_bulk(reinterpret_cast<const uint8_t*>(mine), bf16_lut, lut_s, stage_ring + warp * (STAGE_BUFS * STAGE_CHUNKS), lane,
                               (int)turn, a.planes + (size_t)g * HIVE_PLANES_ELEMS);
+    }
+    if (lane == 0) bulk_wait_read<0>();                         // shared memory must outlive the copy engine's reads
+}
+
+// ==========================================================================================================
+// The queue-driven rollout (hive_step_random_multi, the default for n_steps >= 2): n_steps consecutive OP_RANDOM steps of
+// the whole batch WITHOUT a kernel boundary per step.  Games are independent, so the only order that matters is per
+// group of 32 games: step k+1 of a group after its step k.  Two persistent kernels share the SMs:
+//   hive_rollout_q_kernel  CTAs take tickets t = 0, 1, 2 ... from a global counter; ticket t is step k = t / G of group
+//                          g = t % G (G groups).  A CTA waits until done[g] == k (the group's previous step has left
+//                          whichever CTA ran it) and until the store of the group's step k-2 has read the bit-plane buffer
+//                          this step overwrites, runs the five phases, and publishes done[g] = k + 1.
+//   hive_planes_q_kernel   CTAs take tickets in the same order, wait for done[g] > k, expand the group's bit planes to
+//                          bf16 through the TMA staging ring, and publish stored[g] = k + 1.
+// Against one kernel launch per step and slice: no launch waits for its slowest CTA, no launch gap, no wave of CTAs
+// that finds the SM slots taken -- every resident CTA starts its next group-step the moment it is free.
+// MEASURED SLOWER than the per-step graphs (87 vs 65 us per 16,384-game step; 70 us without the store's work; the
+// flag-chained launches below: 79 / 60 us) and therefore behind HIVE_B200_ROLLOUT_QUEUE: an SM finishes a group-step
+// every ~40 k clocks whether two or three of these CTAs share it (51 k for one CTA alone), the per-step kernels of the
+// graph pipeline one every ~28 k -- what bounds the step is the SM's throughput for this code, not idle SM slots.
+// Synchronisation: thread 0 spins on an acquire load, a block barrier hands the result to the CTA; the publisher's
+// threads have passed a block barrier before thread 0 fences and stores the flag (the split-K semaphore pattern).
+struct RollSync {
+    unsigned ticket_step, ticket_store, error, pad_[29];   // error: 0, or wait kind << 28 | ticket of the first wait that timed out
+    unsigned flags[1];                   // done[G] then stored[G]
+};
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+#ifdef HIVE_EMU
+    return *p;
+#else
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+#endif
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+#ifdef HIVE_EMU
+    *p = v;
+#else
+    __threadfence();
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#endif
+}
+// false: gave up (another CTA has failed, or ~0.3 s without progress: a lost CTA must not hang the GPU); the caller then
+// reports through sync->error and every CTA leaves at its next ticket
+__device__ __forceinline__ bool spin_until_at_least(const unsigned* p, unsigned want, RollSync* sync, unsigned code) {
+#ifdef HIVE_EMU
+    (void)p; (void)want; (void)sync; (void)code;   // (the emulator runs the CTAs one after the other, in ticket order)
+    return true;
+#else
+    for (unsigned spins = 0; ld_acquire_u32(p) < want; spins++) {
+        __nanosleep(64);
+        if ((spins & 1023u) == 1023u && (spins > (1u << 18) || ld_acquire_u32(&sync->error))) {
+            atomicCAS(&sync->error, 0u, code);
+            return false;
+        }
+    }
+    return true;
+#endif
+}
+// a.bits / bits_alt: the two bit-plane buffers (step k of a launch uses buffer k & 1)
+#ifdef HIVE_ROLLQ_MAXNREG
+__global__ void __maxnreg__(HIVE_ROLLQ_MAXNREG) hive_rollout_q_kernel(
+#else
+__global__ void __launch_bounds__(STEP_THREADS, HIVE_STEP_MIN_CTAS) hive_rollout_q_kernel(
+#endif
+    EnvArgs a, uint32_t* bits_alt, int n_steps, RollSync* sync) {
+    __shared__ StepShared s;
+    __shared__ unsigned s_ticket;
+    HIVE_TRACE_SCOPE(6, a);
+    const int tid = threadIdx.x;
+    const unsigned G = (unsigned)((a.n + SG - 1) / SG), total = G * (unsigned)n_steps;
+    unsigned* done = sync->flags;
+    const unsigned* stored = sync->flags + G;
+    for (;;) {
+        __syncthreads();                                        // the previous group-step of this CTA has left shared memory
+        if (tid == 0) {
+            const unsigned t = atomicAdd(&sync->ticket_step, 1u);
+            s_ticket = t;
+            if (t < total) {
+                const unsigned g = t % G, k = t / G;
+                bool ok = spin_until_at_least(done + g, k, sync, (1u << 28) | t);          // the group's step k-1 is complete (records, legal masks)
+                if (ok && k >= 2) ok = spin_until_at_least(stored + g, k - 1, sync, (2u << 28) | t);   // ... and its step k-2 has left this bit-plane buffer
+                if (!ok || ld_acquire_u32(&sync->error)) s_ticket = 0xFFFFFFFFu;
+            }
+        }
+        __syncthreads();
+        const unsigned t = s_ticket;
+        if (t >= total) break;
+        const unsigned g = t % G, k = t / G;
+        EnvArgs b = a;
+        if (k & 1u) b.bits = bits_alt;
+        step_phases(s, b, (int)g);
+        __syncthreads();                                        // every thread's global writes of this group-step are issued
+        if (tid == 0) st_release_u32(done + g, k + 1u);
+    }
+}
+// The same order kept by FLAGS between ordinary launches (hive_step_random_multi, HIVE_B200_ROLLOUT_QUEUE=2): one launch
+// per step over all groups, each launched with programmatic stream serialization -- the next step's CTAs become resident
+// as soon as every CTA of this step has STARTED (griddepcontrol.launch_dependents is the first thing a CTA does), and a
+// CTA of step k waits for done[its group] == k instead of the whole previous grid: the launch gap and the wait for a
+// step's slowest CTA are gone, a freed SM slot goes to the next step at once.  The store is hive_planes_q_kernel.
+#ifdef HIVE_ROLLQ_MAXNREG
+__global__ void __maxnreg__(HIVE_ROLLQ_MAXNREG) hive_step_flow_kernel(EnvArgs a, int k, RollSync* sync) {
+#else
+__global__ void __launch_bounds__(STEP_THREADS, HIVE_STEP_MIN_CTAS) hive_step_flow_kernel(EnvArgs a, int k, RollSync* sync) {
+#endif
+    __shared__ StepShared s;
+    __shared__ unsigned s_ok;
+    HIVE_TRACE_SCOPE(8, a);
+#ifndef HIVE_EMU
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+    const int tid = threadIdx.x;
+    const unsigned g = blockIdx.x, G = gridDim.x;
+    if (tid == 0) {
+        bool ok = spin_until_at_least(sync->flags + g, (unsigned)k, sync, (1u << 28) | ((unsigned)k * G + g));
+        if (ok && k >= 2) ok = spin_until_at_least(sync->flags + G + g, (unsigned)k - 1u, sync, (2u << 28) | ((unsigned)k * G + g));
+        s_ok = ok && !ld_acquire_u32(&sync->error);
+    }
+    __syncthreads();
+    if (!s_ok) return;
+    step_phases(s, a, (int)g);
+    __syncthreads();                                            // every thread's global writes of this group-step are issued
+    if (tid == 0) st_release_u32(sync->flags + g, (unsigned)k + 1u);
+}
+
+#ifndef HIVE_STORE_Q_MIN_CTAS
+#define HIVE_STORE_Q_MIN_CTAS (640 / (HIVE_STORE_WARPS * 32))      // <= 96 registers: two of these fit beside two step CTAs of 80 registers
+#endif
+__global__ void __launch_bounds__(HIVE_STORE_WARPS * 32, HIVE_STORE_Q_MIN_CTAS) hive_planes_q_kernel(EnvArgs a, uint32_t* bits_alt, int n_steps, RollSync* sync) {
+    __shared__ uint4 bf16_lut[256];
+    __shared__ __align__(16) uint32_t planes_s[HIVE_STORE_WARPS][BITS_WORDS];
+    __shared__ unsigned s_ticket;
+    __shared__ uint32_t lut_addr;
+#ifdef HIVE_EMU
+    __shared__ uint4 stage_ring[STORE_STAGE_BYTES / 16];
+#else
+    extern __shared__ __align__(128) uint4 stage_ring[];
+#endif
+    HIVE_TRACE_SCOPE(7, a);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int t = tid; t < 256; t += HIVE_STORE_WARPS * 32) fill_bf16_lut(bf16_lut, t);
+#ifndef HIVE_EMU
+    if (tid == 0) lut_addr = (uint32_t)__cvta_generic_to_shared(bf16_lut);
+#endif
+    __syncthreads();
+    const uint32_t lut_s = *reinterpret_cast<volatile uint32_t*>(&lut_addr);
+    constexpr int NV = BITS_WORDS / 4;                           // 70 uint4 per game
+    const unsigned G = (unsigned)((a.n + SG - 1) / SG), total = G * (unsigned)n_steps;
+    const unsigned* done = sync->flags;
+    unsigned* stored = sync->flags + G;
+    uint32_t* mine = planes_s[warp];
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned t = atomicAdd(&sync->ticket_store, 1u);
+            s_ticket = t;
+            if (t < total) {                                    // the group's step k has written its bit planes
+                if (!spin_until_at_least(done + t % G, t / G + 1u, sync, (3u << 28) | t) || ld_acquire_u32(&sync->error)) s_ticket = 0xFFFFFFFFu;
+            }
+        }
+        __syncthreads();
+        const unsigned t = s_ticket;
+        if (t >= total) break;
+        const unsigned g = t % G, k = t / G;
+        const uint32_t* bits = (k & 1u) ? bits_alt : a.bits;
+        uint4 v[3];
+        auto fetch = [&](int game) {
+            const uint4* src = reinterpret_cast<const uint4*>(bits + (size_t)game * BITS_WORDS);
+#pragma unroll
+            for (int i = 0; i < 3; i++) { const int tt = lane + 32 * i; v[i] = src[tt < NV ? tt : 0]; }
+        };
+        const int g0 = (int)g * SG;
+        if (g0 + warp < a.n) fetch(g0 + warp);
+        for (int slot = warp; slot < SG && g0 + slot < a.n; slot += HIVE_STORE_WARPS) {
+            const int game = g0 + slot;
+            __syncwarp();                                       // the previous game's planes have been expanded
+#pragma unroll
+            for (int i = 0; i < 3; i++) { const int tt = lane + 32 * i; if (tt < NV) reinterpret_cast<uint4*>(mine)[tt] = v[i]; }
+            __syncwarp();
+            const uint32_t live = mine[BITS_LIVE], turn = mine[BITS_TURN];
+            if (slot + HIVE_STORE_WARPS < SG && game + HIVE_STORE_WARPS < a.n) fetch(game + HIVE_STORE_WARPS);
+            if (live)
+                store_planes_bulk(reinterpret_cast<const uint8_t*>(mine), bf16_lut, lut_s, stage_ring + warp * (STAGE_BUFS * STAGE_CHUNKS), lane,
+                                  (int)turn, a.planes + (size_t)game * HIVE_PLANES_ELEMS);
+        }
+        __syncthreads();                                        // every warp has read its games' bit planes: the buffer is free
+        if (tid == 0) st_release_u32(stored + g, k + 1u);
     }
     if (lane == 0) bulk_wait_read<0>();                         // shared memory must outlive the copy engine's reads
 }

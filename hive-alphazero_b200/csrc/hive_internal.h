@@ -46,6 +46,12 @@ struct hive_env {
     int use_graph = 1;
     int stagger_ns = 25000;         // rollout kernel: start offset between the CTAs sharing an SM (HIVE_B200_STAGGER_US)
     int use_rollout_kernel = 0;     // HIVE_B200_ROLLOUT_KERNEL=1: hive_step_random_multi as ONE persistent launch (measured slower; default: per-step kernels in graphs)
+    int rollout_queue = 0;          // HIVE_B200_ROLLOUT_QUEUE: hive_step_random_multi as two persistent kernels whose CTAs take (group, step) tickets
+    int roll_ctas_per_sm = 2;       // step CTAs per SM of the queue-driven rollout (<= 2: the store CTAs must fit beside them)
+    int roll_store_ctas_per_sm = 2; // store CTAs per SM of the queue-driven rollout
+    void* roll_sync = nullptr;      // RollSync: ticket counters, done[G], stored[G]
+    size_t roll_sync_bytes = 0;
+    bool roll_pending = false;      // a queue-driven rollout was launched since the last hive_sync (its error word is unread)
     int32_t* d_actions[2] = {nullptr, nullptr};
     int act_flip = 0;
     cudaEvent_t act_read_ev[2] = {nullptr, nullptr};   // behind the step that read d_actions[b] (hive_step_host)

@@ -37,6 +37,8 @@ def lib():
         L.emu_env_run.restype = ctypes.c_int
         L.emu_env_rollout.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint64]
         L.emu_env_rollout.restype = ctypes.c_int
+        L.emu_env_rollout_q.argtypes = L.emu_env_rollout.argtypes
+        L.emu_env_rollout_q.restype = ctypes.c_int
         L.emu_last_error.restype = ctypes.c_char_p
         L.emu_mcts_create.restype = vp
         L.emu_mcts_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
@@ -100,6 +102,14 @@ class EmuBatch:
         self.sched_seed += 7919
         rc = lib().emu_env_rollout(self.recs.ctypes.data, self.legal.ctypes.data, self.count.ctypes.data, self.status.ctypes.data,
                                    self.planes.ctypes.data, self.n, seed, max_turn, auto_reset, n_steps, self.sched_seed)
+        if rc:
+            raise RuntimeError("emulator: " + lib().emu_last_error().decode())
+
+    def step_random_queue(self, seed, n_steps, max_turn=55, auto_reset=1):
+        """n_steps (1 or 2) random steps through the queue-driven rollout kernels (ticket logic, both bit-plane buffers)."""
+        self.sched_seed += 7919
+        rc = lib().emu_env_rollout_q(self.recs.ctypes.data, self.legal.ctypes.data, self.count.ctypes.data, self.status.ctypes.data,
+                                     self.planes.ctypes.data, self.n, seed, max_turn, auto_reset, n_steps, self.sched_seed)
         if rc:
             raise RuntimeError("emulator: " + lib().emu_last_error().decode())
 

@@ -79,6 +79,34 @@ int emu_env_rollout(void* recs, uint32_t* legal, int32_t* count, uint32_t* statu
     }
     return 0;
 }
+// n_steps (<= 2 here: the emulator runs the CTAs one after the other) OP_RANDOM steps through the queue-driven rollout:
+// the step CTAs take (group, step) tickets, then the store CTAs take them in the same order
+int emu_env_rollout_q(void* recs, uint32_t* legal, int32_t* count, uint32_t* status, uint16_t* planes, int n, uint64_t seed,
+                      int max_turn, int auto_reset, int n_steps, uint64_t sched_seed) {
+    build_lines();
+    if (n_steps < 1 || n_steps > 2) return -1;
+    EnvArgs a;
+    a.recs = (GameRec*)recs; a.legal = legal; a.count = count; a.status = status; a.planes = planes;
+    a.actions = nullptr; a.mask = nullptr; a.chosen = nullptr; a.hop_lines = g_lines.data();
+    a.seed = seed; a.n = n; a.op = OP_RANDOM; a.max_turn = max_turn; a.auto_reset = auto_reset;
+    a.g_offset = 0; a.n_total = n; a.stagger_ns = 0; a.stagger_div = 148; a.shadow = nullptr;
+    std::vector<uint32_t> bits0((size_t)n * BITS_WORDS), bits1((size_t)n * BITS_WORDS);
+    a.bits = bits0.data();
+    const int G = (n + SG - 1) / SG;
+    std::vector<unsigned> sync(32 + 2 * G, 0u);
+    struct Call { EnvArgs a; uint32_t* alt; int n_steps; RollSync* sync; } call = {a, bits1.data(), n_steps, (RollSync*)sync.data()};
+    const int step_blocks = G > 2 ? 2 : G;
+    emu::g_gridDim.x = step_blocks;
+    for (int b = 0; b < step_blocks; b++) {
+        int rc = emu::run_block([](void* p) { Call* c = (Call*)p; hive_rollout_q_kernel(c->a, c->alt, c->n_steps, c->sync); }, &call, b, STEP_THREADS, sched_seed + (uint64_t)b);
+        if (rc) return rc;
+    }
+    for (int b = 0; b < 2; b++) {
+        int rc = emu::run_block([](void* p) { Call* c = (Call*)p; hive_planes_q_kernel(c->a, c->alt, c->n_steps, c->sync); }, &call, b, HIVE_STORE_WARPS * 32, sched_seed + 5000 + (uint64_t)b);
+        if (rc) return rc;
+    }
+    return 0;
+}
 const char* emu_last_error() { return emu::last_error(); }
 int emu_rec_bytes() { return (int)sizeof(GameRec); }
 }

@@ -158,3 +158,17 @@ def test_delta_plane_store_equals_full_store():
     keep = np.arange(56) != 31
     assert (vals[:, keep] == bits[:, keep]).all()
     assert (vals[:, 31] == sh[:, 155].astype(np.float32)[:, None]).all()
+
+
+def test_queue_rollout_equals_single_steps():
+    """hive_rollout_q_kernel + hive_planes_q_kernel (CTAs take (group, step) tickets; the emulator runs them one after the
+    other, so at most two steps per call) leave the batch where single steps leave it -- records, legal masks, planes."""
+    n, seed = 70, 0xFACE                                  # three groups, the last one ragged
+    a, b = EmuBatch(n, sched_seed=41), EmuBatch(n, sched_seed=42)
+    for rnd in range(30):                                 # 60 plies: across the turn-55 cut
+        a.step_random(seed); a.step_random(seed)
+        b.step_random_queue(seed, 2)
+        assert (a.recs == b.recs).all() and (a.legal == b.legal).all() and (a.count == b.count).all(), rnd
+        assert (a.status == b.status).all() and (a.planes == b.planes).all(), rnd
+    a.step_random(seed); b.step_random_queue(seed, 1)
+    assert (a.recs == b.recs).all() and (a.planes == b.planes).all()

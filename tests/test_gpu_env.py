@@ -244,6 +244,27 @@ def test_delta_plane_store_equals_full_store(hb, monkeypatch):
     assert (a.legal_mask()[0] == b.legal_mask()[0]).all()
 
 
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_queue_rollout_equals_step_graphs(hb, monkeypatch, mode):
+    """HIVE_B200_ROLLOUT_QUEUE=1 (two persistent kernels whose CTAs take (group, step) tickets) and =2 (one launch per
+    step, chained by programmatic dependent launch + per-group flags) leave the batch where the default per-step graphs
+    leave it; a rollout whose waits time out is reported by hive_sync instead of hanging the GPU."""
+    n, seed = 4096 + 17, 991                              # a ragged last group
+    a = hb.HiveBatch(n)
+    monkeypatch.setenv("HIVE_B200_ROLLOUT_QUEUE", mode)
+    b = hb.HiveBatch(n)
+    monkeypatch.delenv("HIVE_B200_ROLLOUT_QUEUE")
+    for steps in (2, 37, 60, 5):
+        a.step_random_multi(seed, steps); b.step_random_multi(seed, steps)
+        a.sync(); b.sync()
+        m1, c1 = a.legal_mask()
+        m2, c2 = b.legal_mask()
+        assert (m1 == m2).all() and (c1 == c2).all(), steps
+        assert (a.planes_bf16() == b.planes_bf16()).all(), steps
+        assert [x.tolist() for x in a.status()] == [x.tolist() for x in b.status()], steps
+        assert [x.tolist() for x in a.counters()] == [x.tolist() for x in b.counters()], steps
+
+
 def test_async_host_step_graph_replay_matches_device_policy(hb):
     """hive_step_host_async from one fixed set of page-locked buffers (replayed as one CUDA graph from the second
     call on) == hive_step_random; the same loop from pageable buffers (plain path) gives the same games."""
