@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--sharded-sims", type=int, default=250)
     ap.add_argument("--evaluator-games", type=int, default=1024, help="configs[4]: games per GPU")
     ap.add_argument("--evaluator-sims", type=int, default=500)
+    ap.add_argument("--e2e-drivers", type=int, default=0, help="host-driven path: native driver threads (0: one per part)")
     ap.add_argument("--e2e-parts", type=int, default=0, help="host-driven path: parts of the batch, each its own handle and streams (0: two per driver thread)")
     return ap.parse_args()
 
@@ -483,8 +484,9 @@ def main():
     # host threads of this rank: one driver thread per part, the rest is the policy pool the drivers share
     e2e_budget = int(os.environ.get("HIVE_B200_E2E_THREADS", str(max(2, min(16, host_cores // max(world, 1))))))
     e2e_parts = args.e2e_parts if args.e2e_parts > 0 else max(2, min(4, e2e_budget // 4))
-    os.environ["HIVE_B200_HOST_THREADS"] = str(max(1, e2e_budget - e2e_parts) + 1)      # pool workers + the calling driver
-    loop = hive_b200.HostLoop(n, device=local_rank, parts=e2e_parts, threads=e2e_parts)
+    e2e_drivers = min(e2e_parts, args.e2e_drivers) if args.e2e_drivers > 0 else e2e_parts
+    os.environ["HIVE_B200_HOST_THREADS"] = str(max(1, e2e_budget - e2e_drivers) + 1)    # pool workers + the calling driver
+    loop = hive_b200.HostLoop(n, device=local_rank, parts=e2e_parts, threads=e2e_drivers)
     loop.run(8, seed=seed, max_turn=args.max_turn)                                   # builds the per-part graphs
     pilot = loop.run(20, seed=seed, max_turn=args.max_turn)
     k_e2e = max(args.steps, int(np.ceil(20 * args.min_window_ms * 1e-3 / max(pilot["seconds"], 1e-6))))

@@ -12,6 +12,7 @@
 
 #include "hive_conv_host.h"
 #include "hive_conv_kernel.cuh"
+#include "hive_conv2_kernel.cuh"
 #include "hive_heads_kernel.cuh"
 #include "hive_internal.h"
 
@@ -111,6 +112,15 @@ int launch_conv(hive_net* n, const CUtensorMap& in_map, int layer, const __nv_bf
     ConvArgs a;
     a.weights = n->weights[layer]; a.bias = n->bias[layer]; a.residual = residual; a.out = out;
     a.n_boards = boards; a.n_chunks = n->n_chunks[layer]; a.relu = 1;
+    static const int pair_mode = getenv("HIVE_B200_CONV_PAIR") ? atoi(getenv("HIVE_B200_CONV_PAIR")) : 0;
+    if (pair_mode) {   // CTA pairs (cta_group::2): one cluster of two CTAs per board pair, both out-channel halves
+        const int n_pairs = (boards + 1) / 2, max_clusters = n->sms / 2;
+        const int clusters = n_pairs < max_clusters ? n_pairs : max_clusters;
+        hive_conv3x3_pair_kernel<<<2 * clusters, C2_THREADS, C2_SMEM_BYTES, n->stream>>>(in_map, a);
+        CUDA_TRY(cudaGetLastError());
+        n->launches++;
+        return 0;
+    }
     const int items = 2 * ((boards + CONV_BOARDS - 1) / CONV_BOARDS);
     const int cap = n->sms * CONV_CTAS_PER_SM;
     hive_conv3x3_kernel<<<items < cap ? items : cap, CONV_THREADS, CONV_SMEM_BYTES, n->stream>>>(in_map, a);
@@ -140,6 +150,7 @@ int net_create(int device, void* stream, int max_boards, hive_net_t** out) {
     for (int i = 0; i < 3; i++)
         if (make_board_tensor_map(&n->map_act[i], n->act[i], max_boards, 256, CONV_PADW, CONV_PADH, CONV_KG)) return fail(HIVE_E_CUDA, "net_create: cuTensorMapEncodeTiled failed");
     CUDA_TRY(cudaFuncSetAttribute(hive_conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(hive_conv3x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C2_SMEM_BYTES));
     // heads
     if (make_rows_tensor_map(&n->map_rows, n->act[2], (uint64_t)B * 144, 256, HEAD_M, 8)) return fail(HIVE_E_CUDA, "net_create: cuTensorMapEncodeTiled failed (head rows)");
     const size_t mt = (B + HEAD_M - 1) / HEAD_M;
