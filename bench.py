@@ -303,7 +303,7 @@ def run_selfplay(args, hive_b200, torch, dist, rank, world, local_rank, allsum, 
         return out
 
     res = {"tensor_peak_tflops": tf_peak, "tensor_peak_source": tf_src,
-           "net": "BN-folded bf16, every kernel of a wave hand-written sm_100a: 39 trunk 3x3 convs = tcgen05 implicit GEMM (TMA halo "
+           "net": "BN-folded bf16, every kernel of a wave hand-written sm_100a: 39 trunk 3x3 convs = tcgen05 implicit GEMM on CTA pairs (cta_group::2, M = 256; TMA halo "
                   "tile, TMEM accumulators, fused bias/residual/ReLU); heads = two tcgen05 GEMMs (both 1x1 convs as one, policy fc) "
                   "+ softmax / value-MLP kernel writing into the search's leaf arenas (net_forward)"}
     c2 = selfplay_config("configs[2]: AlphaZero self-play, %d sims/move, model_hive net random-init, %d concurrent games per GPU"

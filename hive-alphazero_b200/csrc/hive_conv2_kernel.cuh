@@ -28,10 +28,10 @@
 namespace hive {
 
 #ifndef HIVE_CONV2_A_STAGES
-#define HIVE_CONV2_A_STAGES 5
+#define HIVE_CONV2_A_STAGES 9           // one chunk's nine taps: the weight stream's latency (L2 -> shared memory, then a hop to the leader) is what starves the MMAs (5 stages: 1,221 TFLOP/s, 9: 1,353)
 #endif
 #ifndef HIVE_CONV2_B_STAGES
-#define HIVE_CONV2_B_STAGES 3
+#define HIVE_CONV2_B_STAGES 2
 #endif
 constexpr int C2_A_STAGES = HIVE_CONV2_A_STAGES, C2_B_STAGES = HIVE_CONV2_B_STAGES;
 constexpr int C2_SLOTS = 3;                        // accumulator slots of 160 columns, used round-robin (two per board pair)
@@ -80,14 +80,16 @@ __device__ __forceinline__ void mma_commit_both(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar, uint32_t cta) {
     uint32_t remote;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+    // (default semantics, release at CTA scope, as CUTLASS's ClusterBarrier::arrive(cta_id): a cluster-scope release would
+    // make an epilogue lane wait for its outstanding global stores before the TMEM slot is handed back)
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {     // the arrivals come from the other CTA
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
         "@p bra DONE_%=;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"

@@ -112,7 +112,7 @@ int launch_conv(hive_net* n, const CUtensorMap& in_map, int layer, const __nv_bf
     ConvArgs a;
     a.weights = n->weights[layer]; a.bias = n->bias[layer]; a.residual = residual; a.out = out;
     a.n_boards = boards; a.n_chunks = n->n_chunks[layer]; a.relu = 1;
-    static const int pair_mode = getenv("HIVE_B200_CONV_PAIR") ? atoi(getenv("HIVE_B200_CONV_PAIR")) : 0;
+    static const int pair_mode = getenv("HIVE_B200_CONV_PAIR") ? atoi(getenv("HIVE_B200_CONV_PAIR")) : 1;     // 0: the single-CTA kernel
     if (pair_mode) {   // CTA pairs (cta_group::2): one cluster of two CTAs per board pair, both out-channel halves
         const int n_pairs = (boards + 1) / 2, max_clusters = n->sms / 2;
         const int clusters = n_pairs < max_clusters ? n_pairs : max_clusters;
