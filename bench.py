@@ -249,6 +249,9 @@ def run_selfplay(args, hive_b200, torch, dist, rank, world, local_rank, allsum, 
     folded = hive_b200.FoldedNet(net, device="cuda").attach_trunk(stream_ptr=stream.cuda_stream, max_boards=max(n2, n3, n4))
     side_stream = torch.cuda.Stream()                          # the second network of the evaluator match runs beside the first
     folded_best = hive_b200.FoldedNet(net_best, device="cuda").attach_trunk(stream_ptr=side_stream.cuda_stream, max_boards=n4)
+    if dist is not None:                                       # warm-up of the in-place reload (first launch of the packing kernels), untimed
+        folded.reload(net); folded_best.reload(net_best)
+        torch.cuda.synchronize()
 
     def timed_collectives_before(model, fold):
         """weight broadcast from rank 0 (bf16 on the wire) + in-place reload of the folded network; seconds, bytes"""

@@ -47,6 +47,7 @@ static int launch_env_kernels(hive_env* h, int op, const int32_t* actions, const
 
 int launch_env(hive_env* h, int op, const int32_t* actions, const uint8_t* mask, uint64_t seed, int max_turn,
                int auto_reset, int32_t* chosen) {
+    h->last_bits = 0;                                        // a single step writes bit-plane buffer 0
     if (h->timing) CUDA_TRY(cudaEventRecord(h->t0, h->stream));
     // (host-driven steps alternate between two staging buffers, so they would never hit the cache)
     const bool graphable = h->use_graph && (op == OP_RANDOM || (op == OP_STEP && actions != h->d_actions[0] && actions != h->d_actions[1]));
@@ -463,6 +464,7 @@ static int queue_host_step(hive_env* h, int32_t* d, const int32_t* actions, uint
         act = d;
     }
     int deferred = 0;
+    h->last_bits = 0;
     int rc = launch_env_kernels(h, OP_STEP, act, nullptr, 0, 0, 0, nullptr, 1, slices > 0 ? slices : h->host_slices, &deferred);
     if (rc) return rc;
     const size_t n = (size_t)h->n;
@@ -548,6 +550,7 @@ int hive_step_random_multi(hive_env_t* h, uint64_t seed, int max_turn, int auto_
     if (max_turn < 1 || max_turn > 250 || n_steps < 1 || n_steps > 4096) return fail(HIVE_E_ARG, "hive_step_random_multi: bad arguments");
     CUDA_TRY(cudaSetDevice(h->device));
     if (h->timing) CUDA_TRY(cudaEventRecord(h->t0, h->stream));
+    h->last_bits = h->use_rollout_kernel ? 0 : (n_steps - 1) & 1;      // step k of a multi-step rollout writes buffer k & 1
     if (h->use_rollout_kernel) {
         // one launch: every CTA walks through the n_steps steps of its 32 games and stores their planes itself
         EnvArgs a = slice_args(h, 0, h->n, OP_RANDOM, nullptr, nullptr, seed, max_turn, auto_reset, nullptr);
@@ -719,6 +722,15 @@ int hive_legal_host(hive_env_t* h, uint64_t* mask, int32_t* count) {
     CUDA_TRY(cudaSetDevice(h->device));
     if (mask) CUDA_TRY(cudaMemcpyAsync(mask, h->legal, (size_t)h->n * LEGAL_WORDS * 4, cudaMemcpyDeviceToHost, h->stream));
     if (count) CUDA_TRY(cudaMemcpyAsync(count, h->count, (size_t)h->n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int hive_bits_host(hive_env_t* h, uint32_t* bits) {
+    if (check(h)) return HIVE_E_HANDLE;
+    if (!bits) return fail(HIVE_E_ARG, "hive_bits_host: null output");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemcpyAsync(bits, h->bits[h->last_bits], (size_t)h->n * BITS_WORDS * 4, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return 0;
 }

@@ -19,6 +19,7 @@ struct hive_env {
     uint32_t* status = nullptr;
     uint16_t* planes = nullptr;
     uint32_t* bits[2] = {nullptr, nullptr};   // bit planes, encode kernel -> plane-store kernel (double-buffered over steps)
+    int last_bits = 0;              // which of the two buffers the last launch wrote (hive_bits_host)
     uint32_t* shadow = nullptr;     // delta plane store: the bit planes whose expansion the planes arena holds right now, [game][word]
     size_t shadow_bytes = 0;
     bool full_store = true;         // every step rewrites all 16 KB of a game's planes (hive_planes_kernel, the TMA store); HIVE_B200_DELTA_STORE=1: only the changed sectors

@@ -16,6 +16,17 @@ from . import config as C
 from ._capi import HiveError, check, lib
 
 
+def bits_to_planes_bf16(bits):
+    """uint32 [..., 56, 5] bit rows (hive_bits_host) -> bf16 bit patterns uint16 [..., 56, 144], the planes they stand for."""
+    bits = np.ascontiguousarray(bits, dtype=np.uint32)
+    lead = bits.shape[:-2]
+    cells = np.unpackbits(bits.view(np.uint8).reshape(lead + (C.STATE_FEATURES, 20)), axis=-1, bitorder="little")[..., :144]
+    out = cells.astype(np.uint16) * np.uint16(0x3F80)                       # bf16(1.0)
+    turn = bits[..., 31, 0].astype(np.float32)
+    out[..., 31, :] = (turn.view(np.uint32) >> 16).astype(np.uint16)[..., None]          # plane 31 = the turn number in every cell
+    return out
+
+
 def _bf16_to_f32(u16):
     return (u16.astype(np.uint32) << 16).view(np.float32)
 
@@ -112,9 +123,20 @@ class HiveBatch:
             return np.nonzero(bits[g])[0].astype(np.int32)
         return [np.nonzero(b)[0].astype(np.int32) for b in bits]
 
-    def planes_bf16(self):
-        out = np.empty((self.n, C.STATE_FEATURES, 144), dtype=np.uint16)
+    def planes_bf16(self, out=None):
+        """bf16 bit patterns [n,56,144]; `out`: array to fill (a page-locked one makes the download several times faster)."""
+        if out is None:
+            out = np.empty((self.n, C.STATE_FEATURES, 144), dtype=np.uint16)
+        assert out.shape == (self.n, C.STATE_FEATURES, 144) and out.dtype == np.uint16 and out.flags.c_contiguous
         check(lib().hive_encode_host(self._h, out.ctypes.data), "hive_encode_host")
+        return out
+
+    def planes_bits(self, out=None):
+        """The planes as bits: uint32 [n,56,5] (hive_bits_host; plane 31: word 0 = turn, word 1 = row valid)."""
+        if out is None:
+            out = np.empty((self.n, C.STATE_FEATURES, 5), dtype=np.uint32)
+        assert out.shape == (self.n, C.STATE_FEATURES, 5) and out.dtype == np.uint32 and out.flags.c_contiguous
+        check(lib().hive_bits_host(self._h, out.ctypes.data), "hive_bits_host")
         return out
 
     def planes(self):

@@ -38,6 +38,20 @@ class SelfPlayBatch:
         self.moves = 0
         self.waves = 0
         self.search_calls = 0
+        self._pin = None                                    # page-locked landing buffers of the per-move read-backs (made on first use)
+
+    def _pinned(self):
+        """Page-locked host buffers for the read-backs of a move (policies 12.7 KB per game; the planes as BITS, 1,120 B per
+        game instead of 16 KB: hive_bits_host): the downloads run at the PCIe rate instead of through the driver's staging of
+        pageable memory (2,048 games: 15 ms -> 1 ms).  Their content is valid until the next move: samples copy what they keep."""
+        if self._pin is None:
+            import torch
+            self._pin_t = (torch.empty((self.n, C.ACTION_SPACE), dtype=torch.float64).pin_memory(),
+                           torch.empty((self.n, C.STATE_FEATURES, 5), dtype=torch.int32).pin_memory(),
+                           torch.empty(self.n, dtype=torch.int32).pin_memory(), torch.empty(self.n, dtype=torch.int32).pin_memory())
+            pi, bits, action, sum_n = (t.numpy() for t in self._pin_t)
+            self._pin = (pi, bits.view(np.uint32), action, sum_n)
+        return self._pin
 
     def _choose(self, pi, mcts_action, legal, turn):
         """The reference's move choice for one game (self_play_with_train.py:169-183)."""
@@ -104,10 +118,11 @@ class SelfPlayBatch:
                     if restart_finished:
                         actions[g] = -3
             else:
-                pi, mcts_action, _ = self.mcts.policy()
+                pin_pi, pin_bits, pin_action, pin_sum = self._pinned()
+                pi, mcts_action, _ = self.mcts.policy(out=(pin_pi, pin_action, pin_sum))
                 mask, count = self.env.legal_mask()
                 legal_bits = np.unpackbits(mask.view(np.uint8), axis=1, bitorder="little")[:, :C.ACTION_SPACE].astype(bool)
-                planes = self.env.planes_bf16() if self.collect else None
+                bits = self.env.planes_bits(out=pin_bits) if self.collect else None
                 chosen = self._choose_batch(pi, mcts_action, legal_bits, count, turn)
                 for g in np.nonzero(over)[0]:
                     self._finish(int(g), int(winner[g]), int(turn[g]))
@@ -115,8 +130,20 @@ class SelfPlayBatch:
                         actions[g] = -3                           # HIVE_RESET
                 actions[live] = chosen[live]
                 if self.collect:
-                    for g in np.nonzero(live)[0]:
-                        self.samples[g].append((planes[g].copy(), pi[g].astype(np.float32), int(turn[g]) % 2))
+                    # the landing buffers are copied out ONCE per move (contiguous when every game is live); a game's sample
+                    # is a view into the copy: (bit rows of its planes uint32 [56,5], pi float32 [1584], side to move).  The planes
+                    # themselves (16 KB) are made from the bits when the game is finished (_finish) -- the packed rows the ranks
+                    # all-gather are those bits, never the expansion.
+                    live_idx = np.nonzero(live)[0]
+                    if len(live_idx) == self.n:
+                        kept_bits, kept_pi = bits.copy(), pi.astype(np.float32)
+                    else:
+                        kept_bits, kept_pi = bits[live_idx], pi[live_idx].astype(np.float32)
+                    if not (kept_bits[:, 31, 1] == 1).all():
+                        raise RuntimeError("self-play: the bit rows of a live game are stale (it was not evaluated by the last step)")
+                    side = (turn % 2).tolist()
+                    for k, g in enumerate(live_idx.tolist()):
+                        self.samples[g].append((kept_bits[k], kept_pi[k], side[g]))
             self.env.step(actions)
             self.moves += int(live.sum())
         self.env.sync()
@@ -130,11 +157,11 @@ class SelfPlayBatch:
         rows = [smp for per_game in self.samples for smp in per_game[-last_moves:]] if last_moves > 0 else []
         if not rows:
             return np.zeros((0, 1960), dtype=np.uint8)
-        planes = np.stack([r[0] for r in rows]).reshape(len(rows), C.STATE_FEATURES, 144)
+        bits = np.stack([r[0] for r in rows])                                            # (N, 56, 5) uint32 bit rows
         pi = np.stack([r[1] for r in rows])
-        bits = np.packbits(planes != 0, axis=2, bitorder="little")                       # (N, 56, 18)
-        turn = ((planes[:, 31, 0].astype(np.uint32) << 16).view(np.float32)).astype(np.uint8)
-        planes_bits = np.concatenate([np.delete(bits, 31, axis=1).reshape(len(rows), 55 * 18), turn[:, None]], axis=1)
+        by = np.ascontiguousarray(bits).view(np.uint8).reshape(len(rows), C.STATE_FEATURES, 20)[:, :, :18]    # 144 cells = 18 bytes
+        turn = bits[:, 31, 0].astype(np.uint8)
+        planes_bits = np.concatenate([np.delete(by, 31, axis=1).reshape(len(rows), 55 * 18), turn[:, None]], axis=1)
         r, c = np.nonzero(pi > 0)                                                        # sparse policy: row-major, ascending actions
         starts = np.searchsorted(r, np.arange(len(rows)))
         pos = np.arange(len(r)) - starts[r]
@@ -154,7 +181,9 @@ class SelfPlayBatch:
             for _, _, side_odd in self.samples[g]:
                 counts[side_odd] += 1
             seen = {1: 0, 0: 0}
-            for planes, pi, side_odd in self.samples[g]:       # side_odd == 1: white to move
+            from .env import bits_to_planes_bf16
+            expanded = bits_to_planes_bf16(np.stack([smp[0] for smp in self.samples[g]])) if self.samples[g] else []
+            for (_, pi, side_odd), planes in zip(self.samples[g], expanded):       # side_odd == 1: white to move
                 seen[side_odd] += 1
                 value = value_white if side_odd == 1 else -value_white
                 if value_white == 0:

@@ -87,6 +87,12 @@ int hive_legal_host(hive_env_t* h, uint64_t* mask /*[n][25]*/, int32_t* count /*
 /* GamePlay.encode_board() (env_hive.py:306-318), bf16, CHW [n][56][144] (the layout
  * api_hive.py:61 feeds the net after transpose(2,0,1)). */
 int hive_encode_host(hive_env_t* h, uint16_t* planes_bf16);
+/* The same planes as BITS, 1,120 B per game instead of 16 KB: [n][56 planes][5 words], bit c of a plane's 160-bit row =
+ * cell c (144 used); plane 31's row holds the turn number in word 0 and in word 1 the flag "this game was evaluated by
+ * the last step / reset / load" -- only rows with that flag set describe the game's current planes (a game the last
+ * launch left alone keeps its planes, but its row here is stale).  What a sample writer wants: the 55 binary planes of
+ * a training row are these bits (self_play.py:160 stores the planes; packing them is ours). */
+int hive_bits_host(hive_env_t* h, uint32_t* bits /*[n][280]*/);
 /* state.turn, winner (0 none / 1 white / 2 black, settings.py:3-4), game_is_over()
  * (move_checker.py:140-165).  Any pointer may be NULL. */
 int hive_status_host(hive_env_t* h, int32_t* turn, int8_t* winner, uint8_t* done);

@@ -211,6 +211,40 @@ def test_multi_step_graph_equals_single_steps(hb):
     assert [x.tolist() for x in a.counters()] == [x.tolist() for x in b.counters()]
 
 
+def test_planes_as_bits_expand_to_the_planes(hb):
+    """hive_bits_host: the bit rows of the games the last launch evaluated expand to exactly their bf16 planes -- after single
+    steps, multi-step graphs of odd and even length (the two bit-plane buffers), masked resets and with idle games."""
+    from importlib import import_module
+    expand = import_module("hive-alphazero_b200.env").bits_to_planes_bf16
+    n, seed = 1024, 31337
+    b = hb.HiveBatch(n)
+
+    def check(evaluated=None):
+        bits, planes = b.planes_bits(), b.planes_bf16()
+        ok = bits[:, 31, 1] == 1
+        if evaluated is not None:
+            assert (ok == evaluated).all()
+        assert ok.any() and (expand(bits[ok]) == planes[ok]).all()
+
+    check(np.ones(n, dtype=bool))
+    for steps in (1, 1, 6, 7, 2):
+        if steps == 1:
+            b.step_random(seed, 55, True)
+        else:
+            b.step_random_multi(seed, steps)
+        check(np.ones(n, dtype=bool))
+    mask = (np.arange(n) % 3 == 0).astype(np.uint8)
+    b.reset(mask)
+    check(mask.astype(bool))
+    acts = np.full(n, -2, dtype=np.int32)                   # everybody idle but a few
+    m, c = b.legal_mask()
+    for g in range(0, n, 5):
+        la = np.nonzero(np.unpackbits(m[g].view(np.uint8), bitorder="little")[:1584])[0]
+        acts[g] = la[0] if len(la) else -1
+    b.step(acts)
+    check(acts != -2)
+
+
 def test_delta_plane_store_equals_full_store(hb, monkeypatch):
     """HIVE_B200_DELTA_STORE=1 (hive_planes_delta_kernel: only the 32-byte sectors that differ from what the planes arena
     holds are rewritten) leaves the same planes as the default full store after single steps, multi-step graphs across
