@@ -28,7 +28,7 @@
 namespace hive {
 
 #ifndef HIVE_CONV2_A_STAGES
-#define HIVE_CONV2_A_STAGES 9           // one chunk's nine taps: the weight stream's latency (L2 -> shared memory, then a hop to the leader) is what starves the MMAs (5 stages: 1,221 TFLOP/s, 9: 1,353)
+#define HIVE_CONV2_A_STAGES 10          // one chunk's nine taps: the weight stream's latency (L2 -> shared memory, then a hop to the leader) is what starves the MMAs (5 stages: 1,221 TFLOP/s, 9: 1,353)
 #endif
 #ifndef HIVE_CONV2_B_STAGES
 #define HIVE_CONV2_B_STAGES 2
@@ -38,14 +38,23 @@ constexpr int C2_SLOTS = 3;                        // accumulator slots of 160 c
 constexpr int C2_TMEM_COLS = 512;
 constexpr int C2_EPI_WARPS = 8;                    // two sets of four (one per TMEM lane quarter): set = board of the pair
 constexpr int C2_THREADS = 64 + 32 * C2_EPI_WARPS;
+constexpr int C2_STAGE_ROWS = 8;                   // rows of a warp's transposition buffer (half a 16-slot column group at a time: the
+                                                   // shared memory saved is the tenth weight stage)
 constexpr int C2_HALF_N = CONV_N / 2;              // pixel slots per board and MMA
-constexpr int C2_SMEM_BYTES = C2_A_STAGES * CONV_A_BYTES + C2_B_STAGES * CONV_BOARD_BYTES + C2_EPI_WARPS * 16 * CONV_STAGE_STRIDE * 4 + 1024;
+constexpr int C2_SMEM_BYTES = C2_A_STAGES * CONV_A_BYTES + C2_B_STAGES * CONV_BOARD_BYTES + C2_EPI_WARPS * C2_STAGE_ROWS * CONV_STAGE_STRIDE * 4 + 1024;
 static_assert(C2_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(CONV_SHIFTS == 1 && CONV_N == 160, "the pair kernel is written for the padded N = 160 tile");
 
 namespace umma2 {
 using umma::smem_u32;
 __device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+// true in exactly one lane of a converged warp (the compiler then knows that a single thread runs the guarded code and
+// keeps its operands in uniform registers instead of broadcasting every descriptor before every MMA)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -168,7 +177,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C2_THREADS, 1) hive_
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ leader: MMA issuer for the pair
-        if (lane == 0) {
+        if (umma2::elect_one()) {
             const uint32_t idesc = idesc_bf16(2 * CONV_OC_TILE, CONV_N);
             const uint64_t a_desc0 = smem_desc(smem_u32(sA), CONV_OC_TILE * 16, 128, 0);     // LBO = k-group stride, SBO = 8 rows
             const uint64_t b_desc0 = smem_desc(smem_u32(sB), CONV_PLANE_BYTES, 128, 0);
@@ -229,7 +238,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C2_THREADS, 1) hive_
         // Warp set s (4 warps = the 4 TMEM lane quarters) takes the 5 column groups of board s.
         const int q = warp & 3;                                    // TMEM lane quarter this warp may read
         const int ew = warp - 2, set = ew >> 2;
-        float* stage = sStage + ew * 16 * CONV_STAGE_STRIDE;
+        float* stage = sStage + ew * C2_STAGE_ROWS * CONV_STAGE_STRIDE;
         const int sl = lane >> 2, ch8 = (lane & 3) * 8;            // phase-2 role: slots sl and sl+8, channels ch8..ch8+7
         constexpr int G = 5;                                       // column groups (16 slots) per board and accumulator
         const int oc0 = (int)rank * CONV_OC_TILE + q * 32;
@@ -273,13 +282,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C2_THREADS, 1) hive_
 #pragma unroll
                 for (int g = 0; g < G; g++) {
 #pragma unroll
-                    for (int i = 0; i < 16; i++) stage[i * CONV_STAGE_STRIDE + lane] = __uint_as_float(v[g][i]) + bias;
-                    __syncwarp();
+                    for (int k = 0; k < 2; k++) {                       // slots 8k .. 8k+7 of the group
+                        if (k) __syncwarp();                            // the first half has been read
 #pragma unroll
-                    for (int k = 0; k < 2; k++) {
+                        for (int i = 0; i < 8; i++) stage[i * CONV_STAGE_STRIDE + lane] = __uint_as_float(v[g][8 * k + i]) + bias;
+                        __syncwarp();
                         const long long o = slot_off(g, k);
-                        const float4 f0 = *reinterpret_cast<const float4*>(stage + (sl + 8 * k) * CONV_STAGE_STRIDE + ch8);
-                        const float4 f1 = *reinterpret_cast<const float4*>(stage + (sl + 8 * k) * CONV_STAGE_STRIDE + ch8 + 4);
+                        const float4 f0 = *reinterpret_cast<const float4*>(stage + sl * CONV_STAGE_STRIDE + ch8);
+                        const float4 f1 = *reinterpret_cast<const float4*>(stage + sl * CONV_STAGE_STRIDE + ch8 + 4);
                         float r[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
                         if (a.residual) {
                             const uint4 rv = rq[g][k];

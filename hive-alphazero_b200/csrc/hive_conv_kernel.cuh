@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(CONV_THREADS, CONV_CTAS_PER_SM) hive_conv3x3_k
 
     if (warp == 0) {
         // ------------------------------------------------------------ producer
-        if (lane == 0) {
+        if (elect_one()) {
             int as = 0, aph = 0, bs = 0, bph = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const int half = item & 1, pair = item >> 1;
@@ -139,7 +139,9 @@ __global__ void __launch_bounds__(CONV_THREADS, CONV_CTAS_PER_SM) hive_conv3x3_k
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        // (elect.sync instead of lane == 0: the compiler then knows that one thread runs this and keeps the descriptors in
+        // uniform registers -- 6 instead of 21 instructions per MMA)
+        if (elect_one()) {
             const uint32_t idesc = idesc_bf16(CONV_OC_TILE, CONV_N);
             const uint64_t a_desc0 = smem_desc(smem_u32(sA), CONV_OC_TILE * 16, 128, 0);     // LBO = k-group stride, SBO = 8 rows
             const uint64_t b_desc0 = smem_desc(smem_u32(sB), CONV_PLANE_BYTES, 128, 0);

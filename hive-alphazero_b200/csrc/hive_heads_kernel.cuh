@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) hive_head_conv_kernel(const _
     const int n_tiles = (a.n_rows + HEAD_M - 1) / HEAD_M;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_expect_tx(&w_full, HC_W_BYTES);
             for (int c = 0; c < HC_CHUNKS; c++) bulk_load(sW + c * (HC_W_BYTES / HC_CHUNKS), a.w + c * (HC_W_BYTES / HC_CHUNKS), HC_W_BYTES / HC_CHUNKS, &w_full);
             int st = 0, ph = 0;
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) hive_head_conv_kernel(const _
                 }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = idesc_bf16(HEAD_M, HC_N);
             const uint64_t a_desc0 = smem_desc(smem_u32(sX), HEAD_M * 16, 128, 0);
             const uint64_t b_desc0 = smem_desc(smem_u32(sW), HC_N * 16, 128, 0);
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) hive_head_fc_kernel(HeadFcArg
     const uint32_t tmem = tmem_base;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             const uint8_t* ga = reinterpret_cast<const uint8_t*>(a.fc_a) + (size_t)mt * FC_CHUNKS * HEAD_A_BYTES;
             const uint8_t* gb = a.w + (size_t)nt * FC_CHUNKS * FC_B_BYTES;
             int st = 0, ph = 0;
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) hive_head_fc_kernel(HeadFcArg
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = idesc_bf16(HEAD_M, FC_N);
             const uint64_t a_desc0 = smem_desc(smem_u32(sA), HEAD_M * 16, 128, 0);
             const uint64_t b_desc0 = smem_desc(smem_u32(sB), FC_N * 16, 128, 0);
