@@ -505,14 +505,17 @@ def main():
     dt = r_e2e["seconds"]
     e2e_value = allsum(float(e2e_steps)) / allmax(dt)
     busy = r_e2e["policy_seconds"] / max(dt, 1e-9)
-    pcie_gbs = (200 + 4 + 4 + 4) * e2e_steps / max(dt, 1e-9) / 1e9
-    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": (200 + 4 + 4) * n,
+    use_lists = os.environ.get("HIVE_B200_HOST_LISTS", "1") != "0"
+    d2h_per_game = (96 + 4) if use_lists else (200 + 4 + 4)         # compact legal lists (96 B per game) + status, or masks + counts + status
+    pcie_gbs = (d2h_per_game + 4) * e2e_steps / max(dt, 1e-9) / 1e9
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": d2h_per_game * n,
+           "legal_sets_as": "compact lists (hive_step_host_async_lists: 96 B per game)" if use_lists else "masks (208 B per game)",
            "steps": k_e2e, "parts": loop.parts, "host_threads_per_rank": e2e_budget, "driver_threads": loop.threads, "host_cores": host_cores,
            "policy_share_of_thread_time": busy, "wait_share_of_thread_time": r_e2e["wait_seconds"] / max(dt, 1e-9),
            "pcie_gbs_this_rank": pcie_gbs,
            "bound": "host threads" if busy > 0.6 else ("PCIe" if pcie_gbs > 40.0 else "GPU step latency of a part"),
            "note": "per-GPU bytes per step of all %d games; %d parts of the batch, each its own environment handle, streams and pinned "
-           "buffers (one CUDA-graph launch per part and step: H2D actions, kernels, D2H masks/counts/status); %d native driver "
+           "buffers (one CUDA-graph launch per part and step: H2D actions, kernels, D2H of the new legal sets and status); %d native driver "
            "threads run the policy (C-ABI twin of the device policy) for their parts while the GPU steps the others; planes stay in "
            "HBM for the net" % (n, loop.parts, loop.threads)}
     loop.close()

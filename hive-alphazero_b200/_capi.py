@@ -9,7 +9,7 @@ _lib = None
 
 ENV_SYMBOLS = [
     "hive_last_error", "hive_abi_version", "hive_create", "hive_destroy", "hive_num_games", "hive_sync",
-    "hive_reset", "hive_step_host", "hive_step", "hive_step_host_async", "hive_wait_results", "hive_step_random", "hive_step_random_multi", "hive_legal_host", "hive_encode_host", "hive_bits_host",
+    "hive_reset", "hive_step_host", "hive_step", "hive_step_host_async", "hive_step_host_async_lists", "hive_host_pick_actions_lists", "hive_wait_results", "hive_step_random", "hive_step_random_multi", "hive_legal_host", "hive_encode_host", "hive_bits_host",
     "hive_status_host", "hive_status_packed_host", "hive_host_pick_actions", "hive_counters_host", "hive_state_key", "hive_load_state", "hive_dump_state",
     "hive_copy_state", "hive_record_host", "hive_dev_state", "hive_dev_legal", "hive_dev_count", "hive_dev_status", "hive_dev_planes",
     "hive_launch_count", "hive_profile_step", "hive_probe_write_stream", "hive_set_timing", "hive_last_kernel_ms",
@@ -56,6 +56,8 @@ def lib():
     L.hive_step_host.argtypes = [vp, vp]
     L.hive_step.argtypes = [vp, vp]
     L.hive_step_host_async.argtypes = [vp, vp, vp, vp, vp]
+    L.hive_step_host_async_lists.argtypes = [vp, vp, vp, vp]
+    L.hive_host_pick_actions_lists.argtypes = [i32, vp, vp, vp, u64, i32, vp, vp]
     L.hive_bits_host.argtypes = [vp, vp]
     L.hive_wait_results.argtypes = [vp]
     L.hive_step_random.argtypes = [vp, u64, i32, i32, vp]

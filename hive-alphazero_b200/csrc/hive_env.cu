@@ -93,6 +93,7 @@ static EnvArgs slice_args(hive_env* h, int s, int per, int op, const int32_t* ac
     a.seed = seed; a.n = cnt > 0 ? cnt : 0; a.op = op; a.max_turn = max_turn; a.auto_reset = auto_reset;
     a.g_offset = off; a.n_total = h->n;
     a.shadow = h->shadow ? h->shadow + (size_t)off * BITS_WORDS : nullptr;
+    a.lists = h->want_lists ? h->lists + (size_t)(off / SG) * LIST_BLOCK_BYTES : nullptr;
     a.stagger_ns = h->stagger_ns; a.stagger_div = h->sm_count > 0 ? h->sm_count : 148;
     return a;
 }
@@ -271,6 +272,7 @@ int hive::create_env(int n_games, int device, void* stream, int slices, hive_env
     h->count = reinterpret_cast<int32_t*>(h->legal + n * LEGAL_WORDS);
     h->status = reinterpret_cast<uint32_t*>(h->count + n);
     CUDA_TRY(cudaMalloc(&h->planes, n * HIVE_PLANES_ELEMS * 2));
+    CUDA_TRY(cudaMalloc(&h->lists, (n + SG - 1) / SG * LIST_BLOCK_BYTES));
     {
         const char* rk0 = getenv("HIVE_B200_ROLLOUT_KERNEL");
         const char* ds = getenv("HIVE_B200_DELTA_STORE");          // 1: hive_planes_delta_kernel (measured: same speed, 4x less HBM traffic)
@@ -363,7 +365,7 @@ int hive_destroy(hive_env_t* h) {
     if (h->multi_graph.exec && h->multi_graph.exec != h->slice_exec[0]) cudaGraphExecDestroy(h->multi_graph.exec);
     for (int s = 0; s < hive_env::MAX_SUB; s++) if (h->slice_exec[s]) cudaGraphExecDestroy(h->slice_exec[s]);
     if (h->host_graph.exec) cudaGraphExecDestroy(h->host_graph.exec);
-    cudaFree(h->recs); cudaFree(h->legal); cudaFree(h->planes); cudaFree(h->bits[0]); cudaFree(h->bits[1]); cudaFree(h->shadow); cudaFree(h->roll_sync);
+    cudaFree(h->recs); cudaFree(h->legal); cudaFree(h->planes); cudaFree(h->lists); cudaFree(h->bits[0]); cudaFree(h->bits[1]); cudaFree(h->shadow); cudaFree(h->roll_sync);
     for (int s = 0; s < h->n_sub; s++) {
         if (h->sub_stream[s]) cudaStreamDestroy(h->sub_stream[s]);
         if (h->store_stream[s]) cudaStreamDestroy(h->store_stream[s]);
@@ -455,7 +457,7 @@ static bool is_pinned_host(const void* p) {
 // they are queued BEFORE the join with the plane stores, and results_ev is recorded behind them, so that
 // hive_wait_results returns while the 16 KB/game of planes are still being written (hive_sync waits for those too).
 static int queue_host_step(hive_env* h, int32_t* d, const int32_t* actions, uint64_t* mask, int32_t* count, uint32_t* packed_status,
-                           int slices) {
+                           int slices, uint8_t* lists = nullptr) {
     // page-locked actions are read by the step kernel straight from host memory (4 B per game, coalesced: one PCIe read
     // per warp) instead of through a copy node of their own; pageable ones are staged
     const int32_t* act = actions;
@@ -465,9 +467,12 @@ static int queue_host_step(hive_env* h, int32_t* d, const int32_t* actions, uint
     }
     int deferred = 0;
     h->last_bits = 0;
+    h->want_lists = lists != nullptr;
     int rc = launch_env_kernels(h, OP_STEP, act, nullptr, 0, 0, 0, nullptr, 1, slices > 0 ? slices : h->host_slices, &deferred);
+    h->want_lists = false;
     if (rc) return rc;
     const size_t n = (size_t)h->n;
+    if (lists) CUDA_TRY(cudaMemcpyAsync(lists, h->lists, (n + SG - 1) / SG * LIST_BLOCK_BYTES, cudaMemcpyDeviceToHost, h->stream));
     if (mask && count && packed_status && reinterpret_cast<uint8_t*>(count) == reinterpret_cast<uint8_t*>(mask) + n * LEGAL_WORDS * 4 &&
         reinterpret_cast<uint8_t*>(packed_status) == reinterpret_cast<uint8_t*>(count) + n * 4) {
         // the caller's buffers are laid out like the device arena: one download
@@ -489,23 +494,31 @@ static int queue_host_step(hive_env* h, int32_t* d, const int32_t* actions, uint
 // set of pinned staging buffers per handle) gets the whole sequence -- action upload, the five kernels of every
 // slice with their fork/join events, the three result downloads -- replayed as ONE CUDA graph launch: the host
 // thread then spends a few microseconds per step instead of ~30 driver calls, which is what bounded this path.
+static int step_host_async(hive_env_t* h, const int32_t* actions, uint64_t* mask, int32_t* count, uint32_t* packed_status, uint8_t* lists);
 int hive_step_host_async(hive_env_t* h, const int32_t* actions, uint64_t* mask, int32_t* count, uint32_t* packed_status) {
+    return step_host_async(h, actions, mask, count, packed_status, nullptr);
+}
+int hive_step_host_async_lists(hive_env_t* h, const int32_t* actions, uint8_t* lists, uint32_t* packed_status) {
+    if (!lists) return fail(HIVE_E_ARG, "hive_step_host_async_lists: null lists");
+    return step_host_async(h, actions, nullptr, nullptr, packed_status, lists);
+}
+static int step_host_async(hive_env_t* h, const int32_t* actions, uint64_t* mask, int32_t* count, uint32_t* packed_status, uint8_t* lists) {
     if (check(h)) return HIVE_E_HANDLE;
     if (!actions) return fail(HIVE_E_ARG, "hive_step_host_async: null actions");
     CUDA_TRY(cudaSetDevice(h->device));
     hive_env::HostGraph& g = h->host_graph;
-    const bool same = g.exec && g.actions == actions && g.mask == mask && g.count == count && g.status == packed_status;
+    const bool same = g.exec && g.actions == actions && g.mask == mask && g.count == count && g.status == packed_status && g.lists == lists;
     if (!same && h->use_graph) {
         // a second call with the same buffers builds the graph; one-off callers stay on the plain path
-        const bool repeat_caller = g.seen_actions == actions && g.seen_mask == mask && g.seen_count == count && g.seen_status == packed_status;
-        g.seen_actions = actions; g.seen_mask = mask; g.seen_count = count; g.seen_status = packed_status;
+        const bool repeat_caller = g.seen_actions == actions && g.seen_mask == mask && g.seen_count == count && g.seen_status == packed_status && g.seen_lists == lists;
+        g.seen_actions = actions; g.seen_mask = mask; g.seen_count = count; g.seen_status = packed_status; g.seen_lists = lists;
         if (repeat_caller && is_pinned_host(actions) && (!mask || is_pinned_host(mask)) && (!count || is_pinned_host(count)) &&
-            (!packed_status || is_pinned_host(packed_status))) {
+            (!packed_status || is_pinned_host(packed_status)) && (!lists || is_pinned_host(lists))) {
             if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
             cudaGraph_t graph = nullptr;
             CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
             const long long l0 = h->launches;
-            int rc = queue_host_step(h, h->d_actions[0], actions, mask, count, packed_status, h->async_slices);
+            int rc = queue_host_step(h, h->d_actions[0], actions, mask, count, packed_status, h->async_slices, lists);
             g.launches = (int)(h->launches - l0);
             h->launches = l0;
             cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
@@ -514,10 +527,10 @@ int hive_step_host_async(hive_env_t* h, const int32_t* actions, uint64_t* mask, 
             e = cudaGraphInstantiate(&g.exec, graph, 0);
             cudaGraphDestroy(graph);
             if (e != cudaSuccess) { g.exec = nullptr; return fail(HIVE_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
-            g.actions = actions; g.mask = mask; g.count = count; g.status = packed_status;
+            g.actions = actions; g.mask = mask; g.count = count; g.status = packed_status; g.lists = lists;
         }
     }
-    if (g.exec && g.actions == actions && g.mask == mask && g.count == count && g.status == packed_status) {
+    if (g.exec && g.actions == actions && g.mask == mask && g.count == count && g.status == packed_status && g.lists == lists) {
         CUDA_TRY(cudaGraphLaunch(g.exec, h->stream));
         h->launches += g.launches;
         return 0;
@@ -525,7 +538,7 @@ int hive_step_host_async(hive_env_t* h, const int32_t* actions, uint64_t* mask, 
     // stream-ordered on h->stream, so one device-side action buffer would do; the two alternate with hive_step_host's
     int32_t* d = h->d_actions[h->act_flip];
     h->act_flip ^= 1;
-    return queue_host_step(h, d, actions, mask, count, packed_status, 0);
+    return queue_host_step(h, d, actions, mask, count, packed_status, 0, lists);
 }
 
 int hive_wait_results(hive_env_t* h) {
@@ -919,6 +932,45 @@ int hive_host_pick_actions(int n, const uint64_t* mask, const int32_t* count, co
         const int g0 = part * chunk, g1 = g0 + chunk < n ? g0 + chunk : n;
         pick_range(g0, g1, n, mask, count, packed_status, episodes, seed, max_turn, actions);
     });
+    return 0;
+}
+
+// The random policy's host twin read from the compact lists (LIST_* in hive_env_kernel.cuh).  Returns in *n_overflow the number
+// of games whose group's lists did not fit (their actions are left untouched: pick them from the mask).
+int hive_host_pick_actions_lists(int n, const uint8_t* lists, const uint32_t* packed_status, uint32_t* episodes, uint64_t seed,
+                                 int max_turn, int32_t* actions, int* n_overflow) {
+    if (n <= 0 || !lists || !packed_status || !episodes || !actions) return fail(HIVE_E_ARG, "hive_host_pick_actions_lists: bad arguments");
+    std::atomic<int> over{0};
+    auto range = [&](int g0, int g1) {
+        int ov = 0;
+        for (int g = g0; g < g1; g++) {
+            const uint8_t* blk = lists + (size_t)(g / SG) * LIST_BLOCK_BYTES;
+            const uint8_t* hdr = blk + (g % SG) * LIST_HDR_BYTES;
+            const uint32_t st = packed_status[g];
+            const int turn = st & 0xFF, done = (st >> 16) & 0xFF;
+            if (done || turn >= max_turn) { actions[g] = HIVE_RESET; episodes[g]++; continue; }
+            if (hdr[9] & 1u) { ov++; continue; }
+            const int count = hdr[8];
+            if (count == 0) { actions[g] = -1; continue; }
+            const uint64_t gid = (uint64_t)g + (uint64_t)n * episodes[g];
+            const int k = (int)(host_splitmix64(seed ^ (gid << 32) ^ (uint64_t)turn) % (uint64_t)count);
+            int p = 0;
+            while (hdr[2 + p] <= k) p++;                         // the 256-id page of the k-th action (cum[6] = count > k: the scan ends)
+            const int off = hdr[0] | (hdr[1] << 8);
+            actions[g] = p * 256 + blk[SG * LIST_HDR_BYTES + off + k];
+        }
+        if (ov) over.fetch_add(ov);
+    };
+    if (n <= 512) range(0, n);
+    else {
+        PickPool* pool = pick_pool();
+        const int threads = (int)pool->workers.size() + 1;
+        int chunk = (n + threads - 1) / threads;
+        if (chunk < 128) chunk = 128;
+        const int parts = (n + chunk - 1) / chunk;
+        pool->run(parts, [&](int part) { const int g0 = part * chunk; range(g0, g0 + chunk < n ? g0 + chunk : n); });
+    }
+    if (n_overflow) *n_overflow = over.load();
     return 0;
 }
 

@@ -25,6 +25,7 @@ struct EnvArgs {
     uint16_t* planes;      // [n][56*144] bf16
     uint32_t* bits;        // [n][BITS_WORDS] bit planes, step kernel -> plane-store kernel (this step's buffer of two)
     uint32_t* shadow;      // [n][BITS_WORDS] the bit planes the planes arena holds right now (delta plane store)
+    uint8_t* lists;        // [ceil(n/SG)][LIST_BLOCK_BYTES] compact legal lists of the host-driven path, or null (see LIST_* below)
     const int32_t* actions;
     const uint8_t* mask;
     int32_t* chosen;
@@ -91,11 +92,20 @@ __device__ unsigned long long g_phase_clk[8];
 #define HIVE_STEP_WARPS 8
 #endif
 constexpr int SG = 32;                                   // games per CTA
+constexpr int SG_GAMES = SG;
 constexpr int SW = HIVE_STEP_WARPS, STEP_THREADS = SW * 32;
 static_assert(SW >= 2 && SW <= 16, "warps per CTA of the step kernel");
 #ifndef HIVE_STEP_MIN_CTAS
 #define HIVE_STEP_MIN_CTAS (768 / (HIVE_STEP_WARPS * 32))
 #endif
+
+// Compact legal lists (EnvArgs::lists; what the host-driven loop downloads instead of the 198-byte masks: 96 B per game).
+// One block of LIST_BLOCK_BYTES per group of SG games: SG headers of 12 bytes, then the games' action ids packed back to back,
+// ascending (GamePlay.actions() is an ascending list, env_hive.py:182,301-304), ONE BYTE per action: the low 8 bits of the id.
+// Header of a game: u16 offset of its ids inside the ids area; u8 cum[7], cum[p] = number of its actions with id < 256 (p+1)
+// (cum[6] = the count), so action k is 256 p + ids[offset + k] with p the first page whose cum exceeds k; u8 flags, bit 0 =
+// the group's lists did not fit (more than LIST_IDS_CAP actions in the group or 256+ in one game: use the mask).
+constexpr int LIST_HDR_BYTES = 12, LIST_BLOCK_BYTES = 3072, LIST_IDS_CAP = LIST_BLOCK_BYTES - SG_GAMES * LIST_HDR_BYTES;
 
 struct __align__(16) StepShared {
     union {
@@ -567,9 +577,9 @@ __device__ __forceinline__ void encode_mobility(const StepShared& s, const Encod
 
 // phases 1..5 of one step of the CTA's 32 games (all threads; ends without a trailing barrier).  Returns the mask of the
 // games evaluated in this step (identical in every thread).
-__device__ __forceinline__ unsigned step_phases(StepShared& s, const EnvArgs& a, int blk) {      // blk: which group of SG games
+__device__ __forceinline__ unsigned step_phases(StepShared& s, const EnvArgs& a, int blk_index) {      // blk_index: which group of SG games
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = blk * SG + lane;
+    const int g = blk_index * SG + lane;
     const uint32_t* geo = a.hop_lines;
     HIVE_PHASE_BEGIN();
     if (warp == 0) step_prologue(s, a, lane, g);
@@ -577,7 +587,7 @@ __device__ __forceinline__ unsigned step_phases(StepShared& s, const EnvArgs& a,
     __syncthreads();
     HIVE_PHASE_MARK(0);
     const unsigned live_mask = s.any_live;
-    if (!live_mask) return 0u;
+    if (!live_mask && !a.lists) return 0u;                  // (with lists the idle games are listed again: the host reads nothing else)
 
     step_stacks(s, warp, lane);
     __syncthreads();
@@ -696,6 +706,43 @@ __device__ __forceinline__ unsigned step_phases(StepShared& s, const EnvArgs& a,
             a.count[g] = (int32_t)n_legal;
             a.status[g] = st;
         }
+    }
+    if (a.lists) {   // ---- compact legal lists (warps SW-4 .. SW-1, beside phase 5; lane <-> game, a warp per range of mask words)
+        uint8_t* blk = reinterpret_cast<uint8_t*>(&s.rows[0][0][0]);             // the move rows are dead: headers, then ids
+        static_assert(sizeof(s.rows) >= LIST_BLOCK_BYTES && SW >= 6, "list block fits the dead move rows; list warps beside warps 0, 1");
+        if (warp >= SW - 4) {
+            const int j = warp - (SW - 4);
+            const int w0 = j == 0 ? 0 : j == 1 ? 13 : j == 2 ? 25 : 38, w1 = j == 0 ? 13 : j == 1 ? 25 : j == 2 ? 38 : 50;
+            const bool in_batch = g < a.n;
+            const uint32_t* gw = a.legal + (size_t)g * LEGAL_WORDS;              // an idle game keeps the mask of an earlier step
+            const uint32_t cnt = live ? s.nlegal[lane] : (in_batch ? (uint32_t)a.count[g] : 0u);
+            uint32_t off = cnt;                                                   // inclusive prefix over the CTA's games
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(FULL, off, d); if (lane >= d) off += o; }
+            const uint32_t total = __shfl_sync(FULL, off, 31);
+            off -= cnt;
+            const bool overflow = total > (uint32_t)LIST_IDS_CAP || __ballot_sync(FULL, cnt > 255u) != 0u;
+            uint32_t r = 0;                                                       // rank of the first action of this warp's word range
+            for (int i = 0; i < w0; i++) r += (uint32_t)__popc(live ? s.legal[i][lane] : (in_batch ? gw[i] : 0u));
+            uint8_t* hdr = blk + lane * LIST_HDR_BYTES;
+            uint8_t* ids = blk + SG * LIST_HDR_BYTES + off;
+            for (int i = w0; i < w1; i++) {
+                uint32_t w = live ? s.legal[i][lane] : (in_batch ? gw[i] : 0u);
+                while (__ballot_sync(FULL, w != 0u)) {                            // warp-uniform trip count
+                    if (w) {
+                        const int b = __ffs(w) - 1; w &= w - 1;
+                        if (!overflow) ids[r] = (uint8_t)((i * 32 + b) & 255);
+                        r++;
+                    }
+                }
+                if ((i & 7) == 7) hdr[2 + (i >> 3)] = (uint8_t)(r < 255u ? r : 255u);      // end of a 256-id page (8 mask words)
+            }
+            if (j == 3) hdr[8] = (uint8_t)(r < 255u ? r : 255u);                  // cum[6] = the count
+            if (j == 0) { hdr[0] = (uint8_t)(off & 255u); hdr[1] = (uint8_t)(off >> 8); hdr[9] = overflow ? 1u : 0u; hdr[10] = 0; hdr[11] = 0; }
+        }
+        __syncthreads();
+        if (tid < LIST_BLOCK_BYTES / 16)
+            reinterpret_cast<uint4*>(a.lists + (size_t)blk_index * LIST_BLOCK_BYTES)[tid] = reinterpret_cast<const uint4*>(blk)[tid];
     }
     HIVE_PHASE_MARK(5);
     return live_mask;

@@ -10,6 +10,7 @@
 // lock and no allocation in the loop; a thread's parts are its own.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -23,6 +24,7 @@
 
 struct hive_host_loop {
     int device = 0, n_games = 0, n_parts = 0, n_threads = 0;
+    bool use_lists = true;                   // HIVE_B200_HOST_LISTS=0: download the 198-byte masks every step (the round-1/2 form)
     struct Part {
         hive_env_t* env = nullptr;
         int n = 0, first = 0;                // games [first, first + n) of the batch
@@ -30,6 +32,10 @@ struct hive_host_loop {
         int32_t* count = nullptr;
         uint32_t* status = nullptr;
         int32_t* actions = nullptr;
+        uint8_t* lists = nullptr;            // page-locked: compact legal lists of the last step (hive_step_host_async_lists)
+        bool have_lists = false;             // false until the first step of this part has run (the first pick reads the masks)
+        std::vector<uint32_t> scratch_ep;    // overflow groups: episode counters for the mask-based re-pick
+        std::vector<int32_t> scratch_act;
         std::vector<uint32_t> episodes;
     };
     std::vector<Part> parts;
@@ -44,6 +50,7 @@ int hive_host_loop_destroy(hive_host_loop_t* l) {
         if (p.env) hive_destroy(p.env);
         if (p.mask) cudaFreeHost(p.mask);
         if (p.actions) cudaFreeHost(p.actions);
+        if (p.lists) cudaFreeHost(p.lists);
     }
     delete l;
     return 0;
@@ -55,6 +62,7 @@ int hive_host_loop_create(int n_games, int device, int n_parts, int n_threads, h
     *out = nullptr;
     hive_host_loop* l = new hive_host_loop();
     l->device = device; l->n_games = n_games; l->n_parts = n_parts; l->n_threads = n_threads < n_parts ? n_threads : n_parts;
+    { const char* e = getenv("HIVE_B200_HOST_LISTS"); l->use_lists = !(e && atoi(e) == 0); }
     l->parts.resize(n_parts);
     int first = 0;
     for (int i = 0; i < n_parts; i++) {
@@ -70,6 +78,7 @@ int hive_host_loop_create(int n_games, int device, int n_parts, int n_threads, h
             p.status = reinterpret_cast<uint32_t*>(p.count + p.n);
             e = cudaHostAlloc(&p.actions, (size_t)p.n * 4, cudaHostAllocDefault);
         }
+        if (e == cudaSuccess) e = cudaHostAlloc(&p.lists, (size_t)((p.n + 31) / 32) * HIVE_LIST_BLOCK_BYTES, cudaHostAllocDefault);
         if (e != cudaSuccess) {
             hive_host_loop_destroy(l);
             return hive::fail(HIVE_E_CUDA, std::string("hive_host_loop_create: cudaHostAlloc: ") + cudaGetErrorString(e));
@@ -117,14 +126,32 @@ int hive_host_loop_run(hive_host_loop_t* l, int n_steps, uint64_t seed, int max_
                 const auto a = clk::now();
                 int rc = hive_wait_results(p.env);          // this part's last downloads have landed (its planes may still be in flight)
                 const auto b = clk::now();
+                const bool lists = l->use_lists && !policy;        // (a caller's policy is handed the masks: its signature says so)
+                const uint64_t pseed = seed + 77ull * (uint64_t)(i + 1);
                 if (!rc) {
                     if (policy) policy(user, i, p.first, p.n, p.mask, p.count, p.status, p.actions);
-                    else rc = hive_host_pick_actions(p.n, p.mask, p.count, p.status, p.episodes.data(),
-                                                     seed + 77ull * (uint64_t)(i + 1), max_turn, p.actions);   // small parts on this thread, large ones over the policy pool
+                    else if (lists && p.have_lists) {
+                        // the k-th legal action from the compact lists (96 B per game came down instead of 208)
+                        int overflow = 0;
+                        p.scratch_ep = p.episodes;                 // (the counters before this pick, for a possible re-pick)
+                        rc = hive_host_pick_actions_lists(p.n, p.lists, p.status, p.episodes.data(), pseed, max_turn, p.actions, &overflow);
+                        if (!rc && overflow) {
+                            // a group's lists did not fit its block (very rare: > 84 legal actions per game on average in a
+                            // group): fetch the masks and pick those games from them
+                            rc = hive_legal_host(p.env, p.mask, p.count);
+                            p.scratch_act.resize(p.n);
+                            if (!rc) rc = hive_host_pick_actions(p.n, p.mask, p.count, p.status, p.scratch_ep.data(), pseed, max_turn, p.scratch_act.data());
+                            for (int g = 0; g < p.n && !rc; g++)
+                                if (p.lists[(size_t)(g / 32) * HIVE_LIST_BLOCK_BYTES + (g % 32) * 12 + 9] & 1u) p.actions[g] = p.scratch_act[g];
+                        }
+                    } else rc = hive_host_pick_actions(p.n, p.mask, p.count, p.status, p.episodes.data(), pseed, max_turn, p.actions);   // small parts on this thread, large ones over the policy pool
                 }
                 const auto c = clk::now();
-                // H2D 4 B/game -> kernels -> D2H (200 + 4 + 4) B/game, all queued; the thread's other parts are handled meanwhile
-                if (!rc) rc = hive_step_host_async(p.env, p.actions, p.mask, p.count, p.status);
+                // H2D 4 B/game -> kernels -> D2H, all queued; the thread's other parts are handled meanwhile
+                if (!rc) {
+                    if (lists) { rc = hive_step_host_async_lists(p.env, p.actions, p.lists, p.status); p.have_lists = true; }
+                    else { rc = hive_step_host_async(p.env, p.actions, p.mask, p.count, p.status); p.have_lists = false; }
+                }
                 tw += std::chrono::duration<double>(b - a).count();
                 tp += std::chrono::duration<double>(c - b).count();
                 if (rc) { rcs[t] = rc; errs[t] = hive_last_error(); break; }

@@ -17,6 +17,8 @@ struct hive_env {
     uint32_t* legal = nullptr;
     int32_t* count = nullptr;
     uint32_t* status = nullptr;
+    uint8_t* lists = nullptr;       // [ceil(n/32)][LIST_BLOCK_BYTES] compact legal lists (written by steps that ask for them)
+    bool want_lists = false;        // the launch being issued writes the lists (hive_step_host_async_lists)
     uint16_t* planes = nullptr;
     uint32_t* bits[2] = {nullptr, nullptr};   // bit planes, encode kernel -> plane-store kernel (double-buffered over steps)
     int last_bits = 0;              // which of the two buffers the last launch wrote (hive_bits_host)
@@ -38,6 +40,7 @@ struct hive_env {
     // the host-driven step (hive_step_host_async) from one fixed set of page-locked buffers: upload, kernels and
     // downloads replayed as one graph
     struct HostGraph { const void* actions = nullptr; const void* mask = nullptr; const void* count = nullptr; const void* status = nullptr;
+                       const void* lists = nullptr; const void* seen_lists = nullptr;
                        const void* seen_actions = nullptr; const void* seen_mask = nullptr; const void* seen_count = nullptr;
                        const void* seen_status = nullptr; int launches = 0; cudaGraphExec_t exec = nullptr; } host_graph;
     int async_slices = 4;           // slices of a graph-replayed host-driven step

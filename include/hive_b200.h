@@ -67,6 +67,14 @@ int hive_step(hive_env_t* h, const int32_t* actions_dev);           /* device in
  * From the second call with the same set of page-locked buffers on, the whole sequence (upload, the kernels of
  * every slice, downloads) is replayed as one CUDA graph launch; pageable buffers stay on the plain path. */
 int hive_step_host_async(hive_env_t* h, const int32_t* actions, uint64_t* mask, int32_t* count, uint32_t* packed_status);
+/* The same step, but the new legal sets come down as COMPACT LISTS instead of 198-byte masks: per group of 32 games one
+ * block of HIVE_LIST_BLOCK_BYTES -- 32 headers of 12 bytes (u16 offset of the game's ids in the ids area; u8 cum[7], cum[p] =
+ * number of its legal actions with id < 256 (p+1), cum[6] = the count; u8 flags, bit 0: the group did not fit, use the mask),
+ * then the games' ids back to back, ascending (as GamePlay.actions(), env_hive.py:182,301-304), one byte (id & 255) each:
+ * action k of a game = 256 p + ids[offset + k], p = the first page with cum[p] > k.  96 B per game instead of 208 on the
+ * wire: the host-driven loop is bound by this download.  lists: page-locked, [ceil(n/32)][3072]. */
+#define HIVE_LIST_BLOCK_BYTES 3072
+int hive_step_host_async_lists(hive_env_t* h, const int32_t* actions, uint8_t* lists, uint32_t* packed_status);
 /* Blocks until the downloads of the last hive_step_host_async have landed in the caller's buffers.  The step's
  * 16 KB/game of planes may still be in flight (they stay in HBM for the network; hive_sync waits for them too), so a
  * host loop that only needs masks / counts / status picks its next actions beside the plane store. */
@@ -104,6 +112,11 @@ int hive_status_packed_host(hive_env_t* h, uint32_t* packed);
  * x = splitmix64(seed ^ (g + n*episodes[g])<<32 ^ turn).  Pure host code, no GPU work. */
 int hive_host_pick_actions(int n, const uint64_t* mask, const int32_t* count, const uint32_t* packed_status,
                            uint32_t* episodes, uint64_t seed, int max_turn, int32_t* actions);
+/* The same rule read from the compact lists of hive_step_host_async_lists (identical actions).  *n_overflow (optional) = games
+ * whose group's lists did not fit: their entries of `actions` are left untouched -- fetch the masks (hive_legal_host) and pick
+ * those with hive_host_pick_actions. */
+int hive_host_pick_actions_lists(int n, const uint8_t* lists, const uint32_t* packed_status, uint32_t* episodes, uint64_t seed,
+                                 int max_turn, int32_t* actions, int* n_overflow);
 /* ---- the host-driven game loop inside the library ----------------------------------------------------------------
  * The reference's self-play worker is a host loop around GamePlay: actions() -> policy -> move()
  * (woker/self_play.py:54-56,116-193).  hive_host_loop_* runs that loop natively for a whole batch: the batch is cut

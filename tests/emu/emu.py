@@ -39,6 +39,7 @@ def lib():
         L.emu_env_rollout.restype = ctypes.c_int
         L.emu_env_rollout_q.argtypes = L.emu_env_rollout.argtypes
         L.emu_env_rollout_q.restype = ctypes.c_int
+        L.emu_env_lists.restype = vp
         L.emu_last_error.restype = ctypes.c_char_p
         L.emu_mcts_create.restype = vp
         L.emu_mcts_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
@@ -87,6 +88,26 @@ class EmuBatch:
                                None if self.shadow is None else self.shadow.ctypes.data)
         if rc:
             raise RuntimeError("emulator: " + lib().emu_last_error().decode())
+
+    def legal_lists(self):
+        """The compact legal lists the last step / reset wrote (EnvArgs::lists), decoded: per game the ascending action ids,
+        or None where the group's overflow flag is set."""
+        nb = (self.n + 31) // 32
+        raw = np.ctypeslib.as_array(ctypes.cast(lib().emu_env_lists(), ctypes.POINTER(ctypes.c_uint8)), shape=(nb, 3072)).copy()
+        out = []
+        for g in range(self.n):
+            blk, hdr = raw[g // 32], raw[g // 32][(g % 32) * 12:(g % 32) * 12 + 12]
+            if hdr[9] & 1:
+                out.append(None)
+                continue
+            off, cum = int(hdr[0]) | (int(hdr[1]) << 8), [int(x) for x in hdr[2:9]]
+            ids, page = [], 0
+            for k in range(cum[6]):
+                while cum[page] <= k:
+                    page += 1
+                ids.append(page * 256 + int(blk[32 * 12 + off + k]))
+            out.append(ids)
+        return out
 
     def reset(self, mask=None):
         self._run(OP_RESET, mask=mask)

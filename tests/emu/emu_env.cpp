@@ -9,6 +9,7 @@
 using namespace hive;
 
 static std::vector<uint32_t> g_lines;
+static std::vector<uint8_t> g_lists;        // compact legal lists written by the last emu_env_run (EnvArgs::lists)
 static void build_lines() {
     if (g_lines.empty()) build_geometry_tables(g_lines);
 }
@@ -33,6 +34,8 @@ int emu_env_run(void* recs, uint32_t* legal, int32_t* count, uint32_t* status, u
     static std::vector<uint32_t> bits;
     if ((int)bits.size() < n * BITS_WORDS) bits.resize((size_t)n * BITS_WORDS);
     a.bits = bits.data(); a.shadow = shadow;
+    g_lists.assign((size_t)((n + SG - 1) / SG) * LIST_BLOCK_BYTES, 0xEE);
+    a.lists = (op == OP_STEP || op == OP_RANDOM || op == OP_RESET) ? g_lists.data() : nullptr;   // (the search's evaluations run without)
     const int blocks = (n + SG - 1) / SG;
     emu::g_gridDim.x = blocks;
     for (int b = 0; b < blocks; b++) {
@@ -66,7 +69,7 @@ int emu_env_rollout(void* recs, uint32_t* legal, int32_t* count, uint32_t* statu
     a.recs = (GameRec*)recs; a.legal = legal; a.count = count; a.status = status; a.planes = planes;
     a.actions = nullptr; a.mask = nullptr; a.chosen = nullptr; a.hop_lines = g_lines.data();
     a.seed = seed; a.n = n; a.op = OP_RANDOM; a.max_turn = max_turn; a.auto_reset = auto_reset;
-    a.g_offset = 0; a.n_total = n; a.stagger_ns = 0; a.stagger_div = 148;
+    a.g_offset = 0; a.n_total = n; a.stagger_ns = 0; a.stagger_div = 148; a.lists = nullptr;
     static std::vector<uint32_t> bits;
     if ((int)bits.size() < n * BITS_WORDS) bits.resize((size_t)n * BITS_WORDS);
     a.bits = bits.data(); a.shadow = nullptr;
@@ -89,7 +92,7 @@ int emu_env_rollout_q(void* recs, uint32_t* legal, int32_t* count, uint32_t* sta
     a.recs = (GameRec*)recs; a.legal = legal; a.count = count; a.status = status; a.planes = planes;
     a.actions = nullptr; a.mask = nullptr; a.chosen = nullptr; a.hop_lines = g_lines.data();
     a.seed = seed; a.n = n; a.op = OP_RANDOM; a.max_turn = max_turn; a.auto_reset = auto_reset;
-    a.g_offset = 0; a.n_total = n; a.stagger_ns = 0; a.stagger_div = 148; a.shadow = nullptr;
+    a.g_offset = 0; a.n_total = n; a.stagger_ns = 0; a.stagger_div = 148; a.shadow = nullptr; a.lists = nullptr;
     std::vector<uint32_t> bits0((size_t)n * BITS_WORDS), bits1((size_t)n * BITS_WORDS);
     a.bits = bits0.data();
     const int G = (n + SG - 1) / SG;
@@ -107,6 +110,7 @@ int emu_env_rollout_q(void* recs, uint32_t* legal, int32_t* count, uint32_t* sta
     }
     return 0;
 }
+const uint8_t* emu_env_lists() { return g_lists.data(); }
 const char* emu_last_error() { return emu::last_error(); }
 int emu_rec_bytes() { return (int)sizeof(GameRec); }
 }

@@ -75,3 +75,52 @@ def test_host_policy_twin_pure_host_code():
             legal = np.nonzero(bits[g])[0]
             h = splitmix64(seed ^ ((g + n * int(ep0[g])) << 32) ^ int(turn[g]))
             assert actions[g] == legal[h % len(legal)]
+
+
+def test_host_policy_twin_from_compact_lists():
+    """hive_host_pick_actions_lists (the k-th legal action read from the 96-byte-per-game compact lists that the host-driven
+    loop downloads) returns exactly the actions of the mask scan; games of a group flagged as overflow are left untouched."""
+    import ctypes
+    import numpy as np
+    from importlib import import_module
+    L = import_module("hive-alphazero_b200._capi").lib()
+    n, seed, max_turn = 1000, 11, 55                       # 32 groups, the last one ragged
+    rng = np.random.RandomState(5)
+    bits = rng.rand(n, 1584) < 0.035
+    bits[::9] = False
+    mask = np.packbits(np.pad(bits, ((0, 0), (0, 16))), axis=1, bitorder="little").view(np.uint64).copy()
+    count = bits.sum(axis=1).astype(np.int32)
+    packed = (rng.randint(1, 60, size=n).astype(np.uint32) | ((rng.rand(n) < 0.05).astype(np.uint32) << 16)).astype(np.uint32)
+    # the device's encoding, restated: per group 32 headers of 12 bytes, then one byte (id & 255) per action
+    nb = (n + 31) // 32
+    lists = np.zeros((nb, 3072), dtype=np.uint8)
+    flagged = np.zeros(n, dtype=bool)
+    for b in range(nb):
+        off = 0
+        over = b == 3                                       # pretend group 3 did not fit
+        for lane in range(32):
+            g = b * 32 + lane
+            ids = np.nonzero(bits[g])[0] if g < n else np.zeros(0, dtype=np.int64)
+            hdr = lists[b, lane * 12:lane * 12 + 12]
+            hdr[0], hdr[1] = off & 255, off >> 8
+            for p in range(7):
+                hdr[2 + p] = min(int((ids < 256 * (p + 1)).sum()), 255)
+            hdr[9] = 1 if over else 0
+            if not over:
+                lists[b, 384 + off:384 + off + len(ids)] = ids & 255
+            if g < n:
+                flagged[g] = over
+            off += len(ids)
+        assert off <= 3072 - 384
+    ep_a = rng.randint(0, 5, size=n).astype(np.uint32)
+    ep_b = ep_a.copy()
+    a = np.empty(n, dtype=np.int32)
+    b_ = np.full(n, -77, dtype=np.int32)
+    hive_b200.host_pick_actions(mask, count, packed, ep_a, seed, max_turn, a)
+    nov = ctypes.c_int(0)
+    assert L.hive_host_pick_actions_lists(n, lists.ctypes.data, packed.ctypes.data, ep_b.ctypes.data, ctypes.c_uint64(seed), max_turn,
+                                          b_.ctypes.data, ctypes.byref(nov)) == 0
+    resets = a == -3
+    keep = ~flagged | resets                                # (a finished game is reset whatever its group's flag says)
+    assert (a[keep] == b_[keep]).all() and (ep_a == ep_b).all()
+    assert (b_[flagged & ~resets] == -77).all() and nov.value == int((flagged & ~resets).sum())

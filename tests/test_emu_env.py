@@ -172,3 +172,24 @@ def test_queue_rollout_equals_single_steps():
         assert (a.status == b.status).all() and (a.planes == b.planes).all(), rnd
     a.step_random(seed); b.step_random_queue(seed, 1)
     assert (a.recs == b.recs).all() and (a.planes == b.planes).all()
+
+
+def test_compact_legal_lists_equal_the_masks():
+    """EnvArgs::lists (what the host-driven loop downloads instead of the masks): every game's decoded list -- live, idle or
+    just reset -- is its legal mask's set bits in ascending order."""
+    n = 45                                                # two groups, the second ragged
+    e = EmuBatch(n, sched_seed=61)
+    for step in range(40):
+        if step % 7 == 3:                                 # some games idle (NOOP): listed again from their unchanged masks
+            acts = np.full(n, -2, dtype=np.int32)
+            for g in range(0, n, 3):
+                la = e.actions(g)
+                acts[g] = la[0] if len(la) else -1
+            e.step(acts)
+        elif step % 11 == 5:
+            e.reset((np.arange(n) % 4 == 1).astype(np.uint8))
+        else:
+            e.step_random(0xC0FFEE, auto_reset=1)
+        lists = e.legal_lists()
+        for g in range(n):
+            assert lists[g] is not None and lists[g] == e.actions(g).tolist(), (step, g)
