@@ -126,7 +126,7 @@ struct __align__(16) StepShared {
     uint32_t nonempty[SG];           // searched pieces with a non-empty move set
     uint32_t nlegal[SG], episode[SG], steps[SG];
     uint32_t n_flood, n_mv[4];       // queue fill: floods; move classes 0 Ant, 1 Grasshopper, 2 Spider, 3 Queen/Beetle
-    uint32_t any_live, next_task, pad_[1];
+    uint32_t any_live, next_task, next_pre;
     uint16_t q_flood[SG * N_PIECE];  // item = slot | piece<<5 | wants_moves<<10
     uint16_t q_mv[4][SG * 6];
 };
@@ -147,6 +147,9 @@ __device__ __forceinline__ void queue_push(uint32_t* counter, uint16_t* q, bool 
 
 // ---- phase 1a (one warp, lane <-> game)
 __device__ __forceinline__ void step_prologue(StepShared& s, const EnvArgs& a, int lane, int g) {
+#ifdef HIVE_PROLOGUE_SPLIT
+    const long long pt0_ = clock64(); long long pta_ = pt0_, ptb_ = pt0_;
+#endif
     bool live = g < a.n;
     uint32_t pc[11];
 #pragma unroll
@@ -167,7 +170,12 @@ __device__ __forceinline__ void step_prologue(StepShared& s, const EnvArgs& a, i
         turn = h11 & 0xFF; winner = (h11 >> 8) & 0xFF;
         const int done = (h11 >> 16) & 0xFF;
         episode = v3.x; steps = v3.y;
-        const uint32_t n_legal_prev = v3.z;
+        uint32_t n_legal_prev = v3.z;
+#ifdef HIVE_PROLOGUE_SPLIT
+        if (a.op == OP_RANDOM) asm volatile("" : "+r"(lrow.v[24].y), "+r"(lrow.v[0].x));
+        asm volatile("" : "+r"(n_legal_prev), "+r"(turn));
+        pta_ = clock64();
+#endif
 
         bool do_reset = false;
         int action = HIVE_NOOP;
@@ -194,6 +202,10 @@ __device__ __forceinline__ void step_prologue(StepShared& s, const EnvArgs& a, i
             }
             if (a.chosen) a.chosen[g] = (do_reset || !live) ? HIVE_NOOP : action;
         }
+#ifdef HIVE_PROLOGUE_SPLIT
+        asm volatile("" : "+r"(action));
+        ptb_ = clock64();
+#endif
         if (live) {
             if (do_reset) {                                     // GamePlay.new_game, env_hive.py:61-97
 #pragma unroll
@@ -238,6 +250,9 @@ __device__ __forceinline__ void step_prologue(StepShared& s, const EnvArgs& a, i
     s.episode[lane] = episode; s.steps[lane] = steps;
     const unsigned lv = __ballot_sync(FULL, live);
     if (lane == 0) s.any_live = lv;
+#ifdef HIVE_PROLOGUE_SPLIT
+    if (lane == 0) atomicAdd(&g_phase_clk[6], (unsigned long long)(pta_ - pt0_) | ((unsigned long long)(ptb_ - pta_) << 32));
+#endif
 }
 
 // ---- phase 1b (all warps; lane <-> game, the warps take the pieces in turn): stacks; which piece tops which cell
@@ -380,6 +395,7 @@ struct EncodeCtx {
     bool live, push;         // every lane runs every task (warp-uniform loops); the lanes without a live game store nothing
     uint32_t has_row, placeable, pin;   // has_row: searched, unpinned pieces with a non-empty move set
     uint32_t* bits;
+    uint32_t* legal_out;     // the game's row of the dense legal mask in global memory
     GameRec* rec;
 };
 __device__ __forceinline__ BB piece_row(const StepShared& s, const EncodeCtx& e, int p) {
@@ -401,23 +417,35 @@ __device__ __forceinline__ void store_plane_quad(const EncodeCtx& e, int first_p
     for (int i = 0; i < 5; i++) dst[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
 }
 
-// dense legal mask a = cell*11 + k of the own pieces k0..k1-1 (env_hive.py:287-304) into shared memory
-__device__ __forceinline__ void encode_legal(StepShared& s, const EncodeCtx& e, int k0, int k1) {
+// dense legal mask a = cell*11 + k (env_hive.py:287-304) of ALL own pieces for the 32 cells of bitboard word `w`, as whole
+// words: cells 32w .. 32w+31 are exactly the actions 352w .. 352w+351 = mask words 11w .. 11w+10 (word 4 holds 16 cells:
+// words 44 .. 49), so the five tasks write disjoint words with plain stores -- no atomics, no zeroing, no data-dependent
+// loop.  A mask word takes two or three consecutive cells of every piece k (bits 11c + k - 32o of word o): those bits of
+// the piece's move-set word are spread to stride 11 by one multiplication (x * (1 + 2^10 + 2^20) puts bit b at b + 10b)
+// and masked; which cells, which shift and which mask are compile-time constants of (o, k).
+__device__ __forceinline__ void encode_legal_words(StepShared& s, const EncodeCtx& e, int w) {
+    uint32_t r[11];
     int cnt = 0;
-    for (int kk = k0; kk < k1; kk++) {
-        const BB m = piece_row(s, e, e.side * 11 + kk);
 #pragma unroll
-        for (int w = 0; w < 5; w++) {
-            uint32_t mm = m.w[w];
-            cnt += __popc(mm);
-            while (__ballot_sync(FULL, mm != 0u)) {          // warp-uniform trip count: the lanes stay together
-                if (mm) {
-                    const int b = __ffs(mm) - 1; mm &= mm - 1;
-                    const int act = (w * 32 + b) * 11 + kk;
-                    atomicOr(&s.legal[act >> 5][e.lane], 1u << (act & 31));
-                }
-            }
+    for (int k = 0; k < 11; k++) {
+        const int p = e.side * 11 + k;
+        r[k] = ((e.has_row >> p) & 1u) ? s.rows[p][w][e.lane] : ((e.placeable >> p) & 1u) ? s.place[w][e.lane] : 0u;
+        cnt += __popc(r[k]);
+    }
+#pragma unroll
+    for (int o = 0; o < 11; o++) {
+        if (o >= 6 && w == 4) break;                        // (warp-uniform) the last bitboard word has 16 cells
+        uint32_t out = 0u;
+#pragma unroll
+        for (int k = 0; k < 11; k++) {
+            const int lo = 32 * o - k, c0 = lo <= 0 ? 0 : (lo + 10) / 11, c1x = (32 * o + 31 - k) / 11, c1 = c1x > 31 ? 31 : c1x;
+            const int n = c1 - c0 + 1, off = 11 * c0 + k - 32 * o;       // n = 2 or 3 cells; bit of cell c0 in this word
+            const uint32_t sel = (1u << n) - 1u, keep = (1u | (n > 1 ? 1u << 11 : 0u) | (n > 2 ? 1u << 22 : 0u)) << off;
+            const uint32_t x = (r[k] >> c0) & sel;
+            out |= (x * (0x00100401u << off)) & keep;
         }
+        s.legal[11 * w + o][e.lane] = out;                  // (the compact lists are built from the shared copy)
+        if (e.live) e.legal_out[11 * w + o] = out;
     }
     if (cnt) atomicAdd(&s.nlegal[e.lane], (uint32_t)cnt);
 }
@@ -444,8 +472,8 @@ __device__ __forceinline__ void encode_piece_planes(const StepShared& s, const E
     }
 }
 
-// planes 24-35: beetle levels, occupancy, the turn slot, occupied queen neighbours, stuck pieces
-__device__ __forceinline__ void encode_misc_planes(const StepShared& s, const EncodeCtx& e, const uint32_t* __restrict__ geo) {
+// planes 24-31: beetle levels, occupancy, the turn slot (nothing here depends on the one-hive tests or the move searches)
+__device__ __forceinline__ void encode_level_planes(const StepShared& s, const EncodeCtx& e) {
     const int own0 = e.side * 11, opp0 = (1 - e.side) * 11;
     uint32_t r[20];
     BB lvl[6];                                               // 24-26 own beetles at level 2,3,4; 27-29 the opponent's
@@ -473,6 +501,11 @@ __device__ __forceinline__ void encode_misc_planes(const StepShared& s, const En
         r[15 + i] = i == 0 ? (uint32_t)e.turn : i == 1 ? 1u : 0u;   // slot of plane 31: turn, "evaluated in this launch"
     }
     store_plane_quad(e, 28, r);
+}
+// planes 32-35: occupied queen neighbours, stuck pieces
+__device__ __forceinline__ void encode_misc_planes(const StepShared& s, const EncodeCtx& e, const uint32_t* __restrict__ geo) {
+    const int own0 = e.side * 11, opp0 = (1 - e.side) * 11;
+    uint32_t r[20];
     // 32 / 33: occupied neighbours of the own / the opponent's queen
     const int q_own = e.side ? e.cq_b : e.cq_w, q_opp = e.side ? e.cq_w : e.cq_b;
 #pragma unroll
@@ -575,6 +608,32 @@ __device__ __forceinline__ void encode_mobility(const StepShared& s, const Encod
     if (e.live) store_words<(WHICH ? 44 : 50) * 5 + 15 * HALF, 15>(e.bits, f);
 }
 
+// the outputs that depend neither on the one-hive tests nor on the move searches (piece planes, beetle levels / occupancy /
+// turn slot, history + push), taken dynamically by the warps that have finished their share of phase 3 -- a phase as long
+// as its longest Ant flood, in which most warps would otherwise wait at the barrier
+__device__ __forceinline__ void step_early_outputs(StepShared& s, const EnvArgs& a, int lane, int g) {
+    const uint32_t flags = s.flags[lane], hd = s.head[lane];
+    EncodeCtx e;
+    e.lane = lane; e.turn = hd & 0xFF; e.cq_w = (hd >> 8) & 0xFF; e.cq_b = (hd >> 16) & 0xFF;
+    e.side = (e.turn & 1) ? 0 : 1;
+    e.live = flags & 1u; e.push = (flags >> 1) & 1u;
+    e.pin = 0u; e.has_row = 0u; e.placeable = 0u;           // (not final yet, and not read by these tasks)
+    e.bits = a.bits + (size_t)g * BITS_WORDS; e.rec = a.recs + g;
+    e.legal_out = nullptr;
+    for (;;) {
+        uint32_t task = 0;
+        if (lane == 0) task = atomicAdd(&s.next_pre, 1u);
+        task = __shfl_sync(FULL, task, 0);
+        if (task >= 4u) break;
+        switch (task) {
+            case 0: encode_level_planes(s, e); break;
+            case 1: encode_piece_planes(s, e, 0); break;
+            case 2: encode_piece_planes(s, e, 1); break;
+            default: encode_history(s, e); break;
+        }
+    }
+}
+
 // phases 1..5 of one step of the CTA's 32 games (all threads; ends without a trailing barrier).  Returns the mask of the
 // games evaluated in this step (identical in every thread).
 __device__ __forceinline__ unsigned step_phases(StepShared& s, const EnvArgs& a, int blk_index) {      // blk_index: which group of SG games
@@ -583,7 +642,7 @@ __device__ __forceinline__ unsigned step_phases(StepShared& s, const EnvArgs& a,
     const uint32_t* geo = a.hop_lines;
     HIVE_PHASE_BEGIN();
     if (warp == 0) step_prologue(s, a, lane, g);
-    else if (warp == SW - 1 && lane < 6) (&s.n_flood)[lane == 5 ? 6 : lane] = 0u;      // queue fills, next_task (never in the prologue's warp: it must stay converged)
+    else if (warp == SW - 1 && lane < 7) (&s.n_flood)[lane >= 5 ? lane + 1 : lane] = 0u;      // queue fills, next_task, next_pre (never in the prologue's warp: it must stay converged)
     __syncthreads();
     HIVE_PHASE_MARK(0);
     const unsigned live_mask = s.any_live;
@@ -616,7 +675,7 @@ __device__ __forceinline__ unsigned step_phases(StepShared& s, const EnvArgs& a,
     }
     __syncthreads();
     HIVE_PHASE_MARK(2);
-    for (int i = tid; i < LEGAL_WORDS * SG; i += STEP_THREADS) (&s.legal[0][0])[i] = 0u;    // the hive graph is dead: its space becomes the legal mask
+    // (the hive graph is dead: its space becomes the legal mask, every word of which a phase-4 task writes)
 
     {   // ---- phase 3: move searches, warps homogeneous in piece class (thread <-> queued piece)
         const int n0 = (int)s.n_mv[0], n1 = (int)s.n_mv[1], n2 = (int)s.n_mv[2], n3 = (int)s.n_mv[3];
@@ -641,6 +700,8 @@ __device__ __forceinline__ unsigned step_phases(StepShared& s, const EnvArgs& a,
                 }
             }
         }
+        __syncwarp();                                           // (the item loop's trip count differs between the lanes)
+        step_early_outputs(s, a, lane, g);
     }
     __syncthreads();
     HIVE_PHASE_MARK(3);
@@ -657,38 +718,30 @@ __device__ __forceinline__ unsigned step_phases(StepShared& s, const EnvArgs& a,
         e.has_row = live ? s.nonempty[lane] : 0u;
         e.placeable = live ? s.placeable[lane] : 0u;
         e.bits = a.bits + (size_t)g * BITS_WORDS; e.rec = a.recs + g;
+        e.legal_out = a.legal + (size_t)g * LEGAL_WORDS;
     }
-    // the outputs are cut into 19 tasks of very different length (longest first); a warp takes the next one when it is free
+    // the outputs that need the move sets are cut into 10 tasks of different length (longest first); a warp takes the next
+    // one when it is free (the four that do not were taken by the warps that left phase 3 early: step_early_outputs)
     for (;;) {
         uint32_t task = 0;
         if (lane == 0) task = atomicAdd(&s.next_task, 1u);
         task = __shfl_sync(FULL, task, 0);
-        if (task >= 19u) break;
+        if (task >= 10u) break;
         {
             switch (task) {
-                case 0: encode_misc_planes(s, e, geo); break;
-                case 1: case 2: case 3: encode_legal(s, e, 7 + (int)task, 8 + (int)task); break;          // Ants
-                case 4: encode_mobility<1, 0>(s, e, geo); break;
-                case 5: encode_mobility<1, 1>(s, e, geo); break;
-                case 6: encode_mobility<0, 0>(s, e, geo); break;
-                case 7: encode_mobility<0, 1>(s, e, geo); break;
-                case 8: case 9: case 10: encode_legal(s, e, (int)task - 3, (int)task - 2); break;         // Grasshoppers
-                case 11: case 12: encode_legal(s, e, (int)task - 8, (int)task - 7); break;                // Spiders
-                case 13: case 14: encode_legal(s, e, (int)task - 12, (int)task - 11); break;              // Beetles
-                case 15: encode_legal(s, e, 0, 1); break;                                                 // Queen
-                case 16: encode_piece_planes(s, e, 0); break;
-                case 17: encode_piece_planes(s, e, 1); break;
-                default: encode_history(s, e); break;
+                case 0: encode_mobility<1, 0>(s, e, geo); break;
+                case 1: encode_mobility<1, 1>(s, e, geo); break;
+                case 2: encode_mobility<0, 0>(s, e, geo); break;
+                case 3: encode_mobility<0, 1>(s, e, geo); break;
+                case 4: case 5: case 6: case 7: case 8: encode_legal_words(s, e, (int)task - 4); break;
+                default: encode_misc_planes(s, e, geo); break;
             }
         }
     }
     __syncthreads();
     HIVE_PHASE_MARK(4);
 
-    if (live && warp < 2) {   // ---- phase 5: legal mask, count, status, record header
-        uint2* out = reinterpret_cast<uint2*>(a.legal + (size_t)g * LEGAL_WORDS);
-        const int i0 = warp ? 13 : 0, i1 = warp ? 25 : 13;
-        for (int i = i0; i < i1; i++) out[i] = make_uint2(s.legal[2 * i][lane], s.legal[2 * i + 1][lane]);
+    if (live) {   // ---- phase 5: count, status, record header (the legal mask went out word by word in phase 4)
         if (warp == 0) {
             const int turn = hd & 0xFF, prev_winner = (flags >> 8) & 0xFF;
             const uint32_t iw = s.info[0][lane], ib = s.info[11][lane];
