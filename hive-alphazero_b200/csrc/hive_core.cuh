@@ -295,14 +295,29 @@ __device__ __forceinline__ BB eval_moves(uint32_t info, const BB& occ, int p, co
                 BB nx = x | slide_step(sl, x);
                 if (bb_eq(nx, x)) break;
                 x = nx;
+#ifdef HIVE_EXP_SHORT_ANT
+                break;                                                   // (measurement aid: results wrong)
+#endif
             }
             mv = bb_andn(x, src);
         } else {                                                         // pieces.py:78-85
             mv = bb_zero();
+            // the first steps the gates allow (usually two: along the hive either way), then one trip of a rolled loop per
+            // first step -- a lane walks only its own paths, and the warp as many trips as its busiest lane
+            uint32_t starts = 0, nb03 = 0, nb45 = 0;
 #pragma unroll
             for (int i = 0; i < 6; i++) {
                 const int c1 = cell_nbr(cell, i);
-                if (!bb_test(sl.g[i], c1)) continue;
+                if (bb_test(sl.g[i], c1)) starts |= 1u << i;
+                if (i < 4) nb03 |= (uint32_t)c1 << (8 * i); else nb45 |= (uint32_t)c1 << (8 * (i - 4));
+            }
+#ifdef HIVE_EXP_SHORT_SPIDER
+            starts &= starts - 1; starts &= starts - 1;                  // (measurement aid: results wrong)
+#endif
+            while (starts) {
+                const int i = __ffs(starts) - 1;
+                starts &= starts - 1;
+                const int c1 = (int)(((i < 4 ? nb03 : nb45) >> (8 * (i & 3))) & 0xFFu);
                 const BB a = bb_bit(c1);
                 const BB b = bb_andn(slide_step(sl, a), src);
                 const BB c = bb_andn(slide_step(sl, b), src | a);
