@@ -295,9 +295,6 @@ __device__ __forceinline__ BB eval_moves(uint32_t info, const BB& occ, int p, co
                 BB nx = x | slide_step(sl, x);
                 if (bb_eq(nx, x)) break;
                 x = nx;
-#ifdef HIVE_EXP_SHORT_ANT
-                break;                                                   // (measurement aid: results wrong)
-#endif
             }
             mv = bb_andn(x, src);
         } else {                                                         // pieces.py:78-85
@@ -311,9 +308,6 @@ __device__ __forceinline__ BB eval_moves(uint32_t info, const BB& occ, int p, co
                 if (bb_test(sl.g[i], c1)) starts |= 1u << i;
                 if (i < 4) nb03 |= (uint32_t)c1 << (8 * i); else nb45 |= (uint32_t)c1 << (8 * (i - 4));
             }
-#ifdef HIVE_EXP_SHORT_SPIDER
-            starts &= starts - 1; starts &= starts - 1;                  // (measurement aid: results wrong)
-#endif
             while (starts) {
                 const int i = __ffs(starts) - 1;
                 starts &= starts - 1;

@@ -419,11 +419,12 @@ __device__ __forceinline__ void store_plane_quad(const EncodeCtx& e, int first_p
 
 // dense legal mask a = cell*11 + k (env_hive.py:287-304) of ALL own pieces for the 32 cells of bitboard word `w`, as whole
 // words: cells 32w .. 32w+31 are exactly the actions 352w .. 352w+351 = mask words 11w .. 11w+10 (word 4 holds 16 cells:
-// words 44 .. 49), so the five tasks write disjoint words with plain stores -- no atomics, no zeroing, no data-dependent
+// words 44 .. 49), so the tasks (two per bitboard word) write disjoint words with plain stores -- no atomics, no zeroing, no data-dependent
 // loop.  A mask word takes two or three consecutive cells of every piece k (bits 11c + k - 32o of word o): those bits of
 // the piece's move-set word are spread to stride 11 by one multiplication (x * (1 + 2^10 + 2^20) puts bit b at b + 10b)
 // and masked; which cells, which shift and which mask are compile-time constants of (o, k).
-__device__ __forceinline__ void encode_legal_words(StepShared& s, const EncodeCtx& e, int w) {
+// `half`: 0 = mask words 11w .. 11w+5 (and the count), 1 = words 11w+6 .. 11w+10 (not for w = 4).
+__device__ __forceinline__ void encode_legal_words(StepShared& s, const EncodeCtx& e, int w, int half) {
     uint32_t r[11];
     int cnt = 0;
 #pragma unroll
@@ -434,7 +435,7 @@ __device__ __forceinline__ void encode_legal_words(StepShared& s, const EncodeCt
     }
 #pragma unroll
     for (int o = 0; o < 11; o++) {
-        if (o >= 6 && w == 4) break;                        // (warp-uniform) the last bitboard word has 16 cells
+        if ((half >= 0 && (o >= 6) != (half != 0)) || (o >= 6 && w == 4)) continue;      // (warp-uniform; half < 0: all words)
         uint32_t out = 0u;
 #pragma unroll
         for (int k = 0; k < 11; k++) {
@@ -447,7 +448,7 @@ __device__ __forceinline__ void encode_legal_words(StepShared& s, const EncodeCt
         s.legal[11 * w + o][e.lane] = out;                  // (the compact lists are built from the shared copy)
         if (e.live) e.legal_out[11 * w + o] = out;
     }
-    if (cnt) atomicAdd(&s.nlegal[e.lane], (uint32_t)cnt);
+    if (cnt && half <= 0) atomicAdd(&s.nlegal[e.lane], (uint32_t)cnt);
 }
 
 // planes 0-11 (which = 0: pieces of the side to move + their union) or 12-23 (which = 1: the opponent's)
@@ -565,9 +566,9 @@ __device__ __forceinline__ void store_words(uint32_t* bits, const uint32_t (&f)[
 // three of the planes 44-49 (WHICH = 1: opponent pieces able to reach the j-th empty neighbour of the own queen) or 50-55
 // (WHICH = 0: own on-board pieces whose action list holds the j-th empty neighbour of the opponent's queen); j = rank of
 // the neighbour in tile.adjacent_tiles order (env_hive.py:448-478; GEO_RANK); HALF = 0: ranks 0-2, 1: ranks 3-5
-template <int WHICH, int HALF>
-__device__ __forceinline__ void encode_mobility(const StepShared& s, const EncodeCtx& e, const uint32_t* __restrict__ geo) {
-    const int col = WHICH ? 1 - e.side : e.side, base = col * 11;
+// (which, half are run-time values: ONE copy of the code, which the four warps that take these tasks run side by side)
+__device__ __forceinline__ void encode_mobility(const StepShared& s, const EncodeCtx& e, const uint32_t* __restrict__ geo, int which, int half) {
+    const int col = which ? 1 - e.side : e.side, base = col * 11;
     const int qc = col ? e.cq_w : e.cq_b;                    // the queen of the other colour than the pieces
     uint32_t nbr_by_rank[3];
     bool any_empty = false;
@@ -580,7 +581,7 @@ __device__ __forceinline__ void encode_mobility(const StepShared& s, const Encod
             const uint32_t nb = ((i < 4 ? n03 : n45) >> (8 * (i & 3))) & 0xFFu, rank = (ranks >> (3 * i)) & 7u;
             const bool empty = !((s.occ[nb >> 5][e.lane] >> (nb & 31)) & 1u);
 #pragma unroll
-            for (int r = 0; r < 3; r++) if (empty && rank == (uint32_t)(r + 3 * HALF)) { nbr_by_rank[r] = nb; any_empty = true; }
+            for (int r = 0; r < 3; r++) if (empty && rank == (uint32_t)(r + 3 * half)) { nbr_by_rank[r] = nb; any_empty = true; }
         }
     }
     BB pl[3];
@@ -605,7 +606,10 @@ __device__ __forceinline__ void encode_mobility(const StepShared& s, const Encod
     for (int r = 0; r < 3; r++)
 #pragma unroll
         for (int i = 0; i < 5; i++) f[r * 5 + i] = pl[r].w[i];
-    if (e.live) store_words<(WHICH ? 44 : 50) * 5 + 15 * HALF, 15>(e.bits, f);
+    if (e.live) {                                            // planes 44-46, 47-49, 50-52, 53-55: four alignments of the 15 words
+        if (which) { if (half) store_words<47 * 5, 15>(e.bits, f); else store_words<44 * 5, 15>(e.bits, f); }
+        else { if (half) store_words<53 * 5, 15>(e.bits, f); else store_words<50 * 5, 15>(e.bits, f); }
+    }
 }
 
 // the outputs that depend neither on the one-hive tests nor on the move searches (piece planes, beetle levels / occupancy /
@@ -627,8 +631,7 @@ __device__ __forceinline__ void step_early_outputs(StepShared& s, const EnvArgs&
         if (task >= 4u) break;
         switch (task) {
             case 0: encode_level_planes(s, e); break;
-            case 1: encode_piece_planes(s, e, 0); break;
-            case 2: encode_piece_planes(s, e, 1); break;
+            case 1: case 2: encode_piece_planes(s, e, (int)task - 1); break;
             default: encode_history(s, e); break;
         }
     }
@@ -729,12 +732,9 @@ __device__ __forceinline__ unsigned step_phases(StepShared& s, const EnvArgs& a,
         if (task >= 10u) break;
         {
             switch (task) {
-                case 0: encode_mobility<1, 0>(s, e, geo); break;
-                case 1: encode_mobility<1, 1>(s, e, geo); break;
-                case 2: encode_mobility<0, 0>(s, e, geo); break;
-                case 3: encode_mobility<0, 1>(s, e, geo); break;
-                case 4: case 5: case 6: case 7: case 8: encode_legal_words(s, e, (int)task - 4); break;
-                default: encode_misc_planes(s, e, geo); break;
+                case 0: case 1: case 2: case 3: encode_mobility(s, e, geo, task < 2u, (int)(task & 1u)); break;
+                case 4: encode_misc_planes(s, e, geo); break;
+                default: encode_legal_words(s, e, (int)task - 5, -1); break;                               // 5 .. 9: bitboard word w
             }
         }
     }
