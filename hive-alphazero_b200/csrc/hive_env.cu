@@ -294,7 +294,7 @@ int hive::create_env(int n_games, int device, void* stream, int slices, hive_env
         while (S > 1 && n_games < S * SG * 2) S--;            // small batches are not worth slicing
         h->n_sub = S;
         const char* ec = getenv("HIVE_B200_STORE_CTAS");
-        h->store_ctas_per_sm = ec && atoi(ec) > 0 ? atoi(ec) : 2;
+        h->store_ctas_per_sm = ec && atoi(ec) > 0 ? atoi(ec) : 3;      // measured: 2 -> 55.3, 3 -> 54.4, 4 -> 56.6 us per 16,384-game step
         const char* hs = getenv("HIVE_B200_HOST_SLICES");
         h->host_slices = hs && atoi(hs) > 0 ? atoi(hs) : 2;
         const char* as = getenv("HIVE_B200_ASYNC_SLICES");

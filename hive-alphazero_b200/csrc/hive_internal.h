@@ -28,7 +28,7 @@ struct hive_env {
     int delta_ctas_per_sm = 4;      // HIVE_B200_DELTA_CTAS: cap of the delta store's grid (all concurrent store launches together)
     static constexpr int MAX_SUB = 16;
     int n_sub = 1;                  // the batch is cut into n_sub slices whose kernel chains overlap on side streams
-    int sm_count = 148, store_ctas_per_sm = 2;   // the persistent plane-store kernels together keep this many CTAs per SM
+    int sm_count = 148, store_ctas_per_sm = 3;   // the persistent plane-store kernels together keep this many CTAs per SM
     int host_slices = 2;            // slices of a step the host launches kernel by kernel (graph replays use n_sub)
     cudaStream_t sub_stream[MAX_SUB] = {}, store_stream[MAX_SUB] = {};
     cudaEvent_t encoded_ev[MAX_SUB] = {}, stored_ev[MAX_SUB][2] = {};
