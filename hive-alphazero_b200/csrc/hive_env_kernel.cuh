@@ -588,16 +588,22 @@ __device__ __forceinline__ void encode_mobility(const StepShared& s, const Encod
 #pragma unroll
     for (int r = 0; r < 3; r++) pl[r] = bb_zero();
     uint32_t todo = any_empty ? (e.has_row >> base) & 0x7FFu : 0u;   // the searched pieces of that colour with a non-empty move set
+    uint32_t nw[3], nsh[3], nok[3];                          // word and bit of the neighbour in a move-set row; 0 / ~0: there is one
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        nok[r] = nbr_by_rank[r] == 0xFFFFu ? 0u : 0xFFFFFFFFu;
+        nw[r] = nok[r] ? nbr_by_rank[r] >> 5 : 0u; nsh[r] = nbr_by_rank[r] & 31u;
+    }
     while (__ballot_sync(FULL, todo != 0u)) {                // warp-uniform trip count: the lanes stay together
         if (todo) {
             const int kk = __ffs(todo) - 1; todo &= todo - 1;
-            const int p = base + kk;
-            const BB m = piece_row(s, e, p);
+            const int p = base + kk;                         // (a searched piece with a non-empty set: its row is in s.rows)
             const BB b = bb_onehot((int)(s.info[p][e.lane] & 0xFFu));
 #pragma unroll
-            for (int r = 0; r < 3; r++) {
-                const uint32_t nb = nbr_by_rank[r];
-                if (nb != 0xFFFFu && bb_test(m, (int)nb)) pl[r] = pl[r] | b;
+            for (int r = 0; r < 3; r++) {                    // one row word per rank instead of the whole row
+                const uint32_t hit = (0u - ((s.rows[p][nw[r]][e.lane] >> nsh[r]) & 1u)) & nok[r];
+#pragma unroll
+                for (int i = 0; i < 5; i++) pl[r].w[i] |= b.w[i] & hit;
             }
         }
     }
