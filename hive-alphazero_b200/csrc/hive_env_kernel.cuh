@@ -380,14 +380,6 @@ __device__ __forceinline__ void step_pieces(StepShared& s, int warp, int lane, c
 __device__ __forceinline__ bool flood_graph(const StepShared& s, int slot, int p) {
     const uint32_t goal = s.graph.adj[p][slot], removed = 1u << p;
     uint32_t reach = goal & (0u - goal), todo = reach;       // reached cells; reached cells whose neighbours are still to be added
-#ifndef HIVE_FLOOD_TWO_NODES
-    while (todo) {                                           // one flat loop (a node per trip): the lanes of a warp stay together
-        if ((reach & goal) == goal) return false;
-        const int i = __ffs(todo) - 1; todo &= todo - 1;
-        const uint32_t nw = s.graph.adj[i][slot] & ~(reach | removed);
-        reach |= nw; todo |= nw;
-    }
-#else
     while (todo) {                                           // one flat loop, two nodes per trip: their two loads are in flight together
         if ((reach & goal) == goal) return false;
         const int i0 = __ffs(todo) - 1; todo &= todo - 1;
@@ -395,7 +387,6 @@ __device__ __forceinline__ bool flood_graph(const StepShared& s, int slot, int p
         const uint32_t nw = (s.graph.adj[i0][slot] | s.graph.adj[i1][slot]) & ~(reach | removed);
         reach |= nw; todo |= nw;
     }
-#endif
     return (reach & goal) != goal;
 }
 
